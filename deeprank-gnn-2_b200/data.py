@@ -1,0 +1,174 @@
+"""``Data`` / ``Batch`` containers and the collate the Trainer's loader performs.
+
+The reference uses ``torch_geometric.data.{Data,Batch}`` and
+``torch_geometric.loader.DataLoader`` (reference ``deeprank2/trainer.py:17,541-557``;
+``dataset.py:1044-1052`` builds each ``Data``).  Only the slice of that interface the
+GNN path touches is mirrored: attribute access/assignment, ``clone()``, ``to()``,
+``num_nodes``, ``Batch.from_data_list`` with PyG's collate rules:
+
+* tensors are concatenated along dim 0, except attributes whose name contains
+  ``index`` (``edge_index``), which are concatenated along dim 1 after adding the
+  cumulative node offset of their graph;
+* ``cluster0`` / ``cluster1`` get NO offset (per-graph local ids; that is why
+  ``get_preloaded_cluster`` exists, ``utils/community_pooling.py:23-27``);
+* ``batch`` (int64 [N], non-decreasing) and ``ptr`` (int64 [B+1]) are added;
+* python attributes (``entry_names``) become lists.
+
+A ``Batch`` also carries the device-side graph index (destination-sorted CSR,
+source-sorted CSC, graph offsets) lazily built by ``deeprank2_b200.graph``; it is
+cached on the object so the four convolutions of a forward pass and their backward
+share one build.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Iterable
+
+import torch
+
+_OFFSET_KEYS = ("index", "face")
+
+
+def _takes_node_offset(key: str) -> bool:
+    return any(tag in key for tag in _OFFSET_KEYS)
+
+
+class Data:
+    """One graph: ``x [n,F]``, ``edge_index [2,E]`` (int64), ``edge_attr [E,Fe]``, ``y``, ``pos`` ..."""
+
+    def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, pos=None, **extra: Any):
+        self.x = x
+        self.edge_index = edge_index
+        self.edge_attr = edge_attr
+        self.y = y
+        self.pos = pos
+        for key, value in extra.items():
+            setattr(self, key, value)
+
+    # -- introspection
+    def _fields(self) -> Iterable[str]:
+        return [k for k in self.__dict__ if not k.startswith("_")]
+
+    @property
+    def keys(self):
+        return [k for k in self._fields() if self.__dict__[k] is not None]
+
+    @property
+    def num_nodes(self) -> int:
+        if self.x is not None:
+            return int(self.x.shape[0])
+        if self.pos is not None:
+            return int(self.pos.shape[0])
+        if self.edge_index is not None and self.edge_index.numel() > 0:
+            return int(self.edge_index.max()) + 1
+        return 0
+
+    @property
+    def num_edges(self) -> int:
+        return 0 if self.edge_index is None else int(self.edge_index.shape[1])
+
+    @property
+    def num_node_features(self) -> int:
+        return 0 if self.x is None else (1 if self.x.dim() == 1 else int(self.x.shape[1]))
+
+    @property
+    def num_edge_features(self) -> int:
+        return 0 if self.edge_attr is None else (1 if self.edge_attr.dim() == 1 else int(self.edge_attr.shape[1]))
+
+    def __contains__(self, key: str) -> bool:
+        return self.__dict__.get(key) is not None
+
+    def __repr__(self) -> str:
+        parts = []
+        for k in self._fields():
+            v = self.__dict__[k]
+            if isinstance(v, torch.Tensor):
+                parts.append(f"{k}={list(v.shape)}")
+            elif v is not None:
+                parts.append(f"{k}={type(v).__name__}")
+        return f"{type(self).__name__}({', '.join(parts)})"
+
+    # -- copies / movement (private caches, e.g. the graph index, are dropped on clone and moved on to())
+    def clone(self):
+        new = type(self).__new__(type(self))
+        for k, v in self.__dict__.items():
+            if k.startswith("_"):
+                continue
+            new.__dict__[k] = v.clone() if isinstance(v, torch.Tensor) else copy.deepcopy(v)
+        return new
+
+    def to(self, device, non_blocking: bool = False):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                self.__dict__[k] = v.to(device, non_blocking=non_blocking)
+            elif k.startswith("_"):
+                self.__dict__.pop(k)
+        return self
+
+    def cuda(self, non_blocking: bool = False):
+        return self.to("cuda", non_blocking=non_blocking)
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def pin_memory(self):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor) and not v.is_cuda:
+                self.__dict__[k] = v.pin_memory()
+        return self
+
+
+class Batch(Data):
+    """A disjoint union of graphs (block-diagonal adjacency)."""
+
+    def __init__(self, batch=None, ptr=None, **kwargs: Any):
+        super().__init__(**kwargs)
+        self.batch = batch
+        if ptr is not None:
+            self.ptr = ptr
+
+    @property
+    def num_graphs(self) -> int:
+        ptr = self.__dict__.get("ptr")
+        if ptr is not None:
+            return int(ptr.numel()) - 1
+        if self.batch is None or self.batch.numel() == 0:
+            return 0
+        return int(self.batch.max()) + 1  # host sync: only hit for hand-made batches without ptr
+
+    @classmethod
+    def from_data_list(cls, data_list: list[Data]) -> "Batch":
+        if len(data_list) == 0:
+            raise ValueError("cannot collate an empty list of graphs")
+        names: list[str] = []
+        for d in data_list:
+            for k in d._fields():
+                if k not in names:
+                    names.append(k)
+        sizes = [d.num_nodes for d in data_list]
+        ptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
+        ptr[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0)
+        out = cls()
+        for k in names:
+            column = [d.__dict__.get(k) for d in data_list]
+            present = [v for v in column if v is not None]
+            if not present:
+                setattr(out, k, None)
+            elif isinstance(present[0], torch.Tensor):
+                if len(present) != len(column):
+                    raise ValueError(f"attribute {k!r} is missing on some graphs of the batch")
+                if _takes_node_offset(k):
+                    setattr(out, k, torch.cat([v + int(o) for v, o in zip(column, ptr[:-1])], dim=1))
+                else:
+                    column = [v.unsqueeze(0) if v.dim() == 0 else v for v in column]
+                    setattr(out, k, torch.cat(column, dim=0))
+            else:
+                setattr(out, k, list(column))
+        out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int64), torch.tensor(sizes, dtype=torch.int64))
+        out.ptr = ptr
+        return out
+
+
+def collate(data_list: list[Data]) -> Batch:
+    """``collate_fn`` for ``torch.utils.data.DataLoader`` (what PyG's ``Collater`` does for ``Data``)."""
+    return Batch.from_data_list(data_list)
