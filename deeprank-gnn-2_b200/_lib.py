@@ -1,0 +1,98 @@
+"""ctypes binding of ``libdrk_b200.so`` (the C ABI declared in ``include/drk_b200.h``).
+
+The library is built in-tree by ``csrc/Makefile`` (``__graft_entry__.build()``).  There is
+no fallback: if it is missing, ``load()`` raises, and every op in this package calls
+``load()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_int32, c_int64, c_size_t, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libdrk_b200.so")
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+
+# constants mirrored from include/drk_b200.h
+ABI_VERSION = 1
+OK = 0
+STATUS_INDEX_RANGE = 1
+STATUS_CROSS_GRAPH = 2
+STATUS_UNSORTED = 4
+ACT_NONE, ACT_RELU = 0, 1
+REDUCE_SUM, REDUCE_MEAN_CLAMP, REDUCE_MEAN_NAN = 0, 1, 2
+
+_P = c_void_p
+_I32 = c_int32
+_I64 = c_int64
+
+# name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
+SIGNATURES = {
+    "drk_abi_version": (c_int32, []),
+    "drk_last_error": (c_char_p, []),
+    "drk_launch_count": (c_int64, []),
+    "drk_graph_index_workspace_bytes": (c_size_t, [_I64, _I32]),
+    "drk_graph_index_build": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "drk_segment_index_workspace_bytes": (c_size_t, [_I64, _I32]),
+    "drk_segment_index_build": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, c_size_t, _P]),
+    "drk_batch_offsets": (c_int32, [_P, _I32, _I32, _P, _P, _P, _P]),
+    "drk_gather_rows": (c_int32, [_P, _I64, _P, _I64, _I32, _P, _I64, _P]),
+    "drk_node_linear": (c_int32, [_P, _I64, _P, _I64, _I32, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "drk_weight_grad_workspace_bytes": (c_size_t, [_I32, _I32]),
+    "drk_weight_grad": (c_int32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, c_size_t, _P]),
+    "drk_spmm": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+    "drk_segment_mean": (c_int32, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
+    "drk_segment_mean_bwd": (c_int32, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
+}
+
+_lib = None
+
+
+class DrkError(RuntimeError):
+    """A C-ABI call returned a negative DRK_E* code."""
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)]
+    if force:
+        subprocess.run(["make", "-C", CSRC_DIR, "clean"], check=True, capture_output=not verbose)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"building libdrk_b200.so failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C deeprank-gnn-2_b200/csrc`). "
+            "deeprank2_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.drk_abi_version() != ABI_VERSION:
+        raise ImportError(f"libdrk_b200.so has ABI {lib.drk_abi_version()}, this package expects {ABI_VERSION}: rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != OK:
+        msg = load().drk_last_error()
+        raise DrkError(f"{what or 'drk call'} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().drk_launch_count())

@@ -1,0 +1,82 @@
+// Shared host/device helpers for the drk_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "drk_b200.h"
+
+namespace drk {
+
+constexpr int kWarp = 32;
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- host side: thread-local error text + launch accounting
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int finish_launch(const char* what, int n_launches = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return DRK_ECUDA;
+  }
+  g_launches.fetch_add(n_launches, std::memory_order_relaxed);
+  return DRK_OK;
+}
+
+#define DRK_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::drk::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+inline T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+// ---- device side
+#ifdef __CUDACC__
+
+// streaming (read-once) loads: keep them out of L1 so the gathered rows stay resident there
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ long long ld_stream_i64(const int64_t* p) {
+  long long v;
+  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// gathered rows: read-only path, allocate in L1 (neighbouring destinations re-use them)
+__device__ __forceinline__ float4 ld_gather_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ld_gather_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+#endif  // __CUDACC__
+
+}  // namespace drk

@@ -1,0 +1,415 @@
+// Dense node-level projections of the message-passing path, fp32 FFMA from shared memory.
+//
+//   drk_node_linear   C = act(A op(B) + bias) [* relu-mask]      self.fc(...) ginet.py:45-46,
+//                     torch.mm(x, wc|wn) foutnet.py:50-51, _edge_mlp/_node_mlp vanilla_gnn.py:22-24,
+//                     and dX = dY W in the backward pass
+//   drk_weight_grad   dW = dY^T X (+ dbias)                       autograd of the above
+//
+// Why not tensor cores: the parity bar is rtol 1e-5 against the reference's fp32 CPU result;
+// TF32 (10-bit mantissa) is ~1e-3.  The contractions are tiny (K <= ~100, M <= 64: 0.25 GFLOP
+// for the whole 77k-node batch) and sit at ~10 FLOP/B, right at the fp32-SIMT ridge of a B200,
+// so the kernels are organised to be FFMA-issue-bound rather than shared-memory-bound:
+// every 128-bit shared-memory load feeds 16 FMAs per thread and the tile strides are chosen
+// so that the 8 (resp. 4) distinct float4 a warp reads per instruction fall in distinct banks.
+#include <algorithm>
+
+#include "drk_common.cuh"
+
+namespace drk {
+
+// smem row stride for a K-chunk of kc floats: multiple of 4 (float4 rows) with stride/4 odd, so that
+// r * stride mod 32 hits 8 distinct 4-bank groups for 8 consecutive rows r.
+static inline int padded_stride(int kc) {
+  int kp = (kc + 3) / 4 * 4;
+  if (((kp / 4) & 1) == 0) kp += 4;
+  return kp;
+}
+
+constexpr int kLinThreads = 128;  // 4 warps
+constexpr int kLinTileN = 128;    // rows per CTA: 4 warps x 8 row-groups x 4 rows
+constexpr int kLinKChunk = 64;    // K is processed in chunks of <= 64
+
+struct LinearArgs {
+  const float* a;
+  int64_t lda;
+  const float* b;
+  int64_t ldb;
+  int32_t trans_b;
+  const float* bias;
+  const float* mask;
+  int64_t ld_mask;
+  float* c;
+  int64_t ldc;
+  int64_t n;
+  int32_t k;
+  int32_t m;
+  int32_t act;
+  int32_t a_vec;  // 4 / 2 / 1: widest aligned vector for loading A rows
+  int32_t c_vec;  // 4 or 1: vector width for storing C (and loading mask)
+};
+
+// CT = output columns per thread (4, 8 or 16) -> CTA column tile of 4*CT = 16 / 32 / 64.
+template <int CT>
+__global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p) {
+  constexpr int kTileM = 4 * CT;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int cg = lane & 3;   // column group
+  const int rg = lane >> 2;  // row group
+  const int64_t row0 = (int64_t)blockIdx.x * kLinTileN;
+  const int m0 = blockIdx.y * kTileM;
+
+  float acc[4][CT];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
+
+  for (int k0 = 0; k0 < p.k; k0 += kLinKChunk) {
+    const int kc = min(kLinKChunk, p.k - k0);
+    const int kp = ((kc + 3) / 4 * 4) + ((((kc + 3) / 4) & 1) == 0 ? 4 : 0);  // == padded_stride(kc)
+    float* sA = smem;                   // [kLinTileN][kp]
+    float* sW = smem + kLinTileN * kp;  // [kTileM][kp], rows permuted
+    if (k0 > 0) __syncthreads();
+
+    // ---- A tile: rows row0.., columns k0..k0+kc, zero padded to kp
+    {
+      const int vec = p.a_vec;
+      const int nv = (kc + vec - 1) / vec;  // vectors per row (kc % vec == 0 whenever vec > 1, see dispatcher)
+      for (int r = warp; r < kLinTileN; r += kLinThreads / 32) {
+        const int64_t gr = row0 + r;
+        float* dst = sA + r * kp;
+        const float* src = p.a + gr * p.lda + k0;
+        for (int v = lane; v * vec < kp; v += 32) {
+          if (vec == 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < p.n && v < nv) t = ld_stream_f4(src + v * 4);
+            *reinterpret_cast<float4*>(dst + v * 4) = t;
+          } else if (vec == 2) {
+            float2 t = make_float2(0.f, 0.f);
+            if (gr < p.n && v < nv) t = __ldg(reinterpret_cast<const float2*>(src + v * 2));
+            *reinterpret_cast<float2*>(dst + v * 2) = t;
+          } else {
+            dst[v] = (gr < p.n && v < kc) ? ld_stream_f32(src + v) : 0.f;
+          }
+        }
+      }
+    }
+    // ---- W tile: logical row m = 4*cg + t + 16*jj is stored at smem row cg + 4*t + 16*jj
+    for (int e = threadIdx.x; e < kTileM * kp; e += kLinThreads) {
+      const int ml = e / kp;  // logical column of C within the tile
+      const int kk = e - ml * kp;
+      const int gm = m0 + ml;
+      float v = 0.f;
+      if (gm < p.m && kk < kc) v = p.trans_b ? __ldg(p.b + (int64_t)gm * p.ldb + (k0 + kk)) : __ldg(p.b + (int64_t)(k0 + kk) * p.ldb + gm);
+      const int srow = ((ml >> 2) & 3) + 4 * (ml & 3) + (ml & ~15);
+      sW[srow * kp + kk] = v;
+    }
+    __syncthreads();
+
+    const float* a_base = sA + (warp * 32 + rg) * kp;
+    const float* w_base = sW + cg * kp;
+    for (int k4 = 0; k4 < kp; k4 += 4) {
+      float4 av[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(a_base + (8 * j) * kp + k4);
+#pragma unroll
+      for (int jj = 0; jj < CT / 4; ++jj) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 bv = *reinterpret_cast<const float4*>(w_base + (4 * t + 16 * jj) * kp + k4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float s = acc[j][jj * 4 + t];
+            s = fmaf(av[j].x, bv.x, s);
+            s = fmaf(av[j].y, bv.y, s);
+            s = fmaf(av[j].z, bv.z, s);
+            s = fmaf(av[j].w, bv.w, s);
+            acc[j][jj * 4 + t] = s;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: bias, activation, relu-mask, store (float4 per (row, 4-column group))
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t gr = row0 + warp * 32 + rg + 8 * j;
+    if (gr >= p.n) continue;
+#pragma unroll
+    for (int jj = 0; jj < CT / 4; ++jj) {
+      const int gm = m0 + 4 * cg + 16 * jj;
+      if (gm >= p.m) continue;
+      float o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float v = acc[j][jj * 4 + t];
+        if (p.bias != nullptr && gm + t < p.m) v += __ldg(p.bias + gm + t);
+        if (p.act == DRK_ACT_RELU) v = v < 0.f ? 0.f : v;
+        o[t] = v;
+      }
+      float* dst = p.c + gr * p.ldc + gm;
+      if (p.c_vec == 4 && gm + 3 < p.m) {
+        if (p.mask != nullptr) {
+          const float4 mk = ld_stream_f4(p.mask + gr * p.ld_mask + gm);
+          o[0] = mk.x <= 0.f ? 0.f : o[0];
+          o[1] = mk.y <= 0.f ? 0.f : o[1];
+          o[2] = mk.z <= 0.f ? 0.f : o[2];
+          o[3] = mk.w <= 0.f ? 0.f : o[3];
+        }
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (gm + t < p.m) {
+            float v = o[t];
+            if (p.mask != nullptr) v = p.mask[gr * p.ld_mask + gm + t] <= 0.f ? 0.f : v;
+            dst[t] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dW[m,k] = sum_n dY[n,m] X[n,k].  Persistent CTAs stride over 64-row tiles of (dY, X) staged in
+// shared memory as loaded (no transpose: the reduction index n is the smem row, so the float4 a warp
+// reads per instruction lie in ONE row -> conflict free for any stride).  Each warp owns a
+// 32(m) x 16(k) block of dW in registers (4x4 per lane); WN warps split the rows of a tile and are
+// combined through shared memory in a fixed order; CTA partials go to the workspace and a second
+// kernel adds them in CTA order.  No atomics -> deterministic.
+constexpr int kWgThreads = 256;
+constexpr int kWgTileN = 64;
+
+struct WgradArgs {
+  const float* dy;
+  int64_t ld_dy;
+  const float* x;
+  int64_t ldx;
+  int64_t n;
+  int32_t k;
+  int32_t m;
+  float* partial;  // [gridDim.x][m_pad][k_pad] (+ [gridDim.x][m_pad] bias partials after it)
+  float* partial_bias;
+  int32_t m_pad;
+  int32_t k_pad;
+};
+
+template <int WM, int WK>
+__global__ void __launch_bounds__(kWgThreads) k_weight_grad(const WgradArgs p) {
+  constexpr int WN = 8 / (WM * WK);
+  constexpr int kTileM = 32 * WM;
+  constexpr int kTileK = 16 * WK;
+  extern __shared__ __align__(16) float smem[];
+  float* sDY = smem;                      // [kWgTileN][kTileM]
+  float* sX = smem + kWgTileN * kTileM;   // [kWgTileN][kTileK]
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int wn = warp % WN;
+  const int wk = (warp / WN) % WK;
+  const int wm = warp / (WN * WK);
+  const int mg = lane & 7;
+  const int kg = lane >> 3;
+  const int m0 = blockIdx.z * kTileM;
+  const int k0 = blockIdx.y * kTileK;
+
+  float acc[4][4];
+  float accb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    accb[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  const bool bias_lane = (wk == 0 && kg == 0 && blockIdx.y == 0);
+
+  const int64_t n_tiles = (p.n + kWgTileN - 1) / kWgTileN;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kWgTileN;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kWgTileN * kTileM; e += kWgThreads) {
+      const int r = e / kTileM;
+      const int c = e - r * kTileM;
+      const int64_t gr = row0 + r;
+      sDY[e] = (gr < p.n && m0 + c < p.m) ? ld_stream_f32(p.dy + gr * p.ld_dy + m0 + c) : 0.f;
+    }
+    for (int e = threadIdx.x; e < kWgTileN * kTileK; e += kWgThreads) {
+      const int r = e / kTileK;
+      const int c = e - r * kTileK;
+      const int64_t gr = row0 + r;
+      sX[e] = (gr < p.n && k0 + c < p.k) ? ld_stream_f32(p.x + gr * p.ldx + k0 + c) : 0.f;
+    }
+    __syncthreads();
+    const float* dyp = sDY + wm * 32 + mg * 4;
+    const float* xp = sX + wk * 16 + kg * 4;
+#pragma unroll 4
+    for (int r = wn; r < kWgTileN; r += WN) {
+      const float4 a = *reinterpret_cast<const float4*>(dyp + r * kTileM);
+      const float4 b = *reinterpret_cast<const float4*>(xp + r * kTileK);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        if (bias_lane) accb[i] += av[i];
+      }
+    }
+  }
+
+  // combine the WN row-splits in fixed order through smem, then write this CTA's partial
+  __syncthreads();
+  float* red = smem;  // [WN][kTileM][kTileK]; the launcher sizes smem as max(tiles, this scratch)
+  float* redb = smem + WN * kTileM * kTileK;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ml = wm * 32 + mg * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(wn * kTileM + ml) * kTileK + wk * 16 + kg * 4 + j] = acc[i][j];
+    if (bias_lane) redb[wn * kTileM + ml] = accb[i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kTileM * kTileK; e += kWgThreads) {
+    const int ml = e / kTileK;
+    const int kl = e - ml * kTileK;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WN; ++w) s += red[(w * kTileM + ml) * kTileK + kl];
+    const int gm = m0 + ml, gk = k0 + kl;
+    if (gm < p.m_pad && gk < p.k_pad) p.partial[((int64_t)blockIdx.x * p.m_pad + gm) * p.k_pad + gk] = s;
+  }
+  if (p.partial_bias != nullptr && blockIdx.y == 0) {
+    for (int ml = threadIdx.x; ml < kTileM; ml += kWgThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WN; ++w) s += redb[w * kTileM + ml];
+      if (m0 + ml < p.m_pad) p.partial_bias[(int64_t)blockIdx.x * p.m_pad + m0 + ml] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_weight_grad_reduce(const float* __restrict__ partial, const float* __restrict__ partial_bias,
+                                                            int32_t n_partials, int32_t m, int32_t k, int32_t m_pad, int32_t k_pad,
+                                                            float* __restrict__ dw, int64_t ld_dw, float* __restrict__ dbias,
+                                                            int32_t accumulate) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m * k) {
+    const int mm = t / k, kk = t - mm * k;
+    float s = 0.f;
+    for (int c = 0; c < n_partials; ++c) s += partial[((int64_t)c * m_pad + mm) * k_pad + kk];
+    float* dst = dw + (int64_t)mm * ld_dw + kk;
+    *dst = accumulate ? *dst + s : s;
+  } else if (dbias != nullptr && t < m * k + m) {
+    const int mm = t - m * k;
+    float s = 0.f;
+    for (int c = 0; c < n_partials; ++c) s += partial_bias[(int64_t)c * m_pad + mm];
+    dbias[mm] = accumulate ? dbias[mm] + s : s;
+  }
+}
+
+struct WgradPlan {
+  int wm, wk;
+  int grid_x, grid_y, grid_z;
+  int m_pad, k_pad;
+  size_t bytes;
+};
+
+static WgradPlan plan_wgrad(int32_t k, int32_t m) {
+  WgradPlan pl{};
+  pl.wm = m > 32 ? 2 : 1;
+  const int k_tiles16 = (k + 15) / 16;
+  const int max_wk = 8 / pl.wm > 4 ? 4 : 8 / pl.wm;
+  pl.wk = k_tiles16 >= 4 ? 4 : (k_tiles16 >= 2 ? 2 : 1);
+  if (pl.wk > max_wk) pl.wk = max_wk;
+  const int tile_m = 32 * pl.wm, tile_k = 16 * pl.wk;
+  pl.grid_z = (m + tile_m - 1) / tile_m;
+  pl.grid_y = (k + tile_k - 1) / tile_k;
+  pl.m_pad = pl.grid_z * tile_m;
+  pl.k_pad = pl.grid_y * tile_k;
+  pl.grid_x = std::max(1, (kNumSM * 2) / (pl.grid_y * pl.grid_z));
+  pl.bytes = ((size_t)pl.grid_x * pl.m_pad * pl.k_pad + (size_t)pl.grid_x * pl.m_pad) * sizeof(float);
+  return pl;
+}
+
+template <int WM, int WK>
+static void launch_wgrad(const WgradArgs& a, const WgradPlan& pl, cudaStream_t st) {
+  constexpr int WN = 8 / (WM * WK);
+  const size_t tile = (size_t)kWgTileN * (32 * WM + 16 * WK);
+  const size_t scratch = (size_t)WN * (32 * WM) * (16 * WK) + (size_t)WN * 32 * WM;  // cross-warp reduction reuses the tile smem
+  const size_t smem = std::max(tile, scratch) * sizeof(float);
+  dim3 grid(pl.grid_x, pl.grid_y, pl.grid_z);
+  k_weight_grad<WM, WK><<<grid, kWgThreads, smem, st>>>(a);
+}
+
+}  // namespace drk
+
+extern "C" {
+
+int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t trans_b, const float* bias, const float* mask,
+                    int64_t ld_mask, float* c, int64_t ldc, int64_t n, int32_t k, int32_t m, int32_t act, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(n >= 0 && k >= 0 && m >= 0, DRK_EINVAL, "node linear: negative size");
+  if (n == 0 || m == 0) return DRK_OK;
+  DRK_REQUIRE(a && b && c, DRK_EINVAL, "node linear: null pointer");
+  DRK_REQUIRE(k >= 1, DRK_EINVAL, "node linear: k must be >= 1");
+  DRK_REQUIRE(act == DRK_ACT_NONE || act == DRK_ACT_RELU, DRK_EINVAL, "node linear: unknown activation %d", act);
+  LinearArgs p{a, lda, b, ldb, trans_b, bias, mask, ld_mask, c, ldc, n, k, m, act, 1, 1};
+  // widest vector that keeps every row start and every K-chunk start aligned
+  if (lda % 4 == 0 && aligned16(a) && (k % 4 == 0)) p.a_vec = 4;
+  else if (lda % 2 == 0 && aligned8(a) && (k % 2 == 0)) p.a_vec = 2;
+  if (ldc % 4 == 0 && aligned16(c) && (mask == nullptr || (ld_mask % 4 == 0 && aligned16(mask)))) p.c_vec = 4;
+  const int kc = std::min(k, kLinKChunk);
+  const int kp = padded_stride(kc);
+  cudaStream_t st = as_stream(stream);
+  const unsigned gx = (unsigned)ceil_div<int64_t>(n, kLinTileN);
+  auto launch = [&](auto kernel, int tile_m) -> int {
+    const size_t smem = (size_t)(kLinTileN + tile_m) * kp * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "node linear: smem opt-in: %s", cudaGetErrorString(e));
+    }
+    dim3 grid(gx, (unsigned)ceil_div(m, tile_m));
+    kernel<<<grid, kLinThreads, smem, st>>>(p);
+    return DRK_OK;
+  };
+  int rc;
+  if (m <= 16) rc = launch(k_node_linear<4>, 16);
+  else if (m <= 32 || (m > 64 && m % 64 != 0 && m % 32 == 0)) rc = launch(k_node_linear<8>, 32);
+  else rc = launch(k_node_linear<16>, 64);
+  if (rc != DRK_OK) return rc;
+  return finish_launch("node linear");
+}
+
+size_t drk_weight_grad_workspace_bytes(int32_t k, int32_t m) {
+  if (k <= 0 || m <= 0) return 0;
+  return drk::plan_wgrad(k, m).bytes;
+}
+
+int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t n, int32_t k, int32_t m, float* dw,
+                    int64_t ld_dw, float* dbias, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(n >= 0 && k >= 1 && m >= 1, DRK_EINVAL, "weight grad: bad size");
+  DRK_REQUIRE(dy && x && dw, DRK_EINVAL, "weight grad: null pointer");
+  const WgradPlan pl = plan_wgrad(k, m);
+  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= pl.bytes, DRK_EWORKSPACE, "weight grad: workspace %zu < %zu bytes",
+              workspace_bytes, pl.bytes);
+  float* partial = static_cast<float*>(workspace);
+  float* partial_bias = partial + (size_t)pl.grid_x * pl.m_pad * pl.k_pad;
+  WgradArgs a{dy, ld_dy, x, ldx, n, k, m, partial, dbias != nullptr ? partial_bias : nullptr, pl.m_pad, pl.k_pad};
+  cudaStream_t st = as_stream(stream);
+  if (pl.wm == 1 && pl.wk == 4) launch_wgrad<1, 4>(a, pl, st);
+  else if (pl.wm == 1 && pl.wk == 2) launch_wgrad<1, 2>(a, pl, st);
+  else if (pl.wm == 1 && pl.wk == 1) launch_wgrad<1, 1>(a, pl, st);
+  else if (pl.wm == 2 && pl.wk == 4) launch_wgrad<2, 4>(a, pl, st);
+  else if (pl.wm == 2 && pl.wk == 2) launch_wgrad<2, 2>(a, pl, st);
+  else launch_wgrad<2, 1>(a, pl, st);
+  const int total = m * k + (dbias != nullptr ? m : 0);
+  k_weight_grad_reduce<<<ceil_div(total, 256), 256, 0, st>>>(partial, partial_bias, pl.grid_x, m, k, pl.m_pad, pl.k_pad, dw, ld_dw, dbias,
+                                                             accumulate);
+  return finish_launch("weight grad", 2);
+}
+
+}  // extern "C"

@@ -1,0 +1,24 @@
+// Library-level state: thread-local error text, ABI version, launch counter.
+#include "drk_common.cuh"
+
+namespace drk {
+
+static thread_local char t_error[768] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace drk
+
+extern "C" {
+
+int drk_abi_version(void) { return DRK_ABI_VERSION; }
+const char* drk_last_error(void) { return drk::t_error; }
+int64_t drk_launch_count(void) { return drk::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// Segmented gather-reduce kernels: the aggregation half of every DeepRank2 convolution and
+// the per-graph readout.
+//
+//   drk_spmm          out[i,:] = epi( reduce_{s in seg i} w[s] * src[idx[s],:] )
+//                     == x[col] -> scatter_sum(.., row)           ginet.py:45,58  vanilla_gnn.py:30,35
+//                     == per-node mean loop of FoutLayer           foutnet.py:56-58 (MEAN_NAN)
+//                     == scatter_mean(edge_attr * .., row, out=0)  sgat.py:68-72    (MEAN_CLAMP, w)
+//   drk_segment_mean  scatter_mean(x, batch, dim=0)               ginet_nocluster.py:103-104
+//
+// Layout: one sub-warp of LPR lanes per destination row, each lane owning VEC consecutive
+// columns (LPR*VEC >= width for the common widths 16/32/64 -> one 128-bit load per lane per
+// gathered row, a full 128 B line per 32-wide row).  Edges of a row are visited in CSR order
+// (ascending edge id = the order of the reference's CPU scatter_add_), accumulated sequentially
+// in fp32, no atomics -> bit-reproducible.  Consecutive rows go to the same CTA so the gathered
+// rows of one graph (~300 x 128 B = 38 KB) stay resident in that SM's L1; the index stream is
+// loaded with L1::no_allocate so it does not evict them.
+#include <algorithm>
+
+#include "drk_common.cuh"
+
+namespace drk {
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = ld_gather_f4(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    const float2 t = ld_gather_f2(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+
+__device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.f ? 0.f : x; }           // torch.relu(NaN) = NaN
+__device__ __forceinline__ float relu_grad_mask(float g, float m) { return m <= 0.f ? 0.f : g; }  // threshold_backward
+
+struct SpmmArgs {
+  const int32_t* ptr;
+  const int32_t* idx;
+  const float* w;
+  const float* src;
+  int64_t ld_src;
+  const float* addend;
+  int64_t ld_addend;
+  const float* mask;
+  int64_t ld_mask;
+  float* out;
+  int64_t ld_out;
+  int32_t n_out;
+  int32_t width;
+  int32_t reduce;
+  int32_t act;
+  int32_t rows_per_block;
+};
+
+constexpr int kSpmmThreads = 256;
+constexpr int kUnroll = 4;
+
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
+  constexpr int kRowsPerWarp = 32 / LPR;
+  constexpr int kRowsPerPass = (kSpmmThreads / 32) * kRowsPerWarp;
+  const int lane = lane_id();
+  const int sub = lane / LPR;
+  const int sl = lane % LPR;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * a.rows_per_block;
+  const int row_end = min(row0 + a.rows_per_block, a.n_out);
+
+  for (int cbase = 0; cbase < a.width; cbase += LPR * VEC) {  // one trip for width <= LPR*VEC
+    const int c = cbase + sl * VEC;
+    const bool col_ok = c < a.width;  // width % VEC == 0 is guaranteed by the dispatcher
+    for (int r = row0 + warp * kRowsPerWarp + sub; r < row_end; r += kRowsPerPass) {
+      const int beg = a.ptr[r];
+      const int end = a.ptr[r + 1];
+      float acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      for (int s = beg; s < end; s += LPR) {
+        const int cnt = min(LPR, end - s);
+        int my_idx = 0;
+        float my_w = 1.f;
+        if (sl < cnt) {
+          my_idx = a.idx != nullptr ? ld_stream_i32(a.idx + s + sl) : s + sl;
+          if (a.w != nullptr) my_w = ld_stream_f32(a.w + s + sl);
+        }
+        for (int j0 = 0; j0 < cnt; j0 += kUnroll) {
+          Vec<VEC> t[kUnroll];
+          float tw[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int j = min(j0 + u, LPR - 1);
+            const int srow = __shfl_sync(gmask, my_idx, j, LPR);
+            tw[u] = a.w != nullptr ? __shfl_sync(gmask, my_w, j, LPR) : 1.f;
+            if (j0 + u < cnt && col_ok) t[u].load(a.src + (int64_t)srow * a.ld_src + c);
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            if (j0 + u < cnt && col_ok) {
+              if (a.w != nullptr) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] = fmaf(tw[u], t[u].v[k], acc[k]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] += t[u].v[k];
+              }
+            }
+          }
+        }
+      }
+      if (!col_ok) continue;
+      if (a.reduce != DRK_REDUCE_SUM) {
+        const float deg = (float)(end - beg);
+        const float den = a.reduce == DRK_REDUCE_MEAN_CLAMP ? fmaxf(deg, 1.f) : deg;  // MEAN_NAN: 0/0 = NaN like torch.mean([])
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = acc[k] / den;
+      }
+      if (a.addend != nullptr) {
+        Vec<VEC> ad;
+        ad.load(a.addend + (int64_t)r * a.ld_addend + c);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += ad.v[k];
+      }
+      if (a.act == DRK_ACT_RELU) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = relu_keep_nan(acc[k]);
+      }
+      if (a.mask != nullptr) {
+        Vec<VEC> m;
+        m.load(a.mask + (int64_t)r * a.ld_mask + c);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = relu_grad_mask(acc[k], m.v[k]);
+      }
+      Vec<VEC> o;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o.v[k] = acc[k];
+      o.store(a.out + (int64_t)r * a.ld_out + c);
+    }
+  }
+}
+
+template <int LPR, int VEC>
+static void launch_spmm(const SpmmArgs& a, int blocks, cudaStream_t stream) {
+  k_spmm<LPR, VEC><<<blocks, kSpmmThreads, 0, stream>>>(a);
+}
+
+// ---------------------------------------------------------------- per-graph mean (one CTA per graph)
+constexpr int kMeanThreads = 256;
+
+template <int VEC>
+__global__ void __launch_bounds__(kMeanThreads) k_segment_mean(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ graph_ptr,
+                                                               int32_t width, float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float partial[];  // [row_lanes][width]
+  const int g = blockIdx.x;
+  const int beg = graph_ptr[g];
+  const int end = graph_ptr[g + 1];
+  const int cv = width / VEC;              // vector columns
+  const int row_lanes = kMeanThreads / cv;  // >= 1 (dispatcher guarantees cv <= kMeanThreads)
+  const int cl = threadIdx.x % cv;
+  const int rl = threadIdx.x / cv;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (rl < row_lanes) {
+    for (int i = beg + rl; i < end; i += row_lanes) {
+      Vec<VEC> t;
+      t.load(x + (int64_t)i * ldx + cl * VEC);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] += t.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) partial[rl * width + cl * VEC + k] = acc[k];
+  }
+  __syncthreads();
+  if (rl == 0) {
+    const float den = fmaxf((float)(end - beg), 1.f);  // scatter_mean: count clamped to >= 1
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float s = 0.f;
+      for (int p = 0; p < row_lanes; ++p) s += partial[p * width + cl * VEC + k];  // fixed order
+      out[(int64_t)g * ld_out + cl * VEC + k] = s / den;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_segment_mean_bwd(const float* __restrict__ dg, int64_t ld_dg, const int32_t* __restrict__ graph_ptr,
+                                                          const int32_t* __restrict__ batch32, const float* __restrict__ mask,
+                                                          int64_t ld_mask, int32_t num_nodes, int32_t width, float* __restrict__ dx,
+                                                          int64_t ld_dx) {
+  const int64_t total = (int64_t)num_nodes * width;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / width);
+    const int c = (int)(t - (int64_t)i * width);
+    const int b = batch32[i];
+    const float den = fmaxf((float)(graph_ptr[b + 1] - graph_ptr[b]), 1.f);
+    float g = dg[(int64_t)b * ld_dg + c] / den;
+    if (mask != nullptr) g = relu_grad_mask(g, mask[(int64_t)i * ld_mask + c]);
+    dx[(int64_t)i * ld_dx + c] = g;
+  }
+}
+
+static int pick_vec(int32_t width, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  int vec = 4;
+  if (width % 4 != 0) vec = width % 2 == 0 ? 2 : 1;
+  for (int64_t ld : lds) {
+    if (vec == 4 && ld % 4 != 0) vec = ld % 2 == 0 ? 2 : 1;
+    if (vec == 2 && ld % 2 != 0) vec = 1;
+  }
+  for (const void* p : ptrs) {
+    if (p == nullptr) continue;
+    if (vec == 4 && !aligned16(p)) vec = aligned8(p) ? 2 : 1;
+    if (vec == 2 && !aligned8(p)) vec = 1;
+  }
+  return vec;
+}
+
+}  // namespace drk
+
+extern "C" {
+
+int drk_spmm(const int32_t* ptr, const int32_t* idx, const float* w, const float* src, int64_t ld_src, const float* addend,
+             int64_t ld_addend, const float* mask, int64_t ld_mask, float* out, int64_t ld_out, int32_t n_out, int32_t width,
+             int32_t reduce, int32_t act, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(n_out >= 0 && width >= 0, DRK_EINVAL, "spmm: negative size");
+  if (n_out == 0 || width == 0) return DRK_OK;
+  DRK_REQUIRE(ptr && src && out, DRK_EINVAL, "spmm: null pointer");
+  DRK_REQUIRE(reduce >= DRK_REDUCE_SUM && reduce <= DRK_REDUCE_MEAN_NAN, DRK_EINVAL, "spmm: unknown reduce %d", reduce);
+  DRK_REQUIRE(act == DRK_ACT_NONE || act == DRK_ACT_RELU, DRK_EINVAL, "spmm: unknown activation %d", act);
+  SpmmArgs a{ptr, idx, w, src, ld_src, addend, ld_addend, mask, ld_mask, out, ld_out, n_out, width, reduce, act, 0};
+  const int vec = pick_vec(width, {src, addend, mask, out}, {ld_src, addend ? ld_addend : 4, mask ? ld_mask : 4, ld_out});
+  const int vcols = width / vec;
+  int lpr = 4;
+  while (lpr < 32 && lpr < vcols) lpr <<= 1;
+  const int rows_per_pass = (kSpmmThreads / 32) * (32 / lpr);
+  // contiguous rows per CTA: aim for ~8 CTAs per SM, at least one pass, at most 8 passes
+  int passes = (int)ceil_div<int64_t>(n_out, (int64_t)kNumSM * 8 * rows_per_pass);
+  passes = std::max(1, std::min(passes, 8));
+  a.rows_per_block = rows_per_pass * passes;
+  const int blocks = ceil_div(n_out, a.rows_per_block);
+  cudaStream_t st = as_stream(stream);
+#define DRK_SPMM_CASE(L, V) \
+  if (lpr == L && vec == V) launch_spmm<L, V>(a, blocks, st)
+  DRK_SPMM_CASE(4, 4); else DRK_SPMM_CASE(8, 4); else DRK_SPMM_CASE(16, 4); else DRK_SPMM_CASE(32, 4);
+  else DRK_SPMM_CASE(4, 2); else DRK_SPMM_CASE(8, 2); else DRK_SPMM_CASE(16, 2); else DRK_SPMM_CASE(32, 2);
+  else DRK_SPMM_CASE(4, 1); else DRK_SPMM_CASE(8, 1); else DRK_SPMM_CASE(16, 1); else DRK_SPMM_CASE(32, 1);
+#undef DRK_SPMM_CASE
+  return finish_launch("spmm");
+}
+
+int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int32_t width, float* out,
+                     int64_t ld_out, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_graphs >= 0 && width >= 0, DRK_EINVAL, "segment mean: negative size");
+  if (num_graphs == 0 || width == 0) return DRK_OK;
+  DRK_REQUIRE(x && graph_ptr && out, DRK_EINVAL, "segment mean: null pointer");
+  int vec = pick_vec(width, {x}, {ldx});
+  while (width / vec > kMeanThreads && vec > 1) vec >>= 1;
+  DRK_REQUIRE(width / vec <= kMeanThreads, DRK_EUNSUPPORTED, "segment mean: width %d too large", width);
+  const int row_lanes = kMeanThreads / (width / vec);
+  const size_t smem = (size_t)row_lanes * width * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  if (vec == 4) k_segment_mean<4><<<num_graphs, kMeanThreads, smem, st>>>(x, ldx, graph_ptr, width, out, ld_out);
+  else if (vec == 2) k_segment_mean<2><<<num_graphs, kMeanThreads, smem, st>>>(x, ldx, graph_ptr, width, out, ld_out);
+  else k_segment_mean<1><<<num_graphs, kMeanThreads, smem, st>>>(x, ldx, graph_ptr, width, out, ld_out);
+  return finish_launch("segment mean");
+}
+
+int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_ptr, const int32_t* batch32, const float* mask,
+                         int64_t ld_mask, int32_t num_nodes, int32_t width, float* dx, int64_t ld_dx, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0 && width >= 0, DRK_EINVAL, "segment mean bwd: negative size");
+  if (num_nodes == 0 || width == 0) return DRK_OK;
+  DRK_REQUIRE(dg && graph_ptr && batch32 && dx, DRK_EINVAL, "segment mean bwd: null pointer");
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>((int64_t)num_nodes * width, 256 * 4), (int64_t)kNumSM * 16);
+  k_segment_mean_bwd<<<blocks, 256, 0, as_stream(stream)>>>(dg, ld_dg, graph_ptr, batch32, mask, ld_mask, num_nodes, width, dx, ld_dx);
+  return finish_launch("segment mean bwd");
+}
+
+}  // extern "C"

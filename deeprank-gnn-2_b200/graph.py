@@ -1,0 +1,140 @@
+"""Device-side graph index of a batch: destination-sorted CSR, source-sorted CSC, graph offsets.
+
+The reference never builds an index: every layer does ``row, col = edge_index`` and lets
+``x[col]`` / ``torch_scatter.scatter_sum(h, row)`` walk the raw int64 edge list
+(``ginet.py:41-58``, ``vanilla_gnn.py:28-35``, ``foutnet.py:56-58``) and lets ``scatter_mean(x,
+batch)`` rediscover the graph boundaries (``ginet_nocluster.py:103``).  Here the Trainer's
+collate path builds that structure ONCE per batch on the GPU (``drk_graph_index_build`` +
+``drk_batch_offsets``) and all convolutions of the forward and backward pass share it.
+
+Index arrays are int32 and bit-exact against ``torch.sort(stable=True)`` / ``bincount`` /
+``cumsum`` (``oracle/restate.py:graph_csr``): inside a destination the edges keep ascending
+edge id, which is also the order in which the reference's CPU ``scatter_add_`` adds them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: deeprank2_b200 has no CPU path (got {t.device})")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_workspaces: dict = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Scratch buffer re-used by every call on (device, current stream); stream order makes that safe."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+class GraphIndex:
+    """CSR (by destination ``edge_index[0]``) + CSC (by source ``edge_index[1]``) + graph offsets."""
+
+    __slots__ = (
+        "num_nodes", "num_edges", "num_graphs", "device",
+        "rowptr", "colidx", "perm", "colptr", "rowidx", "permT",
+        "graph_ptr", "batch32", "status", "_storage", "_key",
+    )
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def build(cls, edge_index: torch.Tensor, num_nodes: int, batch: torch.Tensor | None = None, num_graphs: int | None = None, with_csc: bool = True) -> "GraphIndex":
+        lib = _lib.load()
+        _require_cuda(edge_index, "edge_index")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise TypeError(f"edge_index must be int64 [2, E], got {edge_index.dtype} {tuple(edge_index.shape)}")
+        edge_index = edge_index.contiguous()
+        dev = edge_index.device
+        n, e = int(num_nodes), int(edge_index.shape[1])
+        if batch is not None:
+            _require_cuda(batch, "batch")
+            if batch.dtype != torch.int64 or batch.numel() != n:
+                raise TypeError(f"batch must be int64 [{n}], got {batch.dtype} {tuple(batch.shape)}")
+            if num_graphs is None:
+                # same as scatter_mean without dim_size (ginet_nocluster.py:103): one host sync.
+                # Batches made by Batch.from_data_list carry `ptr`, so the Trainer path never gets here.
+                num_graphs = int(batch.max()) + 1 if n > 0 else 0
+        b = int(num_graphs) if num_graphs is not None else 0
+        gi = cls()
+        gi.num_nodes, gi.num_edges, gi.num_graphs, gi.device = n, e, b, dev
+        # one allocation for every int32 array (each sub-array 16-byte aligned)
+        def pad(v):
+            return (v + 3) // 4 * 4
+        sizes = [pad(n + 1), pad(e), pad(e)]
+        if with_csc:
+            sizes += [pad(n + 1), pad(e), pad(e)]
+        if batch is not None:
+            sizes += [pad(b + 1), pad(n)]
+        sizes += [4]
+        storage = torch.empty(sum(sizes), dtype=torch.int32, device=dev)
+        gi._storage = storage
+        views, off = [], 0
+        for s in sizes:
+            views.append(storage[off : off + s])
+            off += s
+        gi.rowptr, gi.colidx, gi.perm = views[0][: n + 1], views[1][:e], views[2][:e]
+        k = 3
+        if with_csc:
+            gi.colptr, gi.rowidx, gi.permT = views[3][: n + 1], views[4][:e], views[5][:e]
+            k = 6
+        if batch is not None:
+            gi.graph_ptr, gi.batch32 = views[k][: b + 1], views[k + 1][:n]
+        gi.status = views[-1][:1]
+        gi.status.zero_()
+        with torch.cuda.device(dev):
+            ws_bytes = lib.drk_graph_index_workspace_bytes(e, n)
+            ws = workspace(ws_bytes, dev)
+            rc = lib.drk_graph_index_build(
+                edge_index.data_ptr(), e, n,
+                gi.rowptr.data_ptr(), gi.colidx.data_ptr(), gi.perm.data_ptr(),
+                gi.colptr.data_ptr() if with_csc else None,
+                gi.rowidx.data_ptr() if with_csc else None,
+                gi.permT.data_ptr() if with_csc else None,
+                gi.status.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(),
+            )
+            _lib.check(rc, "drk_graph_index_build")
+            if batch is not None:
+                rc = lib.drk_batch_offsets(batch.contiguous().data_ptr(), n, b, gi.graph_ptr.data_ptr(), gi.batch32.data_ptr(), gi.status.data_ptr(), stream_ptr())
+                _lib.check(rc, "drk_batch_offsets")
+        return gi
+
+    # ------------------------------------------------------------------ validation (host sync: call it off the hot path)
+    def check(self) -> None:
+        flags = int(self.status.item())
+        if flags & _lib.STATUS_INDEX_RANGE:
+            raise IndexError("edge_index / batch contains an id outside [0, num_nodes) resp. [0, num_graphs)")
+        if flags & _lib.STATUS_UNSORTED:
+            raise ValueError("batch vector is not sorted: graphs of a Batch must occupy consecutive node ranges")
+
+
+def graph_index(data, with_csc: bool = True) -> GraphIndex:
+    """The (cached) :class:`GraphIndex` of a ``Batch``/``Data`` living on the GPU."""
+    ei = data.edge_index
+    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device), bool(with_csc))
+    cached = data.__dict__.get("_graph_index")
+    if cached is not None and cached._key[:4] == key[:4] and (cached.colptr is not None or not with_csc):
+        return cached
+    batch = getattr(data, "batch", None)
+    ptr = data.__dict__.get("ptr")
+    num_graphs = int(ptr.numel()) - 1 if ptr is not None else None
+    gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc)
+    gi._key = key
+    data.__dict__["_graph_index"] = gi
+    return gi

@@ -1,0 +1,148 @@
+/*
+ * drk_b200.h -- C ABI of the B200-native DeepRank2 message-passing path.
+ *
+ * One shared library (libdrk_b200.so, built for sm_100a from deeprank-gnn-2_b200/csrc/).
+ * The reference (DeepRank2 v3.1.0) has NO native boundary of its own: its GNN path is
+ * Python calling torch / torch_scatter / torch_geometric.  Each entry point below
+ * therefore cites the reference *call site* (file:line under /root/reference) whose
+ * arithmetic it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless marked [host];
+ *   - row-major tensors with an explicit leading dimension (elements, not bytes);
+ *   - float tensors are fp32, graph indices are int32 after drk_graph_index_build
+ *     (the reference's int64 edge_index / batch are the inputs of that call);
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*), no allocation, no
+ *     ownership transfer, no global state: the caller owns outputs and workspaces;
+ *   - return 0 on success, a negative DRK_E* code otherwise; drk_last_error() gives
+ *     the thread-local message.  Data-dependent faults (an out-of-range index) cannot
+ *     be returned synchronously: they are OR-ed into the int32 `status` word the caller
+ *     passes (device memory, may be NULL) -- see DRK_STATUS_*;
+ *   - deterministic: no floating-point atomics anywhere; integer atomics only where
+ *     the result does not depend on their order.
+ */
+#ifndef DRK_B200_H
+#define DRK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DRK_API __attribute__((visibility("default")))
+#else
+#define DRK_API
+#endif
+
+/* return codes */
+#define DRK_OK 0
+#define DRK_EINVAL (-1)    /* bad argument (null pointer, negative size, unsupported width) */
+#define DRK_EWORKSPACE (-2) /* workspace too small */
+#define DRK_ECUDA (-3)     /* a CUDA runtime call failed (message has the cudaError string) */
+#define DRK_EUNSUPPORTED (-4)
+
+/* bits of the device-side status word */
+#define DRK_STATUS_INDEX_RANGE 1 /* an edge endpoint / segment id outside [0, n) */
+#define DRK_STATUS_CROSS_GRAPH 2 /* an edge joins two different graphs of the batch */
+#define DRK_STATUS_UNSORTED 4    /* `batch` is not non-decreasing */
+
+/* activations / epilogues */
+#define DRK_ACT_NONE 0
+#define DRK_ACT_RELU 1
+
+/* segment reductions (drk_spmm `reduce`) */
+#define DRK_REDUCE_SUM 0        /* torch_scatter.scatter_sum                       (ginet.py:58, vanilla_gnn.py:35) */
+#define DRK_REDUCE_MEAN_CLAMP 1 /* torch_scatter.scatter_mean: sum / max(count,1)  (sgat.py:72)                     */
+#define DRK_REDUCE_MEAN_NAN 2   /* torch.mean of the gathered rows: 0/0 = NaN      (foutnet.py:56-58)               */
+
+DRK_API int drk_abi_version(void);
+DRK_API const char* drk_last_error(void);
+/* number of kernels this library has launched from the calling process (all threads); bench.py's gpu_launches */
+DRK_API int64_t drk_launch_count(void);
+
+/* ------------------------------------------------------------------ graph index
+ * Replaces what the reference leaves implicit in `row, col = edge_index` + torch_scatter's
+ * index broadcasting (ginet.py:41,58; vanilla_gnn.py:28,35; foutnet.py:57): a destination-sorted
+ * CSR and a source-sorted CSC of the batch's edge list, both STABLE (edge ids ascending inside
+ * a segment, i.e. torch.sort(stable=True) order == the visiting order of CPU scatter_add_).
+ *
+ *   edge_index  int64 [2,E] row-major (row 0 = destination "row", row 1 = gathered source "col")
+ *   rowptr      int32 [N+1]   colidx  int32 [E] = col[perm]    perm  int32 [E]  (edge ids by destination)
+ *   colptr      int32 [N+1]   rowidx  int32 [E] = row[permT]   permT int32 [E]  (edge ids by source)
+ *   any of the CSC outputs may be NULL as a group (forward-only use).
+ */
+DRK_API size_t drk_graph_index_workspace_bytes(int64_t num_edges, int32_t num_nodes);
+DRK_API int drk_graph_index_build(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes,
+                          int32_t* rowptr, int32_t* colidx, int32_t* perm,
+                          int32_t* colptr, int32_t* rowidx, int32_t* permT,
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Generic stable counting sort of one int64 key vector (the `index` argument of
+ * torch_scatter.scatter_* when it is NOT a graph edge list: cluster ids, community_pooling.py:209,216).
+ *   ptr int32 [num_segments+1], perm int32 [n]. */
+DRK_API size_t drk_segment_index_workspace_bytes(int64_t n, int32_t num_segments);
+DRK_API int drk_segment_index_build(const int64_t* index, int64_t n, int32_t num_segments,
+                            int32_t* ptr, int32_t* perm, int32_t* status,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batch offsets: `ptr` of PyG's Batch.from_data_list from the int64 `batch` vector
+ * (trainer.py:541-557 collate; consumed by scatter_mean(x, batch), ginet_nocluster.py:103).
+ *   batch int64 [N] non-decreasing, graph_ptr int32 [B+1], batch32 int32 [N] (may be NULL). */
+DRK_API int drk_batch_offsets(const int64_t* batch, int32_t num_nodes, int32_t num_graphs,
+                      int32_t* graph_ptr, int32_t* batch32, int32_t* status, void* stream);
+
+/* Gather rows of a per-edge tensor into CSR order: out[s,:] = src[perm[s],:]  (edge_attr for vanilla_gnn.py:31). */
+DRK_API int drk_gather_rows(const float* src, int64_t ld_src, const int32_t* perm, int64_t n, int32_t width,
+                    float* out, int64_t ld_out, void* stream);
+
+/* ------------------------------------------------------------------ dense node projections
+ * C[n,:] = act( A[n,:] * op(B) + bias ),  A [N,K], C [N,M];
+ *   trans_b = 1: B is [M,K] (nn.Linear weight: C = A B^T)   -- self.fc(x[col]) ginet.py:45, _edge_mlp/_node_mlp vanilla_gnn.py:22-24
+ *   trans_b = 0: B is [K,M]                                 -- torch.mm(x, self.wc) foutnet.py:50-51, and dX = dY W in backward
+ * If `mask` != NULL the result is multiplied by (mask[n,m] > 0) AFTER the activation (ReLU backward
+ * fused into the producer of the gradient).  bias may be NULL.  fp32 FFMA, no tensor cores: the
+ * parity bar is rtol 1e-5 (TF32 would be ~1e-3). */
+DRK_API int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t trans_b,
+                    const float* bias, const float* mask, int64_t ld_mask,
+                    float* c, int64_t ldc, int64_t n, int32_t k, int32_t m, int32_t act, void* stream);
+
+/* dW[M,K] = sum_n dY[n,:]^T X[n,:]   (+ dbias[M] = sum_n dY[n,:] if dbias != NULL).
+ * Autograd of the nn.Linear calls above.  Two-stage, fixed-order reduction (deterministic).
+ * If `accumulate` != 0 the result is added to the existing contents of dw/dbias. */
+DRK_API size_t drk_weight_grad_workspace_bytes(int32_t k, int32_t m);
+DRK_API int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t n, int32_t k, int32_t m,
+                    float* dw, int64_t ld_dw, float* dbias, int32_t accumulate,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ segmented gather-reduce ("SpMM")
+ * out[i,:] = epilogue( reduce_{s in [ptr[i],ptr[i+1])}  w[s] * src[idx[s],:] ),  i in [0, n_out)
+ *   - replaces x[col] -> ... -> scatter_sum(h, row, out=zeros)    ginet.py:45,58 (alpha == 1: w = NULL)
+ *   - with reduce = MEAN_NAN: the per-node Python loop of FoutLayer  foutnet.py:56-58
+ *   - with w = edge weight in CSR order: edge_attr * (...) of SGAT   sgat.py:68-72
+ *   - idx == NULL means idx[s] = s (segments of consecutive rows: scatter_mean(x, batch), ginet_nocluster.py:103)
+ * epilogue: act (DRK_ACT_*), then `* (mask[i,:] > 0)` if mask != NULL.  `addend` (may be NULL) is added
+ * before the activation (FoutLayer: x Wc + mean(...) + b is formed as addend + mean).
+ * One sub-warp per output row, edges visited in CSR order, no atomics. */
+DRK_API int drk_spmm(const int32_t* ptr, const int32_t* idx, const float* w,
+             const float* src, int64_t ld_src, const float* addend, int64_t ld_addend,
+             const float* mask, int64_t ld_mask,
+             float* out, int64_t ld_out, int32_t n_out, int32_t width, int32_t reduce, int32_t act, void* stream);
+
+/* Per-graph mean readout  g[b,:] = sum_{i in graph b} x[i,:] / max(n_b, 1)   (one CTA per graph)
+ * scatter_mean(data.x, data.batch, dim=0): ginet_nocluster.py:103-104, ginet.py:117-118, vanilla_gnn.py:62, foutnet.py:114. */
+DRK_API int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int32_t width,
+                     float* out, int64_t ld_out, void* stream);
+/* its backward: dx[i,:] = dg[batch[i],:] / max(n_b,1), optionally * (mask[i,:] > 0) (the ReLU that fed the readout). */
+DRK_API int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_ptr, const int32_t* batch32,
+                         const float* mask, int64_t ld_mask, int32_t num_nodes, int32_t width,
+                         float* dx, int64_t ld_dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRK_B200_H */
