@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native DeepRank2 message-passing path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): GINet train-step graphs/s (and edges/s) on synthetic residue-level PPI batches
+(config C2: 256 graphs x ~300 nodes, 8.5 A contact edges, F_in = 50, F_e = 1), device timed; the
+aggregation kernel's achieved HBM GB/s against the measured peak; the reference's CPU path next to it.
+
+A "step" is one pass of ``Trainer._epoch``'s loop body (trainer.py:682-694) over one 256-graph batch:
+device graph-index build (CSR+CSC+offsets) -> zero_grad -> GINet forward -> MSELoss -> backward -> Adam.
+Each rank owns ``--batches`` distinct pre-collated batches resident in HBM and rotates over them, so the
+inputs of a step were last touched (batches-1) steps and > 126 MB of L2 traffic ago.
+
+One JSON line on stdout (rank 0).  Under torchrun (N > 1) ranks shard the graphs (weak scaling: 256
+graphs per GPU per step), gradients are all-reduced with NCCL every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRAPHS_PER_BATCH = 256
+F_NODE, F_EDGE = 50, 1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batches", type=int, default=6, help="distinct resident batches per rank (rotation defeats L2 reuse)")
+    ap.add_argument("--mode", choices=["graph", "eager"], default="graph", help="replay a captured CUDA graph per batch, or launch eagerly")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-graphs", type=int, default=64, help="graphs per step of the CPU reference arm (bounded sample)")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_steps(n_graphs: int, steps: int, warmup: int, first_graph: int = 0):
+    """The reference's CPU implementation of the step (oracle port: same ATen op sequence as
+    deeprank2/neuralnets/gnn/ginet_nocluster.py + trainer.py:682-694), all host threads."""
+    import torch
+
+    from deeprank2_b200.synthetic import make_batch
+    from oracle import restate as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch = make_batch(n_graphs, first=first_graph, n_node_features=F_NODE, n_edge_features=F_EDGE)
+    torch.manual_seed(0)
+    params = R.as_parameters(R.ginet_nocluster_init(F_NODE, 1, F_EDGE))
+    opt = R.make_adam(params)
+    for _ in range(warmup):
+        R.train_step(R.ginet_nocluster_forward, params, opt, batch, training=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.train_step(R.ginet_nocluster_forward, params, opt, batch, training=True)
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, steps=steps, graphs=n_graphs, nodes=batch.num_nodes, edges=batch.num_edges, threads=torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.ref_graphs, args.steps, max(1, min(args.warmup, 2)))
+    gps = r["graphs"] * r["steps"] / r["seconds"]
+    sample = f"{r['steps']} steps of a {r['graphs']}-graph slice of the C2 batch ({r['nodes']} nodes, {r['edges']} directed edges)"
+    line = {
+        "impl": "reference",
+        "metric": "ginet_train_step_graphs_per_s",
+        "value": gps,
+        "unit": "graphs/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, 1),
+        "edges_per_s": r["edges"] * r["steps"] / r["seconds"],
+        "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": r["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "C2: synthetic residue-level PPI batch, 256 graphs x ~300 nodes, 8.5 A contacts (degree ~20), GINet(no-cluster) F_in=50 F_e=1, fwd+bwd+Adam, MSELoss",
+        "graphs_per_step_per_gpu": GRAPHS_PER_BATCH,
+        "global_graphs_per_step": GRAPHS_PER_BATCH * world,
+        "parallelism": f"dp{world}",
+        "l2_policy": f"rotation over {args.batches} distinct resident batches per rank (> L2 between reuses)",
+        "index_build": "inside every step",
+        "mode": args.mode,
+    }
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from deeprank2_b200 import _lib, ops
+    from deeprank2_b200.graph import graph_index
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.step import GraphedTrainStep, TrainStep
+    from deeprank2_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    # ---- data: every rank owns its own graphs (weak scaling), generated on the host, resident in HBM
+    host_batches = [
+        make_batch(GRAPHS_PER_BATCH, first=(rank * args.batches + b) * GRAPHS_PER_BATCH, n_node_features=F_NODE, n_edge_features=F_EDGE).pin_memory()
+        for b in range(args.batches)
+    ]
+    dev_batches = [hb.clone().to(dev) for hb in host_batches]
+    nodes = [b.num_nodes for b in host_batches]
+    edges = [b.num_edges for b in host_batches]
+
+    torch.manual_seed(0)
+    model = GINet(F_NODE, 1, F_EDGE).to(dev)
+    model.train()
+    if distributed:
+        from deeprank2_b200.parallel import GradAllReduce
+
+        sync = GradAllReduce(model, world)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=(args.mode == "graph"))
+    loss_fn = torch.nn.MSELoss()
+
+    class Step(TrainStep):
+        def __call__(self, batch):
+            if self.rebuild_index:
+                batch.__dict__.pop("_graph_index", None)
+            self.optimizer.zero_grad(set_to_none=True)
+            pred = self.model(batch)
+            loss = self.loss_fn(pred.reshape(-1), batch.y)
+            loss.backward()
+            if distributed:
+                sync()
+            self.optimizer.step()
+            return loss.detach(), pred.detach()
+
+    step = Step(model, opt, loss_fn)
+
+    # launches of OUR kernels in one eager step (what a graph replay re-issues)
+    step(dev_batches[0])
+    torch.cuda.synchronize()
+    c0 = _lib.launch_count()
+    step(dev_batches[0])
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - c0
+
+    if args.mode == "graph":
+        graphed, pool = [], None
+        for b in dev_batches:
+            gs = GraphedTrainStep(step, b, pool=pool, warmup=1)
+            pool = gs.pool
+            graphed.append(gs)
+        run = lambda i: graphed[i % args.batches].replay()  # noqa: E731
+    else:
+        run = lambda i: step(dev_batches[i % args.batches])  # noqa: E731
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        run(i)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for i in range(args.steps):
+            run(i)
+        stop.record()
+        barrier()
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    graphs_total = GRAPHS_PER_BATCH * args.steps * world
+    edges_local = sum(edges[i % args.batches] for i in range(args.steps))
+    et = torch.tensor([edges_local], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(et)
+    value = graphs_total / (ms * 1e-3)
+
+    # ---- end to end through the public API: host (pinned) batch -> .to(device) -> step -> loss.item()
+    e2e_steps = max(5, min(args.steps, 20))
+    eager = Step(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5), loss_fn)
+    h2d = 0
+    for k in ("x", "edge_index", "edge_attr", "batch", "y", "ptr"):
+        v = getattr(host_batches[0], k)
+        h2d += v.numel() * v.element_size()
+    for i in range(3):
+        hb = host_batches[i % args.batches]
+        loss, _ = eager(_to_device(hb, dev))
+        loss.item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        hb = host_batches[i % args.batches]
+        loss, _ = eager(_to_device(hb, dev))
+        loss.item()  # D2H read of the step's result, every step (trainer.py:694)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = GRAPHS_PER_BATCH * e2e_steps * world / float(te.item())
+
+    # ---- roofline of the dominant kernel: the 32-wide... measured per launch with CUDA events on this stream
+    roof = aggregation_roofline(ops, graph_index, dev_batches, args, dev)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_reference_steps(args.ref_graphs, 3, 1)
+            cpu = {
+                "value": r["graphs"] * r["steps"] / r["seconds"],
+                "unit": "graphs/s",
+                "cores": r["threads"],
+                "kind": "port",
+                "sample": f"{r['steps']} train steps of a {r['graphs']}-graph slice of the C2 batch ({r['nodes']} nodes, {r['edges']} edges), oracle port of the reference's CPU path",
+            }
+        line = {
+            "metric": "ginet_train_step_graphs_per_s",
+            "value": value,
+            "unit": "graphs/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": dict(workload_config(args, world), nodes_per_batch=nodes[0], edges_per_batch=edges[0]),
+            "edges_per_s": float(et.item()) / (ms * 1e-3),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps, "mode": "eager, pinned host batch -> device every step, loss.item() every step"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def _to_device(host_batch, dev):
+    import copy
+
+    b = copy.copy(host_batch)
+    b.__dict__ = dict(host_batch.__dict__)
+    b.__dict__.pop("_graph_index", None)
+    return b.to(dev, non_blocking=True)
+
+
+def aggregation_roofline(ops, graph_index, dev_batches, args, dev):
+    """Achieved HBM GB/s of the aggregation kernel (drk_spmm, 32-wide rows = both GINet branches of
+    conv1 stacked would be 32; here the per-layer 16-wide conv1 aggregation, the most frequent launch).
+
+    Algorithmic bytes per launch: read src 4*N*F + write out 4*N*F + colidx 4*E + rowptr 4*(N+1).
+    """
+    import torch
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    width = 16
+    idx = [graph_index(b) for b in dev_batches]
+    srcs = [torch.randn(b.num_nodes, width, device=dev) for b in dev_batches]
+    outs = [torch.empty_like(s) for s in srcs]
+    reps = max(args.steps, 30)
+    for i in range(6):
+        j = i % len(idx)
+        ops.spmm(idx[j].rowptr, idx[j].colidx, srcs[j], srcs[j].shape[0], act=ops.ACT_RELU, out=outs[j])
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total_bytes = 0
+    for i, (a, b) in enumerate(evs):
+        j = i % len(idx)
+        flush.zero_()  # > L2: the kernel's inputs come from HBM
+        a.record()
+        ops.spmm(idx[j].rowptr, idx[j].colidx, srcs[j], srcs[j].shape[0], act=ops.ACT_RELU, out=outs[j])
+        b.record()
+        n, e = srcs[j].shape[0], idx[j].num_edges
+        total_bytes += 4 * n * width * 2 + 4 * e + 4 * (n + 1)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    achieved = total_bytes / (ms * 1e-3) / 1e9
+    return {
+        "bound": "hbm",
+        "kernel": f"drk_spmm (k_spmm<4,4>) width {width}, ReLU epilogue, L2 flushed before every launch",
+        "achieved": achieved,
+        "peak": peak,
+        "peak_source": peak_src,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "us_per_launch": 1e3 * ms / reps,
+        "algorithmic_bytes_per_launch": total_bytes / reps,
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

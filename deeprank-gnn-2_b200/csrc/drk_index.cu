@@ -276,7 +276,7 @@ static int build(const int64_t* key0, const int64_t* key1, const int64_t* other0
   const int keys = key1 != nullptr ? 2 : 1;
   DRK_REQUIRE(n >= 0 && num_segments >= 0, DRK_EINVAL, "index build: negative size");
   DRK_REQUIRE(n < (int64_t)0x7fffffff, DRK_EUNSUPPORTED, "index build: more than 2^31-1 elements");
-  DRK_REQUIRE(ptr0 != nullptr && perm0 != nullptr, DRK_EINVAL, "index build: null output");
+  DRK_REQUIRE(ptr0 != nullptr && (perm0 != nullptr || n == 0), DRK_EINVAL, "index build: null output");
   IndexWorkspace w = carve(workspace, n, num_segments, keys);
   DRK_REQUIRE(workspace != nullptr && workspace_bytes >= w.bytes, DRK_EWORKSPACE, "index build: workspace %zu < %zu bytes",
               workspace_bytes, w.bytes);
@@ -322,9 +322,16 @@ int drk_graph_index_build(const int64_t* edge_index, int64_t num_edges, int32_t 
                           size_t workspace_bytes, void* stream) {
   using namespace drk;
   DRK_REQUIRE(edge_index != nullptr || num_edges == 0, DRK_EINVAL, "graph index: null edge_index");
-  DRK_REQUIRE(rowptr && colidx && perm, DRK_EINVAL, "graph index: null CSR output");
-  const bool with_csc = colptr != nullptr || rowidx != nullptr || permT != nullptr;
-  DRK_REQUIRE(!with_csc || (colptr && rowidx && permT), DRK_EINVAL, "graph index: CSC outputs must be all set or all NULL");
+  DRK_REQUIRE(rowptr && (num_edges == 0 || (colidx && perm)), DRK_EINVAL, "graph index: null CSR output");
+  const bool with_csc = colptr != nullptr;  // (rowidx / permT may legitimately be NULL when E == 0)
+  DRK_REQUIRE(!with_csc || num_edges == 0 || (rowidx && permT), DRK_EINVAL, "graph index: CSC outputs must be all set or all NULL");
+  if (num_edges == 0) {  // no edges: both pointer arrays are all zero, nothing to sort
+    DRK_REQUIRE(num_nodes >= 0, DRK_EINVAL, "graph index: negative size");
+    cudaError_t e = cudaMemsetAsync(rowptr, 0, ((size_t)num_nodes + 1) * sizeof(int32_t), as_stream(stream));
+    if (e == cudaSuccess && with_csc) e = cudaMemsetAsync(colptr, 0, ((size_t)num_nodes + 1) * sizeof(int32_t), as_stream(stream));
+    DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "graph index: memset: %s", cudaGetErrorString(e));
+    return DRK_OK;
+  }
   const int64_t* row = edge_index;
   const int64_t* col = edge_index + num_edges;
   if (with_csc)
