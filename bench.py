@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=6, help="distinct resident batches per rank (rotation defeats L2 reuse)")
     ap.add_argument("--mode", choices=["graph", "eager"], default="graph", help="replay a captured CUDA graph per batch, or launch eagerly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="only the timed steps (no e2e / roofline / cpu legs): the command ncu wraps")
     ap.add_argument("--ref-graphs", type=int, default=64, help="graphs per step of the CPU reference arm (bounded sample)")
     return ap.parse_args()
 
@@ -268,6 +269,13 @@ def run_ours(args):
     if distributed:
         dist.all_reduce(et)
     value = graphs_total / (ms * 1e-3)
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches_per_step": int(launches_per_step)}), flush=True)
+        if distributed:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public API: host (pinned) batch -> .to(device) -> step -> loss.item()
     e2e_steps = max(5, min(args.steps, 20))

@@ -77,6 +77,21 @@ __device__ __forceinline__ float2 ld_gather_f2(const float* p) { return __ldg(re
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// ---- asynchronous global -> shared copies (LDGSTS): fire-and-forget, so one thread keeps dozens of
+// loads in flight without holding registers.  BYTES in {4, 8, 16}; if !pred the destination is zero-filled
+// (src-size 0) and the source is not dereferenced.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src, bool pred) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int src_size = pred ? BYTES : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(gmem_src), "n"(BYTES), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 #endif  // __CUDACC__
 
 }  // namespace drk

@@ -73,28 +73,28 @@ __global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p)
     float* sW = smem + kLinTileN * kp;  // [kTileM][kp], rows permuted
     if (k0 > 0) __syncthreads();
 
-    // ---- A tile: rows row0.., columns k0..k0+kc, zero padded to kp
+    // ---- A tile: rows row0.., columns k0..k0+kc, zero padded to kp.  cp.async: every thread fires all of its
+    // copies back to back (~25 in flight) instead of waiting ~1 us of HBM latency per row.
     {
       const int vec = p.a_vec;
-      const int nv = (kc + vec - 1) / vec;  // vectors per row (kc % vec == 0 whenever vec > 1, see dispatcher)
-      for (int r = warp; r < kLinTileN; r += kLinThreads / 32) {
+      const int nv = kc / vec;            // full vectors per row (kc % vec == 0 whenever vec > 1, see dispatcher)
+      const int pv = (kp - nv * vec);     // zero-padding floats per row
+      for (int e = threadIdx.x; e < kLinTileN * nv; e += kLinThreads) {
+        const int r = e / nv;
+        const int v = e - r * nv;
         const int64_t gr = row0 + r;
-        float* dst = sA + r * kp;
-        const float* src = p.a + gr * p.lda + k0;
-        for (int v = lane; v * vec < kp; v += 32) {
-          if (vec == 4) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < p.n && v < nv) t = ld_stream_f4(src + v * 4);
-            *reinterpret_cast<float4*>(dst + v * 4) = t;
-          } else if (vec == 2) {
-            float2 t = make_float2(0.f, 0.f);
-            if (gr < p.n && v < nv) t = __ldg(reinterpret_cast<const float2*>(src + v * 2));
-            *reinterpret_cast<float2*>(dst + v * 2) = t;
-          } else {
-            dst[v] = (gr < p.n && v < kc) ? ld_stream_f32(src + v) : 0.f;
-          }
-        }
+        const bool ok = gr < p.n;
+        const float* src = p.a + (ok ? gr : 0) * p.lda + k0 + v * vec;
+        float* dst = sA + r * kp + v * vec;
+        if (vec == 4) cp_async<16>(dst, src, ok);
+        else if (vec == 2) cp_async<8>(dst, src, ok);
+        else cp_async<4>(dst, src, ok);
       }
+      for (int e = threadIdx.x; e < kLinTileN * pv; e += kLinThreads) {
+        const int r = e / pv;
+        sA[r * kp + nv * vec + (e - r * pv)] = 0.f;
+      }
+      cp_async_commit();
     }
     // ---- W tile: logical row m = 4*cg + t + 16*jj is stored at smem row cg + 4*t + 16*jj
     for (int e = threadIdx.x; e < kTileM * kp; e += kLinThreads) {
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p)
       const int srow = ((ml >> 2) & 3) + 4 * (ml & 3) + (ml & ~15);
       sW[srow * kp + kk] = v;
     }
+    cp_async_wait<0>();
     __syncthreads();
 
     const float* a_base = sA + (warp * 32 + rg) * kp;
@@ -196,16 +197,35 @@ struct WgradArgs {
   float* partial_bias;
   int32_t m_pad;
   int32_t k_pad;
+  int32_t dy_vec;  // 4 / 2 / 1: widest aligned vector for the dY resp. X tile copies
+  int32_t x_vec;
 };
+
+template <int TILE_W>
+__device__ __forceinline__ void wg_issue_tile(float* dst, const float* src, int64_t ld, int64_t row0, int64_t n, int col0, int width,
+                                              int vec) {
+  // dst[r][c] = src[row0 + r][col0 + c] for r < kWgTileN, c < TILE_W; zero-filled outside the matrix
+  const int nv = TILE_W / vec;
+  for (int e = threadIdx.x; e < kWgTileN * nv; e += kWgThreads) {
+    const int r = e / nv;
+    const int c = (e - r * nv) * vec;
+    const int64_t gr = row0 + r;
+    const bool ok = gr < n && col0 + c < width;  // width % vec == 0 and col0 % vec == 0: a vector is all-in or all-out
+    const float* s = src + (ok ? gr * ld + col0 + c : 0);
+    float* d = dst + r * TILE_W + c;
+    if (vec == 4) cp_async<16>(d, s, ok);
+    else if (vec == 2) cp_async<8>(d, s, ok);
+    else cp_async<4>(d, s, ok);
+  }
+}
 
 template <int WM, int WK>
 __global__ void __launch_bounds__(kWgThreads) k_weight_grad(const WgradArgs p) {
   constexpr int WN = 8 / (WM * WK);
   constexpr int kTileM = 32 * WM;
   constexpr int kTileK = 16 * WK;
+  constexpr int kStage = kWgTileN * (kTileM + kTileK);  // floats per pipeline stage
   extern __shared__ __align__(16) float smem[];
-  float* sDY = smem;                      // [kWgTileN][kTileM]
-  float* sX = smem + kWgTileN * kTileM;   // [kWgTileN][kTileK]
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int wn = warp % WN;
@@ -227,22 +247,24 @@ __global__ void __launch_bounds__(kWgThreads) k_weight_grad(const WgradArgs p) {
   const bool bias_lane = (wk == 0 && kg == 0 && blockIdx.y == 0);
 
   const int64_t n_tiles = (p.n + kWgTileN - 1) / kWgTileN;
+  int stage = 0;
+  if ((int64_t)blockIdx.x < n_tiles) {
+    wg_issue_tile<kTileM>(smem, p.dy, p.ld_dy, (int64_t)blockIdx.x * kWgTileN, p.n, m0, p.m, p.dy_vec);
+    wg_issue_tile<kTileK>(smem + kWgTileN * kTileM, p.x, p.ldx, (int64_t)blockIdx.x * kWgTileN, p.n, k0, p.k, p.x_vec);
+  }
+  cp_async_commit();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kWgTileN;
-    __syncthreads();
-    for (int e = threadIdx.x; e < kWgTileN * kTileM; e += kWgThreads) {
-      const int r = e / kTileM;
-      const int c = e - r * kTileM;
-      const int64_t gr = row0 + r;
-      sDY[e] = (gr < p.n && m0 + c < p.m) ? ld_stream_f32(p.dy + gr * p.ld_dy + m0 + c) : 0.f;
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {  // prefetch the next tile into the other stage while this one is consumed
+      float* nb = smem + (stage ^ 1) * kStage;
+      wg_issue_tile<kTileM>(nb, p.dy, p.ld_dy, next * kWgTileN, p.n, m0, p.m, p.dy_vec);
+      wg_issue_tile<kTileK>(nb + kWgTileN * kTileM, p.x, p.ldx, next * kWgTileN, p.n, k0, p.k, p.x_vec);
     }
-    for (int e = threadIdx.x; e < kWgTileN * kTileK; e += kWgThreads) {
-      const int r = e / kTileK;
-      const int c = e - r * kTileK;
-      const int64_t gr = row0 + r;
-      sX[e] = (gr < p.n && k0 + c < p.k) ? ld_stream_f32(p.x + gr * p.ldx + k0 + c) : 0.f;
-    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* sDY = smem + stage * kStage;
+    const float* sX = sDY + kWgTileN * kTileM;
     const float* dyp = sDY + wm * 32 + mg * 4;
     const float* xp = sX + wk * 16 + kg * 4;
 #pragma unroll 4
@@ -258,11 +280,14 @@ __global__ void __launch_bounds__(kWgThreads) k_weight_grad(const WgradArgs p) {
         if (bias_lane) accb[i] += av[i];
       }
     }
+    __syncthreads();
+    stage ^= 1;
   }
+  cp_async_wait<0>();
 
   // combine the WN row-splits in fixed order through smem, then write this CTA's partial
   __syncthreads();
-  float* red = smem;  // [WN][kTileM][kTileK]; the launcher sizes smem as max(tiles, this scratch)
+  float* red = smem;  // [WN][kTileM][kTileK]; the launcher sizes smem as max(2 stages, this scratch)
   float* redb = smem + WN * kTileM * kTileK;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -291,23 +316,29 @@ __global__ void __launch_bounds__(kWgThreads) k_weight_grad(const WgradArgs p) {
   }
 }
 
+// One warp per output element: lane l adds partials l, l+32, ... in order, then a fixed xor tree.
 __global__ void __launch_bounds__(256) k_weight_grad_reduce(const float* __restrict__ partial, const float* __restrict__ partial_bias,
                                                             int32_t n_partials, int32_t m, int32_t k, int32_t m_pad, int32_t k_pad,
                                                             float* __restrict__ dw, int64_t ld_dw, float* __restrict__ dbias,
                                                             int32_t accumulate) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = lane_id();
+  const int total = m * k + (dbias != nullptr ? m : 0);
+  if (t >= total) return;
+  float s = 0.f;
+  float* dst;
   if (t < m * k) {
     const int mm = t / k, kk = t - mm * k;
-    float s = 0.f;
-    for (int c = 0; c < n_partials; ++c) s += partial[((int64_t)c * m_pad + mm) * k_pad + kk];
-    float* dst = dw + (int64_t)mm * ld_dw + kk;
-    *dst = accumulate ? *dst + s : s;
-  } else if (dbias != nullptr && t < m * k + m) {
+    for (int c = lane; c < n_partials; c += 32) s += partial[((int64_t)c * m_pad + mm) * k_pad + kk];
+    dst = dw + (int64_t)mm * ld_dw + kk;
+  } else {
     const int mm = t - m * k;
-    float s = 0.f;
-    for (int c = 0; c < n_partials; ++c) s += partial_bias[(int64_t)c * m_pad + mm];
-    dbias[mm] = accumulate ? dbias[mm] + s : s;
+    for (int c = lane; c < n_partials; c += 32) s += partial_bias[(int64_t)c * m_pad + mm];
+    dst = dbias + mm;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) *dst = accumulate ? *dst + s : s;
 }
 
 struct WgradPlan {
@@ -337,10 +368,15 @@ static WgradPlan plan_wgrad(int32_t k, int32_t m) {
 template <int WM, int WK>
 static void launch_wgrad(const WgradArgs& a, const WgradPlan& pl, cudaStream_t st) {
   constexpr int WN = 8 / (WM * WK);
-  const size_t tile = (size_t)kWgTileN * (32 * WM + 16 * WK);
+  const size_t tile = (size_t)2 * kWgTileN * (32 * WM + 16 * WK);  // two pipeline stages
   const size_t scratch = (size_t)WN * (32 * WM) * (16 * WK) + (size_t)WN * 32 * WM;  // cross-warp reduction reuses the tile smem
   const size_t smem = std::max(tile, scratch) * sizeof(float);
   dim3 grid(pl.grid_x, pl.grid_y, pl.grid_z);
+  static bool opted_in = false;  // > 48 KB of dynamic shared memory needs a one-time opt-in per kernel
+  if (!opted_in && smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_weight_grad<WM, WK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    opted_in = true;
+  }
   k_weight_grad<WM, WK><<<grid, kWgThreads, smem, st>>>(a);
 }
 
@@ -398,7 +434,11 @@ int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx,
               workspace_bytes, pl.bytes);
   float* partial = static_cast<float*>(workspace);
   float* partial_bias = partial + (size_t)pl.grid_x * pl.m_pad * pl.k_pad;
-  WgradArgs a{dy, ld_dy, x, ldx, n, k, m, partial, dbias != nullptr ? partial_bias : nullptr, pl.m_pad, pl.k_pad};
+  WgradArgs a{dy, ld_dy, x, ldx, n, k, m, partial, dbias != nullptr ? partial_bias : nullptr, pl.m_pad, pl.k_pad, 1, 1};
+  if (ld_dy % 4 == 0 && m % 4 == 0 && aligned16(dy)) a.dy_vec = 4;
+  else if (ld_dy % 2 == 0 && m % 2 == 0 && aligned8(dy)) a.dy_vec = 2;
+  if (ldx % 4 == 0 && k % 4 == 0 && aligned16(x)) a.x_vec = 4;
+  else if (ldx % 2 == 0 && k % 2 == 0 && aligned8(x)) a.x_vec = 2;
   cudaStream_t st = as_stream(stream);
   if (pl.wm == 1 && pl.wk == 4) launch_wgrad<1, 4>(a, pl, st);
   else if (pl.wm == 1 && pl.wk == 2) launch_wgrad<1, 2>(a, pl, st);
@@ -407,7 +447,7 @@ int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx,
   else if (pl.wm == 2 && pl.wk == 2) launch_wgrad<2, 2>(a, pl, st);
   else launch_wgrad<2, 1>(a, pl, st);
   const int total = m * k + (dbias != nullptr ? m : 0);
-  k_weight_grad_reduce<<<ceil_div(total, 256), 256, 0, st>>>(partial, partial_bias, pl.grid_x, m, k, pl.m_pad, pl.k_pad, dw, ld_dw, dbias,
+  k_weight_grad_reduce<<<ceil_div(total * 32, 256), 256, 0, st>>>(partial, partial_bias, pl.grid_x, m, k, pl.m_pad, pl.k_pad, dw, ld_dw, dbias,
                                                              accumulate);
   return finish_launch("weight grad", 2);
 }

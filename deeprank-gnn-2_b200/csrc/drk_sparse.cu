@@ -70,16 +70,19 @@ struct SpmmArgs {
 };
 
 constexpr int kSpmmThreads = 256;
-constexpr int kUnroll = 4;
 
 template <int LPR, int VEC>
 __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
+  // All control flow is WARP-UNIFORM: the 32/LPR rows a warp works on are walked in lock-step up to the
+  // longest of them, shorter rows run predicated.  (Letting each sub-warp loop to its own row length makes
+  // the sub-warps diverge and the hardware then issues them one after the other: 8x slower for LPR = 4.)
   constexpr int kRowsPerWarp = 32 / LPR;
   constexpr int kRowsPerPass = (kSpmmThreads / 32) * kRowsPerWarp;
+  constexpr unsigned kFull = 0xffffffffu;
   const int lane = lane_id();
   const int sub = lane / LPR;
   const int sl = lane % LPR;
-  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int group_base = sub * LPR;
   const int warp = threadIdx.x >> 5;
   const int row0 = blockIdx.x * a.rows_per_block;
   const int row_end = min(row0 + a.rows_per_block, a.n_out);
@@ -87,33 +90,58 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
   for (int cbase = 0; cbase < a.width; cbase += LPR * VEC) {  // one trip for width <= LPR*VEC
     const int c = cbase + sl * VEC;
     const bool col_ok = c < a.width;  // width % VEC == 0 is guaranteed by the dispatcher
-    for (int r = row0 + warp * kRowsPerWarp + sub; r < row_end; r += kRowsPerPass) {
-      const int beg = a.ptr[r];
-      const int end = a.ptr[r + 1];
+    for (int rw = row0 + warp * kRowsPerWarp; rw < row_end; rw += kRowsPerPass) {  // rw is warp-uniform
+      const int r = rw + sub;
+      const bool row_ok = r < row_end;
+      int beg = 0, len = 0;
+      if (row_ok) {
+        beg = a.ptr[r];
+        len = a.ptr[r + 1] - beg;
+      }
+      int max_len = len;
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) max_len = max(max_len, __shfl_xor_sync(kFull, max_len, o));
       float acc[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-      for (int s = beg; s < end; s += LPR) {
-        const int cnt = min(LPR, end - s);
-        int my_idx = 0;
-        float my_w = 1.f;
-        if (sl < cnt) {
-          my_idx = a.idx != nullptr ? ld_stream_i32(a.idx + s + sl) : s + sl;
-          if (a.w != nullptr) my_w = ld_stream_f32(a.w + s + sl);
+      // software pipeline: the index chunk of the NEXT trip is loaded while this trip's gathers are in flight
+      int next_idx = -1;
+      float next_w = 0.f;
+      if (sl < len) {
+        next_idx = a.idx != nullptr ? ld_stream_i32(a.idx + beg + sl) : beg + sl;
+        if (a.w != nullptr) next_w = ld_stream_f32(a.w + beg + sl);
+      }
+      for (int off = 0; off < max_len; off += LPR) {
+        const int my_idx = next_idx;
+        const float my_w = next_w;
+        next_idx = -1;
+        if (off + LPR + sl < len) {
+          next_idx = a.idx != nullptr ? ld_stream_i32(a.idx + beg + off + LPR + sl) : beg + off + LPR + sl;
+          if (a.w != nullptr) next_w = ld_stream_f32(a.w + beg + off + LPR + sl);
         }
-        for (int j0 = 0; j0 < cnt; j0 += kUnroll) {
-          Vec<VEC> t[kUnroll];
-          float tw[kUnroll];
+        Vec<VEC> t[LPR < 8 ? LPR : 8];
+        constexpr int kBatch = LPR < 8 ? LPR : 8;  // gathers in flight per lane
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
-            const int j = min(j0 + u, LPR - 1);
-            const int srow = __shfl_sync(gmask, my_idx, j, LPR);
-            tw[u] = a.w != nullptr ? __shfl_sync(gmask, my_w, j, LPR) : 1.f;
-            if (j0 + u < cnt && col_ok) t[u].load(a.src + (int64_t)srow * a.ld_src + c);
+        for (int j0 = 0; j0 < LPR; j0 += kBatch) {
+          int srow[kBatch];
+          float tw[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            srow[u] = __shfl_sync(kFull, my_idx, group_base + j0 + u);
+            tw[u] = a.w != nullptr ? __shfl_sync(kFull, my_w, group_base + j0 + u) : 1.f;
           }
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
-            if (j0 + u < cnt && col_ok) {
+          for (int u = 0; u < kBatch; ++u) {
+            if (srow[u] >= 0 && col_ok) {
+              t[u].load(a.src + (int64_t)srow[u] * a.ld_src + c);
+            } else {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) t[u].v[k] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (srow[u] >= 0) {  // keep exact sequential order; skipping (instead of adding 0) keeps -0.0 / NaN semantics
               if (a.w != nullptr) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) acc[k] = fmaf(tw[u], t[u].v[k], acc[k]);
@@ -125,9 +153,9 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
           }
         }
       }
-      if (!col_ok) continue;
+      if (!col_ok || !row_ok) continue;
       if (a.reduce != DRK_REDUCE_SUM) {
-        const float deg = (float)(end - beg);
+        const float deg = (float)len;
         const float den = a.reduce == DRK_REDUCE_MEAN_CLAMP ? fmaxf(deg, 1.f) : deg;  // MEAN_NAN: 0/0 = NaN like torch.mean([])
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = acc[k] / den;

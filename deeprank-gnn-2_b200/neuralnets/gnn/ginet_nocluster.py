@@ -10,6 +10,7 @@ import torch
 from torch import nn
 from torch.nn.functional import dropout, relu
 
+from ... import ops
 from ...graph import graph_index
 from ._common import GINetConvLayer, mean_readout  # noqa: F401  (GINetConvLayer is part of this module's API)
 
@@ -31,20 +32,32 @@ class GINet(nn.Module):
         self.fc2 = nn.Linear(128, output_shape)
         self.dropout = 0.4
 
+    def _stackable(self) -> bool:
+        """The stacked path needs bias-free convolutions of equal shapes in both branches (always true
+        for the reference architecture; a user-modified net falls back to layer-by-layer)."""
+        convs = (self.conv1, self.conv1_ext, self.conv2, self.conv2_ext)
+        return (
+            all(c.fc.bias is None for c in convs)
+            and self.conv1.fc.weight.shape == self.conv1_ext.fc.weight.shape
+            and self.conv2.fc.weight.shape == self.conv2_ext.fc.weight.shape
+            and self.conv2.fc.weight.shape[1] == self.conv1.fc.weight.shape[0]
+            and self.conv1.fc.weight.shape[0] % 4 == 0
+        )
+
     def forward(self, data):
         g = graph_index(data)  # CSR/CSC + graph offsets, built once on the device and shared by all layers
-        x0 = data.x
         # the reference deep-copies the batch (data.clone(), :86) and overwrites data.x in place (:90,:93);
         # neither has a numerical effect, so no copy is made here.
-        x = self.conv1(x0, data.edge_index, data.edge_attr, graph=g, relu=True)
-        x = self.conv2(x, data.edge_index, data.edge_attr, graph=g, relu=True)
-        x_ext = self.conv1_ext(x0, data.edge_index, data.edge_attr, graph=g, relu=True)
-        x_ext = self.conv2_ext(x_ext, data.edge_index, data.edge_attr, graph=g, relu=True)
-
-        x = mean_readout(x, data)
-        x_ext = mean_readout(x_ext, data)
-
-        x = torch.cat([x, x_ext], dim=1)
+        if self._stackable():
+            # both branches + readout as one fused autograd node: x -> [B, 64]
+            x = ops.ginet_stack(data.x, self.conv1, self.conv1_ext, self.conv2, self.conv2_ext, g)
+        else:
+            x0 = data.x
+            x = self.conv1(x0, data.edge_index, data.edge_attr, graph=g, relu=True)
+            x = self.conv2(x, data.edge_index, data.edge_attr, graph=g, relu=True)
+            x_ext = self.conv1_ext(x0, data.edge_index, data.edge_attr, graph=g, relu=True)
+            x_ext = self.conv2_ext(x_ext, data.edge_index, data.edge_attr, graph=g, relu=True)
+            x = torch.cat([mean_readout(x, data), mean_readout(x_ext, data)], dim=1)
         x = relu(self.fc1(x))
         x = dropout(x, self.dropout, training=self.training)
         return self.fc2(x)

@@ -78,6 +78,18 @@ def test_ginet_nocluster_train_step_vs_reference(case):
     _train_step_vs_golden(g, "ginet_nocluster", net)
 
 
+@pytest.mark.parametrize("case", ["toy_edgecases", "fixture_1ATN"])
+def test_ginet_nocluster_layerwise_fallback_vs_reference(case, monkeypatch):
+    """A user-modified net (biases, unequal branches) takes the layer-by-layer path: same parity bar."""
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+
+    monkeypatch.setattr(GINet, "_stackable", lambda self: False)
+    g = load_golden(case)
+    d = g.inputs()
+    net = _load(GINet(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("ginet_nocluster/w"))
+    _train_step_vs_golden(g, "ginet_nocluster", net)
+
+
 def test_ginet_nocluster_c2_batch_vs_oracle_and_deterministic():
     """Config C2 at reduced batch (32 graphs x ~300 nodes, degree ~20): CUDA path vs the CPU oracle on
     identical inputs and weights; two CUDA runs must agree bit for bit (no float atomics)."""
