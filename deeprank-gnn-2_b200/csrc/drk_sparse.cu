@@ -30,6 +30,7 @@ struct Vec<4> {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+  __device__ __forceinline__ void fence() { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])); }
 };
 template <>
 struct Vec<2> {
@@ -39,12 +40,14 @@ struct Vec<2> {
     v[0] = t.x; v[1] = t.y;
   }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  __device__ __forceinline__ void fence() { asm volatile("" : "+f"(v[0]), "+f"(v[1])); }
 };
 template <>
 struct Vec<1> {
   float v[1];
   __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+  __device__ __forceinline__ void fence() { asm volatile("" : "+f"(v[0])); }
 };
 
 __device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.f ? 0.f : x; }           // torch.relu(NaN) = NaN
@@ -55,13 +58,13 @@ struct SpmmArgs {
   const int32_t* idx;
   const float* w;
   const float* src;
-  int64_t ld_src;
   const float* addend;
-  int64_t ld_addend;
   const float* mask;
-  int64_t ld_mask;
   float* out;
-  int64_t ld_out;
+  uint32_t ld_src;  // leading dimensions in ELEMENTS; 32-bit: tensors of up to 2^32 elements (16 GB)
+  uint32_t ld_addend;
+  uint32_t ld_mask;
+  uint32_t ld_out;
   int32_t n_out;
   int32_t width;
   int32_t reduce;
@@ -71,13 +74,17 @@ struct SpmmArgs {
 
 constexpr int kSpmmThreads = 256;
 
-template <int LPR, int VEC>
-__global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
-  // All control flow is WARP-UNIFORM: the 32/LPR rows a warp works on are walked in lock-step up to the
-  // longest of them, shorter rows run predicated.  (Letting each sub-warp loop to its own row length makes
-  // the sub-warps diverge and the hardware then issues them one after the other: 8x slower for LPR = 4.)
+// LPR lanes per destination row, VEC floats per lane.  All control flow is WARP-UNIFORM: the 32/LPR rows a
+// warp works on are walked in lock-step up to the longest of them, shorter rows run predicated.  (Letting
+// each sub-warp loop to its own row length makes the sub-warps diverge and the hardware then issues them
+// one after the other: 8x slower for LPR = 4.)  Per trip every lane has kInFlight gathers outstanding.
+template <int LPR, int VEC, bool HAS_W, bool HAS_IDX>
+__global__ void __launch_bounds__(kSpmmThreads, 4) k_spmm(const SpmmArgs a) {
   constexpr int kRowsPerWarp = 32 / LPR;
   constexpr int kRowsPerPass = (kSpmmThreads / 32) * kRowsPerWarp;
+  constexpr int kChunks = LPR >= 8 ? 1 : 8 / LPR;  // index chunks (of LPR edges) per trip
+  constexpr int kInFlight = kChunks * LPR;         // edges consumed per trip
+  constexpr int kBatch = 8;                        // gathers in flight per lane (8 x float4 = 32 registers)
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = lane_id();
   const int sub = lane / LPR;
@@ -86,17 +93,19 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
   const int warp = threadIdx.x >> 5;
   const int row0 = blockIdx.x * a.rows_per_block;
   const int row_end = min(row0 + a.rows_per_block, a.n_out);
+  const uint32_t ld_src_bytes = a.ld_src * 4u;
 
   for (int cbase = 0; cbase < a.width; cbase += LPR * VEC) {  // one trip for width <= LPR*VEC
     const int c = cbase + sl * VEC;
     const bool col_ok = c < a.width;  // width % VEC == 0 is guaranteed by the dispatcher
+    const char* src_c = reinterpret_cast<const char*>(a.src + c);
     for (int rw = row0 + warp * kRowsPerWarp; rw < row_end; rw += kRowsPerPass) {  // rw is warp-uniform
       const int r = rw + sub;
       const bool row_ok = r < row_end;
       int beg = 0, len = 0;
       if (row_ok) {
-        beg = a.ptr[r];
-        len = a.ptr[r + 1] - beg;
+        beg = __ldg(a.ptr + r);
+        len = __ldg(a.ptr + r + 1) - beg;
       }
       int max_len = len;
 #pragma unroll
@@ -104,51 +113,53 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
       float acc[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-      // software pipeline: the index chunk of the NEXT trip is loaded while this trip's gathers are in flight
-      int next_idx = -1;
-      float next_w = 0.f;
-      if (sl < len) {
-        next_idx = a.idx != nullptr ? ld_stream_i32(a.idx + beg + sl) : beg + sl;
-        if (a.w != nullptr) next_w = ld_stream_f32(a.w + beg + sl);
-      }
-      for (int off = 0; off < max_len; off += LPR) {
-        const int my_idx = next_idx;
-        const float my_w = next_w;
-        next_idx = -1;
-        if (off + LPR + sl < len) {
-          next_idx = a.idx != nullptr ? ld_stream_i32(a.idx + beg + off + LPR + sl) : beg + off + LPR + sl;
-          if (a.w != nullptr) next_w = ld_stream_f32(a.w + beg + off + LPR + sl);
-        }
-        Vec<VEC> t[LPR < 8 ? LPR : 8];
-        constexpr int kBatch = LPR < 8 ? LPR : 8;  // gathers in flight per lane
+
+      // software pipeline: the index chunks of the NEXT trip are loaded while this trip's gathers are in flight
+      int next_idx[kChunks];
+      float next_w[kChunks];
 #pragma unroll
-        for (int j0 = 0; j0 < LPR; j0 += kBatch) {
+      for (int q = 0; q < kChunks; ++q) {
+        const int e = q * LPR + sl;
+        next_idx[q] = -1;
+        next_w[q] = 0.f;
+        if (e < len) {
+          next_idx[q] = HAS_IDX ? ld_stream_i32(a.idx + beg + e) : beg + e;
+          if (HAS_W) next_w[q] = ld_stream_f32(a.w + beg + e);
+        }
+      }
+      for (int off = 0; off < max_len; off += kInFlight) {
+        int my_idx[kChunks];
+        float my_w[kChunks];
+#pragma unroll
+        for (int q = 0; q < kChunks; ++q) {
+          my_idx[q] = next_idx[q];
+          my_w[q] = next_w[q];
+          const int e = off + kInFlight + q * LPR + sl;
+          next_idx[q] = -1;
+          if (e < len) {
+            next_idx[q] = HAS_IDX ? ld_stream_i32(a.idx + beg + e) : beg + e;
+            if (HAS_W) next_w[q] = ld_stream_f32(a.w + beg + e);
+          }
+        }
+#pragma unroll
+        for (int u0 = 0; u0 < kInFlight; u0 += kBatch) {
+          Vec<VEC> t[kBatch];
           int srow[kBatch];
           float tw[kBatch];
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
-            srow[u] = __shfl_sync(kFull, my_idx, group_base + j0 + u);
-            tw[u] = a.w != nullptr ? __shfl_sync(kFull, my_w, group_base + j0 + u) : 1.f;
+            srow[u] = __shfl_sync(kFull, my_idx[(u0 + u) / LPR], group_base + ((u0 + u) % LPR));
+            if (HAS_W) tw[u] = __shfl_sync(kFull, my_w[(u0 + u) / LPR], group_base + ((u0 + u) % LPR));
           }
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
-            if (srow[u] >= 0 && col_ok) {
-              t[u].load(a.src + (int64_t)srow[u] * a.ld_src + c);
-            } else {
-#pragma unroll
-              for (int k = 0; k < VEC; ++k) t[u].v[k] = 0.f;
-            }
+            if (srow[u] >= 0 && col_ok) t[u].load(reinterpret_cast<const float*>(src_c + (uint64_t)(uint32_t)srow[u] * ld_src_bytes));
           }
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
-            if (srow[u] >= 0) {  // keep exact sequential order; skipping (instead of adding 0) keeps -0.0 / NaN semantics
-              if (a.w != nullptr) {
+            if (srow[u] >= 0 && col_ok) {  // strictly sequential accumulation in CSR order
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[k] = fmaf(tw[u], t[u].v[k], acc[k]);
-              } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[k] += t[u].v[k];
-              }
+              for (int k = 0; k < VEC; ++k) acc[k] = HAS_W ? fmaf(tw[u], t[u].v[k], acc[k]) : acc[k] + t[u].v[k];
             }
           }
         }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
       }
       if (a.addend != nullptr) {
         Vec<VEC> ad;
-        ad.load(a.addend + (int64_t)r * a.ld_addend + c);
+        ad.load(a.addend + (size_t)r * a.ld_addend + c);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] += ad.v[k];
       }
@@ -172,21 +183,25 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
       }
       if (a.mask != nullptr) {
         Vec<VEC> m;
-        m.load(a.mask + (int64_t)r * a.ld_mask + c);
+        m.load(a.mask + (size_t)r * a.ld_mask + c);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = relu_grad_mask(acc[k], m.v[k]);
       }
       Vec<VEC> o;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) o.v[k] = acc[k];
-      o.store(a.out + (int64_t)r * a.ld_out + c);
+      o.store(a.out + (size_t)r * a.ld_out + c);
     }
   }
 }
 
 template <int LPR, int VEC>
 static void launch_spmm(const SpmmArgs& a, int blocks, cudaStream_t stream) {
-  k_spmm<LPR, VEC><<<blocks, kSpmmThreads, 0, stream>>>(a);
+  const bool has_w = a.w != nullptr, has_idx = a.idx != nullptr;
+  if (has_w && has_idx) k_spmm<LPR, VEC, true, true><<<blocks, kSpmmThreads, 0, stream>>>(a);
+  else if (has_w) k_spmm<LPR, VEC, true, false><<<blocks, kSpmmThreads, 0, stream>>>(a);
+  else if (has_idx) k_spmm<LPR, VEC, false, true><<<blocks, kSpmmThreads, 0, stream>>>(a);
+  else k_spmm<LPR, VEC, false, false><<<blocks, kSpmmThreads, 0, stream>>>(a);
 }
 
 // ---------------------------------------------------------------- per-graph mean (one CTA per graph)
@@ -228,19 +243,34 @@ __global__ void __launch_bounds__(kMeanThreads) k_segment_mean(const float* __re
   }
 }
 
-__global__ void __launch_bounds__(256) k_segment_mean_bwd(const float* __restrict__ dg, int64_t ld_dg, const int32_t* __restrict__ graph_ptr,
+template <int VEC>
+__global__ void __launch_bounds__(256) k_segment_mean_bwd(const float* __restrict__ dg, uint32_t ld_dg, const int32_t* __restrict__ graph_ptr,
                                                           const int32_t* __restrict__ batch32, const float* __restrict__ mask,
-                                                          int64_t ld_mask, int32_t num_nodes, int32_t width, float* __restrict__ dx,
-                                                          int64_t ld_dx) {
-  const int64_t total = (int64_t)num_nodes * width;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(t / width);
-    const int c = (int)(t - (int64_t)i * width);
-    const int b = batch32[i];
-    const float den = fmaxf((float)(graph_ptr[b + 1] - graph_ptr[b]), 1.f);
-    float g = dg[(int64_t)b * ld_dg + c] / den;
-    if (mask != nullptr) g = relu_grad_mask(g, mask[(int64_t)i * ld_mask + c]);
-    dx[(int64_t)i * ld_dx + c] = g;
+                                                          uint32_t ld_mask, int32_t num_nodes, int32_t width, float* __restrict__ dx,
+                                                          uint32_t ld_dx) {
+  // thread -> (node i, vector column cv); cols = width / VEC vector columns per node (32-bit index math only)
+  const uint32_t cols = (uint32_t)width / VEC;
+  const uint32_t total = (uint32_t)num_nodes * cols;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t i = t / cols;
+    const uint32_t c = (t - i * cols) * VEC;
+    const int b = __ldg(batch32 + i);
+    const float den = fmaxf((float)(__ldg(graph_ptr + b + 1) - __ldg(graph_ptr + b)), 1.f);  // true division, like scatter_mean
+    Vec<VEC> g;
+    g.load(dg + (size_t)b * ld_dg + c);
+    float o[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o[k] = g.v[k] / den;
+    if (mask != nullptr) {
+      Vec<VEC> m;
+      m.load(mask + (size_t)i * ld_mask + c);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = relu_grad_mask(o[k], m.v[k]);
+    }
+    Vec<VEC> ov;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) ov.v[k] = o[k];
+    ov.store(dx + (size_t)i * ld_dx + c);
   }
 }
 
@@ -272,7 +302,11 @@ int drk_spmm(const int32_t* ptr, const int32_t* idx, const float* w, const float
   DRK_REQUIRE(ptr && src && out, DRK_EINVAL, "spmm: null pointer");
   DRK_REQUIRE(reduce >= DRK_REDUCE_SUM && reduce <= DRK_REDUCE_MEAN_NAN, DRK_EINVAL, "spmm: unknown reduce %d", reduce);
   DRK_REQUIRE(act == DRK_ACT_NONE || act == DRK_ACT_RELU, DRK_EINVAL, "spmm: unknown activation %d", act);
-  SpmmArgs a{ptr, idx, w, src, ld_src, addend, ld_addend, mask, ld_mask, out, ld_out, n_out, width, reduce, act, 0};
+  DRK_REQUIRE(ld_src >= 0 && ld_src < (int64_t)1 << 30 && ld_out >= 0 && ld_out < (int64_t)1 << 30 && ld_addend < (int64_t)1 << 30 &&
+                  ld_mask < (int64_t)1 << 30,
+              DRK_EUNSUPPORTED, "spmm: leading dimension out of range");
+  SpmmArgs a{ptr, idx, w, src, addend, mask, out, (uint32_t)ld_src, (uint32_t)ld_addend, (uint32_t)ld_mask, (uint32_t)ld_out,
+             n_out, width, reduce, act, 0};
   const int vec = pick_vec(width, {src, addend, mask, out}, {ld_src, addend ? ld_addend : 4, mask ? ld_mask : 4, ld_out});
   const int vcols = width / vec;
   int lpr = 4;
@@ -317,8 +351,14 @@ int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_pt
   DRK_REQUIRE(num_nodes >= 0 && width >= 0, DRK_EINVAL, "segment mean bwd: negative size");
   if (num_nodes == 0 || width == 0) return DRK_OK;
   DRK_REQUIRE(dg && graph_ptr && batch32 && dx, DRK_EINVAL, "segment mean bwd: null pointer");
-  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>((int64_t)num_nodes * width, 256 * 4), (int64_t)kNumSM * 16);
-  k_segment_mean_bwd<<<blocks, 256, 0, as_stream(stream)>>>(dg, ld_dg, graph_ptr, batch32, mask, ld_mask, num_nodes, width, dx, ld_dx);
+  DRK_REQUIRE((int64_t)num_nodes * width < (int64_t)1 << 31, DRK_EUNSUPPORTED, "segment mean bwd: more than 2^31 elements");
+  const int vec = pick_vec(width, {dg, mask, dx}, {ld_dg, mask ? ld_mask : 4, ld_dx});
+  const int64_t work = (int64_t)num_nodes * (width / vec);
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)kNumSM * 32);
+  cudaStream_t st = as_stream(stream);
+  if (vec == 4) k_segment_mean_bwd<4><<<blocks, 256, 0, st>>>(dg, (uint32_t)ld_dg, graph_ptr, batch32, mask, (uint32_t)ld_mask, num_nodes, width, dx, (uint32_t)ld_dx);
+  else if (vec == 2) k_segment_mean_bwd<2><<<blocks, 256, 0, st>>>(dg, (uint32_t)ld_dg, graph_ptr, batch32, mask, (uint32_t)ld_mask, num_nodes, width, dx, (uint32_t)ld_dx);
+  else k_segment_mean_bwd<1><<<blocks, 256, 0, st>>>(dg, (uint32_t)ld_dg, graph_ptr, batch32, mask, (uint32_t)ld_mask, num_nodes, width, dx, (uint32_t)ld_dx);
   return finish_launch("segment mean bwd");
 }
 
