@@ -40,11 +40,20 @@ SIGNATURES = {
     "drk_batch_offsets": (c_int32, [_P, _I32, _I32, _P, _P, _P, _P]),
     "drk_gather_rows": (c_int32, [_P, _I64, _P, _I64, _I32, _P, _I64, _P]),
     "drk_node_linear": (c_int32, [_P, _I64, _P, _I64, _I32, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "drk_node_linear2": (c_int32, [_P, _I64, _P, _I64, _I32, _P, _I64, _P, _I64, _I32, _I32, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "drk_weight_grad_workspace_bytes": (c_size_t, [_I32, _I32]),
     "drk_weight_grad": (c_int32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, c_size_t, _P]),
     "drk_spmm": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P]),
     "drk_segment_mean": (c_int32, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
     "drk_segment_mean_bwd": (c_int32, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
+    "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
+    "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
+    "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),
+    "drk_cluster_offsets": (c_int32, [_P, _P, _P, _I32, _I32, _P, _P, c_size_t, _P]),
+    "drk_edge_msg_fwd": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _I32, _P, _I64, _P, _I64, _P, _P, _I32, _P]),
+    "drk_edge_msg_bwd_src": (c_int32, [_P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _P]),
+    "drk_edge_msg_bwd_c_workspace_bytes": (c_size_t, []),
+    "drk_edge_msg_bwd_c": (c_int32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _P, _I64, _I32, _P, c_size_t, _P]),
 }
 
 _lib = None

@@ -46,6 +46,13 @@ struct LinearArgs {
   int32_t act;
   int32_t a_vec;  // 4 / 2 / 1: widest aligned vector for loading A rows
   int32_t c_vec;  // 4 or 1: vector width for storing C (and loading mask)
+  // optional second operand pair: C = act(A op(B) + A2 op(B2) + bias) -- a concat-free Linear on [A | A2]
+  const float* a2;
+  int64_t lda2;
+  const float* b2;
+  int64_t ldb2;
+  int32_t k2;
+  int32_t a2_vec;
 };
 
 // CT = output columns per thread (4, 8 or 16) -> CTA column tile of 4*CT = 16 / 32 / 64.
@@ -66,17 +73,27 @@ __global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p)
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
 
-  for (int k0 = 0; k0 < p.k; k0 += kLinKChunk) {
-    const int kc = min(kLinKChunk, p.k - k0);
+  const int chunks1 = (p.k + kLinKChunk - 1) / kLinKChunk;
+  const int chunks2 = (p.k2 + kLinKChunk - 1) / kLinKChunk;
+  for (int chunk = 0; chunk < chunks1 + chunks2; ++chunk) {
+    const bool second = chunk >= chunks1;
+    const int k0 = (second ? chunk - chunks1 : chunk) * kLinKChunk;
+    const int ktot = second ? p.k2 : p.k;
+    const float* __restrict__ pa = second ? p.a2 : p.a;
+    const float* __restrict__ pb = second ? p.b2 : p.b;
+    const int64_t lda = second ? p.lda2 : p.lda;
+    const int64_t ldb = second ? p.ldb2 : p.ldb;
+    const int avec = second ? p.a2_vec : p.a_vec;
+    const int kc = min(kLinKChunk, ktot - k0);
     const int kp = ((kc + 3) / 4 * 4) + ((((kc + 3) / 4) & 1) == 0 ? 4 : 0);  // == padded_stride(kc)
     float* sA = smem;                   // [kLinTileN][kp]
     float* sW = smem + kLinTileN * kp;  // [kTileM][kp], rows permuted
-    if (k0 > 0) __syncthreads();
+    if (chunk > 0) __syncthreads();
 
     // ---- A tile: rows row0.., columns k0..k0+kc, zero padded to kp.  cp.async: every thread fires all of its
     // copies back to back (~25 in flight) instead of waiting ~1 us of HBM latency per row.
     {
-      const int vec = p.a_vec;
+      const int vec = avec;
       const int nv = kc / vec;            // full vectors per row (kc % vec == 0 whenever vec > 1, see dispatcher)
       const int pv = (kp - nv * vec);     // zero-padding floats per row
       for (int e = threadIdx.x; e < kLinTileN * nv; e += kLinThreads) {
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p)
         const int v = e - r * nv;
         const int64_t gr = row0 + r;
         const bool ok = gr < p.n;
-        const float* src = p.a + (ok ? gr : 0) * p.lda + k0 + v * vec;
+        const float* src = pa + (ok ? gr : 0) * lda + k0 + v * vec;
         float* dst = sA + r * kp + v * vec;
         if (vec == 4) cp_async<16>(dst, src, ok);
         else if (vec == 2) cp_async<8>(dst, src, ok);
@@ -102,7 +119,7 @@ __global__ void __launch_bounds__(kLinThreads) k_node_linear(const LinearArgs p)
       const int kk = e - ml * kp;
       const int gm = m0 + ml;
       float v = 0.f;
-      if (gm < p.m && kk < kc) v = p.trans_b ? __ldg(p.b + (int64_t)gm * p.ldb + (k0 + kk)) : __ldg(p.b + (int64_t)(k0 + kk) * p.ldb + gm);
+      if (gm < p.m && kk < kc) v = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + (k0 + kk)) : __ldg(pb + (int64_t)(k0 + kk) * ldb + gm);
       const int srow = ((ml >> 2) & 3) + 4 * (ml & 3) + (ml & ~15);
       sW[srow * kp + kk] = v;
     }
@@ -384,20 +401,28 @@ static void launch_wgrad(const WgradArgs& a, const WgradPlan& pl, cudaStream_t s
 
 extern "C" {
 
-int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t trans_b, const float* bias, const float* mask,
-                    int64_t ld_mask, float* c, int64_t ldc, int64_t n, int32_t k, int32_t m, int32_t act, void* stream) {
+static int a_vector_width(const float* a, int64_t lda, int32_t k) {
+  if (lda % 4 == 0 && drk::aligned16(a) && (k % 4 == 0)) return 4;
+  if (lda % 2 == 0 && drk::aligned8(a) && (k % 2 == 0)) return 2;
+  return 1;
+}
+
+int drk_node_linear2(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t k, const float* a2, int64_t lda2, const float* b2,
+                     int64_t ldb2, int32_t k2, int32_t trans_b, const float* bias, const float* mask, int64_t ld_mask, float* c,
+                     int64_t ldc, int64_t n, int32_t m, int32_t act, void* stream) {
   using namespace drk;
-  DRK_REQUIRE(n >= 0 && k >= 0 && m >= 0, DRK_EINVAL, "node linear: negative size");
+  DRK_REQUIRE(n >= 0 && k >= 0 && k2 >= 0 && m >= 0, DRK_EINVAL, "node linear: negative size");
   if (n == 0 || m == 0) return DRK_OK;
   DRK_REQUIRE(a && b && c, DRK_EINVAL, "node linear: null pointer");
   DRK_REQUIRE(k >= 1, DRK_EINVAL, "node linear: k must be >= 1");
+  DRK_REQUIRE(k2 == 0 || (a2 && b2), DRK_EINVAL, "node linear: null second operand");
   DRK_REQUIRE(act == DRK_ACT_NONE || act == DRK_ACT_RELU, DRK_EINVAL, "node linear: unknown activation %d", act);
-  LinearArgs p{a, lda, b, ldb, trans_b, bias, mask, ld_mask, c, ldc, n, k, m, act, 1, 1};
+  LinearArgs p{a, lda, b, ldb, trans_b, bias, mask, ld_mask, c, ldc, n, k, m, act, 1, 1, a2, lda2, b2, ldb2, k2, 1};
   // widest vector that keeps every row start and every K-chunk start aligned
-  if (lda % 4 == 0 && aligned16(a) && (k % 4 == 0)) p.a_vec = 4;
-  else if (lda % 2 == 0 && aligned8(a) && (k % 2 == 0)) p.a_vec = 2;
+  p.a_vec = a_vector_width(a, lda, k);
+  if (k2 > 0) p.a2_vec = a_vector_width(a2, lda2, k2);
   if (ldc % 4 == 0 && aligned16(c) && (mask == nullptr || (ld_mask % 4 == 0 && aligned16(mask)))) p.c_vec = 4;
-  const int kc = std::min(k, kLinKChunk);
+  const int kc = std::min(std::max(k, k2), kLinKChunk);
   const int kp = padded_stride(kc);
   cudaStream_t st = as_stream(stream);
   const unsigned gx = (unsigned)ceil_div<int64_t>(n, kLinTileN);
@@ -417,6 +442,11 @@ int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, in
   else rc = launch(k_node_linear<16>, 64);
   if (rc != DRK_OK) return rc;
   return finish_launch("node linear");
+}
+
+int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t trans_b, const float* bias, const float* mask,
+                    int64_t ld_mask, float* c, int64_t ldc, int64_t n, int32_t k, int32_t m, int32_t act, void* stream) {
+  return drk_node_linear2(a, lda, b, ldb, k, nullptr, 0, nullptr, 0, 0, trans_b, bias, mask, ld_mask, c, ldc, n, m, act, stream);
 }
 
 size_t drk_weight_grad_workspace_bytes(int32_t k, int32_t m) {

@@ -363,3 +363,427 @@ int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_pt
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Per-edge ReLU messages of VanillaConvolutionalLayer (vanilla_gnn.py:26-35), message size 32:
+//   m_e = relu( U[row_e] + V[col_e] + C attr_e ),   S[i] = sum_{e in row i} m_e
+// with U = x Wa^T + b (destination half of _edge_mlp), V = x Wb^T (source half), C = the edge-feature
+// columns of _edge_mlp.  The reference materialises cat[x_i, x_j, e] as an [E, 2F+Fe] matrix and runs a
+// dense GEMM over it (7.4 GFLOP per layer at C2); here the two node halves are projected once per NODE
+// and only the 32-wide V rows are gathered per edge.
+//   forward also emits, per edge (by ORIGINAL edge id), the 32-bit ReLU mask, and per node cnt[i,c] =
+//   number of active edges of channel c (both consumed by the backward kernels).
+// =====================================================================================================
+namespace drk {
+
+constexpr int kMsg = 32;       // message size fixed by the reference (vanilla_gnn.py:20)
+constexpr int kMaxEdgeFeat = 8;
+
+struct EdgeMsgArgs {
+  const int32_t* ptr;    // CSR by destination
+  const int32_t* idx;    // source node of each CSR slot
+  const int32_t* perm;   // original edge id of each CSR slot
+  const float* uv;       // [N, 64]: U | V
+  const float* attr;     // [E, fe] in ORIGINAL edge order
+  const float* cmat;     // [32, ldc]: edge-feature block of the edge-MLP weight (row-major, row stride ldc)
+  float* s;              // [N, 32]
+  float* cnt;            // [N, 32] (may be NULL)
+  uint32_t* mask;        // [E] by original edge id (may be NULL)
+  uint32_t ld_uv, ld_attr, ldc, ld_s;
+  int32_t n, fe, rows_per_block;
+};
+
+// 8 lanes per destination row (4 columns each), 4 rows per warp -- same walk as k_spmm<8,4>.
+__global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = lane_id();
+  const int sub = lane >> 3, sl = lane & 7;
+  const int group_base = sub * 8;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * a.rows_per_block;
+  const int row_end = min(row0 + a.rows_per_block, a.n);
+  const int c = sl * 4;
+  float cw[4][kMaxEdgeFeat];  // this lane's 4 rows of C
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int k = 0; k < kMaxEdgeFeat; ++k) cw[q][k] = k < a.fe ? __ldg(a.cmat + (size_t)(c + q) * a.ldc + k) : 0.f;
+
+  for (int rw = row0 + warp * 4; rw < row_end; rw += 32) {
+    const int r = rw + sub;
+    const bool row_ok = r < row_end;
+    int beg = 0, len = 0;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok) {
+      beg = __ldg(a.ptr + r);
+      len = __ldg(a.ptr + r + 1) - beg;
+      u = ld_gather_f4(a.uv + (size_t)r * a.ld_uv + c);
+    }
+    int max_len = len;
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 16));
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 8));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float cn[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int off = 0; off < max_len; off += 8) {
+      int my_src = -1, my_eid = 0;
+      if (off + sl < len) {
+        my_src = ld_stream_i32(a.idx + beg + off + sl);
+        my_eid = ld_stream_i32(a.perm + beg + off + sl);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int srow = __shfl_sync(kFull, my_src, group_base + j);
+        const int eid = __shfl_sync(kFull, my_eid, group_base + j);
+        const bool on_edge = srow >= 0;  // uniform inside the 8-lane group; everything below is predicated, not branched
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on_edge) v = ld_gather_f4(a.uv + (size_t)srow * a.ld_uv + kMsg + c);
+        float m[4] = {u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w};
+        for (int k = 0; k < a.fe; ++k) {
+          const float av = on_edge ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = fmaf(cw[q][k], av, m[q]);
+        }
+        unsigned bits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool on = on_edge && m[q] > 0.f;
+          bits |= on ? (1u << q) : 0u;
+          acc[q] += on ? m[q] : 0.f;
+          cn[q] += on ? 1.f : 0.f;
+        }
+        if (a.mask != nullptr) {  // warp-uniform branch
+          // assemble the 32-bit mask of the edge from the 8 lanes of the group (4 bits each); xor 1/2/4 stay in the group
+          unsigned word = bits << (4 * sl);
+          word |= __shfl_xor_sync(kFull, word, 1);
+          word |= __shfl_xor_sync(kFull, word, 2);
+          word |= __shfl_xor_sync(kFull, word, 4);
+          if (on_edge && sl == 0) a.mask[eid] = word;
+        }
+      }
+    }
+    if (!row_ok) continue;
+    *reinterpret_cast<float4*>(a.s + (size_t)r * a.ld_s + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (a.cnt != nullptr) *reinterpret_cast<float4*>(a.cnt + (size_t)r * kMsg + c) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  }
+}
+
+// backward, source side:  dV[j,c] = sum_{t in CSC segment j} dS[row_t, c] * mask[eid_t][c]
+struct EdgeMsgBwdSrcArgs {
+  const int32_t* ptr;   // CSC by source
+  const int32_t* idx;   // destination node of each CSC slot
+  const int32_t* perm;  // original edge id of each CSC slot
+  const float* ds;      // [N, 32]
+  const uint32_t* mask; // [E]
+  float* dv;            // [N, 32] (strided: ld_dv)
+  uint32_t ld_ds, ld_dv;
+  int32_t n, rows_per_block;
+};
+
+__global__ void __launch_bounds__(256) k_edge_msg_bwd_src(const EdgeMsgBwdSrcArgs a) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = lane_id();
+  const int sub = lane >> 3, sl = lane & 7;
+  const int group_base = sub * 8;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * a.rows_per_block;
+  const int row_end = min(row0 + a.rows_per_block, a.n);
+  const int c = sl * 4;
+  for (int rw = row0 + warp * 4; rw < row_end; rw += 32) {
+    const int r = rw + sub;
+    const bool row_ok = r < row_end;
+    int beg = 0, len = 0;
+    if (row_ok) {
+      beg = __ldg(a.ptr + r);
+      len = __ldg(a.ptr + r + 1) - beg;
+    }
+    int max_len = len;
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 16));
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 8));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int off = 0; off < max_len; off += 8) {
+      int my_dst = -1;
+      unsigned my_mask = 0;
+      if (off + sl < len) {
+        my_dst = ld_stream_i32(a.idx + beg + off + sl);
+        my_mask = a.mask[ld_stream_i32(a.perm + beg + off + sl)];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int drow = __shfl_sync(kFull, my_dst, group_base + j);
+        const unsigned word = __shfl_sync(kFull, my_mask, group_base + j);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (drow >= 0) g = ld_gather_f4(a.ds + (size_t)drow * a.ld_ds + c);
+        const unsigned bits = drow >= 0 ? word >> (4 * sl) : 0u;
+        acc[0] += (bits & 1u) ? g.x : 0.f;
+        acc[1] += (bits & 2u) ? g.y : 0.f;
+        acc[2] += (bits & 4u) ? g.z : 0.f;
+        acc[3] += (bits & 8u) ? g.w : 0.f;
+      }
+    }
+    if (row_ok) *reinterpret_cast<float4*>(a.dv + (size_t)r * a.ld_dv + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// backward, edge-feature weights:  dC[c,k] = sum_e dS[row_e,c] * mask_e[c] * attr[e,k]
+// per destination row: t[c,k] = sum_{e in row} mask_e[c] attr[e,k];  partial[block][c,k] += dS[i,c] t[c,k]
+struct EdgeMsgBwdCArgs {
+  const int32_t* ptr;
+  const int32_t* perm;
+  const float* ds;
+  const uint32_t* mask;
+  const float* attr;
+  float* partial;  // [gridDim.x][32][kMaxEdgeFeat]
+  uint32_t ld_ds, ld_attr;
+  int32_t n, fe;
+};
+
+__global__ void __launch_bounds__(256) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a) {
+  // thread -> channel c = threadIdx & 31; the 8 warps of the block stride over this block's rows
+  __shared__ float red[8][kMsg][kMaxEdgeFeat];
+  const int c = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float acc[kMaxEdgeFeat];
+#pragma unroll
+  for (int k = 0; k < kMaxEdgeFeat; ++k) acc[k] = 0.f;
+  const int rows_per_block = (a.n + gridDim.x - 1) / gridDim.x;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row_end = min(row0 + rows_per_block, a.n);
+  for (int r = row0 + warp; r < row_end; r += 8) {
+    const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
+    const float g = __ldg(a.ds + (size_t)r * a.ld_ds + c);
+    float t[kMaxEdgeFeat];
+#pragma unroll
+    for (int k = 0; k < kMaxEdgeFeat; ++k) t[k] = 0.f;
+    for (int s = beg; s < end; ++s) {
+      const int eid = __ldg(a.perm + s);  // warp-uniform
+      const bool on = (a.mask[eid] >> c) & 1u;
+#pragma unroll
+      for (int k = 0; k < kMaxEdgeFeat; ++k)
+        if (k < a.fe) t[k] += on ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxEdgeFeat; ++k) acc[k] = fmaf(g, t[k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxEdgeFeat; ++k) red[warp][c][k] = acc[k];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < kMaxEdgeFeat; ++k) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w][c][k];
+      a.partial[((size_t)blockIdx.x * kMsg + c) * kMaxEdgeFeat + k] = s;
+    }
+  }
+}
+
+__global__ void k_edge_msg_bwd_c_reduce(const float* __restrict__ partial, int n_partials, int fe, float* __restrict__ dc, int64_t ld_dc) {
+  const int c = threadIdx.x & 31;
+  const int k = threadIdx.x >> 5;
+  if (k >= fe) return;
+  float s = 0.f;
+  for (int p = 0; p < n_partials; ++p) s += partial[((size_t)p * kMsg + c) * kMaxEdgeFeat + k];
+  dc[(size_t)c * ld_dc + k] = s;
+}
+
+static int rows_per_block_for(int n, int rows_per_pass) {
+  int passes = (int)ceil_div<int64_t>(n, (int64_t)kNumSM * 8 * rows_per_pass);
+  passes = std::max(1, std::min(passes, 8));
+  return rows_per_pass * passes;
+}
+
+}  // namespace drk
+
+extern "C" {
+
+int drk_edge_msg_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm, const float* uv, int64_t ld_uv,
+                     const float* edge_attr, int64_t ld_attr, int32_t num_edge_features, const float* cmat, int64_t ld_c, float* s,
+                     int64_t ld_s, float* cnt, uint32_t* mask, int32_t num_nodes, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0 && num_edge_features >= 0, DRK_EINVAL, "edge msg: negative size");
+  DRK_REQUIRE(num_edge_features <= kMaxEdgeFeat, DRK_EUNSUPPORTED, "edge msg: at most %d edge features are supported", kMaxEdgeFeat);
+  if (num_nodes == 0) return DRK_OK;
+  DRK_REQUIRE(rowptr && uv && s && (num_edge_features == 0 || (edge_attr && cmat)), DRK_EINVAL, "edge msg: null pointer");
+  DRK_REQUIRE(ld_uv % 4 == 0 && ld_s % 4 == 0 && aligned16(uv) && aligned16(s) && (cnt == nullptr || aligned16(cnt)), DRK_EUNSUPPORTED,
+              "edge msg: U|V and S must be 16-byte aligned with leading dimensions divisible by 4");
+  EdgeMsgArgs a{rowptr, colidx, perm, uv, edge_attr, cmat, s, cnt, mask, (uint32_t)ld_uv, (uint32_t)ld_attr, (uint32_t)ld_c, (uint32_t)ld_s,
+                num_nodes, num_edge_features, rows_per_block_for(num_nodes, 32)};
+  k_edge_msg_fwd<<<ceil_div(num_nodes, a.rows_per_block), 256, 0, as_stream(stream)>>>(a);
+  return finish_launch("edge msg fwd");
+}
+
+int drk_edge_msg_bwd_src(const int32_t* colptr, const int32_t* rowidx, const int32_t* permT, const float* ds, int64_t ld_ds,
+                         const uint32_t* mask, float* dv, int64_t ld_dv, int32_t num_nodes, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0, DRK_EINVAL, "edge msg bwd src: negative size");
+  if (num_nodes == 0) return DRK_OK;
+  DRK_REQUIRE(colptr && ds && mask && dv, DRK_EINVAL, "edge msg bwd src: null pointer");
+  DRK_REQUIRE(ld_ds % 4 == 0 && ld_dv % 4 == 0 && aligned16(ds) && aligned16(dv), DRK_EUNSUPPORTED, "edge msg bwd src: alignment");
+  EdgeMsgBwdSrcArgs a{colptr, rowidx, permT, ds, mask, dv, (uint32_t)ld_ds, (uint32_t)ld_dv, num_nodes, rows_per_block_for(num_nodes, 32)};
+  k_edge_msg_bwd_src<<<ceil_div(num_nodes, a.rows_per_block), 256, 0, as_stream(stream)>>>(a);
+  return finish_launch("edge msg bwd src");
+}
+
+size_t drk_edge_msg_bwd_c_workspace_bytes(void) { return (size_t)drk::kNumSM * 2 * drk::kMsg * drk::kMaxEdgeFeat * sizeof(float); }
+
+int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const float* ds, int64_t ld_ds, const uint32_t* mask,
+                       const float* edge_attr, int64_t ld_attr, int32_t num_edge_features, float* dc, int64_t ld_dc, int32_t num_nodes,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0 && num_edge_features >= 0 && num_edge_features <= kMaxEdgeFeat, DRK_EINVAL, "edge msg bwd c: bad size");
+  if (num_edge_features == 0) return DRK_OK;
+  DRK_REQUIRE(rowptr && perm && ds && mask && edge_attr && dc, DRK_EINVAL, "edge msg bwd c: null pointer");
+  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_edge_msg_bwd_c_workspace_bytes(), DRK_EWORKSPACE, "edge msg bwd c: workspace too small");
+  const int blocks = kNumSM * 2;
+  EdgeMsgBwdCArgs a{rowptr, perm, ds, mask, edge_attr, static_cast<float*>(workspace), (uint32_t)ld_ds, (uint32_t)ld_attr, num_nodes, num_edge_features};
+  k_edge_msg_bwd_c<<<blocks, 256, 0, as_stream(stream)>>>(a);
+  k_edge_msg_bwd_c_reduce<<<1, 32 * kMaxEdgeFeat, 0, as_stream(stream)>>>(static_cast<float*>(workspace), blocks, num_edge_features, dc, ld_dc);
+  return finish_launch("edge msg bwd c", 2);
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Segment max with argmax (torch_scatter.scatter_max, community_pooling.py:209; max_pool_x ginet.py:103)
+// and the cluster-offset pass of get_preloaded_cluster (community_pooling.py:23-27).
+// =====================================================================================================
+namespace drk {
+
+// thread -> (segment c, column f).  Elements of a segment are visited in ascending element id, ">" keeps the
+// FIRST maximum (torch_scatter's CPU rule); an empty segment gives out = 0, arg = n_src.
+__global__ void __launch_bounds__(256) k_segment_max(const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                                                     const float* __restrict__ src, uint32_t ld_src, int32_t n_src, int32_t n_seg,
+                                                     int32_t width, float* __restrict__ out, uint32_t ld_out, int32_t* __restrict__ arg) {
+  const uint32_t total = (uint32_t)n_seg * (uint32_t)width;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t c = t / (uint32_t)width;
+    const uint32_t f = t - c * (uint32_t)width;
+    const int beg = __ldg(ptr + c), end = __ldg(ptr + c + 1);
+    float best = 0.f;
+    int best_i = n_src;
+    for (int s = beg; s < end; ++s) {
+      const int i = perm != nullptr ? __ldg(perm + s) : s;
+      const float v = __ldg(src + (size_t)i * ld_src + f);
+      if (s == beg || v > best || (v != v && best == best)) {  // NaN propagates like torch's max
+        best = v;
+        best_i = i;
+      }
+    }
+    out[(size_t)c * ld_out + f] = best;
+    if (arg != nullptr) arg[(size_t)c * width + f] = best_i;
+  }
+}
+
+// dsrc must be zero-filled by the caller; each (c,f) owns a distinct target element -> no atomics.
+__global__ void __launch_bounds__(256) k_segment_max_bwd(const float* __restrict__ dout, uint32_t ld_dout, const int32_t* __restrict__ arg,
+                                                         int32_t n_src, int32_t n_seg, int32_t width, float* __restrict__ dsrc,
+                                                         uint32_t ld_dsrc) {
+  const uint32_t total = (uint32_t)n_seg * (uint32_t)width;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t c = t / (uint32_t)width;
+    const uint32_t f = t - c * (uint32_t)width;
+    const int i = arg[t];
+    if (i >= 0 && i < n_src) dsrc[(size_t)i * ld_dsrc + f] = dout[(size_t)c * ld_dout + f];
+  }
+}
+
+// get_preloaded_cluster: cluster[i] += sum_{h < batch[i]} (max_{j in graph h} cluster[j] + 1)
+__global__ void __launch_bounds__(256) k_cluster_graph_max(const int64_t* __restrict__ cluster, const int32_t* __restrict__ graph_ptr,
+                                                           long long* __restrict__ gmax) {
+  __shared__ long long red[8];
+  const int g = blockIdx.x;
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  long long m = -1;  // empty graph contributes max+1 = 0
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) m = max(m, (long long)cluster[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane_id() == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+    gmax[g] = m;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_cluster_offsets_scan(const long long* __restrict__ gmax, int32_t num_graphs, long long* __restrict__ offs) {
+  // single block; offs[g] = sum_{h<g} (gmax[h] + 1), offs[num_graphs] = total number of cluster ids
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < num_graphs; base += 1024) {
+    const int g = base + threadIdx.x;
+    const long long v = g < num_graphs ? gmax[g] + 1 : 0;
+    long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane_id() >= o) incl += up;
+    }
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_tot[w];
+    if (g < num_graphs) offs[g] = carry + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += woff + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[num_graphs] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_cluster_add_offsets(int64_t* __restrict__ cluster, const int32_t* __restrict__ batch32,
+                                                             const long long* __restrict__ offs, int32_t n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cluster[i] += offs[batch32[i]];
+}
+
+}  // namespace drk
+
+extern "C" {
+
+int drk_segment_max(const int32_t* ptr, const int32_t* perm, const float* src, int64_t ld_src, int32_t n_src, int32_t n_seg, int32_t width,
+                    float* out, int64_t ld_out, int32_t* arg, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(n_src >= 0 && n_seg >= 0 && width >= 0, DRK_EINVAL, "segment max: negative size");
+  if (n_seg == 0 || width == 0) return DRK_OK;
+  DRK_REQUIRE(ptr && out && (src || n_src == 0), DRK_EINVAL, "segment max: null pointer");
+  DRK_REQUIRE((int64_t)n_seg * width < (int64_t)1 << 31, DRK_EUNSUPPORTED, "segment max: more than 2^31 outputs");
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>((int64_t)n_seg * width, 256), (int64_t)kNumSM * 32);
+  k_segment_max<<<blocks, 256, 0, as_stream(stream)>>>(ptr, perm, src, (uint32_t)ld_src, n_src, n_seg, width, out, (uint32_t)ld_out, arg);
+  return finish_launch("segment max");
+}
+
+int drk_segment_max_bwd(const float* dout, int64_t ld_dout, const int32_t* arg, int32_t n_src, int32_t n_seg, int32_t width, float* dsrc,
+                        int64_t ld_dsrc, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(n_src >= 0 && n_seg >= 0 && width >= 0, DRK_EINVAL, "segment max bwd: negative size");
+  if (n_seg == 0 || width == 0 || n_src == 0) return DRK_OK;
+  DRK_REQUIRE(dout && arg && dsrc, DRK_EINVAL, "segment max bwd: null pointer");
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>((int64_t)n_seg * width, 256), (int64_t)kNumSM * 32);
+  k_segment_max_bwd<<<blocks, 256, 0, as_stream(stream)>>>(dout, (uint32_t)ld_dout, arg, n_src, n_seg, width, dsrc, (uint32_t)ld_dsrc);
+  return finish_launch("segment max bwd");
+}
+
+size_t drk_cluster_offsets_workspace_bytes(int32_t num_graphs) { return num_graphs < 0 ? 0 : ((size_t)2 * num_graphs + 2) * sizeof(long long); }
+
+int drk_cluster_offsets(int64_t* cluster, const int32_t* graph_ptr, const int32_t* batch32, int32_t num_nodes, int32_t num_graphs,
+                        int64_t* total_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0 && num_graphs >= 0, DRK_EINVAL, "cluster offsets: negative size");
+  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_cluster_offsets_workspace_bytes(num_graphs), DRK_EWORKSPACE,
+              "cluster offsets: workspace too small");
+  if (num_graphs == 0) return DRK_OK;
+  DRK_REQUIRE(graph_ptr && batch32 && (cluster || num_nodes == 0), DRK_EINVAL, "cluster offsets: null pointer");
+  long long* gmax = static_cast<long long*>(workspace);
+  long long* offs = gmax + num_graphs;
+  cudaStream_t st = as_stream(stream);
+  k_cluster_graph_max<<<num_graphs, 256, 0, st>>>(cluster, graph_ptr, gmax);
+  k_cluster_offsets_scan<<<1, 1024, 0, st>>>(gmax, num_graphs, offs);
+  if (num_nodes > 0) k_cluster_add_offsets<<<ceil_div(num_nodes, 256), 256, 0, st>>>(cluster, batch32, offs, num_nodes);
+  if (total_ids != nullptr) {
+    cudaError_t e = cudaMemcpyAsync(total_ids, offs + num_graphs, sizeof(long long), cudaMemcpyDeviceToDevice, st);
+    DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "cluster offsets: copy: %s", cudaGetErrorString(e));
+  }
+  return finish_launch("cluster offsets", 3);
+}
+
+}  // extern "C"

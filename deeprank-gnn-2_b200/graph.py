@@ -46,7 +46,7 @@ class GraphIndex:
     __slots__ = (
         "num_nodes", "num_edges", "num_graphs", "device",
         "rowptr", "colidx", "perm", "colptr", "rowidx", "permT",
-        "graph_ptr", "batch32", "status", "_storage", "_key",
+        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree",
     )
 
     def __init__(self):
@@ -115,6 +115,12 @@ class GraphIndex:
                 _lib.check(rc, "drk_batch_offsets")
         return gi
 
+    def degree(self) -> torch.Tensor:
+        """float32 [N]: number of edges per destination node (cached)."""
+        if self._degree is None:
+            self._degree = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+        return self._degree
+
     # ------------------------------------------------------------------ validation (host sync: call it off the hot path)
     def check(self) -> None:
         flags = int(self.status.item())
@@ -133,7 +139,7 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
         return cached
     batch = getattr(data, "batch", None)
     ptr = data.__dict__.get("ptr")
-    num_graphs = int(ptr.numel()) - 1 if ptr is not None else None
+    num_graphs = int(ptr.numel()) - 1 if ptr is not None else data.__dict__.get("_num_graphs")
     gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc)
     gi._key = key
     data.__dict__["_graph_index"] = gi

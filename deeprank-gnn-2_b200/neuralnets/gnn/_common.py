@@ -65,3 +65,12 @@ class GINetConvLayer(nn.Module):
 
 def mean_readout(x, data):
     return ops.mean_readout(x, graph_index(data))
+
+
+def num_graphs_of(data):
+    """Number of graphs of a batch without touching the device: ``ptr`` from the collate, or the hint pooled batches
+    carry; ``None`` means "unknown" (callers then fall back to ``batch.max()+1`` like torch_scatter does)."""
+    ptr = data.__dict__.get("ptr")
+    if ptr is not None:
+        return int(ptr.numel()) - 1
+    return data.__dict__.get("_num_graphs")

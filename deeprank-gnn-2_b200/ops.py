@@ -298,3 +298,356 @@ def ginet_stack(x, conv1, conv1_ext, conv2, conv2_ext, graph):
     for layer in (conv1, conv2, conv1_ext, conv2_ext):
         dead += [layer.fc_edge_attr.weight, layer.fc_attention.weight]
     return GINetStackFunction.apply(x, conv1.fc.weight, conv1_ext.fc.weight, conv2.fc.weight, conv2_ext.fc.weight, graph, *dead)
+
+
+# ------------------------------------------------------------------------------ Vanilla ("Naive") convolution
+def node_linear2(a, b, a2, b2, trans_b=True, bias=None, mask=None, act=ACT_NONE, out=None):
+    """``act(a @ op(b) + a2 @ op(b2) + bias)``: a Linear over the concatenation [a | a2] without building it."""
+    lib = _lib.load()
+    a, b, a2, b2 = _f32_cuda(a, "a"), _f32_cuda(b, "b"), _f32_cuda(a2, "a2"), _f32_cuda(b2, "b2")
+    n, k = a.shape
+    k2 = a2.shape[1]
+    m = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=a.device)
+    if mask is not None:
+        mask = _f32_cuda(mask, "mask")
+    if bias is not None:
+        bias = bias.contiguous()
+    with torch.cuda.device(a.device):
+        rc = lib.drk_node_linear2(_p(a), _ld(a), _p(b), _ld(b), k, _p(a2), _ld(a2), _p(b2), _ld(b2), k2, 1 if trans_b else 0, _p(bias),
+                                  _p(mask), _ld(mask) if mask is not None else 0, _p(out), _ld(out), n, m, act, stream_ptr())
+    _lib.check(rc, "drk_node_linear2")
+    return out
+
+
+MESSAGE_SIZE = 32  # vanilla_gnn.py:20
+
+
+def edge_msg_fwd(graph: GraphIndex, uv, edge_attr, cmat):
+    """S[i] = sum_e relu(U[i] + V[col_e] + C attr_e); returns (S [N,32], cnt [N,32], mask uint32 [E])."""
+    lib = _lib.load()
+    uv = _f32_cuda(uv, "uv")
+    n = uv.shape[0]
+    fe = 0 if edge_attr is None else edge_attr.shape[1]
+    if fe:
+        edge_attr = _f32_cuda(edge_attr, "edge_attr")
+    s = torch.empty((n, MESSAGE_SIZE), dtype=torch.float32, device=uv.device)
+    cnt = torch.empty_like(s)
+    mask = torch.empty(max(graph.num_edges, 1), dtype=torch.int32, device=uv.device)
+    with torch.cuda.device(uv.device):
+        rc = lib.drk_edge_msg_fwd(_p(graph.rowptr), _p(graph.colidx), _p(graph.perm), _p(uv), _ld(uv), _p(edge_attr) if fe else None,
+                                  _ld(edge_attr) if fe else 0, fe, _p(cmat) if fe else None, int(cmat.stride(0)) if fe else 0, _p(s), _ld(s),
+                                  _p(cnt), _p(mask), n, stream_ptr())
+    _lib.check(rc, "drk_edge_msg_fwd")
+    return s, cnt, mask
+
+
+def edge_msg_bwd_src(graph: GraphIndex, ds, mask, out):
+    lib = _lib.load()
+    ds = _f32_cuda(ds, "ds")
+    with torch.cuda.device(ds.device):
+        rc = lib.drk_edge_msg_bwd_src(_p(graph.colptr), _p(graph.rowidx), _p(graph.permT), _p(ds), _ld(ds), _p(mask), _p(out), _ld(out),
+                                      ds.shape[0], stream_ptr())
+    _lib.check(rc, "drk_edge_msg_bwd_src")
+    return out
+
+
+def edge_msg_bwd_c(graph: GraphIndex, ds, mask, edge_attr, out):
+    lib = _lib.load()
+    ds = _f32_cuda(ds, "ds")
+    edge_attr = _f32_cuda(edge_attr, "edge_attr")
+    with torch.cuda.device(ds.device):
+        ws = workspace(lib.drk_edge_msg_bwd_c_workspace_bytes(), ds.device)
+        rc = lib.drk_edge_msg_bwd_c(_p(graph.rowptr), _p(graph.perm), _p(ds), _ld(ds), _p(mask), _p(edge_attr), _ld(edge_attr),
+                                    edge_attr.shape[1], _p(out), int(out.stride(0)), ds.shape[0], _p(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "drk_edge_msg_bwd_c")
+    return out
+
+
+class VanillaConvFunction(torch.autograd.Function):
+    """``VanillaConvolutionalLayer.forward`` (reference ``vanilla_gnn.py:26-38``) as one autograd node.
+
+    The edge MLP ``Linear(2F+Fe, 32)`` on ``cat[x_i, x_j, e]`` is split by columns into a destination part
+    Wa, a source part Wb and an edge-feature part C, so that
+        message_e = relu( (x Wa^T + b)[i] + (x Wb^T)[j] + C e ),
+    i.e. two NODE-level projections (one 64-wide GEMM over N rows instead of a 32-wide one over E rows of
+    width 2F+Fe) and a 32-wide gather per edge.  The node MLP on ``cat[x, sums]`` is a two-source Linear.
+    """
+
+    @staticmethod
+    def forward(ctx, x, edge_attr, we, be, wn, bn, graph: GraphIndex):
+        n, f = x.shape
+        fe = we.shape[1] - 2 * f
+        if we.shape[0] != MESSAGE_SIZE or fe < 0:
+            raise ValueError(f"edge MLP weight has shape {tuple(we.shape)}, expected [32, 2*{f}+Fe]")
+        if fe > 0 and (edge_attr is None or edge_attr.dim() != 2 or edge_attr.shape[1] != fe):
+            raise ValueError(f"edge_attr must be [E, {fe}] (2-D, like the reference requires), got {None if edge_attr is None else tuple(edge_attr.shape)}")
+        wab = torch.cat([we[:, :f], we[:, f : 2 * f]], dim=0)                       # [64, F]
+        bias64 = torch.cat([be, torch.zeros_like(be)]) if be is not None else None  # b belongs to U only
+        uv = node_linear(x, wab, True, bias64)                                        # [N, 64] = U | V
+        cmat = we[:, 2 * f :]                                                         # [32, Fe] view, row stride 2F+Fe
+        s, cnt, mask = edge_msg_fwd(graph, uv, edge_attr if fe else None, cmat)
+        out = node_linear2(x, wn[:, :f], s, wn[:, f:], True, bn, act=ACT_RELU)        # relu(cat[x, s] Wn^T + bn)
+        ctx.graph = graph
+        ctx.f, ctx.fe = f, fe
+        ctx.has_be, ctx.has_bn = be is not None, bn is not None
+        ctx.save_for_backward(x, edge_attr if fe else None, we, wn, wab, s, cnt, mask, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, edge_attr, we, wn, wab, s, cnt, mask, out = ctx.saved_tensors
+        g = ctx.graph
+        f, fe = ctx.f, ctx.fe
+        n = x.shape[0]
+        dz = torch.ops.aten.threshold_backward(dout.contiguous(), out, 0.0)          # ReLU of the node MLP
+        # node MLP: dWn = dZ^T [x | s], dbn = sum dZ, dS = dZ Wn[:, F:]
+        dwn = torch.empty_like(wn)
+        dbn = None
+        if ctx.has_bn:
+            _, dbn = weight_grad(dz, x, want_bias=True, dw=dwn[:, :f])
+        else:
+            weight_grad(dz, x, dw=dwn[:, :f])
+        weight_grad(dz, s, dw=dwn[:, f:])
+        ds = node_linear(dz, wn[:, f:], False)                                        # [N, 32]
+        # edge messages: dU = dS * cnt (every active edge of row i adds dS[i]), dV over the CSC half
+        duv = torch.empty((n, 2 * MESSAGE_SIZE), dtype=torch.float32, device=x.device)
+        torch.mul(ds, cnt, out=duv[:, :MESSAGE_SIZE])
+        edge_msg_bwd_src(g, ds, mask, duv[:, MESSAGE_SIZE:])
+        dwe = torch.empty_like(we)
+        dwab, dbe64 = weight_grad(duv, x, want_bias=True)                             # [64, F], [64]
+        dwe[:, :f].copy_(dwab[:MESSAGE_SIZE])
+        dwe[:, f : 2 * f].copy_(dwab[MESSAGE_SIZE:])
+        if fe:
+            edge_msg_bwd_c(g, ds, mask, edge_attr, dwe[:, 2 * f :])
+        dbe = dbe64[:MESSAGE_SIZE] if ctx.has_be else None
+        dx = node_linear2(dz, wn[:, :f], duv, wab, False) if ctx.needs_input_grad[0] else None
+        return dx, None, dwe, dbe, dwn, dbn, None
+
+
+def vanilla_conv(x, edge_attr, edge_mlp: torch.nn.Linear, node_mlp: torch.nn.Linear, graph):
+    return VanillaConvFunction.apply(x, edge_attr, edge_mlp.weight, edge_mlp.bias, node_mlp.weight, node_mlp.bias, graph)
+
+
+# ------------------------------------------------------------------------------ Fout convolution
+class FoutConvFunction(torch.autograd.Function):
+    """``FoutLayer.forward`` (reference ``foutnet.py:48-66``): ``x Wc + mean_{j in N(i)} (x Wn)[j] + b``.
+
+    The reference loops over nodes in Python (O(N*E)); here one [N, 2Fo] projection ``x [Wc | Wn]`` and one
+    segmented mean over the CSR.  A node without neighbours gets a NaN row exactly like ``torch.mean`` of
+    the empty slice ``beta[index]`` does (``foutnet.py:58``)."""
+
+    @staticmethod
+    def forward(ctx, x, wc, wn, bias, graph: GraphIndex, relu: bool):
+        n = x.shape[0]
+        fo = wc.shape[1]
+        wcat = torch.cat([wc, wn], dim=1)                                    # [Fi, 2Fo]
+        bias2 = torch.cat([bias, torch.zeros_like(bias)]) if bias is not None else None
+        ab = node_linear(x, wcat, False, bias2)                              # alpha + b | beta
+        out = spmm(graph.rowptr, graph.colidx, ab[:, fo:], n, addend=ab[:, :fo], reduce=REDUCE_MEAN_NAN, act=ACT_RELU if relu else ACT_NONE)
+        ctx.graph, ctx.relu, ctx.fo, ctx.has_bias = graph, relu, fo, bias is not None
+        ctx.save_for_backward(x, wcat, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wcat, out = ctx.saved_tensors
+        g, fo = ctx.graph, ctx.fo
+        n = x.shape[0]
+        dout = dout.contiguous()
+        if ctx.relu:
+            dout = torch.ops.aten.threshold_backward(dout, out, 0.0)
+        dab = torch.empty((n, 2 * fo), dtype=torch.float32, device=x.device)
+        dab[:, :fo].copy_(dout)
+        # d beta[j] = sum_{e: col_e = j} dout[row_e] / deg(row_e): scale rows once, then A^T through the CSC half
+        scaled = dout / g.degree().unsqueeze(1)
+        spmm(g.colptr, g.rowidx, scaled, n, out=dab[:, fo:])
+        dwcat = weight_grad(x, dab)                                          # x^T dab = [Fi, 2Fo]
+        db2 = dout.sum(0) if ctx.has_bias else None
+        dx = node_linear(dab, wcat, True) if ctx.needs_input_grad[0] else None
+        return dx, dwcat[:, :fo], dwcat[:, fo:], db2, None, None
+
+
+def fout_conv(x, wc, wn, bias, graph, relu=False):
+    return FoutConvFunction.apply(x, wc, wn, bias, graph, relu)
+
+
+# ------------------------------------------------------------------------------ torch_scatter-compatible functions
+# Function-level seam of the reference (SURVEY.md 8b-1): scatter_sum / scatter_mean / scatter_max with an arbitrary
+# int64 index along dim 0.  The index is counting-sorted on the device (drk_segment_index_build) and the reduction
+# walks each segment in ascending element id -- the visiting order of the reference's CPU scatter_add_ -- without
+# atomics.  As in torch_scatter, the output size is `dim_size` or index.max()+1 (the latter costs a host sync).
+class SegmentPlan:
+    """ptr/perm of one index vector; re-usable across scatter calls that share the index."""
+
+    def __init__(self, index: torch.Tensor, dim_size: int | None = None):
+        if index.dim() != 1:
+            raise ValueError("only 1-D indices along dim 0 are supported (the reference uses nothing else)")
+        if dim_size is None:
+            dim_size = int(index.max()) + 1 if index.numel() > 0 else 0
+        self.index = index
+        self.n_seg = int(dim_size)
+        self.n_src = int(index.numel())
+        self.ptr, self.perm, self.status = segment_index(index, self.n_seg)
+
+    def count(self) -> torch.Tensor:
+        return (self.ptr[1:] - self.ptr[:-1]).to(torch.float32)
+
+
+def _as_2d(src: torch.Tensor):
+    if src.dim() == 1:
+        return src.unsqueeze(1), True
+    if src.dim() != 2:
+        raise ValueError("scatter_*: src must be 1-D or 2-D")
+    return src, False
+
+
+class _ScatterReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, plan: SegmentPlan, reduce: int, init):
+        out = spmm(plan.ptr, plan.perm, src, plan.n_seg, addend=init, reduce=reduce)
+        ctx.plan, ctx.reduce = plan, reduce
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan = ctx.plan
+        g = dout
+        if ctx.reduce == REDUCE_MEAN_CLAMP:
+            g = dout / plan.count().clamp(min=1).unsqueeze(1)
+        dsrc = g.index_select(0, plan.index) if ctx.needs_input_grad[0] else None
+        dinit = dout if ctx.needs_input_grad[3] else None
+        return dsrc, None, None, dinit
+
+
+def scatter_sum(src, index, dim=0, out=None, dim_size=None, plan: SegmentPlan | None = None):
+    """``torch_scatter.scatter_sum`` along dim 0 (``ginet.py:58``, ``vanilla_gnn.py:35``).  ``out`` is summed into."""
+    if dim not in (0, -src.dim()):
+        raise NotImplementedError("scatter_sum: only dim=0 is used on the DeepRank2 path")
+    src2, squeeze = _as_2d(src)
+    if plan is None:
+        plan = SegmentPlan(index, dim_size if dim_size is not None else (out.shape[0] if out is not None else None))
+    init = None if out is None else _as_2d(out)[0]
+    res = _ScatterReduce.apply(src2, plan, REDUCE_SUM, init)
+    res = res.squeeze(1) if squeeze else res
+    if out is not None:
+        out.data.copy_(res.detach())
+    return res
+
+
+def scatter_mean(src, index, dim=0, out=None, dim_size=None, plan: SegmentPlan | None = None):
+    """``torch_scatter.scatter_mean``: sum / max(count, 1); a passed ``out`` joins the sum before the divide
+    (``sgat.py:72``; readout ``ginet.py:117-118``; position pooling ``community_pooling.py:216``)."""
+    if dim not in (0, -src.dim()):
+        raise NotImplementedError("scatter_mean: only dim=0 is used on the DeepRank2 path")
+    src2, squeeze = _as_2d(src)
+    if plan is None:
+        plan = SegmentPlan(index, dim_size if dim_size is not None else (out.shape[0] if out is not None else None))
+    if out is None:
+        res = _ScatterReduce.apply(src2, plan, REDUCE_MEAN_CLAMP, None)
+    else:
+        total = _ScatterReduce.apply(src2, plan, REDUCE_SUM, _as_2d(out)[0])
+        res = total / plan.count().clamp(min=1).unsqueeze(1)
+    res = res.squeeze(1) if squeeze else res
+    if out is not None:
+        out.data.copy_(res.detach())
+    return res
+
+
+class _ScatterMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, plan: SegmentPlan):
+        lib = _lib.load()
+        src = _f32_cuda(src, "src")
+        width = src.shape[1]
+        out = torch.empty((plan.n_seg, width), dtype=torch.float32, device=src.device)
+        arg = torch.empty((plan.n_seg, width), dtype=torch.int32, device=src.device)
+        with torch.cuda.device(src.device):
+            rc = lib.drk_segment_max(_p(plan.ptr), _p(plan.perm), _p(src), _ld(src), src.shape[0], plan.n_seg, width, _p(out), _ld(out), _p(arg), stream_ptr())
+        _lib.check(rc, "drk_segment_max")
+        ctx.plan, ctx.n_src = plan, src.shape[0]
+        ctx.save_for_backward(arg)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, dout, _darg):
+        lib = _lib.load()
+        (arg,) = ctx.saved_tensors
+        dout = _f32_cuda(dout, "dout")
+        width = dout.shape[1]
+        dsrc = torch.zeros((ctx.n_src, width), dtype=torch.float32, device=dout.device)
+        with torch.cuda.device(dout.device):
+            rc = lib.drk_segment_max_bwd(_p(dout), _ld(dout), _p(arg), ctx.n_src, ctx.plan.n_seg, width, _p(dsrc), _ld(dsrc), stream_ptr())
+        _lib.check(rc, "drk_segment_max_bwd")
+        return dsrc, None
+
+
+def scatter_max(src, index, dim=0, out=None, dim_size=None, plan: SegmentPlan | None = None):
+    """``torch_scatter.scatter_max`` -> ``(out, argmax)``: first maximum wins, empty segment -> (0, len(src)),
+    gradient flows to the argmax element only (``community_pooling.py:209``)."""
+    if dim not in (0, -src.dim()) or out is not None:
+        raise NotImplementedError("scatter_max: only dim=0 without out= is used on the DeepRank2 path")
+    src2, squeeze = _as_2d(src)
+    if plan is None:
+        plan = SegmentPlan(index, dim_size)
+    res, arg = _ScatterMax.apply(src2, plan)
+    arg = arg.to(torch.int64)
+    return (res.squeeze(1), arg.squeeze(1)) if squeeze else (res, arg)
+
+
+def cluster_offsets(cluster: torch.Tensor, graph: GraphIndex) -> torch.Tensor:
+    """In-place ``get_preloaded_cluster`` on the device; returns the device scalar holding the id count."""
+    lib = _lib.load()
+    if not cluster.is_cuda or cluster.dtype != torch.int64 or not cluster.is_contiguous():
+        raise TypeError("cluster must be a contiguous int64 CUDA tensor")
+    total = torch.empty(1, dtype=torch.int64, device=cluster.device)
+    with torch.cuda.device(cluster.device):
+        ws = workspace(lib.drk_cluster_offsets_workspace_bytes(graph.num_graphs), cluster.device)
+        rc = lib.drk_cluster_offsets(_p(cluster), _p(graph.graph_ptr), _p(graph.batch32), cluster.numel(), graph.num_graphs, _p(total), _p(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "drk_cluster_offsets")
+    return total
+
+
+# ------------------------------------------------------------------------------ SGAT convolution
+class SGATConvFunction(torch.autograd.Function):
+    """``SGraphAttentionLayer.forward`` (``sgat.py:56-84``, undirected): see the module docstring of
+    ``neuralnets/gnn/sgat.py`` for the algebra.  ``a`` is the edge attribute in ORIGINAL edge order."""
+
+    @staticmethod
+    def forward(ctx, x, a, weight, bias, graph: GraphIndex):
+        n, fi = x.shape
+        fo = weight.shape[1]
+        wcat = torch.cat([weight[:fi], weight[fi:]], dim=1)          # [Fi, 2Fo] = Wt | Wb
+        pq = node_linear(x, wcat, False)                             # P | Q
+        a_csr = a.index_select(0, graph.perm.long()).contiguous()    # edge attribute in CSR order
+        asum = spmm(graph.rowptr, None, a_csr.unsqueeze(1), n).squeeze(1)   # sum_j a_ij per destination
+        deg = graph.degree().clamp(min=1)
+        wq = spmm(graph.rowptr, graph.colidx, pq[:, fo:], n, w=a_csr)       # sum_j a_ij Q_j
+        out = (pq[:, :fo] * asum.unsqueeze(1) + wq) / deg.unsqueeze(1)
+        if bias is not None:
+            out = out + bias
+        ctx.graph, ctx.fo, ctx.has_bias = graph, fo, bias is not None
+        ctx.save_for_backward(x, a, wcat, asum, deg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, a, wcat, asum, deg = ctx.saved_tensors
+        g, fo = ctx.graph, ctx.fo
+        n = x.shape[0]
+        dmean = dout / deg.unsqueeze(1)                               # [N, Fo]
+        dpq = torch.empty((n, 2 * fo), dtype=torch.float32, device=x.device)
+        torch.mul(dmean, asum.unsqueeze(1), out=dpq[:, :fo])          # dP_i = dmean_i * sum_j a_ij
+        a_csc = a.index_select(0, g.permT.long()).contiguous()
+        spmm(g.colptr, g.rowidx, dmean, n, w=a_csc, out=dpq[:, fo:])  # dQ_j = sum_{e: col=j} a_e dmean[row_e]
+        dwcat = weight_grad(x, dpq)                                   # [Fi, 2Fo]
+        dweight = torch.cat([dwcat[:, :fo], dwcat[:, fo:]], dim=0)
+        dbias = dout.sum(0) if ctx.has_bias else None
+        dx = node_linear(dpq, wcat, True) if ctx.needs_input_grad[0] else None
+        return dx, None, dweight, dbias, None
+
+
+def sgat_conv(x, a, weight, bias, graph):
+    return SGATConvFunction.apply(x, a, weight, bias, graph)

@@ -111,6 +111,14 @@ DRK_API int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t
                     const float* bias, const float* mask, int64_t ld_mask,
                     float* c, int64_t ldc, int64_t n, int32_t k, int32_t m, int32_t act, void* stream);
 
+/* Concat-free Linear on [A | A2]:  C = act(A op(B) + A2 op(B2) + bias) [* mask]; k2 = 0 disables the second pair.
+ * node_input = cat([node_features, message_sums]) -> _node_mlp   (vanilla_gnn.py:37-38) without materialising the cat,
+ * and dX = dZ Wx + dUV Wab in its backward. */
+DRK_API int drk_node_linear2(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t k,
+                     const float* a2, int64_t lda2, const float* b2, int64_t ldb2, int32_t k2, int32_t trans_b,
+                     const float* bias, const float* mask, int64_t ld_mask,
+                     float* c, int64_t ldc, int64_t n, int32_t m, int32_t act, void* stream);
+
 /* dW[M,K] = sum_n dY[n,:]^T X[n,:]   (+ dbias[M] = sum_n dY[n,:] if dbias != NULL).
  * Autograd of the nn.Linear calls above.  Two-stage, fixed-order reduction (deterministic).
  * If `accumulate` != 0 the result is added to the existing contents of dw/dbias. */
@@ -141,6 +149,42 @@ DRK_API int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_p
 DRK_API int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_ptr, const int32_t* batch32,
                          const float* mask, int64_t ld_mask, int32_t num_nodes, int32_t width,
                          float* dx, int64_t ld_dx, void* stream);
+
+/* ------------------------------------------------------------------ per-edge ReLU messages (VanillaConvolutionalLayer)
+ * vanilla_gnn.py:26-35:  messages = relu(_edge_mlp(cat[x_i, x_j, e]));  S = scatter_sum(messages, node0)
+ * with the edge MLP split as  U = x Wa^T + b (destination half), V = x Wb^T (source half), C = edge-feature block:
+ *   m_e = relu(U[row_e] + V[col_e] + C attr_e),  S[i] = sum_{e in row i} m_e            (message size fixed at 32)
+ *   uv [N,64] = U | V;  edge_attr [E,Fe] in ORIGINAL edge order (Fe <= 8);  cmat [32, ld_c]
+ *   outputs: s [N,32];  cnt [N,32] = active edges per (node, channel) (dU = dS * cnt);  mask uint32 [E] per edge id.
+ * backward:  drk_edge_msg_bwd_src  dV[j] = sum_{e: col_e = j} dS[row_e] * mask_e   (over the CSC half)
+ *            drk_edge_msg_bwd_c    dC[c,k] = sum_e dS[row_e,c] mask_e[c] attr[e,k]  (two-stage fixed-order reduction) */
+DRK_API int drk_edge_msg_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
+                     const float* uv, int64_t ld_uv, const float* edge_attr, int64_t ld_attr, int32_t num_edge_features,
+                     const float* cmat, int64_t ld_c, float* s, int64_t ld_s, float* cnt, uint32_t* mask,
+                     int32_t num_nodes, void* stream);
+DRK_API int drk_edge_msg_bwd_src(const int32_t* colptr, const int32_t* rowidx, const int32_t* permT,
+                         const float* ds, int64_t ld_ds, const uint32_t* mask, float* dv, int64_t ld_dv,
+                         int32_t num_nodes, void* stream);
+DRK_API size_t drk_edge_msg_bwd_c_workspace_bytes(void);
+DRK_API int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const float* ds, int64_t ld_ds, const uint32_t* mask,
+                       const float* edge_attr, int64_t ld_attr, int32_t num_edge_features, float* dc, int64_t ld_dc,
+                       int32_t num_nodes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ community pooling
+ * drk_segment_max: torch_scatter.scatter_max(x, cluster, dim=0) (community_pooling.py:209) and PyG max_pool_x
+ *   (ginet.py:103): out[c,:] = max over the segment, arg = element id of the FIRST maximum, empty segment -> (0, n_src).
+ *   Segments come from drk_segment_index_build (ptr, perm); perm == NULL means consecutive elements.
+ * drk_segment_max_bwd: routes dout[c,f] to dsrc[arg[c,f], f] (dsrc zero-filled by the caller).
+ * drk_cluster_offsets: get_preloaded_cluster (community_pooling.py:23-27) without its per-graph host loop:
+ *   cluster[i] += sum_{h < batch[i]} (max(cluster in graph h) + 1), in place on the int64 vector;
+ *   total_ids (device int64, may be NULL) receives the number of ids after offsetting. */
+DRK_API int drk_segment_max(const int32_t* ptr, const int32_t* perm, const float* src, int64_t ld_src, int32_t n_src,
+                    int32_t n_seg, int32_t width, float* out, int64_t ld_out, int32_t* arg, void* stream);
+DRK_API int drk_segment_max_bwd(const float* dout, int64_t ld_dout, const int32_t* arg, int32_t n_src, int32_t n_seg,
+                        int32_t width, float* dsrc, int64_t ld_dsrc, void* stream);
+DRK_API size_t drk_cluster_offsets_workspace_bytes(int32_t num_graphs);
+DRK_API int drk_cluster_offsets(int64_t* cluster, const int32_t* graph_ptr, const int32_t* batch32, int32_t num_nodes,
+                        int32_t num_graphs, int64_t* total_ids, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -132,3 +132,107 @@ def test_module_on_cpu_raises():
         setattr(b, k, v)
     with pytest.raises(RuntimeError):
         GINet(d.x.shape[1], 1, 1)(b)
+
+
+# ------------------------------------------------------------------ Vanilla / Fout / SGAT layers and nets
+def _layer_vs_golden(g, tag, layer, call):
+    d = g.inputs()
+    layer = _load(layer, g.group(f"{tag}/w"))
+    x = d.x.to(DEV).requires_grad_(True)
+    z = call(layer, x, d)
+    assert_close(z, g.t(f"{tag}/out/z"), f"{g.case}:{tag}:z")
+    z.backward(g.t(f"{tag}/gout/z").to(DEV))
+    assert_close(x.grad, g.t(f"{tag}/grad/x"), f"{g.case}:{tag}:dx")
+    for k, p in layer.named_parameters():
+        assert p.grad is not None, k
+        assert_close(p.grad, g.t(f"{tag}/grad/{k}"), f"{g.case}:{tag}:d{k}")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_vanilla_conv_layer_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaConvolutionalLayer
+
+    g = load_golden(case)
+    d = g.inputs()
+    layer = VanillaConvolutionalLayer(d.x.shape[1], d.edge_attr.shape[1])
+    _layer_vs_golden(g, "vanilla_conv", layer, lambda m, x, d: m(x, d.edge_index.to(DEV), d.edge_attr.to(DEV)))
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_fout_conv_layer_vs_reference(case):
+    """includes the NaN rows of nodes without neighbours (toy cases) -- NaN positions must coincide"""
+    from deeprank2_b200.neuralnets.gnn.foutnet import FoutLayer
+
+    g = load_golden(case)
+    d = g.inputs()
+    _layer_vs_golden(g, "fout_conv", FoutLayer(d.x.shape[1], 16), lambda m, x, d: m(x, d.edge_index.to(DEV)))
+
+
+@pytest.mark.parametrize("case", ["toy_edgecases", "synthetic_small", "fixture_1ATN"])
+def test_sgat_conv_layer_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.sgat import SGraphAttentionLayer
+
+    g = load_golden(case)
+    d = g.inputs()
+    _layer_vs_golden(g, "sgat_conv", SGraphAttentionLayer(d.x.shape[1], 16), lambda m, x, d: m(x, d.edge_index.to(DEV), d.edge_attr.to(DEV)))
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_vanilla_train_step_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.vanilla_gnn import NaiveNetwork, VanillaNetwork
+
+    assert NaiveNetwork is VanillaNetwork
+    g = load_golden(case)
+    d = g.inputs()
+    net = _load(VanillaNetwork(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("vanilla/w"))
+    _train_step_vs_golden(g, "vanilla", net)
+
+
+@pytest.mark.parametrize("case", ["synthetic_small", "fixture_1ATN", "fixture_variants_fe5"])
+def test_clustered_ginet_train_step_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.ginet import GINet
+
+    g = load_golden(case)
+    d = g.inputs()
+    net = _load(GINet(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("ginet/w"))
+    _train_step_vs_golden(g, "ginet", net)
+
+
+@pytest.mark.parametrize("case", ["synthetic_small", "fixture_1ATN", "fixture_variants_fe5"])
+def test_foutnet_train_step_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.foutnet import FoutNet
+
+    g = load_golden(case)
+    d = g.inputs()
+    net = _load(FoutNet(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("foutnet/w"))
+    _train_step_vs_golden(g, "foutnet", net)
+
+
+@pytest.mark.parametrize("case", ["synthetic_small", "fixture_1ATN"])
+def test_sgat_train_step_vs_reference(case):
+    from deeprank2_b200.neuralnets.gnn.sgat import SGAT
+
+    g = load_golden(case)
+    d = g.inputs()
+    net = _load(SGAT(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("sgat/w"))
+    _train_step_vs_golden(g, "sgat", net)
+
+
+def test_vanilla_c2_batch_vs_oracle():
+    """Config C4: VanillaNetwork on C2-style batches (16 graphs), CUDA vs CPU oracle incl. all gradients."""
+    from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
+    from deeprank2_b200.synthetic import make_batch
+
+    batch = make_batch(16)
+    torch.manual_seed(1)
+    net = VanillaNetwork(50, 1, 1)
+    params = R.as_parameters(net.state_dict())
+    pred_ref, loss_ref = R.train_step(R.vanilla_forward, params, R.make_adam(params), batch)
+    net = net.to(DEV)
+    gb = batch.clone().to(DEV)
+    pred = net(gb)
+    loss = torch.nn.functional.mse_loss(pred.reshape(-1), gb.y)
+    loss.backward()
+    assert_close(pred, pred_ref, "pred")
+    for (k, p_ref), p in zip(params.items(), net.parameters()):
+        assert_close(p.grad, p_ref.grad, f"grad:{k}")

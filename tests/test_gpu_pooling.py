@@ -1,0 +1,112 @@
+"""GPU: community pooling chain and the torch_scatter-compatible functions -- integer outputs
+bit-exact against the golden vectors recorded from the reference, floats at the fp32 bar."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from conftest import CLUSTERED_CASES, assert_close, assert_equal_int, load_golden
+from oracle import thirdparty as tp
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _batch(g):
+    from deeprank2_b200.data import Batch
+
+    b = Batch()
+    for k, v in vars(g.inputs()).items():
+        setattr(b, k, v.clone())
+    return b.to(DEV)
+
+
+@pytest.mark.parametrize("case", CLUSTERED_CASES)
+def test_pooling_chain_vs_reference(case):
+    from deeprank2_b200.utils.community_pooling import community_pooling, get_preloaded_cluster, max_pool_x
+
+    g = load_golden(case)
+    b = _batch(g)
+    ng = int(b.ptr.numel()) - 1
+    c0 = get_preloaded_cluster(b.cluster0, b.batch, ng)
+    assert c0.data_ptr() == b.cluster0.data_ptr(), "in place, like the reference"
+    assert_equal_int(c0, g.t("pooling/out/cluster0_global"), "cluster0 offsets")
+    pooled = community_pooling(c0, b)
+    assert_equal_int(pooled.edge_index, g.t("pooling/out/pool_edge_index"), "pooled edge_index")
+    assert_equal_int(pooled.batch, g.t("pooling/out/pool_batch"), "pooled batch")
+    assert torch.equal(pooled.x.cpu(), g.t("pooling/out/pool_x")), "segment max is exact"
+    assert_close(pooled.edge_attr, g.t("pooling/out/pool_edge_attr"), "pooled edge_attr")
+    assert_close(pooled.pos, g.t("pooling/out/pool_pos"), "pooled pos")
+    c1 = get_preloaded_cluster(pooled.cluster1, pooled.batch, ng)
+    assert_equal_int(c1, g.t("pooling/out/cluster1_global"), "cluster1 offsets")
+    x2, b2 = max_pool_x(c1, pooled.x, pooled.batch)
+    assert torch.equal(x2.cpu(), g.t("pooling/out/pool2_x"))
+    assert_equal_int(b2, g.t("pooling/out/pool2_batch"), "pool2 batch")
+
+
+def test_community_pooling_docstring_example():
+    """the 2 x 6-node example of the reference docstring (community_pooling.py:181-191) with fixed clusters"""
+    from deeprank2_b200.data import Batch, Data
+    from deeprank2_b200.utils.community_pooling import community_pooling
+
+    edge_index = torch.tensor([[0, 1, 1, 2, 3, 4, 4, 5], [1, 0, 2, 1, 4, 3, 5, 4]], dtype=torch.long)
+    x = torch.tensor([[0.0], [1.0], [2.0], [3.0], [4.0], [5.0]])
+    pos = torch.arange(18, dtype=torch.float32).reshape(6, 3)
+    d = Data(x=x, edge_index=edge_index, edge_attr=torch.ones(8, 1), pos=pos)
+    batch = Batch.from_data_list([d, d]).to(DEV)
+    cluster = torch.tensor([0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3], device=DEV)
+    out = community_pooling(cluster, batch)
+    assert out.x.flatten().tolist() == [2.0, 5.0, 2.0, 5.0]
+    assert out.edge_index.numel() == 0  # the two triangles are disconnected components: only self loops remain
+    assert out.batch.tolist() == [0, 0, 1, 1]
+    # reference semantics on the same input
+    ref = tp.Batch.from_data_list([tp.Data(x=x, edge_index=edge_index, edge_attr=torch.ones(8, 1), pos=pos)] * 2)
+    rc, rperm = tp.consecutive_cluster(cluster.cpu())
+    assert_close(out.pos, tp.scatter_mean(ref.pos, rc, dim=0), "pos")
+
+
+@pytest.mark.parametrize("width", [1, 3, 16, 50])
+def test_scatter_functions_match_torch_scatter_semantics(width):
+    from deeprank2_b200 import ops
+
+    gen = torch.Generator().manual_seed(width)
+    n, segs = 777, 41
+    index = torch.randint(0, segs, (n,), generator=gen)
+    index[index == 7] = 8  # an empty segment
+    src = torch.randn(n, width, generator=gen)
+    s_dev = src.to(DEV).requires_grad_(True)
+    s_cpu = src.clone().requires_grad_(True)
+    got = ops.scatter_sum(s_dev, index.to(DEV), dim=0, dim_size=segs)
+    ref = tp.scatter_sum(s_cpu, index, dim=0, dim_size=segs)
+    assert_close(got, ref, "sum")
+    gout = torch.randn(segs, width, generator=gen)
+    got.backward(gout.to(DEV))
+    ref.backward(gout)
+    assert_close(s_dev.grad, s_cpu.grad, "sum grad")
+
+    assert_close(ops.scatter_mean(src.to(DEV), index.to(DEV), dim=0, dim_size=segs), tp.scatter_mean(src, index, dim=0, dim_size=segs), "mean")
+    init = torch.randn(segs, width, generator=gen)
+    got = ops.scatter_mean(src.to(DEV), index.to(DEV), dim=0, out=init.clone().to(DEV))
+    assert_close(got, tp.scatter_mean(src, index, dim=0, out=init.clone()), "mean with out=")
+
+    s_dev = src.to(DEV).requires_grad_(True)
+    s_cpu = src.clone().requires_grad_(True)
+    gmax, garg = ops.scatter_max(s_dev, index.to(DEV), dim=0, dim_size=segs)
+    rmax, rarg = tp.scatter_max(s_cpu, index, dim=0, dim_size=segs)
+    assert torch.equal(gmax.detach().cpu(), rmax.detach())
+    assert_equal_int(garg, rarg, "argmax (first max wins, empty -> n)")
+    gmax.backward(gout.to(DEV))
+    rmax.backward(gout)
+    assert_close(s_dev.grad, s_cpu.grad, "max grad")
+    # without dim_size the output has index.max()+1 rows, like torch_scatter
+    assert ops.scatter_sum(src.to(DEV), index.to(DEV), dim=0).shape[0] == int(index.max()) + 1
+
+
+def test_scatter_max_ties_pick_first():
+    from deeprank2_b200 import ops
+
+    src = torch.tensor([[1.0], [3.0], [3.0], [2.0], [3.0]], device=DEV)
+    index = torch.tensor([0, 0, 0, 1, 0], device=DEV)
+    out, arg = ops.scatter_max(src, index, dim=0, dim_size=3)
+    assert out.flatten().tolist() == [3.0, 2.0, 0.0]
+    assert arg.flatten().tolist() == [1, 3, 5]
