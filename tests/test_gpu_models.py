@@ -65,7 +65,8 @@ def _train_step_vs_golden(g, tag, module):
         assert_close(p.grad, g.t(f"{tag}/grad/{k}"), f"{g.case}:{tag}:grad:{k}")
     opt.step()
     for k, v in module.state_dict().items():
-        assert_adam_close(v, g.t(f"{tag}/adam/{k}"), f"{g.case}:{tag}:adam:{k}")
+        gk = f"{tag}/grad/{k}"
+        assert_adam_close(v, g.t(f"{tag}/adam/{k}"), f"{g.case}:{tag}:adam:{k}", g.t(gk) if g.has(gk) else None, g.t(f"{tag}/w/{k}"))
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)

@@ -71,7 +71,8 @@ def _net_check(g, tag, forward):
     assert_close(torch.tensor(loss), g.t(f"{tag}/out/loss"), f"{g.case}:{tag}:loss")
     for k, v in p.items():
         assert_close(v.grad, g.t(f"{tag}/grad/{k}"), f"{g.case}:{tag}:grad:{k}")
-        assert_adam_close(v, g.t(f"{tag}/adam/{k}"), f"{g.case}:{tag}:adam:{k}")
+        gk = f"{tag}/grad/{k}"
+        assert_adam_close(v, g.t(f"{tag}/adam/{k}"), f"{g.case}:{tag}:adam:{k}", g.t(gk) if g.has(gk) else None, g.t(f"{tag}/w/{k}"))
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
