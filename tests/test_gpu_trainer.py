@@ -1,0 +1,89 @@
+"""GPU: the Trainer driving the CUDA nets end to end on in-memory synthetic graphs (no HDF5 on the GPU box):
+a few epochs run, losses are finite and decrease, parameters live on the GPU, the step launches drk kernels,
+and one Trainer epoch reproduces the CPU oracle's epoch (same batches, same weights) within tolerance."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from conftest import assert_adam_close, assert_close
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _graphs(n, clusters=False, seed=1000):
+    from deeprank2_b200.synthetic import RESIDUE, make_graph
+
+    level = dict(RESIDUE, n_lo=30, n_hi=60)
+    return [make_graph(g, 50, 1, level=level, seed=seed, with_clusters=clusters) for g in range(n)]
+
+
+class _Collect:
+    """minimal exporter recording what the Trainer hands over"""
+
+    def __init__(self):
+        self.calls = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return None
+
+    def process(self, pass_name, epoch, names, outputs, targets_, loss):
+        self.calls.append((pass_name, epoch, list(names), list(outputs), list(targets_), loss))
+
+    def is_compatible_with(self, *a):
+        return True
+
+
+@pytest.mark.parametrize("net_name", ["ginet_nocluster", "vanilla", "ginet", "foutnet", "sgat"])
+def test_trainer_trains_every_net_on_gpu(net_name, tmp_path):
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn import foutnet, ginet, ginet_nocluster, sgat, vanilla_gnn
+    from deeprank2_b200.trainer import Trainer
+
+    net = {"ginet_nocluster": ginet_nocluster.GINet, "vanilla": vanilla_gnn.VanillaNetwork, "ginet": ginet.GINet, "foutnet": foutnet.FoutNet, "sgat": sgat.SGAT}[net_name]
+    clustered = net_name in ("ginet", "foutnet", "sgat")
+    ds = InMemoryGraphDataset(_graphs(24, clusters=clustered), clustering_method="mcl" if clustered else None)
+    sink = _Collect()
+    torch.manual_seed(0)
+    trainer = Trainer(net, ds, val_size=4, cuda=True, output_exporters=[sink])
+    assert all(p.is_cuda for p in trainer.model.parameters())  # reference: tests/test_trainer.py:94-97
+    before = _lib.launch_count()
+    trainer.train(nepoch=3, batch_size=8, validate=True, filename=str(tmp_path / "m.pth.tar"))
+    assert _lib.launch_count() > before, "the CUDA extension must be what runs"
+    train_losses = [c[5] for c in sink.calls if c[0] == "training"]
+    assert len(train_losses) == 4 and all(l == l for l in train_losses)  # epoch 0 eval + 3 epochs, no NaN
+    assert train_losses[-1] < train_losses[0]
+    names = sink.calls[0][2]
+    assert len(names) == 20 and len(sink.calls[0][3]) == 20 and len(sink.calls[0][4]) == 20
+    trainer.test()
+
+
+def test_trainer_epoch_matches_cpu_oracle_epoch():
+    """Trainer._epoch on the GPU == the reference's loop body (oracle port) over the same three mini-batches."""
+    from deeprank2_b200.data import Batch
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.trainer import Trainer
+
+    graphs = _graphs(12)
+    ds = InMemoryGraphDataset([g.clone() for g in graphs])
+    torch.manual_seed(3)
+    trainer = Trainer(GINet, ds, cuda=True, output_exporters=[])
+    params = R.as_parameters({k: v.cpu() for k, v in trainer.model.state_dict().items()})
+    opt = R.make_adam(params)
+    trainer.model.eval()  # dropout off on both sides: it draws from different RNG streams on CPU and GPU
+    trainer.train_loader = trainer._loader(ds, 4, False)
+    loss_gpu = trainer._run_pass(trainer.train_loader, 1, "training", train=True)
+    losses = []
+    for start in range(0, 12, 4):
+        batch = Batch.from_data_list([g.clone() for g in graphs[start : start + 4]])
+        _, l = R.train_step(R.ginet_nocluster_forward, params, opt, batch, training=False)
+        losses.append(l * 4)
+    assert abs(loss_gpu - sum(losses) / 12) <= 1e-5 * abs(sum(losses) / 12) + 1e-7
+    for (k, p_ref), p in zip(params.items(), trainer.model.parameters()):
+        assert_adam_close(p, p_ref, f"weights after 3 steps: {k}")
