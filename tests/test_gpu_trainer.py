@@ -50,7 +50,7 @@ def test_trainer_trains_every_net_on_gpu(net_name, tmp_path):
     ds = InMemoryGraphDataset(_graphs(24, clusters=clustered), clustering_method="mcl" if clustered else None)
     sink = _Collect()
     torch.manual_seed(0)
-    trainer = Trainer(net, ds, val_size=4, cuda=True, output_exporters=[sink])
+    trainer = Trainer(net, ds, val_size=4, test_size=4, cuda=True, output_exporters=[sink])
     assert all(p.is_cuda for p in trainer.model.parameters())  # reference: tests/test_trainer.py:94-97
     before = _lib.launch_count()
     trainer.train(nepoch=3, batch_size=8, validate=True, filename=str(tmp_path / "m.pth.tar"))
@@ -59,8 +59,9 @@ def test_trainer_trains_every_net_on_gpu(net_name, tmp_path):
     assert len(train_losses) == 4 and all(l == l for l in train_losses)  # epoch 0 eval + 3 epochs, no NaN
     assert train_losses[-1] < train_losses[0]
     names = sink.calls[0][2]
-    assert len(names) == 20 and len(sink.calls[0][3]) == 20 and len(sink.calls[0][4]) == 20
+    assert len(names) == 16 and len(sink.calls[0][3]) == 16 and len(sink.calls[0][4]) == 16
     trainer.test()
+    assert sink.calls[-1][0] == "testing" and len(sink.calls[-1][2]) == 4
 
 
 def test_trainer_epoch_matches_cpu_oracle_epoch():
