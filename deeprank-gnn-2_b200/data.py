@@ -49,6 +49,12 @@ class Data:
     def _fields(self) -> Iterable[str]:
         return [k for k in self.__dict__ if not k.startswith("_")]
 
+    def meta(self, key: str, default=None):
+        return self.__dict__.get(self._META_KEY, {}).get(key, default)
+
+    def set_meta(self, key: str, value) -> None:
+        self.__dict__.setdefault(self._META_KEY, {})[key] = value
+
     @property
     def keys(self):
         return [k for k in self._fields() if self.__dict__[k] is not None]
@@ -89,10 +95,14 @@ class Data:
         return f"{type(self).__name__}({', '.join(parts)})"
 
     # -- copies / movement (private caches, e.g. the graph index, are dropped on clone and moved on to())
+    # host-side facts about the batch that survive clone()/to(): {"num_graphs", "max_graph_nodes"}
+    _META_KEY = "_meta"
+    _DEVICE_CACHES = ("_graph_index",)
+
     def clone(self):
         new = type(self).__new__(type(self))
         for k, v in self.__dict__.items():
-            if k.startswith("_"):
+            if k in self._DEVICE_CACHES:
                 continue
             new.__dict__[k] = v.clone() if isinstance(v, torch.Tensor) else copy.deepcopy(v)
         return new
@@ -101,7 +111,7 @@ class Data:
         for k, v in list(self.__dict__.items()):
             if isinstance(v, torch.Tensor):
                 self.__dict__[k] = v.to(device, non_blocking=non_blocking)
-            elif k.startswith("_"):
+            elif k in self._DEVICE_CACHES:
                 self.__dict__.pop(k)
         return self
 
@@ -166,6 +176,7 @@ class Batch(Data):
                 setattr(out, k, list(column))
         out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int64), torch.tensor(sizes, dtype=torch.int64))
         out.ptr = ptr
+        out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes)}
         return out
 
 

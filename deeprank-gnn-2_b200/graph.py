@@ -140,7 +140,27 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
     batch = getattr(data, "batch", None)
     ptr = data.__dict__.get("ptr")
     num_graphs = int(ptr.numel()) - 1 if ptr is not None else data.__dict__.get("_num_graphs")
+    if num_graphs is None and hasattr(data, "meta"):
+        num_graphs = data.meta("num_graphs")
     gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc)
     gi._key = key
     data.__dict__["_graph_index"] = gi
     return gi
+
+
+def max_graph_nodes(data, gi: GraphIndex) -> int:
+    """Largest graph of the batch (sizes shared memory of the per-graph kernels).  Known on the host for batches made
+    by ``Batch.from_data_list``; otherwise read back once (one host sync) and remembered on the batch."""
+    known = data.meta("max_graph_nodes") if hasattr(data, "meta") else None
+    if known is None:
+        known = data.__dict__.get("_max_graph_nodes")
+    if known is None:
+        if gi.graph_ptr is None or gi.num_graphs == 0:
+            known = gi.num_nodes
+        else:
+            known = int((gi.graph_ptr[1:] - gi.graph_ptr[:-1]).max().item())
+        if hasattr(data, "set_meta"):
+            data.set_meta("max_graph_nodes", known)
+        else:
+            data.__dict__["_max_graph_nodes"] = known
+    return int(known)

@@ -651,3 +651,60 @@ class SGATConvFunction(torch.autograd.Function):
 
 def sgat_conv(x, a, weight, bias, graph):
     return SGATConvFunction.apply(x, a, weight, bias, graph)
+
+
+# ------------------------------------------------------------------------------ fused per-graph GINet
+def ginet_fused_max_nodes(fi: int) -> int:
+    return int(_lib.load().drk_ginet_fused_max_nodes(int(fi)))
+
+
+class GINetFusedFunction(torch.autograd.Function):
+    """The same computation as :class:`GINetStackFunction` in TWO kernel launches (+ a 2 KB partial reduction): one CTA
+    per graph, all intermediates in shared memory (``csrc/drk_ginet_fused.cu``).  Used when every graph of the batch fits
+    the shared-memory budget (``ginet_fused_max_nodes``) and F <= 64."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w1e, w2, w2e, graph: GraphIndex, max_nodes: int, *dead):
+        lib = _lib.load()
+        x = _f32_cuda(x, "x")
+        n, fi = x.shape
+        w1s = torch.cat([w1, w1e], dim=0).contiguous()
+        w2c, w2ec = w2.contiguous(), w2e.contiguous()
+        need_grad = any(ctx.needs_input_grad[1:5])
+        h1 = torch.empty((n, 32), dtype=torch.float32, device=x.device) if need_grad else None
+        a2 = torch.empty((n, 32), dtype=torch.float32, device=x.device) if need_grad else None
+        g = torch.empty((graph.num_graphs, 64), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.drk_ginet_fused_fwd(_p(x), _ld(x), fi, _p(graph.graph_ptr), _p(graph.rowptr), _p(graph.colidx), _p(w1s), _p(w2c), _p(w2ec),
+                                         _p(h1), _p(a2), _p(g), graph.num_graphs, max_nodes, _p(graph.status), stream_ptr())
+        _lib.check(rc, "drk_ginet_fused_fwd")
+        ctx.graph, ctx.max_nodes, ctx.dead = graph, max_nodes, dead
+        ctx.save_for_backward(x, w2c, w2ec, h1, a2)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        lib = _lib.load()
+        x, w2c, w2ec, h1, a2 = ctx.saved_tensors
+        graph = ctx.graph
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("the fused GINet path does not produce d/dx (node features are inputs); use the unfused path")
+        fi = x.shape[1]
+        dg = dg.contiguous()
+        dw1s = torch.empty((32, fi), dtype=torch.float32, device=x.device)
+        dw2 = torch.empty((32, 16), dtype=torch.float32, device=x.device)
+        dw2e = torch.empty((32, 16), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = workspace(lib.drk_ginet_fused_bwd_workspace_bytes(), x.device)
+            rc = lib.drk_ginet_fused_bwd(_p(x), _ld(x), fi, _p(graph.graph_ptr), _p(graph.colptr), _p(graph.rowidx), _p(w2c), _p(w2ec), _p(h1), _p(a2),
+                                         _p(dg), _p(dw1s), _p(dw2), _p(dw2e), graph.num_graphs, ctx.max_nodes, _p(graph.status), _p(ws), ws.numel(), stream_ptr())
+        _lib.check(rc, "drk_ginet_fused_bwd")
+        dead = tuple(torch.zeros_like(t) if ctx.needs_input_grad[7 + i] else None for i, t in enumerate(ctx.dead))
+        return (None, dw1s[:16], dw1s[16:], dw2, dw2e, None, None) + dead
+
+
+def ginet_fused(x, conv1, conv1_ext, conv2, conv2_ext, graph, max_nodes):
+    dead = []
+    for layer in (conv1, conv2, conv1_ext, conv2_ext):
+        dead += [layer.fc_edge_attr.weight, layer.fc_attention.weight]
+    return GINetFusedFunction.apply(x, conv1.fc.weight, conv1_ext.fc.weight, conv2.fc.weight, conv2_ext.fc.weight, graph, max_nodes, *dead)

@@ -70,13 +70,20 @@ def _train_step_vs_golden(g, tag, module):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_ginet_nocluster_train_step_vs_reference(case):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-per-graph", "stacked-layer-kernels"])
+def test_ginet_nocluster_train_step_vs_reference(case, fused):
+    from deeprank2_b200 import _lib
     from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
 
     g = load_golden(case)
     d = g.inputs()
     net = _load(GINet(d.x.shape[1], 1, d.edge_attr.shape[1]), g.group("ginet_nocluster/w"))
+    net.fused = fused
+    before = _lib.launch_count()
     _train_step_vs_golden(g, "ginet_nocluster", net)
+    launched = _lib.launch_count() - before
+    # index build (6) + offsets (1) + [fused: fwd 1 + bwd 2 | stacked: 6 + 11]
+    assert launched == (10 if fused else 24), launched
 
 
 @pytest.mark.parametrize("case", ["toy_edgecases", "fixture_1ATN"])
@@ -105,6 +112,7 @@ def test_ginet_nocluster_c2_batch_vs_oracle_and_deterministic():
     pred_ref, loss_ref = R.train_step(R.ginet_nocluster_forward, params, opt, batch)
 
     net = net.to(DEV).eval()
+    assert net.fused
     gb = copy.copy(batch).clone().to(DEV)
     outs = []
     for _ in range(2):
