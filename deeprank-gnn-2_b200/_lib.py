@@ -47,9 +47,9 @@ SIGNATURES = {
     "drk_segment_mean": (c_int32, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
     "drk_segment_mean_bwd": (c_int32, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
     "drk_ginet_fused_max_nodes": (c_int32, [_I32]),
-    "drk_ginet_fused_fwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
+    "drk_ginet_fused_fwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "drk_ginet_fused_bwd_workspace_bytes": (c_size_t, []),
-    "drk_ginet_fused_bwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, c_size_t, _P]),
+    "drk_ginet_fused_bwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, c_size_t, _P]),
     "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),

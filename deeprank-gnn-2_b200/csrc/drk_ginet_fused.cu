@@ -50,53 +50,98 @@ struct GinetFwdArgs {
   int32_t num_graphs;
   int32_t rows_cap;  // shared-memory capacity in rows
   int32_t x_vec;     // 4 / 2 / 1
+  int32_t idx_cap;   // shared-memory capacity in edge slots
 };
 
-// One aggregation over the graph's rows: dst[i] = epi( sum_{s in row i} src[idx[s] - node0] ), src/dst tiles in smem
-// ([rows][32] floats).  8 lanes per row, 4 rows per warp, warp-uniform trip count, CSR order.
-// MODE 0: relu, MODE 1: none, MODE 2: multiply by (mask_global[row] > 0)
-template <int MODE>
-__device__ __forceinline__ void fused_aggregate(const float* __restrict__ s_src, float* __restrict__ s_dst, const int32_t* __restrict__ ptr,
-                                                const int32_t* __restrict__ idx, int node0, int n, float* __restrict__ g_out,
-                                                const float* __restrict__ g_mask, int32_t* status) {
+// Stage the graph's slice of a CSR/CSC into shared memory: s_ptr[i] = ptr[node0+i] - ptr[node0] (n+1 entries) and, for every
+// slot, the BYTE offset of the gathered row inside a [rows][32] fp32 tile.  Slots whose endpoint lies outside the graph
+// (cannot happen for a collated batch) point at the all-zero row `rows_cap` and raise DRK_STATUS_CROSS_GRAPH, so the gather
+// loop itself needs no range check.  Returns false (uniformly) if the graph has more edges than the staging buffer.
+__device__ __forceinline__ bool fused_stage_index(int32_t* __restrict__ s_ptr, int32_t* __restrict__ s_off, const int32_t* __restrict__ ptr,
+                                                  const int32_t* __restrict__ idx, int node0, int n, int idx_cap, int rows_cap,
+                                                  int32_t* status) {
+  const int e0 = __ldg(ptr + node0);
+  const int ne = __ldg(ptr + node0 + n) - e0;
+  for (int i = threadIdx.x; i <= n; i += kFusedThreads) s_ptr[i] = __ldg(ptr + node0 + i) - e0;
+  if (ne > idx_cap) return false;
+  bool bad = false;
+  for (int e = threadIdx.x; e < ne; e += 4 * kFusedThreads) {
+    int raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = (e + u * kFusedThreads < ne) ? ld_stream_i32(idx + e0 + e + u * kFusedThreads) : node0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (e + u * kFusedThreads < ne) {
+        const int local = raw[u] - node0;
+        const bool ok = (unsigned)local < (unsigned)n;
+        bad |= !ok;
+        s_off[e + u * kFusedThreads] = (ok ? local : rows_cap) * (kS1 * 4);
+      }
+    }
+  }
+  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
+  return true;
+}
+
+// One aggregation over the graph's rows: dst[i] = epi( sum_{s in row i} src[slot s] ), src/dst tiles in smem ([rows][32] floats,
+// src has an all-zero row at index rows_cap).  8 lanes per row, 4 rows per warp, warp-uniform trip count, CSR order.
+// MODE 0: relu, MODE 1: none, MODE 2: multiply by (mask_global[row] > 0).
+// STAGED: slots come from shared memory (byte offsets, padding slots read the zero row -> no predicates in the inner loop);
+// otherwise they are streamed from global memory (graphs with more edges than the staging buffer).
+template <int MODE, bool STAGED>
+__device__ __forceinline__ void fused_aggregate(const float* __restrict__ s_src, float* __restrict__ s_dst, const int32_t* __restrict__ s_ptr,
+                                                const int32_t* __restrict__ s_off, const int32_t* __restrict__ g_ptr,
+                                                const int32_t* __restrict__ g_idx, int node0, int n, int rows_cap,
+                                                float* __restrict__ g_out, const float* __restrict__ g_mask) {
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
   const int group_base = sub * 8;
-  bool bad = false;
+  const int zero_off = rows_cap * (kS1 * 4);
+  const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
+  const int e0 = STAGED ? 0 : __ldg(g_ptr + node0);
   for (int rw = warp * 4; rw < n; rw += kFusedWarps * 4) {
     const int r = rw + sub;
     const bool row_ok = r < n;
     int beg = 0, len = 0;
     if (row_ok) {
-      beg = __ldg(ptr + node0 + r);
-      len = __ldg(ptr + node0 + r + 1) - beg;
+      beg = s_ptr[r];
+      len = s_ptr[r + 1] - beg;
     }
     int max_len = len;
     max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 16));
     max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 8));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int next_idx = -1;
-    if (sl < len) next_idx = ld_stream_i32(idx + beg + sl) - node0;
     for (int off = 0; off < max_len; off += 8) {
-      const int my_idx = next_idx;
-      next_idx = -1;
-      if (off + 8 + sl < len) next_idx = ld_stream_i32(idx + beg + off + 8 + sl) - node0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int srow = __shfl_sync(kFull, my_idx, group_base + j);
-        const bool on = (off + j) < len;
-        if (on && (unsigned)srow >= (unsigned)n) {  // an edge leaving the graph: keep memory safe, flag it
-          bad = true;
-          srow = 0;
+      int my_off = zero_off;
+      if (off + sl < len) {
+        if (STAGED) {
+          my_off = s_off[beg + off + sl];
+        } else {
+          const int local = ld_stream_i32(g_idx + e0 + beg + off + sl) - node0;
+          my_off = ((unsigned)local < (unsigned)n ? local : rows_cap) * (kS1 * 4);
         }
-        if (on) {
-          const float4 v = *reinterpret_cast<const float4*>(s_src + srow * kS1 + sl * 4);
-          acc.x += v.x;
-          acc.y += v.y;
-          acc.z += v.z;
-          acc.w += v.w;
+      }
+      // shared memory delivers one 128 B row per cycle per SM and this loop is bound by exactly that: padding slots
+      // (rows shorter than the longest of the warp's four) are predicated off rather than pointed at the zero row
+      const int rem = len - off;
+#pragma unroll
+      for (int j0 = 0; j0 < 8; j0 += 4) {  // four rows in flight per lane (16 registers)
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = __shfl_sync(kFull, my_off, group_base + j0 + j);
+          if (j0 + j < rem) v[j] = *reinterpret_cast<const float4*>(lane_base + o);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j0 + j < rem) {
+            acc.x += v[j].x;
+            acc.y += v[j].y;
+            acc.z += v[j].z;
+            acc.w += v[j].w;
+          }
         }
       }
     }
@@ -116,7 +161,14 @@ __device__ __forceinline__ void fused_aggregate(const float* __restrict__ s_src,
     *reinterpret_cast<float4*>(s_dst + r * kS1 + sl * 4) = acc;
     if (g_out != nullptr) *reinterpret_cast<float4*>(g_out + (size_t)(node0 + r) * kS1 + sl * 4) = acc;
   }
-  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
+}
+
+template <int MODE>
+__device__ __forceinline__ void fused_aggregate_any(bool staged, const float* s_src, float* s_dst, const int32_t* s_ptr, const int32_t* s_off,
+                                                    const int32_t* g_ptr, const int32_t* g_idx, int node0, int n, int rows_cap, float* g_out,
+                                                    const float* g_mask) {
+  if (staged) fused_aggregate<MODE, true>(s_src, s_dst, s_ptr, s_off, g_ptr, g_idx, node0, n, rows_cap, g_out, g_mask);
+  else fused_aggregate<MODE, false>(s_src, s_dst, s_ptr, s_off, g_ptr, g_idx, node0, n, rows_cap, g_out, g_mask);
 }
 
 // copy rows [node0, node0+n) of a row-major global matrix (ld elements, width fi) into smem with row stride kp,
@@ -143,15 +195,19 @@ __device__ __forceinline__ void fused_stage_rows(float* __restrict__ s_dst, cons
 __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_fwd(const GinetFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int kp = fused_kp(a.fi);
-  // smem carve-up (floats): W1 [32][kp] | W2 [2][32][16] | colsum scratch [8][64] | tile A [cap][max(kp,32)] | tile B [cap][32]
+  // smem carve-up (floats): W1 [32][kp] | W2 [2][32][16] | colsum scratch [8][64] | tile A [cap][max(kp,32)] + zero row |
+  //                         tile B [cap+1][32] (row cap = zeros) | row pointers [cap+1] | slot offsets [idx_cap]
   float* sW1 = smem;
   float* sW2 = sW1 + kS1 * kp;
   float* sRed = sW2 + 2 * kF2 * kF1;
   float* sA = sRed + 8 * kS2;                    // x tile, later H1
   const int wa = kp > kS1 ? kp : kS1;
-  float* sB = sA + (size_t)a.rows_cap * wa;      // P, later A2
+  float* sB = sA + (size_t)a.rows_cap * wa + kS1;  // P, later A2
+  int32_t* sPtr = reinterpret_cast<int32_t*>(sB + (size_t)(a.rows_cap + 1) * kS1);
+  int32_t* sOff = sPtr + a.rows_cap + 4;
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x < kS1) sB[a.rows_cap * kS1 + threadIdx.x] = 0.f;  // tile B's zero row is never overwritten
 
   // weights once per CTA.  W1 rows permuted for conflict-free float4 reads: logical m = 4*cg + t + 16*jj -> row cg + 4*t + 16*jj
   for (int e = threadIdx.x; e < kS1 * kp; e += kFusedThreads) {
@@ -172,9 +228,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_fwd(const Gine
       if (threadIdx.x == 0 && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
       continue;
     }
-    // ---- stage x rows
+    // ---- stage x rows (async) and the graph's CSR slice
     fused_stage_rows(sA, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
+    const bool staged = fused_stage_index(sPtr, sOff, a.rowptr, a.colidx, node0, n, a.idx_cap, a.rows_cap, a.status);
     cp_async_wait<0>();
     __syncthreads();
 
@@ -225,11 +282,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_fwd(const Gine
       }
     }
     __syncthreads();
-    // ---- H1 = relu(A P)  (tile A is free: x is consumed)
-    fused_aggregate<0>(sB, sA, a.rowptr, a.colidx, node0, n, a.h1s, nullptr, a.status);
+    // ---- H1 = relu(A P)  (tile A is free: x is consumed; re-create its zero row, which the x tile overlapped)
+    if (threadIdx.x < kS1) sA[a.rows_cap * kS1 + threadIdx.x] = 0.f;
+    fused_aggregate_any<0>(staged, sB, sA, sPtr, sOff, a.rowptr, a.colidx, node0, n, a.rows_cap, a.h1s, nullptr);
     __syncthreads();
     // ---- A2 = A H1
-    fused_aggregate<1>(sA, sB, a.rowptr, a.colidx, node0, n, a.a2s, nullptr, a.status);
+    fused_aggregate_any<1>(staged, sA, sB, sPtr, sOff, a.rowptr, a.colidx, node0, n, a.rows_cap, a.a2s, nullptr);
     __syncthreads();
     // ---- H2 = relu(A2 W2^T) per branch, column sums for the readout.  thread -> column c (0..63), row lane rl (0..7)
     {
@@ -240,18 +298,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_fwd(const Gine
 #pragma unroll
       for (int k = 0; k < kF1; ++k) w[k] = sW2[branch * kF2 * kF1 + (c & 31) * kF1 + k];
       float colsum = 0.f;
-      for (int r = rl; r < n; r += 8) {
-        const float* arow = sB + r * kS1 + branch * kF1;
-        float z = 0.f;
+      for (int r = rl; r < n; r += 32) {  // four independent rows per trip (ILP); rows are still added in ascending order
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k4 = 0; k4 < kF1; k4 += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(arow + k4);
-          z = fmaf(v.x, w[k4], z);
-          z = fmaf(v.y, w[k4 + 1], z);
-          z = fmaf(v.z, w[k4 + 2], z);
-          z = fmaf(v.w, w[k4 + 3], z);
+        for (int u = 0; u < 4; ++u) {
+          const int rr = min(r + 8 * u, a.rows_cap - 1);
+          const float* arow = sB + rr * kS1 + branch * kF1;
+#pragma unroll
+          for (int k4 = 0; k4 < kF1; k4 += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + k4);
+            z[u] = fmaf(v.x, w[k4], z[u]);
+            z[u] = fmaf(v.y, w[k4 + 1], z[u]);
+            z[u] = fmaf(v.z, w[k4 + 2], z[u]);
+            z[u] = fmaf(v.w, w[k4 + 3], z[u]);
+          }
         }
-        colsum += z < 0.f ? 0.f : z;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r + 8 * u < n) colsum += z[u] < 0.f ? 0.f : z[u];
       }
       sRed[rl * kS2 + c] = colsum;
     }
@@ -283,9 +347,12 @@ struct GinetBwdArgs {
   int32_t num_graphs;
   int32_t rows_cap;
   int32_t x_vec;
+  int32_t idx_cap;
 };
 
 constexpr int kBwdBlockRows = 64;          // rows per dZ2 block
+constexpr int kDzStride = kS2 + 4;         // 68: consecutive rows start 4 banks apart -> conflict-free float4 reads
+constexpr int kWtStride = kF2 + 4;         // 36: same for the rows of W2^T
 constexpr int kPartialW1 = kS1 * 64;       // dW1s partial, k padded to 64
 constexpr int kPartialW2 = kS2 * kF1;      // dW2 | dW2e partial
 constexpr int kPartial = kPartialW1 + kPartialW2;
@@ -293,23 +360,30 @@ constexpr int kPartial = kPartialW1 + kPartialW2;
 __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_bwd(const GinetBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int kp = fused_kp(a.fi);
-  // smem (floats): W2 [2][32][16] | W2T [2][16][32] | dZ2 block [64][64] | tile A [cap][32] | tile B [cap][32] | x tile [cap][kp]
+  // smem (floats): W2 [2][32][16] | W2T [2][16][32] | dZ2 block [64][64] | tile A [cap+1][32] | tile B [cap+1][32] (row cap = zeros)
+  //                | x tile [cap][kp] | column pointers [cap+1] | slot offsets [idx_cap]
   float* sW2 = smem;
   float* sW2T = sW2 + 2 * kF2 * kF1;
-  float* sDZ = sW2T + 2 * kF2 * kF1;
-  float* sA = sDZ + kBwdBlockRows * kS2;
-  float* sB = sA + (size_t)a.rows_cap * kS1;
-  float* sX = sB + (size_t)a.rows_cap * kS1;
+  float* sDZ = sW2T + 2 * kF1 * kWtStride;
+  float* sA = sDZ + kBwdBlockRows * kDzStride;
+  float* sB = sA + (size_t)(a.rows_cap + 1) * kS1;
+  float* sX = sB + (size_t)(a.rows_cap + 1) * kS1;
+  int32_t* sPtr = reinterpret_cast<int32_t*>(sX + (size_t)a.rows_cap * kp);
+  int32_t* sOff = sPtr + a.rows_cap + 4;
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x < kS1) {
+    sA[a.rows_cap * kS1 + threadIdx.x] = 0.f;
+    sB[a.rows_cap * kS1 + threadIdx.x] = 0.f;
+  }
 
   for (int e = threadIdx.x; e < kF2 * kF1; e += kFusedThreads) {
     const float va = __ldg(a.w2a + e), vb = __ldg(a.w2b + e);
     sW2[e] = va;
     sW2[kF2 * kF1 + e] = vb;
     const int c = e / kF1, k = e - c * kF1;
-    sW2T[k * kF2 + c] = va;
-    sW2T[kF2 * kF1 + k * kF2 + c] = vb;
+    sW2T[k * kWtStride + c] = va;                     // W2^T: [k (16)][c (32)], row stride 36
+    sW2T[kF1 * kWtStride + k * kWtStride + c] = vb;
   }
 
   // register-resident partial weight gradients, accumulated over all graphs of this CTA
@@ -340,6 +414,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_bwd(const Gine
     cp_async_commit();
     fused_stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
+    const bool staged = fused_stage_index(sPtr, sOff, a.colptr, a.rowidx, node0, n, a.idx_cap, a.rows_cap, a.status);
     cp_async_wait<1>();
     __syncthreads();
 
@@ -366,43 +441,56 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_ginet_fused_bwd(const Gine
 #pragma unroll
         for (int k = 0; k < kF1; ++k) z = fmaf(av[k], w[k], z);
         const float dz = z <= 0.f ? 0.f : dgc;  // threshold_backward on relu(z)
-        sDZ[r * kS2 + c2] = dz;
+        sDZ[r * kDzStride + c2] = dz;
 #pragma unroll
         for (int k = 0; k < kF1; ++k) dw2[k] = fmaf(dz, av[k], dw2[k]);
       }
       __syncthreads();
-      // (b) dA2[r, 4q..4q+3] = sum_c dZ2[r, branch*32 + c] * W2[c, k]   thread -> (row = tid >> 3, q = tid & 7)
-      {
-        const int r = threadIdx.x >> 3;
-        const int q = threadIdx.x & 7;
-        if (r < rows) {
-          const int br = q >> 2;              // q 0..3 -> branch a (k 0..15), q 4..7 -> branch b
-          const int k0 = (q & 3) * 4;
-          const float* dzrow = sDZ + r * kS2 + br * kF2;
-          const float* wt = sW2T + br * kF2 * kF1 + k0 * kF2;  // [k][c]
-          float o[4] = {0.f, 0.f, 0.f, 0.f};
+      // (b) dA2[r, br*16 + k] = sum_c dZ2[r, br*32 + c] * W2[c, k]: per branch a [64 x 32] x [32 x 16] product.
+      //     warp -> (branch br = warp & 1, 32-row half hv = (warp >> 1) & 1); lane -> (rg = lane >> 2: rows rg + 8j,
+      //     cg = lane & 3: outputs 4cg..4cg+3).  Warps 4..15 have nothing to do in this (short) phase.
+      if (warp < 4) {
+        const int br = warp & 1, hv = warp >> 1;
+        const int rg = lane >> 2, cg = lane & 3;
+        float o[4][4];
 #pragma unroll
-          for (int c4 = 0; c4 < kF2; c4 += 4) {
-            const float4 dzv = *reinterpret_cast<const float4*>(dzrow + c4);
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const float4 wv = *reinterpret_cast<const float4*>(wt + kk * kF2 + c4);
-              o[kk] = fmaf(dzv.x, wv.x, o[kk]);
-              o[kk] = fmaf(dzv.y, wv.y, o[kk]);
-              o[kk] = fmaf(dzv.z, wv.z, o[kk]);
-              o[kk] = fmaf(dzv.w, wv.w, o[kk]);
+          for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
+        const float* dzb = sDZ + (hv * 32 + rg) * kDzStride + br * kF2;
+        const float* wtb = sW2T + br * kF1 * kWtStride + (4 * cg) * kWtStride;
+#pragma unroll
+        for (int c4 = 0; c4 < kF2; c4 += 4) {
+          float4 dzv[4], wv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dzv[j] = *reinterpret_cast<const float4*>(dzb + (8 * j) * kDzStride + c4);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) wv[t] = *reinterpret_cast<const float4*>(wtb + t * kWtStride + c4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float acc = o[j][t];
+              acc = fmaf(dzv[j].x, wv[t].x, acc);
+              acc = fmaf(dzv[j].y, wv[t].y, acc);
+              acc = fmaf(dzv[j].z, wv[t].z, acc);
+              acc = fmaf(dzv[j].w, wv[t].w, acc);
+              o[j][t] = acc;
             }
-          }
-          *reinterpret_cast<float4*>(sB + (r0 + r) * kS1 + br * kF1 + k0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = hv * 32 + rg + 8 * j;
+          if (r < rows) *reinterpret_cast<float4*>(sB + (r0 + r) * kS1 + br * kF1 + 4 * cg) = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
         }
       }
       __syncthreads();
     }
     // ---- dZ1 = (A^T dA2) * (H1 > 0)   (tile A is free: A2 is consumed)
-    fused_aggregate<2>(sB, sA, a.colptr, a.rowidx, node0, n, nullptr, a.h1s, a.status);
+    fused_aggregate_any<2>(staged, sB, sA, sPtr, sOff, a.colptr, a.rowidx, node0, n, a.rows_cap, nullptr, a.h1s);
     __syncthreads();
     // ---- Q = A^T dZ1
-    fused_aggregate<1>(sA, sB, a.colptr, a.rowidx, node0, n, nullptr, nullptr, a.status);
+    fused_aggregate_any<1>(staged, sA, sB, sPtr, sOff, a.colptr, a.rowidx, node0, n, a.rows_cap, nullptr, nullptr);
     cp_async_wait<0>();
     __syncthreads();
     // ---- dW1s[m, k] += sum_r Q[r, m] x[r, k]
@@ -479,15 +567,25 @@ __global__ void __launch_bounds__(256) k_ginet_fused_bwd_reduce(const float* __r
   if (lane == 0) *dst = s;
 }
 
-static size_t fused_bwd_smem_bytes(int fi, int rows_cap) {
+static size_t fused_bwd_smem_bytes(int fi, int rows_cap) {  // without the slot-offset buffer
   const int kp = fused_kp(fi);
-  return ((size_t)4 * kF2 * kF1 + kBwdBlockRows * kS2 + (size_t)rows_cap * (2 * kS1 + kp)) * sizeof(float);
+  return ((size_t)2 * kF2 * kF1 + 2 * kF1 * kWtStride + kBwdBlockRows * kDzStride + (size_t)(rows_cap + 1) * 2 * kS1 + (size_t)rows_cap * kp + rows_cap + 4) * sizeof(float);
 }
 
-static size_t fused_fwd_smem_bytes(int fi, int rows_cap) {
+static size_t fused_fwd_smem_bytes(int fi, int rows_cap) {  // without the slot-offset buffer
   const int kp = fused_kp(fi);
   const int wa = std::max(kp, kS1);
-  return ((size_t)kS1 * kp + 2 * kF2 * kF1 + 8 * kS2 + (size_t)rows_cap * wa + (size_t)rows_cap * kS1) * sizeof(float);
+  return ((size_t)kS1 * kp + 2 * kF2 * kF1 + 8 * kS2 + (size_t)rows_cap * wa + kS1 + (size_t)(rows_cap + 1) * kS1 + rows_cap + 4) * sizeof(float);
+}
+
+constexpr size_t kSmemBudget = 227 * 1024;
+
+// slots that fit next to the tiles, capped by what the batch needs (max_graph_edges <= 0: unknown -> take what is left)
+static int fused_idx_cap(size_t base_bytes, int max_graph_edges) {
+  if (base_bytes >= kSmemBudget) return 0;
+  int cap = (int)((kSmemBudget - base_bytes) / 4);
+  if (max_graph_edges > 0) cap = std::min(cap, (max_graph_edges + 3) / 4 * 4);
+  return cap;
 }
 
 }  // namespace drk
@@ -497,7 +595,7 @@ extern "C" {
 int32_t drk_ginet_fused_max_nodes(int32_t fi) {
   using namespace drk;
   if (fi < 1 || fi > 64) return 0;
-  const size_t budget = 227 * 1024;
+  const size_t budget = kSmemBudget;
   int cap = 0;
   for (int c = 32; c <= 4096; c += 32) {
     if (fused_fwd_smem_bytes(fi, c) <= budget && fused_bwd_smem_bytes(fi, c) <= budget) cap = c;
@@ -508,16 +606,18 @@ int32_t drk_ginet_fused_max_nodes(int32_t fi) {
 
 int drk_ginet_fused_fwd(const float* x, int64_t ldx, int32_t fi, const int32_t* graph_ptr, const int32_t* rowptr, const int32_t* colidx,
                         const float* w1s, const float* w2a, const float* w2b, float* h1s, float* a2s, float* g, int32_t num_graphs,
-                        int32_t max_graph_nodes, int32_t* status, void* stream) {
+                        int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* status, void* stream) {
   using namespace drk;
   DRK_REQUIRE(num_graphs >= 0 && max_graph_nodes >= 0, DRK_EINVAL, "ginet fused fwd: negative size");
   if (num_graphs == 0) return DRK_OK;
   DRK_REQUIRE(x && graph_ptr && rowptr && w1s && w2a && w2b && g, DRK_EINVAL, "ginet fused fwd: null pointer");
   DRK_REQUIRE(fi >= 1 && fi <= 64, DRK_EUNSUPPORTED, "ginet fused fwd: 1 <= F <= 64 node features supported, got %d", fi);
   const int rows_cap = std::max(32, (max_graph_nodes + 31) / 32 * 32);
-  const size_t smem = fused_fwd_smem_bytes(fi, rows_cap);
-  DRK_REQUIRE(smem <= 227 * 1024, DRK_EUNSUPPORTED, "ginet fused fwd: a %d-node graph needs %zu bytes of shared memory", max_graph_nodes, smem);
-  GinetFwdArgs a{x, ldx, fi, graph_ptr, rowptr, colidx, w1s, w2a, w2b, h1s, a2s, g, status, num_graphs, rows_cap, 1};
+  const size_t base = fused_fwd_smem_bytes(fi, rows_cap);
+  DRK_REQUIRE(base <= kSmemBudget, DRK_EUNSUPPORTED, "ginet fused fwd: a %d-node graph needs %zu bytes of shared memory", max_graph_nodes, base);
+  const int idx_cap = fused_idx_cap(base, max_graph_edges);
+  const size_t smem = base + (size_t)idx_cap * 4;
+  GinetFwdArgs a{x, ldx, fi, graph_ptr, rowptr, colidx, w1s, w2a, w2b, h1s, a2s, g, status, num_graphs, rows_cap, 1, idx_cap};
   if (ldx % 4 == 0 && fi % 4 == 0 && aligned16(x)) a.x_vec = 4;
   else if (ldx % 2 == 0 && fi % 2 == 0 && aligned8(x)) a.x_vec = 2;
   cudaError_t e = cudaFuncSetAttribute(k_ginet_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -532,17 +632,19 @@ size_t drk_ginet_fused_bwd_workspace_bytes(void) { return (size_t)drk::kNumSM * 
 
 int drk_ginet_fused_bwd(const float* x, int64_t ldx, int32_t fi, const int32_t* graph_ptr, const int32_t* colptr, const int32_t* rowidx,
                         const float* w2a, const float* w2b, const float* h1s, const float* a2s, const float* dg, float* dw1s, float* dw2a,
-                        float* dw2b, int32_t num_graphs, int32_t max_graph_nodes, int32_t* status, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        float* dw2b, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* status, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   using namespace drk;
   DRK_REQUIRE(num_graphs >= 0 && max_graph_nodes >= 0, DRK_EINVAL, "ginet fused bwd: negative size");
   DRK_REQUIRE(x && graph_ptr && colptr && w2a && w2b && h1s && a2s && dg && dw1s && dw2a && dw2b, DRK_EINVAL, "ginet fused bwd: null pointer");
   DRK_REQUIRE(fi >= 1 && fi <= 64, DRK_EUNSUPPORTED, "ginet fused bwd: 1 <= F <= 64 node features supported, got %d", fi);
   DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_ginet_fused_bwd_workspace_bytes(), DRK_EWORKSPACE, "ginet fused bwd: workspace too small");
   const int rows_cap = std::max(32, (max_graph_nodes + 31) / 32 * 32);
-  const size_t smem = fused_bwd_smem_bytes(fi, rows_cap);
-  DRK_REQUIRE(smem <= 227 * 1024, DRK_EUNSUPPORTED, "ginet fused bwd: a %d-node graph needs %zu bytes of shared memory", max_graph_nodes, smem);
-  GinetBwdArgs a{x, ldx, fi, graph_ptr, colptr, rowidx, w2a, w2b, h1s, a2s, dg, static_cast<float*>(workspace), status, num_graphs, rows_cap, 1};
+  const size_t base = fused_bwd_smem_bytes(fi, rows_cap);
+  DRK_REQUIRE(base <= kSmemBudget, DRK_EUNSUPPORTED, "ginet fused bwd: a %d-node graph needs %zu bytes of shared memory", max_graph_nodes, base);
+  const int idx_cap = fused_idx_cap(base, max_graph_edges);
+  const size_t smem = base + (size_t)idx_cap * 4;
+  GinetBwdArgs a{x, ldx, fi, graph_ptr, colptr, rowidx, w2a, w2b, h1s, a2s, dg, static_cast<float*>(workspace), status, num_graphs, rows_cap, 1, idx_cap};
   if (ldx % 4 == 0 && fi % 4 == 0 && aligned16(x)) a.x_vec = 4;
   else if (ldx % 2 == 0 && fi % 2 == 0 && aligned8(x)) a.x_vec = 2;
   cudaError_t e = cudaFuncSetAttribute(k_ginet_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

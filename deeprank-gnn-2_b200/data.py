@@ -176,7 +176,7 @@ class Batch(Data):
                 setattr(out, k, list(column))
         out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int64), torch.tensor(sizes, dtype=torch.int64))
         out.ptr = ptr
-        out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes)}
+        out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(d.num_edges for d in data_list)}
         return out
 
 

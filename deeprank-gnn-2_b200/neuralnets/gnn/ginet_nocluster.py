@@ -63,7 +63,7 @@ class GINet(nn.Module):
             biggest = max_graph_nodes(data, g) if fusable else 0
             if fusable and biggest <= ops.ginet_fused_max_nodes(fi):
                 # one CTA per graph, intermediates in shared memory (2 launches per train step)
-                x = ops.ginet_fused(data.x, self.conv1, self.conv1_ext, self.conv2, self.conv2_ext, g, biggest)
+                x = ops.ginet_fused(data.x, self.conv1, self.conv1_ext, self.conv2, self.conv2_ext, g, biggest, data.meta("max_graph_edges", 0) if hasattr(data, "meta") else 0)
             else:
                 x = ops.ginet_stack(data.x, self.conv1, self.conv1_ext, self.conv2, self.conv2_ext, g)
         else:

@@ -664,7 +664,7 @@ class GINetFusedFunction(torch.autograd.Function):
     the shared-memory budget (``ginet_fused_max_nodes``) and F <= 64."""
 
     @staticmethod
-    def forward(ctx, x, w1, w1e, w2, w2e, graph: GraphIndex, max_nodes: int, *dead):
+    def forward(ctx, x, w1, w1e, w2, w2e, graph: GraphIndex, max_nodes: int, max_edges: int, *dead):
         lib = _lib.load()
         x = _f32_cuda(x, "x")
         n, fi = x.shape
@@ -676,9 +676,9 @@ class GINetFusedFunction(torch.autograd.Function):
         g = torch.empty((graph.num_graphs, 64), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             rc = lib.drk_ginet_fused_fwd(_p(x), _ld(x), fi, _p(graph.graph_ptr), _p(graph.rowptr), _p(graph.colidx), _p(w1s), _p(w2c), _p(w2ec),
-                                         _p(h1), _p(a2), _p(g), graph.num_graphs, max_nodes, _p(graph.status), stream_ptr())
+                                         _p(h1), _p(a2), _p(g), graph.num_graphs, max_nodes, max_edges, _p(graph.status), stream_ptr())
         _lib.check(rc, "drk_ginet_fused_fwd")
-        ctx.graph, ctx.max_nodes, ctx.dead = graph, max_nodes, dead
+        ctx.graph, ctx.max_nodes, ctx.max_edges, ctx.dead = graph, max_nodes, max_edges, dead
         ctx.save_for_backward(x, w2c, w2ec, h1, a2)
         return g
 
@@ -697,14 +697,14 @@ class GINetFusedFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             ws = workspace(lib.drk_ginet_fused_bwd_workspace_bytes(), x.device)
             rc = lib.drk_ginet_fused_bwd(_p(x), _ld(x), fi, _p(graph.graph_ptr), _p(graph.colptr), _p(graph.rowidx), _p(w2c), _p(w2ec), _p(h1), _p(a2),
-                                         _p(dg), _p(dw1s), _p(dw2), _p(dw2e), graph.num_graphs, ctx.max_nodes, _p(graph.status), _p(ws), ws.numel(), stream_ptr())
+                                         _p(dg), _p(dw1s), _p(dw2), _p(dw2e), graph.num_graphs, ctx.max_nodes, ctx.max_edges, _p(graph.status), _p(ws), ws.numel(), stream_ptr())
         _lib.check(rc, "drk_ginet_fused_bwd")
-        dead = tuple(torch.zeros_like(t) if ctx.needs_input_grad[7 + i] else None for i, t in enumerate(ctx.dead))
-        return (None, dw1s[:16], dw1s[16:], dw2, dw2e, None, None) + dead
+        dead = tuple(torch.zeros_like(t) if ctx.needs_input_grad[8 + i] else None for i, t in enumerate(ctx.dead))
+        return (None, dw1s[:16], dw1s[16:], dw2, dw2e, None, None, None) + dead
 
 
-def ginet_fused(x, conv1, conv1_ext, conv2, conv2_ext, graph, max_nodes):
+def ginet_fused(x, conv1, conv1_ext, conv2, conv2_ext, graph, max_nodes, max_edges=0):
     dead = []
     for layer in (conv1, conv2, conv1_ext, conv2_ext):
         dead += [layer.fc_edge_attr.weight, layer.fc_attention.weight]
-    return GINetFusedFunction.apply(x, conv1.fc.weight, conv1_ext.fc.weight, conv2.fc.weight, conv2_ext.fc.weight, graph, max_nodes, *dead)
+    return GINetFusedFunction.apply(x, conv1.fc.weight, conv1_ext.fc.weight, conv2.fc.weight, conv2_ext.fc.weight, graph, max_nodes, max_edges, *dead)

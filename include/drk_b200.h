@@ -193,16 +193,19 @@ DRK_API int drk_cluster_offsets(int64_t* cluster, const int32_t* graph_ptr, cons
  *   backward: dW1s [32,F] (rows 0-15 conv1.fc.weight, 16-31 conv1_ext.fc.weight), dW2a, dW2b [32,16] from dg [B,64]
  * w1s is the row-stack of the two conv1 weights; h1s / a2s [N,32] are the activations saved between the two calls.
  * F <= 64; graphs of more than drk_ginet_fused_max_nodes(F) nodes -> DRK_EUNSUPPORTED (use the unfused kernels).
+ * max_graph_edges (<= 0: unknown) sizes the shared-memory staging of each graph's CSR slice; graphs with more edges stream
+ * their indices from global memory instead.
  * Edges must stay inside their graph (true for any collated batch); a violation sets DRK_STATUS_CROSS_GRAPH. */
 DRK_API int32_t drk_ginet_fused_max_nodes(int32_t num_node_features);
 DRK_API int drk_ginet_fused_fwd(const float* x, int64_t ldx, int32_t num_node_features, const int32_t* graph_ptr,
                         const int32_t* rowptr, const int32_t* colidx, const float* w1s, const float* w2a, const float* w2b,
-                        float* h1s, float* a2s, float* g, int32_t num_graphs, int32_t max_graph_nodes, int32_t* status, void* stream);
+                        float* h1s, float* a2s, float* g, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges,
+                        int32_t* status, void* stream);
 DRK_API size_t drk_ginet_fused_bwd_workspace_bytes(void);
 DRK_API int drk_ginet_fused_bwd(const float* x, int64_t ldx, int32_t num_node_features, const int32_t* graph_ptr,
                         const int32_t* colptr, const int32_t* rowidx, const float* w2a, const float* w2b,
                         const float* h1s, const float* a2s, const float* dg, float* dw1s, float* dw2a, float* dw2b,
-                        int32_t num_graphs, int32_t max_graph_nodes, int32_t* status,
+                        int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -82,8 +82,8 @@ def test_ginet_nocluster_train_step_vs_reference(case, fused):
     before = _lib.launch_count()
     _train_step_vs_golden(g, "ginet_nocluster", net)
     launched = _lib.launch_count() - before
-    # index build (6) + offsets (1) + [fused: fwd 1 + bwd 2 | stacked: 6 + 11]
-    assert launched == (10 if fused else 24), launched
+    # index build (5) + offsets (1) + [fused: fwd 1 + bwd 2 | stacked: 6 + 11]
+    assert launched == (9 if fused else 23), launched
 
 
 @pytest.mark.parametrize("case", ["toy_edgecases", "fixture_1ATN"])
