@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libdrk_b200.so")
@@ -23,6 +23,7 @@ STATUS_CROSS_GRAPH = 2
 STATUS_UNSORTED = 4
 ACT_NONE, ACT_RELU = 0, 1
 REDUCE_SUM, REDUCE_MEAN_CLAMP, REDUCE_MEAN_NAN = 0, 1, 2
+LOSS_MSE, LOSS_CROSS_ENTROPY = 0, 1
 
 _P = c_void_p
 _I32 = c_int32
@@ -50,6 +51,16 @@ SIGNATURES = {
     "drk_ginet_fused_fwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "drk_ginet_fused_bwd_workspace_bytes": (c_size_t, []),
     "drk_ginet_fused_bwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, c_size_t, _P]),
+    "drk_edge_ptr": (c_int32, [_P, _I64, _P, _I32, _P, _P]),
+    "drk_graph_index_blocked_supported": (c_int32, [_I32, _I32]),
+    "drk_graph_index_build_blocked": (c_int32, [_P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
+    "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),
+    "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _I32, _I32,   # x .. max_graph_edges
+                                 _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
+                                 _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
+                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients
+                                 _P, _P, _P, c_size_t, _P]),                                 # counter, status, workspace, stream
     "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),

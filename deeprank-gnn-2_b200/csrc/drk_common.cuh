@@ -86,6 +86,11 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src, b
   const int src_size = pred ? BYTES : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(gmem_src), "n"(BYTES), "r"(src_size) : "memory");
 }
+// 16-byte copy that bypasses L1 (data another phase of the same CTA wrote to global memory)
+__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

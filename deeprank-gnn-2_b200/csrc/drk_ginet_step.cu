@@ -1,0 +1,1150 @@
+// Whole GINet(no-cluster) step for a collated batch, ONE CTA per graph, everything between the raw batch tensors and the
+// per-graph gradient contributions in shared memory (reference: deeprank2/neuralnets/gnn/ginet_nocluster.py:37-111 for the
+// model, deeprank2/trainer.py:682-694 for the step, torch_geometric collate for the edge layout).
+//
+//   phase 0   graph index: the graph's slice of the int64 edge list -> destination-sorted CSR and source-sorted CSC of
+//             LOCAL 16-bit row ids in shared memory.  Stable (edges of a segment keep ascending edge id = the order in
+//             which the reference's CPU scatter_add_ / index_put_ add them), built without atomics:
+//             per-warp histograms over contiguous edge chunks -> (node, warp) scan -> ordered placement with match_any.
+//   forward   P = x [W1;W1e]^T -> H1 = relu(A P) -> A2 = A H1 -> Z2 = [A2a W2^T | A2b W2e^T], H2 = relu(Z2)
+//             G = mean_i H2[i]  (scatter_mean readout) -> h = dropout(relu(fc1 G)) -> pred = fc2 h -> loss term
+//   backward  dG -> dZ2 = (Z2 > 0) dG / n  (kept as a 64-bit row mask) ; dW2 = dG/n * (masked column sums of A2, gathered
+//             during the forward pass) ; dA2 = dZ2 W2 ; dZ1 = (A^T dA2) * (H1 > 0) ; Q = A^T dZ1 ; dW1 = Q^T x
+//
+// All gathers read a [n x 32] fp32 tile in shared memory (128 B rows, 8 lanes x float4 per row, 4 rows per warp
+// instruction): the four aggregations of a step run at the shared-memory rate of one row per clock per SM and HBM only
+// sees x, the edge list and ~10 KB of per-graph results.  Per-graph weight-gradient contributions go to global memory
+// indexed by GRAPH (not by CTA) and are summed in graph order by k_step_finalize, so results are bit-reproducible and
+// independent of the dynamic graph->CTA schedule.  No floating-point atomics anywhere.
+//
+// Graphs that do not fit (nodes, edges or features beyond the shared-memory plan) make the wrapper return
+// DRK_EUNSUPPORTED; the host then runs the layer kernels (same results, more launches).
+#include <algorithm>
+
+#include "drk_common.cuh"
+
+namespace drk {
+namespace gs {
+
+constexpr int kT = 512;  // threads per CTA
+constexpr int kNW = kT / 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kS1 = 32;   // stacked conv1 outputs (2 x 16)
+constexpr int kF1 = 16;   // conv1 outputs per branch = conv2 inputs per branch
+constexpr int kS2 = 64;   // stacked conv2 outputs (2 x 32)
+constexpr int kF2 = 32;
+constexpr int kHid = 128;  // fc1 outputs
+constexpr int kMaxOut = 8;
+constexpr size_t kSmemBudget = 227 * 1024 - 64;  // 64 B for the kernels' static shared variables
+
+__host__ __device__ inline int pad_kp(int fi) {  // smem row stride of the x tile: multiple of 4 with (kp/4) odd -> conflict-free float4 rows
+  int kp = (fi + 3) / 4 * 4;
+  if (((kp / 4) & 1) == 0) kp += 4;
+  return kp;
+}
+__host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
+
+// byte offsets of the shared-memory regions
+struct Layout {
+  int kp, t0, t1, x, idx, rinfo, cinfo, w1, w2, s, v, maskz, red, head, total;
+};
+__host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap) {
+  Layout L;
+  L.kp = pad_kp(fi);
+  int o = 0;
+  L.t0 = o; o += rows_cap * kS1 * 4;
+  L.t1 = o; o += rows_cap * kS1 * 4;
+  L.x = o; o += rows_cap * L.kp * 4;
+  L.idx = o; o += align16(ent_cap * 2);
+  L.rinfo = o; o += align16(rows_cap * 4);
+  L.cinfo = o; o += align16(rows_cap * 4);
+  L.w1 = o; o += kS1 * L.kp * 4;
+  L.w2 = o; o += 2 * kF2 * kF1 * 4;
+  L.s = o; o += kS2 * kF1 * 4;
+  L.v = o; o += kS2 * kF1 * 4;
+  L.maskz = o; o += align16(rows_cap * 8);
+  L.red = o; o += 8 * kS2 * 4;
+  L.head = o; o += 704 * 4;
+  L.total = o;
+  return L;
+}
+// head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[32] ...
+constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528;
+
+struct StepArgs {
+  const float* x; int64_t ldx; int32_t fi;
+  const int64_t* erow; const int64_t* ecol;
+  const int32_t* graph_ptr; const int32_t* edge_ptr; const int32_t* order; int32_t* counter; int32_t num_graphs;
+  const float* w1a; const float* w1b; const float* w2a; const float* w2b;
+  const float* fc1_w; const float* fc1_b; const float* fc2_w; const float* fc2_b; int32_t out_dim;
+  int32_t loss_kind; const float* y; const int64_t* y_cls; float dloss_scale;
+  float drop_p; unsigned long long seed; const int64_t* rng_step;
+  float* pred; float* loss_terms; float* part; int32_t part_stride;
+  float* gvec; float* hvec; float* dhvec; float* dpvec;
+  uint16_t* csc_spill; int32_t* status;
+  int32_t rows_cap, e_cap, ent_cap, mode_b, x_vec;
+};
+
+// ---------------------------------------------------------------------------------------------- small helpers
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// exclusive scan of one value per thread over the CTA; `scratch` has kNW + 1 words; returns the exclusive prefix, `total` = CTA sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t val, uint32_t* scratch, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < kNW ? scratch[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < kNW) scratch[lane] = winc - w;
+    if (lane == kNW - 1) scratch[kNW] = winc;
+  }
+  __syncthreads();
+  total = scratch[kNW];
+  const uint32_t res = scratch[warp] + inc - val;
+  __syncthreads();
+  return res;
+}
+
+// Philox4x32-10 (counter-based RNG): dropout masks are a pure function of (seed, step, graph, unit)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// copy rows [node0, node0+n) of a row-major global matrix (ld elements, width fi) into smem with row stride kp,
+// zero-filling the padding columns; asynchronous (cp.async), the caller commits / waits.
+__device__ __forceinline__ void stage_rows(float* __restrict__ s_dst, const float* __restrict__ src, int64_t ld, int fi, int kp, int node0,
+                                           int n, int vec) {
+  const int nv = fi / vec;
+  for (int e = threadIdx.x; e < n * nv; e += kT) {
+    const int r = e / nv;
+    const int v = e - r * nv;
+    const float* s = src + (int64_t)(node0 + r) * ld + v * vec;
+    float* d = s_dst + r * kp + v * vec;
+    if (vec == 4) cp_async<16>(d, s, true);
+    else if (vec == 2) cp_async<8>(d, s, true);
+    else cp_async<4>(d, s, true);
+  }
+  const int pv = kp - nv * vec;
+  for (int e = threadIdx.x; e < n * pv; e += kT) {
+    const int r = e / pv;
+    s_dst[r * kp + nv * vec + (e - r * pv)] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- graph index in shared memory
+// Segment r of the CSR occupies entries [4*info[r].x, 4*info[r].x + info[r].y); an entry is 8 * (local source row), i.e. the
+// byte offset of the gathered 128-byte tile row divided by 16.  Same for the CSC (keyed by source, entries = destinations).
+struct IndexPlan {
+  uint32_t* stash;    // [e_cap] packed (r | c << 16) per edge, 0xffffffff = edge leaves the graph
+  uint16_t* cnt_r;    // [kNW][cstride] per-warp-chunk histograms, then per-warp running offsets
+  uint16_t* cnt_c;
+  int cstride;
+  ushort2* rinfo;
+  ushort2* cinfo;
+  uint16_t* csr;
+  uint16_t* csc;
+  uint32_t* scan;  // kNW + 1 words
+};
+
+// returns the number of CSC entries (padded), or -1 (uniformly) when the graph does not fit / is malformed
+template <bool WANT_CSC>
+__device__ __noinline__ int build_index(const IndexPlan& p, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
+                                           int node0, int n, int32_t* status) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  // zero the histograms
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(p.cnt_r);
+    const int words = kNW * p.cstride / 2;
+    for (int i = threadIdx.x; i < words; i += kT) z[i] = 0u;
+    if (WANT_CSC) {
+      z = reinterpret_cast<uint32_t*>(p.cnt_c);
+      for (int i = threadIdx.x; i < words; i += kT) z[i] = 0u;
+    }
+  }
+  const int chunk = ((ne + kNW - 1) / kNW + 31) & ~31;
+  const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
+  // pass 1: stream the warp's chunk of the edge list (independent 8-byte loads, 4 edges in flight per lane)
+  bool bad = false;
+  for (int i0 = wb; i0 < we; i0 += 128) {
+    long long rr[4], cc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      rr[u] = i < we ? ld_stream_i64(erow + e0 + i) : 0;
+      cc[u] = i < we ? ld_stream_i64(ecol + e0 + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      if (i < we) {
+        const unsigned long long r = (unsigned long long)(rr[u] - node0), c = (unsigned long long)(cc[u] - node0);
+        const bool ok = r < (unsigned long long)n && c < (unsigned long long)n;
+        bad |= !ok;
+        p.stash[i] = ok ? ((unsigned)r | ((unsigned)c << 16)) : 0xffffffffu;
+      }
+    }
+  }
+  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
+  __syncthreads();  // histograms are zero, the stash is complete
+  // pass 2: per-warp histograms of destinations / sources (warp-private rows: plain read-modify-write by one leader lane)
+  {
+    uint16_t* my_r = p.cnt_r + warp * p.cstride;
+    uint16_t* my_c = p.cnt_c + warp * p.cstride;
+    for (int i0 = wb; i0 < we; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pk = i < we ? p.stash[i] : 0xffffffffu;
+      const bool ok = pk != 0xffffffffu;
+      const unsigned r = pk & 0xffffu, c = pk >> 16;
+      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
+      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(my_r[r] + __popc(mr));
+      if (WANT_CSC) {
+        const unsigned mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
+        if (ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(my_c[c] + __popc(mc));
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // pass 3: (node, warp)-ordered exclusive scan: running offset of every warp chunk inside its segment, padded segment starts
+  uint32_t carry = 0;
+  for (int vb = 0; vb < n; vb += kT) {
+    const int v = vb + threadIdx.x;
+    uint32_t dr = 0, dc = 0;
+    if (v < n) {
+#pragma unroll
+      for (int w = 0; w < kNW; ++w) {
+        const uint32_t t = p.cnt_r[w * p.cstride + v];
+        p.cnt_r[w * p.cstride + v] = (uint16_t)dr;
+        dr += t;
+      }
+      if (WANT_CSC) {
+#pragma unroll
+        for (int w = 0; w < kNW; ++w) {
+          const uint32_t t = p.cnt_c[w * p.cstride + v];
+          p.cnt_c[w * p.cstride + v] = (uint16_t)dc;
+          dc += t;
+        }
+      }
+    }
+    const uint32_t packed = ((dr + 3u) & ~3u) | (((dc + 3u) & ~3u) << 16);
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(packed, p.scan, total) + carry;
+    if (v < n) {
+      p.rinfo[v] = make_ushort2((unsigned short)((ex & 0xffffu) >> 2), (unsigned short)dr);
+      if (WANT_CSC) p.cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
+    }
+    carry += total;
+  }
+  __syncthreads();
+  // pass 4: ordered placement.  Lanes hold consecutive edges; equal keys inside the 32-edge group are ranked by lane.
+  {
+    uint16_t* my_r = p.cnt_r + warp * p.cstride;
+    uint16_t* my_c = p.cnt_c + warp * p.cstride;
+    for (int i0 = wb; i0 < we; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pk = i < we ? p.stash[i] : 0xffffffffu;
+      const bool ok = pk != 0xffffffffu;
+      const unsigned r = pk & 0xffffu, c = pk >> 16;
+      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
+      unsigned mc = 0;
+      if (WANT_CSC) mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
+      int base_r = 0, base_c = 0;
+      if (ok) {
+        base_r = my_r[r];
+        p.csr[4 * p.rinfo[r].x + base_r + __popc(mr & lt)] = (uint16_t)(c * 8u);
+        if (WANT_CSC) {
+          base_c = my_c[c];
+          p.csc[4 * p.cinfo[c].x + base_c + __popc(mc & lt)] = (uint16_t)(r * 8u);
+        }
+      }
+      __syncwarp();
+      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(base_r + __popc(mr));
+      if (WANT_CSC && ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  return (int)(carry >> 16);
+}
+
+// ---------------------------------------------------------------------------------------------- aggregation over a smem tile
+// dst[i] = epi( sum_{s in segment i} src[entry s] ), tiles are [rows][32] floats.  8 lanes per row (float4 each), 4 rows per warp,
+// warp-uniform trip count, entries of a segment in CSR order (= ascending edge id).
+// MODE 0: relu ; MODE 1: none ; MODE 2: in place, dst = sum * (dst > 0)
+template <int MODE>
+__device__ __noinline__ void aggregate(const float* __restrict__ s_src, float* s_dst, const ushort2* __restrict__ info,
+                                          const uint16_t* __restrict__ idx, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, sl = lane & 7;
+  const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
+  for (int rw = warp * 4; rw < n; rw += kNW * 4) {
+    const int r = rw + sub;
+    const bool row_ok = r < n;
+    int len = 0;
+    const uint16_t* seg = idx;
+    if (row_ok) {
+      const ushort2 inf = info[r];
+      len = inf.y;
+      seg = idx + 4 * (int)inf.x;
+    }
+    int max_len = len;
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 16));
+    max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 8));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int off = 0; off < max_len; off += 8) {
+      const int rem = len - off;
+      uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
+      if (rem > 0) pa = *reinterpret_cast<const uint2*>(seg + off);
+      if (rem > 4) pb = *reinterpret_cast<const uint2*>(seg + off + 4);
+      const unsigned ent[8] = {pa.x & 0xffffu, pa.x >> 16, pa.y & 0xffffu, pa.y >> 16, pb.x & 0xffffu, pb.x >> 16, pb.y & 0xffffu, pb.y >> 16};
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < rem) v[j] = *reinterpret_cast<const float4*>(lane_base + (ent[j] << 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < rem) {
+          acc.x += v[j].x;
+          acc.y += v[j].y;
+          acc.z += v[j].z;
+          acc.w += v[j].w;
+        }
+    }
+    if (!row_ok) continue;
+    float4* out = reinterpret_cast<float4*>(s_dst + r * kS1 + sl * 4);
+    if (MODE == 0) {
+      acc.x = acc.x < 0.f ? 0.f : acc.x;
+      acc.y = acc.y < 0.f ? 0.f : acc.y;
+      acc.z = acc.z < 0.f ? 0.f : acc.z;
+      acc.w = acc.w < 0.f ? 0.f : acc.w;
+    } else if (MODE == 2) {
+      const float4 m = *out;
+      acc.x = m.x <= 0.f ? 0.f : acc.x;
+      acc.y = m.y <= 0.f ? 0.f : acc.y;
+      acc.z = m.z <= 0.f ? 0.f : acc.z;
+      acc.w = m.w <= 0.f ? 0.f : acc.w;
+    }
+    *out = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- dense phases
+// P = x W1s^T -> tile.  warp tile = 32 rows x 16 outputs (one branch), lane = 4 rows (rg + 8j) x 4 outputs (4cg..4cg+3)
+__device__ __noinline__ void project_x(const float* __restrict__ sX, const float* __restrict__ sW1, float* __restrict__ sP, int n, int rows_cap, int kp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane & 3, rg = lane >> 2;
+  const int n_tiles = 2 * ((n + 31) / 32);
+  for (int tl = warp; tl < n_tiles; tl += kNW) {
+    const int h = tl & 1, base = (tl >> 1) * 32;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[j][t] = 0.f;
+    const float* xr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xr[j] = sX + min(base + rg + 8 * j, rows_cap - 1) * kp;  // rows beyond n: results are not stored
+    const float* wb = sW1 + (h * 16 + cg) * 4;
+    for (int k4 = 0; k4 < kp; k4 += 4) {
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(xr[j] + k4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) bv[t] = *reinterpret_cast<const float4*>(wb + k4 * kS1 + 16 * t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float s = acc[j][t];
+          s = fmaf(av[j].x, bv[t].x, s);
+          s = fmaf(av[j].y, bv[t].y, s);
+          s = fmaf(av[j].z, bv[t].z, s);
+          s = fmaf(av[j].w, bv[t].w, s);
+          acc[j][t] = s;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = base + rg + 8 * j;
+      if (r < n) *reinterpret_cast<float4*>(sP + r * kS1 + h * 16 + 4 * cg) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    }
+  }
+}
+
+// Z2 = A2 W2^T per branch: column sums of relu(Z2) (readout) -> sRed[8][64]; when TRAIN also the sign mask of Z2 (one 32-bit word
+// per row and branch) and the masked column sums of A2 (dW2 = dG/n * those), left as 8 row-lane partials [rl][c][k] in the A2 tile.
+template <bool TRAIN>
+__device__ __noinline__ void conv2_readout(float* sA2, const float* __restrict__ sW2, uint32_t* __restrict__ sMaskZ, float* __restrict__ sRed, int n) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c = tid & 63, rl = tid >> 6, br = c >> 5;
+  float w[kF1], s[kF1];
+#pragma unroll
+  for (int k = 0; k < kF1; ++k) {
+    w[k] = sW2[(br * kF2 + (c & 31)) * kF1 + k];
+    s[k] = 0.f;
+  }
+  float colsum = 0.f;
+  for (int r = rl; r < n; r += 8) {
+    const float* arow = sA2 + r * kS1 + br * kF1;
+    float av[kF1];
+#pragma unroll
+    for (int k4 = 0; k4 < kF1; k4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(arow + k4);
+      av[k4] = v.x; av[k4 + 1] = v.y; av[k4 + 2] = v.z; av[k4 + 3] = v.w;
+    }
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kF1; k += 2) {
+      z0 = fmaf(av[k], w[k], z0);
+      z1 = fmaf(av[k + 1], w[k + 1], z1);
+    }
+    const float z = z0 + z1;
+    const bool pos = z > 0.f;
+    if (pos) colsum += z;
+    if (TRAIN) {
+#pragma unroll
+      for (int k = 0; k < kF1; ++k)
+        if (pos) s[k] += av[k];
+      const unsigned word = __ballot_sync(kFull, pos);
+      if (lane == 0) sMaskZ[r * 2 + br] = word;
+    }
+  }
+  sRed[rl * kS2 + c] = colsum;
+  if (TRAIN) {
+    __syncthreads();  // every warp is done reading A2: reuse the tile as the 8-way reduction scratch
+#pragma unroll
+    for (int k4 = 0; k4 < kF1; k4 += 4)
+      *reinterpret_cast<float4*>(sA2 + ((rl * kS2 + c) * kF1 + k4)) = make_float4(s[k4], s[k4 + 1], s[k4 + 2], s[k4 + 3]);
+  }
+}
+
+// dA2[r, br*16 + k] = sum_{c in branch, Z2[r,c] > 0} V[c, k] -> tile.  lane -> row, warp -> (branch, 8 outputs)
+__device__ __noinline__ void conv2_backward_input(const float* __restrict__ sV, const uint32_t* __restrict__ sMaskZ, float* __restrict__ sOut, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int combo = warp & 3, br = combo >> 1, kh = combo & 1;
+  const float* vb = sV + br * kF2 * kF1 + kh * 8;
+  for (int r = (warp >> 2) * 32 + lane; r < n; r += 128) {
+    const unsigned m = sMaskZ[r * 2 + br];
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kF2; ++c) {
+      const float4 v0 = *reinterpret_cast<const float4*>(vb + c * kF1);
+      const float4 v1 = *reinterpret_cast<const float4*>(vb + c * kF1 + 4);
+      if (m & (1u << c)) {
+        o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
+        o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
+      }
+    }
+    float* out = sOut + r * kS1 + br * kF1 + kh * 8;
+    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// dW1s[m, k] = sum_r Q[r, m] x[r, k]: lane -> (mg: 4 outputs m, kgl: 4 features k), warp -> (k block of 16, row split wn);
+// the four row-split partials go to sScr[wn][m][kp]
+__device__ __noinline__ void conv1_weight_grad(const float* __restrict__ sQ, const float* __restrict__ sX, float* __restrict__ sScr, int n, int kp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wk = warp & 3, wn = warp >> 2;
+  const int mg = lane & 7, kgl = lane >> 3;
+  const int k0 = wk * 16 + kgl * 4;
+  if (k0 >= kp) return;  // kp is a multiple of 4: a float4 of features is all-in or all-out
+  float dw[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dw[i][j] = 0.f;
+  const float* qp = sQ + mg * 4;
+  const float* xp = sX + k0;
+  for (int r = wn; r < n; r += 4) {
+    const float4 qa = *reinterpret_cast<const float4*>(qp + r * kS1);
+    const float4 xb = *reinterpret_cast<const float4*>(xp + r * kp);
+    const float qv[4] = {qa.x, qa.y, qa.z, qa.w};
+    const float xv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dw[i][j] = fmaf(qv[i], xv[j], dw[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(sScr + (wn * kS1 + mg * 4 + i) * kp + k0) = make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]);
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+template <bool TRAIN>
+__global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_next;
+  const Layout L = make_layout(a.fi, a.rows_cap, a.ent_cap);
+  const int kp = L.kp;
+  float* sT0 = reinterpret_cast<float*>(smem + L.t0);
+  float* sT1 = reinterpret_cast<float*>(smem + L.t1);
+  float* sX = reinterpret_cast<float*>(smem + L.x);
+  uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.idx);
+  ushort2* sRinfo = reinterpret_cast<ushort2*>(smem + L.rinfo);
+  ushort2* sCinfo = reinterpret_cast<ushort2*>(smem + L.cinfo);
+  float* sW1 = reinterpret_cast<float*>(smem + L.w1);
+  float* sW2 = reinterpret_cast<float*>(smem + L.w2);
+  float* sS = reinterpret_cast<float*>(smem + L.s);
+  float* sV = reinterpret_cast<float*>(smem + L.v);
+  uint32_t* sMaskZ = reinterpret_cast<uint32_t*>(smem + L.maskz);
+  float* sRed = reinterpret_cast<float*>(smem + L.red);
+  float* sHead = reinterpret_cast<float*>(smem + L.head);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  IndexPlan plan;
+  plan.cstride = a.rows_cap;
+  if (!a.mode_b) {  // low degree: stash in tile 1, histograms + CSC staging in tile 0, x prefetched under the index build
+    plan.stash = reinterpret_cast<uint32_t*>(sT1);
+    plan.cnt_r = reinterpret_cast<uint16_t*>(sT0);
+    plan.cnt_c = plan.cnt_r + kNW * a.rows_cap;
+    plan.csc = plan.cnt_c + kNW * a.rows_cap;
+  } else {  // high degree: stash in the x region (x is loaded afterwards), CSC staging in tile 1
+    plan.stash = reinterpret_cast<uint32_t*>(sX);
+    plan.cnt_r = reinterpret_cast<uint16_t*>(sT0);
+    plan.cnt_c = plan.cnt_r + kNW * a.rows_cap;
+    plan.csc = reinterpret_cast<uint16_t*>(sT1);
+  }
+  plan.rinfo = sRinfo;
+  plan.cinfo = sCinfo;
+  plan.csr = sIdx;
+  plan.scan = reinterpret_cast<uint32_t*>(sHead + kHScan);
+
+  // ---- weights once per CTA.  W1 as [k/4][pos][4]: logical output m = 16*h + 4*cg + t sits at pos = 16*h + cg + 4*t, so the four
+  // lanes cg = 0..3 of a quad read four consecutive 16-byte chunks (conflict-free)
+  for (int e = tid; e < kS1 * kp; e += kT) {
+    const int m = e / kp, k = e - m * kp;
+    const int pos = (m & 16) + ((m & 15) >> 2) + 4 * (m & 3);
+    const float* w = m < kF1 ? a.w1a + (size_t)m * a.fi : a.w1b + (size_t)(m - kF1) * a.fi;
+    sW1[((k >> 2) * kS1 + pos) * 4 + (k & 3)] = k < a.fi ? __ldg(w + k) : 0.f;
+  }
+  for (int e = tid; e < kF2 * kF1; e += kT) {
+    sW2[e] = __ldg(a.w2a + e);
+    sW2[kF2 * kF1 + e] = __ldg(a.w2b + e);
+  }
+
+  int g_slot = blockIdx.x;
+  while (g_slot < a.num_graphs) {
+    const int g = a.order != nullptr ? __ldg(a.order + g_slot) : g_slot;
+    const int node0 = __ldg(a.graph_ptr + g);
+    const int n = __ldg(a.graph_ptr + g + 1) - node0;
+    const int e0 = __ldg(a.edge_ptr + g);
+    const int ne = __ldg(a.edge_ptr + g + 1) - e0;
+    __syncthreads();  // previous graph is finished with every region; weights are visible
+    if (tid == 0) s_next = a.counter != nullptr ? atomicAdd(a.counter, 1) + (int)gridDim.x : g_slot + (int)gridDim.x;
+    const bool fits = n <= a.rows_cap && ne <= a.e_cap && ne + 3 * n <= a.ent_cap && n >= 0 && ne >= 0;
+    if (!fits) {
+      if (tid == 0 && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+      __syncthreads();
+      g_slot = s_next;
+      continue;
+    }
+    // ---- x rows (async) and the graph index
+    if (!a.mode_b) {
+      stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
+      cp_async_commit();
+    }
+    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status);
+    uint16_t* spill = TRAIN ? a.csc_spill + (size_t)blockIdx.x * a.ent_cap : nullptr;
+    if (TRAIN) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
+      const uint4* src = reinterpret_cast<const uint4*>(plan.csc);
+      uint4* dst = reinterpret_cast<uint4*>(spill);
+      for (int i = tid; i < (csc_entries + 7) / 8; i += kT) dst[i] = src[i];
+    }
+    if (a.mode_b) {
+      __syncthreads();  // stash (x region) and CSC staging are consumed
+      stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    project_x(sX, sW1, sT0, n, a.rows_cap, kp);
+    __syncthreads();
+    // ---- H1 = relu(A P) -> tile 1 ; A2 = A H1 -> tile 0
+    aggregate<0>(sT0, sT1, sRinfo, sIdx, n);
+    __syncthreads();
+    aggregate<1>(sT1, sT0, sRinfo, sIdx, n);
+    __syncthreads();
+    if (TRAIN) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
+      const int chunks = (csc_entries + 7) / 8;
+      for (int i = tid; i < chunks; i += kT) cp_async_cg16(sIdx + i * 8, spill + i * 8);  // L2 only: this CTA wrote it moments ago
+      cp_async_commit();
+    }
+    conv2_readout<TRAIN>(sT0, sW2, sMaskZ, sRed, n);
+    __syncthreads();
+    float* hG = sHead + kHG;
+    float* hDG = sHead + kHDG;
+    float* hH = sHead + kHH;
+    float* hHM = sHead + kHHM;
+    float* hDH = sHead + kHDH;
+    float* hPred = sHead + kHPred;
+    float* hDPred = sHead + kHDPred;
+    const float cnt = fmaxf((float)n, 1.f);  // scatter_mean: count clamped to >= 1
+    if (tid < kS2) {
+      float s = 0.f;
+#pragma unroll
+      for (int rl = 0; rl < 8; ++rl) s += sRed[rl * kS2 + tid];
+      const float gm = s / cnt;
+      hG[tid] = gm;
+      if (a.gvec != nullptr) a.gvec[(size_t)g * kS2 + tid] = gm;
+    }
+    if (TRAIN) {
+      for (int e = tid; e < kS2 * kF1; e += kT) {
+        float s = 0.f;
+#pragma unroll
+        for (int rl = 0; rl < 8; ++rl) s += sT0[rl * kS2 * kF1 + e];
+        sS[e] = s;
+      }
+    }
+    __syncthreads();
+    // ---- head: h = dropout(relu(fc1 G + b1)); pred = fc2 h + b2
+    {
+      const int j = tid >> 2, q = tid & 3;
+      const float4* wrow = reinterpret_cast<const float4*>(a.fc1_w + (size_t)j * kS2 + q * 16);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 wv = __ldg(wrow + i);
+        const float4 gv = *reinterpret_cast<const float4*>(hG + q * 16 + i * 4);
+        s = fmaf(wv.x, gv.x, s);
+        s = fmaf(wv.y, gv.y, s);
+        s = fmaf(wv.z, gv.z, s);
+        s = fmaf(wv.w, gv.w, s);
+      }
+      s += __shfl_xor_sync(kFull, s, 1);
+      s += __shfl_xor_sync(kFull, s, 2);
+      if (q == 0) {
+        const float pre = s + __ldg(a.fc1_b + j);
+        float scale = 1.f;
+        if (TRAIN && a.drop_p > 0.f) {
+          const unsigned long long step = a.rng_step != nullptr ? (unsigned long long)*a.rng_step : 0ull;
+          const uint4 rnd = philox4x32(make_uint4((unsigned)g, (unsigned)(j >> 2), (unsigned)step, (unsigned)(step >> 32)),
+                                       make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+          const unsigned bits = (j & 3) == 0 ? rnd.x : (j & 3) == 1 ? rnd.y : (j & 3) == 2 ? rnd.z : rnd.w;
+          const float u = (float)(bits >> 8) * (1.f / 16777216.f);  // uniform [0, 1)
+          scale = u < a.drop_p ? 0.f : 1.f / (1.f - a.drop_p);
+        }
+        const float hv = pre > 0.f ? pre * scale : 0.f;
+        hH[j] = hv;
+        hHM[j] = pre > 0.f ? scale : 0.f;  // d h / d pre
+        if (TRAIN) a.hvec[(size_t)g * kHid + j] = hv;
+      }
+    }
+    __syncthreads();
+    if (warp < a.out_dim) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(a.fc2_w + (size_t)warp * kHid) + lane);
+      const float4 hv = *reinterpret_cast<const float4*>(hH + lane * 4);
+      float s = fmaf(wv.x, hv.x, fmaf(wv.y, hv.y, fmaf(wv.z, hv.z, wv.w * hv.w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+      if (lane == 0) {
+        const float pv = s + __ldg(a.fc2_b + warp);
+        hPred[warp] = pv;
+        a.pred[(size_t)g * a.out_dim + warp] = pv;
+      }
+    }
+    if (!TRAIN) {
+      __syncthreads();
+      g_slot = s_next;
+      continue;
+    }
+    __syncthreads();
+    // ---- loss term and d loss / d pred (thread 0: out_dim <= 8 values)
+    if (tid == 0) {
+      float term = 0.f;
+      if (a.loss_kind == DRK_LOSS_MSE) {  // mean over all B*out elements: d/dpred = 2 (pred - y) * dloss_scale
+        for (int o = 0; o < a.out_dim; ++o) {
+          const float d = hPred[o] - __ldg(a.y + (size_t)g * a.out_dim + o);
+          term += d * d;
+          hDPred[o] = 2.f * d * a.dloss_scale;
+        }
+      } else {  // cross entropy over the out_dim logits, mean over graphs
+        const int t = (int)__ldg(a.y_cls + g);
+        float m = hPred[0];
+        for (int o = 1; o < a.out_dim; ++o) m = fmaxf(m, hPred[o]);
+        float se = 0.f;
+        for (int o = 0; o < a.out_dim; ++o) se += expf(hPred[o] - m);
+        const float lse = m + logf(se);
+        const bool t_ok = t >= 0 && t < a.out_dim;
+        if (!t_ok && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+        term = t_ok ? lse - hPred[t] : 0.f;
+        for (int o = 0; o < a.out_dim; ++o) hDPred[o] = t_ok ? (expf(hPred[o] - lse) - (o == t ? 1.f : 0.f)) * a.dloss_scale : 0.f;
+      }
+      a.loss_terms[g] = term;
+      for (int o = 0; o < a.out_dim; ++o) a.dpvec[(size_t)g * a.out_dim + o] = hDPred[o];
+    }
+    __syncthreads();
+    // ---- d pre-activation of fc1
+    if (tid < kHid) {
+      float s = 0.f;
+      for (int o = 0; o < a.out_dim; ++o) s = fmaf(hDPred[o], __ldg(a.fc2_w + (size_t)o * kHid + tid), s);
+      s *= hHM[tid];
+      hDH[tid] = s;
+      a.dhvec[(size_t)g * kHid + tid] = s;
+    }
+    __syncthreads();
+    // ---- dG = fc1_w^T dh: thread -> (column c, 16 rows j of fc1_w), coalesced rows
+    {
+      const int c = tid & 63, jg = tid >> 6;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = jg * 16 + i;
+        s = fmaf(hDH[j], __ldg(a.fc1_w + (size_t)j * kS2 + c), s);
+      }
+      sRed[jg * kS2 + c] = s;
+    }
+    __syncthreads();
+    if (tid < kS2) {
+      float s = 0.f;
+#pragma unroll
+      for (int jg = 0; jg < 8; ++jg) s += sRed[jg * kS2 + tid];
+      hDG[tid] = s / cnt;  // d mean / d row = dG / max(n, 1) (true division)
+    }
+    __syncthreads();
+    // ---- dW2 contribution of this graph and V = diag(dG/n) W2
+    float* part = a.part + (size_t)g * a.part_stride;
+    for (int e = tid; e < kS2 * kF1; e += kT) {
+      const int c = e / kF1;
+      const float dgc = hDG[c];
+      part[kS1 * kp + e] = dgc * sS[e];
+      sV[e] = dgc * sW2[e];
+    }
+    __syncthreads();
+    conv2_backward_input(sV, sMaskZ, sT0, n);
+    cp_async_wait<0>();  // the CSC is back in the index region
+    __syncthreads();
+    // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
+    aggregate<2>(sT0, sT1, sCinfo, sIdx, n);
+    __syncthreads();
+    aggregate<1>(sT1, sT0, sCinfo, sIdx, n);
+    __syncthreads();
+    conv1_weight_grad(sT0, sX, sT1, n, kp);
+    __syncthreads();
+    for (int e = tid; e < kS1 * kp; e += kT) {
+      float s = 0.f;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) s += sT1[w4 * kS1 * kp + e];
+      part[e] = s;
+    }
+    __syncthreads();
+    g_slot = s_next;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+// Sums the per-graph contributions in graph order (bit-reproducible), forms the head's weight gradients from the per-graph
+// vectors, reduces the loss, advances the dropout step counter and re-arms the work counter.
+struct FinalArgs {
+  const float* part; int32_t part_stride; const float* gvec; const float* hvec; const float* dhvec; const float* dpvec; const float* loss_terms;
+  int32_t num_graphs, fi, kp, out_dim;
+  float* dw1a; float* dw1b; float* dw2a; float* dw2b; float* dfc1_w; float* dfc1_b; float* dfc2_w; float* dfc2_b; float* loss;
+  float loss_scale; int64_t* rng_step; int32_t* counter;
+};
+
+__global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int B = a.num_graphs;
+  const int n1 = kS1 * a.fi, n2 = kS2 * kF1, n3 = kHid * kS2, n4 = kHid, n5 = a.out_dim * kHid, n6 = a.out_dim;
+  if (t == 0) {
+    if (a.rng_step != nullptr) *a.rng_step += 1;
+    if (a.counter != nullptr) *a.counter = 0;
+  }
+  int e = t;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float* dst = nullptr;
+  if (e < n1) {
+    const int m = e / a.fi, k = e - m * a.fi;
+    const float* p = a.part + m * a.kp + k;
+    for (int g = 0; g < B; ++g) acc[g & 3] += p[(size_t)g * a.part_stride];
+    dst = m < kF1 ? a.dw1a + e : a.dw1b + (e - kF1 * a.fi);
+  } else if ((e -= n1) < n2) {
+    const float* p = a.part + kS1 * a.kp + e;
+    for (int g = 0; g < B; ++g) acc[g & 3] += p[(size_t)g * a.part_stride];
+    dst = e < kF2 * kF1 ? a.dw2a + e : a.dw2b + (e - kF2 * kF1);
+  } else if ((e -= n2) < n3) {
+    const int j = e / kS2, c = e - j * kS2;
+    for (int g = 0; g < B; ++g) acc[g & 3] = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc[g & 3]);
+    dst = a.dfc1_w + e;
+  } else if ((e -= n3) < n4) {
+    for (int g = 0; g < B; ++g) acc[g & 3] += a.dhvec[(size_t)g * kHid + e];
+    dst = a.dfc1_b + e;
+  } else if ((e -= n4) < n5) {
+    const int o = e / kHid, j = e - o * kHid;
+    for (int g = 0; g < B; ++g) acc[g & 3] = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc[g & 3]);
+    dst = a.dfc2_w + e;
+  } else if ((e -= n5) < n6) {
+    for (int g = 0; g < B; ++g) acc[g & 3] += a.dpvec[(size_t)g * a.out_dim + e];
+    dst = a.dfc2_b + e;
+  } else if ((e -= n6) == 0) {
+    for (int g = 0; g < B; ++g) acc[g & 3] += a.loss_terms[g];
+    acc[0] *= a.loss_scale; acc[1] *= a.loss_scale; acc[2] *= a.loss_scale; acc[3] *= a.loss_scale;
+    dst = a.loss;
+  }
+  if (dst != nullptr) *dst = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// ---------------------------------------------------------------------------------------------- standalone per-graph index build
+// The same shared-memory index builder, written out as the batch's global CSR / CSC (int32, unpadded) -- the fast replacement of
+// drk_graph_index_build for collated batches (edges of a graph contiguous), and the hook the parity tests use to check the
+// in-kernel index bit for bit.
+struct BlockedIndexArgs {
+  const int64_t* erow; const int64_t* ecol; const int32_t* graph_ptr; const int32_t* edge_ptr; int32_t num_graphs;
+  int32_t* rowptr; int32_t* colidx; int32_t* perm; int32_t* colptr; int32_t* rowidx; int32_t* permT; int32_t* status;
+  int32_t rows_cap, e_cap, num_nodes; int64_t num_edges;
+};
+
+__global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // regions: stash [e_cap] u32 | cnt_r, cnt_c [kNW][rows_cap] u16 | degrees/starts [rows_cap] u32 x2 | scan
+  uint32_t* stash = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* cnt_r = reinterpret_cast<uint16_t*>(stash + a.e_cap);
+  uint16_t* cnt_c = cnt_r + kNW * a.rows_cap;
+  uint32_t* start_r = reinterpret_cast<uint32_t*>(cnt_c + kNW * a.rows_cap);
+  uint32_t* start_c = start_r + a.rows_cap;
+  uint32_t* scan = start_c + a.rows_cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = lanemask_lt();
+  const bool want_csc = a.colptr != nullptr;
+  for (int g = blockIdx.x; g < a.num_graphs; g += gridDim.x) {
+    const int node0 = __ldg(a.graph_ptr + g);
+    const int n = __ldg(a.graph_ptr + g + 1) - node0;
+    const int e0 = __ldg(a.edge_ptr + g);
+    const int ne = __ldg(a.edge_ptr + g + 1) - e0;
+    __syncthreads();
+    if (n > a.rows_cap || ne > a.e_cap || n < 0 || ne < 0) {
+      if (tid == 0) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+      continue;
+    }
+    {
+      uint32_t* z = reinterpret_cast<uint32_t*>(cnt_r);
+      for (int i = tid; i < kNW * a.rows_cap; i += kT) z[i] = 0u;  // both histograms (2 x kNW*rows_cap u16)
+    }
+    const int chunk = ((ne + kNW - 1) / kNW + 31) & ~31;
+    const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
+    bool bad = false;
+    for (int i0 = wb; i0 < we; i0 += 128) {
+      long long rr[4], cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        rr[u] = i < we ? ld_stream_i64(a.erow + e0 + i) : 0;
+        cc[u] = i < we ? ld_stream_i64(a.ecol + e0 + i) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i < we) {
+          const unsigned long long r = (unsigned long long)(rr[u] - node0), c = (unsigned long long)(cc[u] - node0);
+          const bool ok = r < (unsigned long long)n && c < (unsigned long long)n;
+          bad |= !ok;
+          stash[i] = ok ? ((unsigned)r | ((unsigned)c << 16)) : 0xffffffffu;
+        }
+      }
+    }
+    if (bad) atomicOr(a.status, DRK_STATUS_CROSS_GRAPH);
+    __syncthreads();
+    uint16_t* my_r = cnt_r + warp * a.rows_cap;
+    uint16_t* my_c = cnt_c + warp * a.rows_cap;
+    for (int i0 = wb; i0 < we; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pk = i < we ? stash[i] : 0xffffffffu;
+      const bool ok = pk != 0xffffffffu;
+      const unsigned r = pk & 0xffffu, c = pk >> 16;
+      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
+      const unsigned mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
+      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(my_r[r] + __popc(mr));
+      if (ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(my_c[c] + __popc(mc));
+      __syncwarp();
+    }
+    __syncthreads();
+    uint32_t carry_r = 0, carry_c = 0;
+    for (int vb = 0; vb < n; vb += kT) {
+      const int v = vb + tid;
+      uint32_t dr = 0, dc = 0;
+      if (v < n) {
+        for (int w = 0; w < kNW; ++w) {
+          const uint32_t t = cnt_r[w * a.rows_cap + v];
+          cnt_r[w * a.rows_cap + v] = (uint16_t)dr;
+          dr += t;
+          const uint32_t u = cnt_c[w * a.rows_cap + v];
+          cnt_c[w * a.rows_cap + v] = (uint16_t)dc;
+          dc += u;
+        }
+      }
+      uint32_t tot_r, tot_c;
+      const uint32_t ex_r = block_excl_scan(dr, scan, tot_r) + carry_r;
+      const uint32_t ex_c = block_excl_scan(dc, scan, tot_c) + carry_c;
+      if (v < n) {
+        start_r[v] = ex_r;
+        start_c[v] = ex_c;
+        a.rowptr[node0 + v] = e0 + (int)ex_r;
+        if (want_csc) a.colptr[node0 + v] = e0 + (int)ex_c;
+      }
+      carry_r += tot_r;
+      carry_c += tot_c;
+    }
+    // edges dropped as malformed leave a gap at the end of the graph's slice: keep the arrays well defined
+    for (int i = (int)carry_r + tid; i < ne; i += kT) {
+      a.colidx[e0 + i] = node0;
+      a.perm[e0 + i] = e0 + i;
+    }
+    if (want_csc)
+      for (int i = (int)carry_c + tid; i < ne; i += kT) {
+        a.rowidx[e0 + i] = node0;
+        a.permT[e0 + i] = e0 + i;
+      }
+    if (g == a.num_graphs - 1 && tid == 0) {
+      a.rowptr[a.num_nodes] = (int)a.num_edges;
+      if (want_csc) a.colptr[a.num_nodes] = (int)a.num_edges;
+    }
+    __syncthreads();
+    for (int i0 = wb; i0 < we; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pk = i < we ? stash[i] : 0xffffffffu;
+      const bool ok = pk != 0xffffffffu;
+      const unsigned r = pk & 0xffffu, c = pk >> 16;
+      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
+      const unsigned mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
+      int base_r = 0, base_c = 0;
+      if (ok) {
+        base_r = my_r[r];
+        const int pos = e0 + (int)start_r[r] + base_r + __popc(mr & lt);
+        a.colidx[pos] = node0 + (int)c;
+        a.perm[pos] = e0 + i;
+        base_c = my_c[c];
+        if (want_csc) {
+          const int posc = e0 + (int)start_c[c] + base_c + __popc(mc & lt);
+          a.rowidx[posc] = node0 + (int)r;
+          a.permT[posc] = e0 + i;
+        }
+      }
+      __syncwarp();
+      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(base_r + __popc(mr));
+      if (ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
+      __syncwarp();
+    }
+  }
+}
+
+// edge_ptr[g] = first edge whose destination is >= graph_ptr[g] (binary search; valid when the edges of a collated batch are
+// grouped by graph, which the per-graph kernels verify edge by edge)
+__global__ void k_edge_ptr(const int64_t* __restrict__ erow, int64_t num_edges, const int32_t* __restrict__ graph_ptr, int num_graphs,
+                           int32_t* __restrict__ edge_ptr) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > num_graphs) return;
+  const long long target = __ldg(graph_ptr + g);
+  int64_t lo = 0, hi = num_edges;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(erow + mid) < target) lo = mid + 1;
+    else hi = mid;
+  }
+  edge_ptr[g] = (int32_t)lo;
+}
+
+struct PlanResult {
+  int rows_cap, e_cap, ent_cap, mode_b;
+  size_t smem;
+};
+
+static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
+  if (fi < 1 || fi > 64 || max_nodes < 0 || max_edges < 0) return false;
+  // tiles double as scratch: the dW2 reduction needs 8*64*16 floats (256 rows), the dW1 reduction 4*32*kp floats (4*kp rows)
+  p.rows_cap = std::max(std::max(256, 4 * pad_kp(fi)), (max_nodes + 7) / 8 * 8);
+  p.e_cap = std::max(32, (max_edges + 31) / 32 * 32);
+  p.ent_cap = (max_edges + 3 * max_nodes + 15) / 8 * 8;
+  if (p.ent_cap > 65528 || p.rows_cap > 8184) return false;
+  const Layout L = make_layout(fi, p.rows_cap, p.ent_cap);
+  p.smem = (size_t)L.total;
+  if (p.smem > kSmemBudget) return false;
+  const size_t tile = (size_t)p.rows_cap * kS1 * 4;
+  const size_t cnt = (size_t)2 * kNW * p.rows_cap * 2;
+  const size_t xreg = (size_t)p.rows_cap * L.kp * 4;
+  if ((size_t)p.e_cap * 4 <= tile && cnt + (size_t)p.ent_cap * 2 <= tile) {
+    p.mode_b = 0;
+  } else if ((size_t)p.e_cap * 4 <= xreg && cnt <= tile && (size_t)p.ent_cap * 2 <= tile) {
+    p.mode_b = 1;
+  } else {
+    return false;
+  }
+  return true;
+}
+
+}  // namespace gs
+}  // namespace drk
+
+extern "C" {
+
+int drk_ginet_step_supported(int32_t fi, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges) {
+  drk::gs::PlanResult p;
+  return (out_dim >= 1 && out_dim <= drk::gs::kMaxOut && drk::gs::make_plan(fi, max_graph_nodes, max_graph_edges, p)) ? 1 : 0;
+}
+
+size_t drk_ginet_step_workspace_bytes(int32_t fi, int32_t out_dim, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges) {
+  using namespace drk::gs;
+  PlanResult p;
+  if (!make_plan(fi, max_graph_nodes, max_graph_edges, p)) return 0;
+  const size_t part_stride = (size_t)kS1 * pad_kp(fi) + kS2 * kF1;
+  size_t b = 0;
+  b += (size_t)num_graphs * part_stride * 4;                    // per-graph conv weight-gradient contributions
+  b += (size_t)num_graphs * (kS2 + 2 * kHid + out_dim + 1) * 4;  // G, h, dh, dpred, loss term
+  b = (b + 255) / 256 * 256;
+  b += (size_t)drk::kNumSM * p.ent_cap * 2;                     // CSC spill, one slot per CTA
+  return b + 256;
+}
+
+int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_index, int64_t num_edges, const int32_t* graph_ptr,
+                   const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges,
+                   const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
+                   const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
+                   float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train, float* pred, float* loss, float* dw1a, float* dw1b,
+                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, int32_t* counter, int32_t* status,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace drk;
+  using namespace drk::gs;
+  DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0, DRK_EINVAL, "ginet step: negative size");
+  DRK_REQUIRE(out_dim >= 1 && out_dim <= kMaxOut, DRK_EUNSUPPORTED, "ginet step: 1 <= output_shape <= %d supported, got %d", kMaxOut, out_dim);
+  PlanResult p;
+  DRK_REQUIRE(make_plan(fi, max_graph_nodes, max_graph_edges, p), DRK_EUNSUPPORTED,
+              "ginet step: graphs of %d nodes / %d edges with %d features do not fit the shared-memory plan", max_graph_nodes, max_graph_edges, fi);
+  if (num_graphs == 0) return DRK_OK;
+  DRK_REQUIRE(x && edge_index && graph_ptr && edge_ptr && w1a && w1b && w2a && w2b && fc1_w && fc1_b && fc2_w && fc2_b && pred, DRK_EINVAL,
+              "ginet step: null pointer");
+  DRK_REQUIRE(aligned16(fc1_w) && aligned16(fc2_w), DRK_EINVAL, "ginet step: head weights must be 16-byte aligned");
+  if (train) {
+    DRK_REQUIRE(target && loss && dw1a && dw1b && dw2a && dw2b && dfc1_w && dfc1_b && dfc2_w && dfc2_b, DRK_EINVAL, "ginet step: null pointer (train)");
+    DRK_REQUIRE(loss_kind == DRK_LOSS_MSE || loss_kind == DRK_LOSS_CROSS_ENTROPY, DRK_EINVAL, "ginet step: unknown loss kind %d", loss_kind);
+    DRK_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, DRK_EINVAL, "ginet step: dropout probability must be in [0, 1)");
+    DRK_REQUIRE(workspace && workspace_bytes >= drk_ginet_step_workspace_bytes(fi, out_dim, num_graphs, max_graph_nodes, max_graph_edges), DRK_EWORKSPACE,
+                "ginet step: workspace too small");
+  }
+  StepArgs a{};
+  a.x = x; a.ldx = ldx; a.fi = fi;
+  a.erow = edge_index; a.ecol = edge_index + num_edges;
+  a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.counter = counter; a.num_graphs = num_graphs;
+  a.w1a = w1a; a.w1b = w1b; a.w2a = w2a; a.w2b = w2b;
+  a.fc1_w = fc1_w; a.fc1_b = fc1_b; a.fc2_w = fc2_w; a.fc2_b = fc2_b; a.out_dim = out_dim;
+  a.loss_kind = loss_kind;
+  a.y = loss_kind == DRK_LOSS_MSE ? static_cast<const float*>(target) : nullptr;
+  a.y_cls = loss_kind == DRK_LOSS_CROSS_ENTROPY ? static_cast<const int64_t*>(target) : nullptr;
+  a.dloss_scale = inv_loss_count;
+  a.drop_p = dropout_p; a.seed = seed; a.rng_step = rng_step;
+  a.pred = pred; a.status = status;
+  a.rows_cap = p.rows_cap; a.e_cap = p.e_cap; a.ent_cap = p.ent_cap; a.mode_b = p.mode_b;
+  a.x_vec = 1;
+  if (ldx % 4 == 0 && fi % 4 == 0 && aligned16(x)) a.x_vec = 4;
+  else if (ldx % 2 == 0 && fi % 2 == 0 && aligned8(x)) a.x_vec = 2;
+  const int kp = pad_kp(fi);
+  a.part_stride = kS1 * kp + kS2 * kF1;
+  if (train) {
+    float* w = static_cast<float*>(workspace);
+    a.part = w; w += (size_t)num_graphs * a.part_stride;
+    a.gvec = w; w += (size_t)num_graphs * kS2;
+    a.hvec = w; w += (size_t)num_graphs * kHid;
+    a.dhvec = w; w += (size_t)num_graphs * kHid;
+    a.dpvec = w; w += (size_t)num_graphs * out_dim;
+    a.loss_terms = w; w += num_graphs;
+    const size_t used = ((size_t)(reinterpret_cast<char*>(w) - static_cast<char*>(workspace)) + 255) / 256 * 256;
+    a.csc_spill = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + used);
+  }
+  cudaStream_t st = as_stream(stream);
+  const int grid = std::min(num_graphs, kNumSM);
+  cudaError_t e;
+  if (train) {
+    e = cudaFuncSetAttribute(k_ginet_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "ginet step: smem opt-in: %s", cudaGetErrorString(e));
+    k_ginet_step<true><<<grid, kT, p.smem, st>>>(a);
+    FinalArgs f{};
+    f.part = a.part; f.part_stride = a.part_stride; f.gvec = a.gvec; f.hvec = a.hvec; f.dhvec = a.dhvec; f.dpvec = a.dpvec; f.loss_terms = a.loss_terms;
+    f.num_graphs = num_graphs; f.fi = fi; f.kp = kp; f.out_dim = out_dim;
+    f.dw1a = dw1a; f.dw1b = dw1b; f.dw2a = dw2a; f.dw2b = dw2b; f.dfc1_w = dfc1_w; f.dfc1_b = dfc1_b; f.dfc2_w = dfc2_w; f.dfc2_b = dfc2_b; f.loss = loss;
+    f.loss_scale = loss_kind == DRK_LOSS_MSE ? inv_loss_count : inv_loss_count;
+    f.rng_step = rng_step; f.counter = counter;
+    const int total = kS1 * fi + kS2 * kF1 + kHid * kS2 + kHid + out_dim * kHid + out_dim + 1;
+    k_step_finalize<<<ceil_div(total, 256), 256, 0, st>>>(f);
+    return finish_launch("ginet step", 2);
+  }
+  e = cudaFuncSetAttribute(k_ginet_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "ginet step: smem opt-in: %s", cudaGetErrorString(e));
+  k_ginet_step<false><<<grid, kT, p.smem, st>>>(a);
+  if (counter != nullptr) cudaMemsetAsync(counter, 0, sizeof(int32_t), st);
+  return finish_launch("ginet step (inference)", 1);
+}
+
+int drk_edge_ptr(const int64_t* edge_index, int64_t num_edges, const int32_t* graph_ptr, int32_t num_graphs, int32_t* edge_ptr, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0 && num_edges < (int64_t)1 << 31, DRK_EINVAL, "edge ptr: bad size");
+  DRK_REQUIRE(graph_ptr && edge_ptr && (edge_index || num_edges == 0), DRK_EINVAL, "edge ptr: null pointer");
+  gs::k_edge_ptr<<<ceil_div(num_graphs + 1, 128), 128, 0, as_stream(stream)>>>(edge_index, num_edges, graph_ptr, num_graphs, edge_ptr);
+  return finish_launch("edge ptr");
+}
+
+int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges) {
+  if (max_graph_nodes < 0 || max_graph_edges < 0 || max_graph_nodes > 65535 || max_graph_edges > 65535) return 0;
+  const size_t rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8), e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
+  const size_t smem = e_cap * 4 + 2 * drk::gs::kNW * rows_cap * 2 + 2 * rows_cap * 4 + 128;
+  return smem <= drk::gs::kSmemBudget ? 1 : 0;
+}
+
+int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes, const int32_t* graph_ptr, const int32_t* edge_ptr,
+                                  int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* rowptr, int32_t* colidx,
+                                  int32_t* perm, int32_t* colptr, int32_t* rowidx, int32_t* permT, int32_t* status, void* stream) {
+  using namespace drk;
+  using namespace drk::gs;
+  DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0 && num_nodes >= 0, DRK_EINVAL, "blocked index: negative size");
+  DRK_REQUIRE(drk_graph_index_blocked_supported(max_graph_nodes, max_graph_edges), DRK_EUNSUPPORTED,
+              "blocked index: graphs of %d nodes / %d edges do not fit shared memory", max_graph_nodes, max_graph_edges);
+  DRK_REQUIRE(graph_ptr && edge_ptr && rowptr && colidx && perm && status && (edge_index || num_edges == 0), DRK_EINVAL, "blocked index: null pointer");
+  DRK_REQUIRE((colptr == nullptr) == (rowidx == nullptr) && (colptr == nullptr) == (permT == nullptr), DRK_EINVAL, "blocked index: CSC outputs come together");
+  DRK_REQUIRE(num_graphs > 0 || num_nodes == 0, DRK_EINVAL, "blocked index: nodes without graphs");
+  if (num_graphs == 0) {
+    cudaMemsetAsync(rowptr, 0, sizeof(int32_t), as_stream(stream));
+    if (colptr) cudaMemsetAsync(colptr, 0, sizeof(int32_t), as_stream(stream));
+    return DRK_OK;
+  }
+  BlockedIndexArgs a{};
+  a.erow = edge_index; a.ecol = edge_index + num_edges; a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.num_graphs = num_graphs;
+  a.rowptr = rowptr; a.colidx = colidx; a.perm = perm; a.colptr = colptr; a.rowidx = rowidx; a.permT = permT; a.status = status;
+  a.rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8);
+  a.e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
+  a.num_nodes = num_nodes; a.num_edges = num_edges;
+  const size_t smem = (size_t)a.e_cap * 4 + (size_t)2 * kNW * a.rows_cap * 2 + (size_t)2 * a.rows_cap * 4 + 128;
+  cudaError_t e = cudaFuncSetAttribute(k_index_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "blocked index: smem opt-in: %s", cudaGetErrorString(e));
+  const int ctas_per_sm = std::max<int>(1, std::min<int>(4, (int)(kSmemBudget / (smem + 1024))));
+  const int grid = std::min(num_graphs, kNumSM * ctas_per_sm);
+  k_index_blocked<<<grid, kT, smem, as_stream(stream)>>>(a);
+  return finish_launch("blocked index");
+}
+
+}  // extern "C"

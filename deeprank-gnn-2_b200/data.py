@@ -97,7 +97,7 @@ class Data:
     # -- copies / movement (private caches, e.g. the graph index, are dropped on clone and moved on to())
     # host-side facts about the batch that survive clone()/to(): {"num_graphs", "max_graph_nodes"}
     _META_KEY = "_meta"
-    _DEVICE_CACHES = ("_graph_index",)
+    _DEVICE_CACHES = ("_graph_index", "_block_info")
 
     def clone(self):
         new = type(self).__new__(type(self))
@@ -176,7 +176,18 @@ class Batch(Data):
                 setattr(out, k, list(column))
         out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int64), torch.tensor(sizes, dtype=torch.int64))
         out.ptr = ptr
-        out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(d.num_edges for d in data_list)}
+        # what the per-graph kernels need and PyG's Batch does not keep: int32 node / edge offsets of every graph (the edges of a
+        # graph are a contiguous slice of edge_index) and the graphs sorted by size, largest first (issue order of the CTAs).
+        # Private attributes: they follow the batch through clone()/to()/pin_memory() but are not part of `keys`.
+        e_sizes = [d.num_edges for d in data_list]
+        if ptr[-1] < 2**31 and sum(e_sizes) < 2**31:
+            eptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
+            eptr[1:] = torch.cumsum(torch.tensor(e_sizes, dtype=torch.int64), 0)
+            out.__dict__["_node_ptr32"] = ptr.to(torch.int32)
+            out.__dict__["_edge_ptr32"] = eptr.to(torch.int32)
+            work = torch.tensor(e_sizes, dtype=torch.int64) + 8 * torch.tensor(sizes, dtype=torch.int64)
+            out.__dict__["_order32"] = torch.argsort(work, descending=True, stable=True).to(torch.int32)
+        out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(e_sizes), "num_edges_total": sum(e_sizes)}
         return out
 
 

@@ -1,0 +1,232 @@
+"""The whole GINet step as one per-graph kernel (``csrc/drk_ginet_step.cu``).
+
+``Trainer._epoch``'s loop body (reference ``deeprank2/trainer.py:682-694``) is, for the benchmark model
+``ginet_nocluster.GINet`` with ``MSELoss`` / ``CrossEntropyLoss``::
+
+    pred = model(batch); loss = lossfunction(pred, y); loss.backward(); optimizer.step()
+
+:class:`GINetFusedStep` performs the first three in TWO kernel launches (one CTA per graph: graph index,
+both convolution branches, readout, head, loss term and the full backward pass in shared memory; then a
+finalize kernel that sums the per-graph gradient contributions in graph order) and hands the gradients to the
+unchanged ``torch.optim`` optimizer.  :func:`ginet_infer` is the forward-only variant used under
+``torch.no_grad()``.  Both need a *collated* batch (edges of a graph contiguous in ``edge_index``), which is what
+``Batch.from_data_list`` / PyG's collate produce; the kernels verify it edge by edge and raise
+``DRK_STATUS_CROSS_GRAPH`` otherwise.
+
+There is no CPU path: everything here raises if the extension is missing or a tensor is not on a CUDA device.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+from .graph import stream_ptr, workspace
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class BlockInfo:
+    """Per-graph offsets of a collated batch on the device: ``node_ptr``/``edge_ptr`` int32 [B+1], issue ``order``
+    int32 [B] (or None), the largest graph's node / edge count, and the batch's status word."""
+
+    __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status")
+
+
+def block_info(data) -> BlockInfo:
+    """The (cached) :class:`BlockInfo` of a device-resident ``Batch``.
+
+    Batches made by ``Batch.from_data_list`` carry the offsets (computed by the collate on the host, moved with the batch).
+    For any other batch they are derived on the device from ``batch`` and ``edge_index`` (``drk_batch_offsets`` +
+    ``drk_edge_ptr``) with one host read-back of the largest graph size, remembered on the batch."""
+    lib = _lib.load()
+    ei = data.edge_index
+    if not ei.is_cuda:
+        raise RuntimeError(f"the batch must live on a CUDA device: deeprank2_b200 has no CPU path (got {ei.device})")
+    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device))
+    cached = data.__dict__.get("_block_info")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    info = BlockInfo()
+    dev = ei.device
+    node_ptr, edge_ptr = data.__dict__.get("_node_ptr32"), data.__dict__.get("_edge_ptr32")
+    meta = data.__dict__.get(data._META_KEY, {}) if hasattr(data, "_META_KEY") else {}
+    collated = (
+        node_ptr is not None and edge_ptr is not None and node_ptr.is_cuda and edge_ptr.is_cuda
+        and meta.get("num_edges_total") == int(ei.shape[1]) and meta.get("max_graph_nodes") is not None
+    )
+    if collated:
+        info.node_ptr, info.edge_ptr = node_ptr, edge_ptr
+        order = data.__dict__.get("_order32")
+        info.order = order if order is not None and order.is_cuda else None
+        info.num_graphs = int(node_ptr.numel()) - 1
+        info.max_nodes, info.max_edges = int(meta["max_graph_nodes"]), int(meta["max_graph_edges"])
+    else:
+        from .graph import graph_index
+
+        g = graph_index(data, with_csc=False)
+        if g.graph_ptr is None:
+            raise ValueError("the batch has no `batch` vector: per-graph kernels need the graph boundaries")
+        info.node_ptr = g.graph_ptr
+        info.num_graphs = g.num_graphs
+        info.edge_ptr = torch.empty(info.num_graphs + 1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.drk_edge_ptr(_p(ei), int(ei.shape[1]), _p(info.node_ptr), info.num_graphs, _p(info.edge_ptr), stream_ptr()), "drk_edge_ptr")
+        info.order = None
+        sizes = torch.stack([(info.node_ptr[1:] - info.node_ptr[:-1]).max(), (info.edge_ptr[1:] - info.edge_ptr[:-1]).max()]) if info.num_graphs else torch.zeros(2)
+        info.max_nodes, info.max_edges = (int(v) for v in sizes.tolist())  # one host sync, remembered on the batch
+    info.status = torch.zeros(1, dtype=torch.int32, device=dev)
+    data.__dict__["_block_info"] = (key, info)
+    return info
+
+
+def check_status(info: BlockInfo) -> None:
+    """Host sync: raise if a per-graph kernel flagged the batch (call off the hot path, e.g. at the end of a pass)."""
+    flags = int(info.status.item())
+    if flags & _lib.STATUS_CROSS_GRAPH:
+        raise ValueError("edge_index is not grouped by graph (an edge joins two graphs of the batch): not a collated batch")
+    if flags & _lib.STATUS_INDEX_RANGE:
+        raise IndexError("a graph of the batch exceeds the sizes the kernel was planned for, or a class index is out of range")
+
+
+def _standard_ginet(model) -> bool:
+    from .neuralnets.gnn.ginet_nocluster import GINet
+
+    if not isinstance(model, GINet) or not model._stackable():
+        return False
+    fi = model.conv1.fc.weight.shape[1]
+    return (
+        tuple(model.conv1.fc.weight.shape) == (16, fi)
+        and tuple(model.conv2.fc.weight.shape) == (32, 16)
+        and tuple(model.fc1.weight.shape) == (128, 64)
+        and model.fc1.bias is not None
+        and model.fc2.weight.shape[1] == 128
+        and model.fc2.bias is not None
+        and 1 <= model.fc2.weight.shape[0] <= 8
+        and fi <= 64
+        and all(p.dtype == torch.float32 and p.is_cuda and p.is_contiguous() for p in model.parameters())
+    )
+
+
+def _loss_kind(loss_fn):
+    if isinstance(loss_fn, nn.MSELoss) and loss_fn.reduction == "mean":
+        return _lib.LOSS_MSE
+    if isinstance(loss_fn, nn.CrossEntropyLoss) and loss_fn.reduction == "mean" and loss_fn.weight is None and getattr(loss_fn, "label_smoothing", 0.0) == 0.0:
+        return _lib.LOSS_CROSS_ENTROPY
+    return None
+
+
+def step_supported(model, data) -> bool:
+    """True if ``model`` is the reference GINet architecture on the GPU and every graph of ``data`` fits the kernel's plan."""
+    if not _standard_ginet(model) or not data.x.is_cuda or data.x.dtype != torch.float32 or data.x.dim() != 2:
+        return False
+    if data.x.shape[1] != model.conv1.fc.weight.shape[1] or data.x.requires_grad or data.x.stride(1) != 1:
+        return False
+    info = block_info(data)
+    return bool(_lib.load().drk_ginet_step_supported(int(data.x.shape[1]), int(model.fc2.weight.shape[0]), info.max_nodes, info.max_edges))
+
+
+def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, rng_step, pred, loss, grads, counter):
+    lib = _lib.load()
+    x = data.x
+    fi = int(x.shape[1])
+    out_dim = int(model.fc2.weight.shape[0])
+    ei = data.edge_index if data.edge_index.is_contiguous() else data.edge_index.contiguous()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.drk_ginet_step_workspace_bytes(fi, out_dim, info.num_graphs, info.max_nodes, info.max_edges) if train else 0
+        ws = workspace(ws_bytes, x.device) if train else None
+        rc = lib.drk_ginet_step(
+            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), info.num_graphs, info.max_nodes, info.max_edges,
+            _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
+            _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
+            int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(rng_step), 1 if train else 0,
+            _p(pred), _p(loss), *[_p(g) for g in grads], _p(counter), _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
+        )
+    _lib.check(rc, "drk_ginet_step")
+
+
+def ginet_infer(model, data) -> torch.Tensor:
+    """``model(data)`` for the reference GINet without autograd: one kernel, [B, out] predictions."""
+    info = block_info(data)
+    pred = torch.empty((info.num_graphs, int(model.fc2.weight.shape[0])), dtype=torch.float32, device=data.x.device)
+    _call_step(model, data, info, train=False, loss_kind=_lib.LOSS_MSE, target=None, inv_loss_count=0.0, dropout_p=0.0, seed=0, rng_step=None,
+               pred=pred, loss=None, grads=[None] * 8, counter=None)
+    return pred
+
+
+class GINetFusedStep:
+    """``loss, pred = step(batch)``: forward + loss + backward of the reference GINet in two launches, then ``optimizer.step()``.
+
+    The gradients land in one flat fp32 buffer whose views are the parameters' ``.grad`` (the dead ``fc_edge_attr`` /
+    ``fc_attention`` parameters keep exact-zero gradients, as in the reference).  With ``world_size > 1`` the flat buffer
+    is summed over ranks with one NCCL all-reduce; ``global_size`` (graphs in the global mini-batch) scales the loss terms
+    so that the sum is the single-process gradient, ragged tails included.
+    ``target_fn(batch) -> tensor`` supplies the targets (float [B(,out)] for MSE, int64 class indices for cross entropy).
+    """
+
+    def __init__(self, model, optimizer, loss_fn, target_fn=None, world_size: int = 1, group=None, seed: int | None = None):
+        if not _standard_ginet(model):
+            raise ValueError("GINetFusedStep needs the reference ginet_nocluster.GINet architecture on a CUDA device")
+        kind = _loss_kind(loss_fn)
+        if kind is None:
+            raise ValueError(f"GINetFusedStep supports MSELoss / CrossEntropyLoss (mean reduction, no class weights), got {loss_fn}")
+        self.model, self.optimizer, self.loss_fn, self.kind = model, optimizer, loss_fn, kind
+        self.target_fn = target_fn or (lambda b: b.y)
+        self.world, self.group = int(world_size), group
+        dev = model.fc1.weight.device
+        self.params = list(model.parameters())
+        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat_grad[off : off + p.numel()].view_as(p))
+            off += p.numel()
+        by_id = {id(p): v for p, v in zip(self.params, self.views)}
+        m = model
+        self.grads = [by_id[id(t)] for t in (m.conv1.fc.weight, m.conv1_ext.fc.weight, m.conv2.fc.weight, m.conv2_ext.fc.weight, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)]
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seed = int(torch.initial_seed() if seed is None else seed)
+        self._pred = {}
+
+    @staticmethod
+    def supports(model, loss_fn, batch=None) -> bool:
+        return _standard_ginet(model) and _loss_kind(loss_fn) is not None and (batch is None or step_supported(model, batch))
+
+    def forward_backward(self, batch, global_size: int | None = None):
+        """Everything but the optimizer: returns (loss, pred); ``p.grad`` of every parameter is set."""
+        info = block_info(batch)
+        out_dim = int(self.model.fc2.weight.shape[0])
+        target = self.target_fn(batch)
+        if self.kind == _lib.LOSS_MSE:
+            target = target.to(torch.float32).contiguous()
+            if target.numel() != info.num_graphs * out_dim:
+                raise ValueError(f"MSELoss target has {target.numel()} elements, predictions {info.num_graphs * out_dim}")
+            count = (global_size or info.num_graphs) * out_dim
+        else:
+            target = target.to(torch.int64).contiguous()
+            if target.numel() != info.num_graphs:
+                raise ValueError(f"CrossEntropyLoss target has {target.numel()} elements for {info.num_graphs} graphs")
+            count = global_size or info.num_graphs
+        key = (info.num_graphs, out_dim)
+        pred = self._pred.get(key)
+        if pred is None:
+            pred = self._pred[key] = torch.empty(key, dtype=torch.float32, device=batch.x.device)
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+        drop = float(self.model.dropout) if self.model.training else 0.0
+        _call_step(self.model, batch, info, train=True, loss_kind=self.kind, target=target, inv_loss_count=1.0 / max(count, 1), dropout_p=drop,
+                   seed=self.seed, rng_step=self.rng_step, pred=pred, loss=self.loss, grads=self.grads, counter=self.counter)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        return self.loss, pred
+
+    def __call__(self, batch, global_size: int | None = None):
+        loss, pred = self.forward_backward(batch, global_size)
+        self.optimizer.step()
+        return loss, pred

@@ -46,6 +46,11 @@ class GINet(nn.Module):
         )
 
     def forward(self, data):
+        if self.fused and not torch.is_grad_enabled() and not (self.training and self.dropout > 0):
+            from ... import fused as _fused
+
+            if data.x.is_cuda and _fused.step_supported(self, data):
+                return _fused.ginet_infer(self, data)  # inference: the whole forward pass as one per-graph kernel
         g = graph_index(data)  # CSR/CSC + graph offsets, built once on the device and shared by all layers
         # the reference deep-copies the batch (data.clone(), :86) and overwrites data.x in place (:90,:93);
         # neither has a numerical effect, so no copy is made here.

@@ -208,6 +208,59 @@ DRK_API int drk_ginet_fused_bwd(const float* x, int64_t ldx, int32_t num_node_fe
                         int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ per-graph index build for collated batches
+ * PyG's collate (torch_geometric Batch.from_data_list; dataset.py:944-948 per graph) concatenates the graphs' edge lists, so
+ * the edges of graph g are the contiguous slice [edge_ptr[g], edge_ptr[g+1]) of edge_index.  One CTA per graph builds the
+ * same bit-exact, stable CSR / CSC as drk_graph_index_build inside shared memory (per-warp histograms, ordered placement;
+ * no atomics, no global sort).  drk_edge_ptr derives edge_ptr from edge_index + graph_ptr when collate did not keep it.
+ * An edge whose endpoints leave its graph sets DRK_STATUS_CROSS_GRAPH (the caller falls back to drk_graph_index_build).
+ * colptr/rowidx/permT may be NULL together (no CSC). */
+DRK_API int drk_edge_ptr(const int64_t* edge_index, int64_t num_edges, const int32_t* graph_ptr, int32_t num_graphs,
+                 int32_t* edge_ptr, void* stream);
+DRK_API int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges);
+DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes,
+                                  const int32_t* graph_ptr, const int32_t* edge_ptr, int32_t num_graphs,
+                                  int32_t max_graph_nodes, int32_t max_graph_edges, int32_t* rowptr, int32_t* colidx,
+                                  int32_t* perm, int32_t* colptr, int32_t* rowidx, int32_t* permT, int32_t* status,
+                                  void* stream);
+
+/* ------------------------------------------------------------------ whole GINet step per graph (SURVEY 8a rows B, B', C, D, E, K)
+ * One pass of Trainer._epoch's loop body (trainer.py:682-694) for ginet_nocluster.GINet (ginet_nocluster.py:72-111) on a
+ * collated batch, as ONE kernel with one CTA per graph + one small finalize kernel:
+ *   graph index (CSR + CSC of the graph's edge slice, in shared memory) -> conv1/conv1_ext -> ReLU -> conv2/conv2_ext ->
+ *   ReLU -> scatter_mean readout -> fc1 -> ReLU -> dropout -> fc2 -> loss term -> full backward -> per-graph gradient
+ *   contributions, summed in graph order by the finalize kernel (bit-reproducible; no floating-point atomics).
+ * train == 0: forward only (pred is written, nothing else).
+ * loss_kind: DRK_LOSS_MSE            target = float [B, out] (MSELoss on pred.reshape(-1), trainer.py:807-835 regress)
+ *            DRK_LOSS_CROSS_ENTROPY  target = int64 [B] class indices (CrossEntropyLoss without class weights)
+ * inv_loss_count = 1 / (number of loss elements of the GLOBAL mini-batch): B_global*out for MSE, B_global for CE; with
+ *   data-parallel ranks the summed gradients of all ranks then equal the single-process gradient.
+ * dropout: keep-mask from Philox4x32-10(seed, *rng_step, graph, unit); rng_step (device int64) is advanced by the finalize
+ *   kernel so CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.
+ * order (may be NULL): graph ids in the order they should be issued (largest first balances the 148 CTAs); counter
+ *   (device int32, zero before the first call, re-armed by the call; may be NULL = static round-robin).
+ * Outputs: pred [B,out]; loss [1]; gradients of conv1.fc.weight / conv1_ext.fc.weight [16,F], conv2.fc.weight /
+ *   conv2_ext.fc.weight [32,16], fc1.{weight [128,64], bias [128]}, fc2.{weight [out,128], bias [out]}.
+ * The gradients of fc_edge_attr / fc_attention are identically zero in the reference (softmax over a singleton axis,
+ * ginet_nocluster.py:48-51) and are not produced here.
+ * drk_ginet_step_supported: 1 if graphs of that size fit the shared-memory plan (else use the layer kernels). */
+#define DRK_LOSS_MSE 0
+#define DRK_LOSS_CROSS_ENTROPY 1
+DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
+DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
+                                      int32_t max_graph_nodes, int32_t max_graph_edges);
+DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_features, const int64_t* edge_index, int64_t num_edges,
+                   const int32_t* graph_ptr, const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs,
+                   int32_t max_graph_nodes, int32_t max_graph_edges,
+                   const float* w1a, const float* w1b, const float* w2a, const float* w2b,
+                   const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, int32_t out_dim,
+                   int32_t loss_kind, const void* target, float inv_loss_count,
+                   float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train,
+                   float* pred, float* loss,
+                   float* dw1a, float* dw1b, float* dw2a, float* dw2b,
+                   float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
+                   int32_t* counter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

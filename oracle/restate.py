@@ -180,14 +180,16 @@ def ginet_nocluster_init(input_shape, output_shape=1, input_shape_edge=1, genera
     return _ginet_init(input_shape, output_shape, input_shape_edge, generator)
 
 
-def _ginet_head(g, p, training, dropout_p):
-    """fc1 -> ReLU -> dropout(0.4, training) -> fc2 (``ginet_nocluster.py:106-109``)."""
+def _ginet_head(g, p, training, dropout_p, keep=None):
+    """fc1 -> ReLU -> dropout(0.4, training) -> fc2 (``ginet_nocluster.py:106-109``).
+    ``keep`` ([B,128] of 0 or 1/(1-p)) replays a given dropout mask instead of drawing one (the CUDA path draws its
+    masks with Philox on the device; the parity test feeds them back here)."""
     g = F.relu(F.linear(g, p["fc1.weight"], p["fc1.bias"]))
-    g = F.dropout(g, dropout_p, training=training)
+    g = g * keep if keep is not None else F.dropout(g, dropout_p, training=training)
     return F.linear(g, p["fc2.weight"], p["fc2.bias"])
 
 
-def ginet_nocluster_forward(p, data, training=False, dropout_p=0.4):
+def ginet_nocluster_forward(p, data, training=False, dropout_p=0.4, keep=None):
     """``ginet_nocluster.GINet.forward`` (``ginet_nocluster.py:84-111``): two branches of
     conv(50->16) -> ReLU -> conv(16->32) -> ReLU on the same graph, per-graph mean, MLP head."""
     x, ei, ea = data.x, data.edge_index, data.edge_attr
@@ -196,7 +198,7 @@ def ginet_nocluster_forward(p, data, training=False, dropout_p=0.4):
     b = F.relu(ginet_conv(x, ei, ea, p, "conv1_ext."))
     b = F.relu(ginet_conv(b, ei, ea, p, "conv2_ext."))
     g = torch.cat([mean_readout(a, data.batch), mean_readout(b, data.batch)], dim=1)
-    return _ginet_head(g, p, training, dropout_p)
+    return _ginet_head(g, p, training, dropout_p, keep)
 
 
 # =========================================================================== rows I/J: community pooling
