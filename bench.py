@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batches", type=int, default=6, help="distinct resident batches per rank (rotation defeats L2 reuse)")
     ap.add_argument("--mode", choices=["graph", "eager"], default="graph", help="replay a captured CUDA graph per batch, or launch eagerly")
+    ap.add_argument("--path", choices=["fused", "fused2", "layers"], default="fused",
+                    help="fused: whole step as one per-graph kernel; fused2: per-graph forward and backward kernels through autograd; layers: one kernel per layer op")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="only the timed steps (no e2e / roofline / cpu legs): the command ncu wraps")
     ap.add_argument("--ref-graphs", type=int, default=64, help="graphs per step of the CPU reference arm (bounded sample)")
@@ -164,18 +166,26 @@ def workload_config(args, world):
         "l2_policy": f"rotation over {args.batches} distinct resident batches per rank (> L2 between reuses)",
         "index_build": "inside every step",
         "mode": args.mode,
+        "path": getattr(args, "path", "fused"),
     }
 
 
 # --------------------------------------------------------------------------------------- our arm
+def algorithmic_step_bytes(n_nodes: int, n_edges: int) -> int:
+    """compulsory traffic of one GINet(no-cluster, F_in = 50) train step with int32 CSR and every
+    intermediate written and read once = 2472 N + 24 E bytes (the denominator stays fixed across builds)."""
+    return 2472 * n_nodes + 24 * n_edges
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from deeprank2_b200 import _lib, ops
-    from deeprank2_b200.graph import graph_index
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.fused import GINetFusedStep, block_info, check_status
     from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
-    from deeprank2_b200.step import GraphedTrainStep, TrainStep
+    from deeprank2_b200.pipeline import DevicePrefetcher, batch_nbytes
+    from deeprank2_b200.step import GraphedTrainStep
     from deeprank2_b200.synthetic import make_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,27 +212,36 @@ def run_ours(args):
     torch.manual_seed(0)
     model = GINet(F_NODE, 1, F_EDGE).to(dev)
     model.train()
-    if distributed:
-        from deeprank2_b200.parallel import GradAllReduce
-
-        sync = GradAllReduce(model, world)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=(args.mode == "graph"))
     loss_fn = torch.nn.MSELoss()
+    global_graphs = GRAPHS_PER_BATCH * world
 
-    class Step(TrainStep):
-        def __call__(self, batch):
-            if self.rebuild_index:
-                batch.__dict__.pop("_graph_index", None)
-            self.optimizer.zero_grad(set_to_none=True)
-            pred = self.model(batch)
-            loss = self.loss_fn(pred.reshape(-1), batch.y)
+    if args.path == "fused":
+        # the whole step as one per-graph kernel + finalize (csrc/drk_ginet_step.cu), then the stock fused Adam
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=True)
+        fused = GINetFusedStep(model, opt, loss_fn, world_size=world)
+
+        def step(batch):
+            loss, pred = fused(batch, global_size=global_graphs)
+            return loss, pred
+    else:
+        # layer kernels through autograd (the generic path every other network uses)
+        if distributed:
+            from deeprank2_b200.parallel import GradAllReduce
+
+            sync = GradAllReduce(model, world)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=(args.mode == "graph"))
+        model.fused = args.path == "fused2"
+
+        def step(batch):
+            batch.__dict__.pop("_graph_index", None)  # the index build is part of every step, like PyG's collate
+            opt.zero_grad(set_to_none=True)
+            pred = model(batch)
+            loss = loss_fn(pred.reshape(-1), batch.y)
             loss.backward()
             if distributed:
                 sync()
-            self.optimizer.step()
+            opt.step()
             return loss.detach(), pred.detach()
-
-    step = Step(model, opt, loss_fn)
 
     # launches of OUR kernels in one eager step (what a graph replay re-issues)
     step(dev_batches[0])
@@ -269,6 +288,9 @@ def run_ours(args):
     if distributed:
         dist.all_reduce(et)
     value = graphs_total / (ms * 1e-3)
+    if args.path == "fused":
+        for b in dev_batches:
+            check_status(block_info(b))  # the kernels' data-dependent status words (host sync, outside the timed region)
 
     if args.profile:
         if rank == 0:
@@ -277,23 +299,22 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- end to end through the public API: host (pinned) batch -> .to(device) -> step -> loss.item()
-    e2e_steps = max(5, min(args.steps, 20))
-    eager = Step(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5), loss_fn)
-    h2d = 0
-    for k in ("x", "edge_index", "edge_attr", "batch", "y", "ptr"):
-        v = getattr(host_batches[0], k)
-        h2d += v.numel() * v.element_size()
-    for i in range(3):
-        hb = host_batches[i % args.batches]
-        loss, _ = eager(_to_device(hb, dev))
-        loss.item()
+    # ---- end to end through the public API: pinned host batches -> device (copy stream, one batch ahead) -> step -> loss.item()
+    e2e_steps = max(10, min(args.steps, 40))
+    h2d = batch_nbytes(host_batches[0])
+
+    def e2e_pass(n_steps):
+        feed = DevicePrefetcher((host_batches[i % args.batches] for i in range(n_steps)), dev)
+        last = None
+        for b in feed:
+            loss, _ = step(b)
+            last = loss.item()  # D2H read of the step's result, every step (trainer.py:694)
+        return last
+
+    e2e_pass(4)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        hb = host_batches[i % args.batches]
-        loss, _ = eager(_to_device(hb, dev))
-        loss.item()  # D2H read of the step's result, every step (trainer.py:694)
+    e2e_pass(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -301,8 +322,8 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = GRAPHS_PER_BATCH * e2e_steps * world / float(te.item())
 
-    # ---- roofline of the dominant kernel: the 32-wide... measured per launch with CUDA events on this stream
-    roof = aggregation_roofline(ops, graph_index, dev_batches, args, dev)
+    # ---- roofline of the dominant kernel, timed per launch with CUDA events on this stream, L2 flushed before every launch
+    roof = step_roofline(args, dev, dev_batches, model, loss_fn) if args.path == "fused" else aggregation_roofline(dev_batches, args, dev)
 
     if rank == 0:
         cpu = None
@@ -331,7 +352,8 @@ def run_ours(args):
             "config": dict(workload_config(args, world), nodes_per_batch=nodes[0], edges_per_batch=edges[0]),
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps, "mode": "eager, pinned host batch -> device every step, loss.item() every step"},
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "mode": "eager launches; pinned host batch -> device on a copy stream one batch ahead; loss.item() every step"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof,
@@ -342,28 +364,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _to_device(host_batch, dev):
-    import copy
-
-    b = copy.copy(host_batch)
-    b.__dict__ = dict(host_batch.__dict__)
-    b.__dict__.pop("_graph_index", None)
-    return b.to(dev, non_blocking=True)
-
-
-def aggregation_roofline(ops, graph_index, dev_batches, args, dev):
-    """Achieved HBM GB/s of the aggregation kernel (drk_spmm, 32-wide rows = both GINet branches of
-    conv1 stacked would be 32; here the per-layer 16-wide conv1 aggregation, the most frequent launch).
-
-    Algorithmic bytes per launch: read src 4*N*F + write out 4*N*F + colidx 4*E + rowptr 4*(N+1).
-    """
-    import torch
-
+def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def step_roofline(args, dev, dev_batches, model, loss_fn):
+    """Achieved algorithmic GB/s of the per-graph step kernel (k_ginet_step + its finalize) against the measured HBM peak.
+    Algorithmic bytes per launch: SURVEY.md 8(d) step formula 2472 N + 24 E for the batch the launch processes."""
+    import torch
+
+    from deeprank2_b200.fused import GINetFusedStep
+
+    peak, peak_src = _peak()
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    fused = GINetFusedStep(model, opt, loss_fn)
+    reps = max(args.steps, 30)
+    for i in range(6):
+        fused.forward_backward(dev_batches[i % len(dev_batches)])
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total_bytes = 0
+    for i, (a, b) in enumerate(evs):
+        batch = dev_batches[i % len(dev_batches)]
+        flush.zero_()  # > L2: the kernel's inputs come from HBM
+        a.record()
+        fused.forward_backward(batch)
+        b.record()
+        total_bytes += algorithmic_step_bytes(batch.num_nodes, batch.num_edges)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    achieved = total_bytes / (ms * 1e-3) / 1e9
+    return {
+        "bound": "hbm",
+        "kernel": "drk_ginet_step (k_ginet_step<train> + k_step_finalize): index build + forward + loss + backward of one 256-graph batch, L2 flushed before every launch",
+        "achieved": achieved,
+        "peak": peak,
+        "peak_source": peak_src,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "us_per_launch": 1e3 * ms / reps,
+        "algorithmic_bytes_per_launch": total_bytes / reps,
+        "algorithmic_model": "SURVEY 8(d): 2472*N + 24*E bytes per train step (every intermediate of the layer-by-layer path written and read once)",
+    }
+
+
+def aggregation_roofline(dev_batches, args, dev):
+    """Achieved HBM GB/s of the layer path's aggregation kernel (drk_spmm, 16-wide conv1 aggregation).
+    Algorithmic bytes per launch: read src 4*N*F + write out 4*N*F + colidx 4*E + rowptr 4*(N+1)."""
+    import torch
+
+    from deeprank2_b200 import ops
+    from deeprank2_b200.graph import graph_index
+
+    peak, peak_src = _peak()
     width = 16
     idx = [graph_index(b) for b in dev_batches]
     srcs = [torch.randn(b.num_nodes, width, device=dev) for b in dev_batches]

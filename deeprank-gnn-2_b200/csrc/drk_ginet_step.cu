@@ -86,6 +86,15 @@ struct StepArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- small helpers
+// One dynamic shared-memory array for every kernel of this file.  The phase functions below are __noinline__ (each gets its own
+// register allocation) and take BYTE OFFSETS into this array instead of pointers: a pointer passed through a call would
+// lose its address space and turn every LDS/STS into a generic 64-bit access.
+extern __shared__ __align__(16) unsigned char g_smem[];
+template <typename T>
+__device__ __forceinline__ T* sm(int byte_offset) {
+  return reinterpret_cast<T*>(g_smem + byte_offset);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -158,24 +167,28 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ s_dst, const floa
 // ---------------------------------------------------------------------------------------------- graph index in shared memory
 // Segment r of the CSR occupies entries [4*info[r].x, 4*info[r].x + info[r].y); an entry is 8 * (local source row), i.e. the
 // byte offset of the gathered 128-byte tile row divided by 16.  Same for the CSC (keyed by source, entries = destinations).
-struct IndexPlan {
-  uint32_t* stash;    // [e_cap] packed (r | c << 16) per edge, 0xffffffff = edge leaves the graph
-  uint16_t* cnt_r;    // [kNW][cstride] per-warp-chunk histograms, then per-warp running offsets
-  uint16_t* cnt_c;
+struct IndexPlan {  // byte offsets into g_smem
+  int stash;    // uint32 [e_cap] packed (r | c << 16) per edge, 0xffffffff = edge leaves the graph
+  int cnt_r;    // uint16 [kNW][cstride] per-warp-chunk histograms, then per-warp running offsets
+  int cnt_c;
   int cstride;
-  ushort2* rinfo;
-  ushort2* cinfo;
-  uint16_t* csr;
-  uint16_t* csc;
-  uint32_t* scan;  // kNW + 1 words
+  int rinfo;    // ushort2 [rows]
+  int cinfo;
+  int csr;      // uint16 entries
+  int csc;
+  int scan;     // kNW + 1 words
 };
 
 // returns the number of CSC entries (padded), or -1 (uniformly) when the graph does not fit / is malformed
 template <bool WANT_CSC>
-__device__ __noinline__ int build_index(const IndexPlan& p, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
-                                           int node0, int n, int32_t* status) {
+__device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
+                                        int node0, int n, int32_t* status) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
+  struct {
+    uint32_t* stash; uint16_t* cnt_r; uint16_t* cnt_c; int cstride; ushort2* rinfo; ushort2* cinfo; uint16_t* csr; uint16_t* csc; uint32_t* scan;
+  } p = {sm<uint32_t>(pl.stash), sm<uint16_t>(pl.cnt_r), sm<uint16_t>(pl.cnt_c), pl.cstride, sm<ushort2>(pl.rinfo), sm<ushort2>(pl.cinfo),
+         sm<uint16_t>(pl.csr), sm<uint16_t>(pl.csc), sm<uint32_t>(pl.scan)};
   // zero the histograms
   {
     uint32_t* z = reinterpret_cast<uint32_t*>(p.cnt_r);
@@ -297,8 +310,11 @@ __device__ __noinline__ int build_index(const IndexPlan& p, const int64_t* __res
 // warp-uniform trip count, entries of a segment in CSR order (= ascending edge id).
 // MODE 0: relu ; MODE 1: none ; MODE 2: in place, dst = sum * (dst > 0)
 template <int MODE>
-__device__ __noinline__ void aggregate(const float* __restrict__ s_src, float* s_dst, const ushort2* __restrict__ info,
-                                          const uint16_t* __restrict__ idx, int n) {
+__device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, int idx_off, int n) {
+  const float* s_src = sm<float>(src_off);
+  float* s_dst = sm<float>(dst_off);
+  const ushort2* info = sm<ushort2>(info_off);
+  const uint16_t* idx = sm<uint16_t>(idx_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
   const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
@@ -312,30 +328,46 @@ __device__ __noinline__ void aggregate(const float* __restrict__ s_src, float* s
       len = inf.y;
       seg = idx + 4 * (int)inf.x;
     }
-    int max_len = len;
+    int max_len = len, min_len = len;
     max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 16));
     max_len = max(max_len, __shfl_xor_sync(kFull, max_len, 8));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int off = 0; off < max_len; off += 8) {
-      const int rem = len - off;
-      uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
-      if (rem > 0) pa = *reinterpret_cast<const uint2*>(seg + off);
-      if (rem > 4) pb = *reinterpret_cast<const uint2*>(seg + off + 4);
+    min_len = min(min_len, __shfl_xor_sync(kFull, min_len, 16));
+    min_len = min(min_len, __shfl_xor_sync(kFull, min_len, 8));
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+    int off = 0;
+    // chunks of 8 sources that every one of the warp's four rows still has: no predicates
+    for (; off + 8 <= min_len; off += 8) {
+      const uint2 pa = *reinterpret_cast<const uint2*>(seg + off);
+      const uint2 pb = *reinterpret_cast<const uint2*>(seg + off + 4);
       const unsigned ent[8] = {pa.x & 0xffffu, pa.x >> 16, pa.y & 0xffffu, pa.y >> 16, pb.x & 0xffffu, pb.x >> 16, pb.y & 0xffffu, pb.y >> 16};
       float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(lane_base + (ent[j] << 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a01 = __fadd2_rn(a01, make_float2(v[j].x, v[j].y));
+        a23 = __fadd2_rn(a23, make_float2(v[j].z, v[j].w));
+      }
+    }
+    // ragged tail: chunks of 4, slots beyond a row's own length predicated off
+    for (; off < max_len; off += 4) {
+      const int rem = len - off;
+      uint2 pa = make_uint2(0u, 0u);
+      if (rem > 0) pa = *reinterpret_cast<const uint2*>(seg + off);
+      const unsigned ent[4] = {pa.x & 0xffffu, pa.x >> 16, pa.y & 0xffffu, pa.y >> 16};
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
         if (j < rem) v[j] = *reinterpret_cast<const float4*>(lane_base + (ent[j] << 4));
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 4; ++j)
         if (j < rem) {
-          acc.x += v[j].x;
-          acc.y += v[j].y;
-          acc.z += v[j].z;
-          acc.w += v[j].w;
+          a01 = __fadd2_rn(a01, make_float2(v[j].x, v[j].y));
+          a23 = __fadd2_rn(a23, make_float2(v[j].z, v[j].w));
         }
     }
     if (!row_ok) continue;
+    float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
     float4* out = reinterpret_cast<float4*>(s_dst + r * kS1 + sl * 4);
     if (MODE == 0) {
       acc.x = acc.x < 0.f ? 0.f : acc.x;
@@ -354,18 +386,24 @@ __device__ __noinline__ void aggregate(const float* __restrict__ s_src, float* s
 }
 
 // ---------------------------------------------------------------------------------------------- dense phases
+// Packed fp32 (FFMA2 / FADD2, sm_100): two independent fp32 operations per instruction, each rounded exactly like the scalar
+// one.  Dot products keep an (even k, odd k) pair of partial sums that is added once at the end.
+
 // P = x W1s^T -> tile.  warp tile = 32 rows x 16 outputs (one branch), lane = 4 rows (rg + 8j) x 4 outputs (4cg..4cg+3)
-__device__ __noinline__ void project_x(const float* __restrict__ sX, const float* __restrict__ sW1, float* __restrict__ sP, int n, int rows_cap, int kp) {
+__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp) {
+  const float* sX = sm<float>(x_off);
+  const float* sW1 = sm<float>(w1_off);
+  float* sP = sm<float>(p_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane & 3, rg = lane >> 2;
   const int n_tiles = 2 * ((n + 31) / 32);
   for (int tl = warp; tl < n_tiles; tl += kNW) {
     const int h = tl & 1, base = (tl >> 1) * 32;
-    float acc[4][4];
+    float2 acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) acc[j][t] = 0.f;
+      for (int t = 0; t < 4; ++t) acc[j][t] = make_float2(0.f, 0.f);
     const float* xr[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) xr[j] = sX + min(base + rg + 8 * j, rows_cap - 1) * kp;  // rows beyond n: results are not stored
@@ -380,18 +418,16 @@ __device__ __noinline__ void project_x(const float* __restrict__ sX, const float
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          float s = acc[j][t];
-          s = fmaf(av[j].x, bv[t].x, s);
-          s = fmaf(av[j].y, bv[t].y, s);
-          s = fmaf(av[j].z, bv[t].z, s);
-          s = fmaf(av[j].w, bv[t].w, s);
-          acc[j][t] = s;
+          acc[j][t] = __ffma2_rn(make_float2(av[j].x, av[j].y), make_float2(bv[t].x, bv[t].y), acc[j][t]);
+          acc[j][t] = __ffma2_rn(make_float2(av[j].z, av[j].w), make_float2(bv[t].z, bv[t].w), acc[j][t]);
         }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = base + rg + 8 * j;
-      if (r < n) *reinterpret_cast<float4*>(sP + r * kS1 + h * 16 + 4 * cg) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      if (r < n)
+        *reinterpret_cast<float4*>(sP + r * kS1 + h * 16 + 4 * cg) =
+            make_float4(acc[j][0].x + acc[j][0].y, acc[j][1].x + acc[j][1].y, acc[j][2].x + acc[j][2].y, acc[j][3].x + acc[j][3].y);
     }
   }
 }
@@ -399,37 +435,43 @@ __device__ __noinline__ void project_x(const float* __restrict__ sX, const float
 // Z2 = A2 W2^T per branch: column sums of relu(Z2) (readout) -> sRed[8][64]; when TRAIN also the sign mask of Z2 (one 32-bit word
 // per row and branch) and the masked column sums of A2 (dW2 = dG/n * those), left as 8 row-lane partials [rl][c][k] in the A2 tile.
 template <bool TRAIN>
-__device__ __noinline__ void conv2_readout(float* sA2, const float* __restrict__ sW2, uint32_t* __restrict__ sMaskZ, float* __restrict__ sRed, int n) {
+__device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off, int red_off, int n) {
+  float* sA2 = sm<float>(a2_off);
+  const float* sW2 = sm<float>(w2_off);
+  uint32_t* sMaskZ = sm<uint32_t>(maskz_off);
+  float* sRed = sm<float>(red_off);
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = tid & 63, rl = tid >> 6, br = c >> 5;
-  float w[kF1], s[kF1];
+  float2 w[kF1 / 2], s[kF1 / 2];
 #pragma unroll
-  for (int k = 0; k < kF1; ++k) {
-    w[k] = sW2[(br * kF2 + (c & 31)) * kF1 + k];
-    s[k] = 0.f;
+  for (int k = 0; k < kF1 / 2; ++k) {
+    w[k] = *reinterpret_cast<const float2*>(sW2 + (br * kF2 + (c & 31)) * kF1 + 2 * k);
+    s[k] = make_float2(0.f, 0.f);
   }
   float colsum = 0.f;
   for (int r = rl; r < n; r += 8) {
     const float* arow = sA2 + r * kS1 + br * kF1;
-    float av[kF1];
+    float2 av[kF1 / 2];
 #pragma unroll
-    for (int k4 = 0; k4 < kF1; k4 += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(arow + k4);
-      av[k4] = v.x; av[k4 + 1] = v.y; av[k4 + 2] = v.z; av[k4 + 3] = v.w;
+    for (int k4 = 0; k4 < kF1 / 4; ++k4) {
+      const float4 v = *reinterpret_cast<const float4*>(arow + 4 * k4);
+      av[2 * k4] = make_float2(v.x, v.y);
+      av[2 * k4 + 1] = make_float2(v.z, v.w);
     }
-    float z0 = 0.f, z1 = 0.f;
+    float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < kF1; k += 2) {
-      z0 = fmaf(av[k], w[k], z0);
-      z1 = fmaf(av[k + 1], w[k + 1], z1);
+    for (int k = 0; k < kF1 / 2; k += 2) {
+      z0 = __ffma2_rn(av[k], w[k], z0);
+      z1 = __ffma2_rn(av[k + 1], w[k + 1], z1);
     }
-    const float z = z0 + z1;
+    const float z = (z0.x + z0.y) + (z1.x + z1.y);
     const bool pos = z > 0.f;
     if (pos) colsum += z;
     if (TRAIN) {
+      if (pos) {
 #pragma unroll
-      for (int k = 0; k < kF1; ++k)
-        if (pos) s[k] += av[k];
+        for (int k = 0; k < kF1 / 2; ++k) s[k] = __fadd2_rn(s[k], av[k]);
+      }
       const unsigned word = __ballot_sync(kFull, pos);
       if (lane == 0) sMaskZ[r * 2 + br] = word;
     }
@@ -438,70 +480,78 @@ __device__ __noinline__ void conv2_readout(float* sA2, const float* __restrict__
   if (TRAIN) {
     __syncthreads();  // every warp is done reading A2: reuse the tile as the 8-way reduction scratch
 #pragma unroll
-    for (int k4 = 0; k4 < kF1; k4 += 4)
-      *reinterpret_cast<float4*>(sA2 + ((rl * kS2 + c) * kF1 + k4)) = make_float4(s[k4], s[k4 + 1], s[k4 + 2], s[k4 + 3]);
+    for (int k4 = 0; k4 < kF1 / 4; ++k4)
+      *reinterpret_cast<float4*>(sA2 + ((rl * kS2 + c) * kF1 + 4 * k4)) = make_float4(s[2 * k4].x, s[2 * k4].y, s[2 * k4 + 1].x, s[2 * k4 + 1].y);
   }
 }
 
 // dA2[r, br*16 + k] = sum_{c in branch, Z2[r,c] > 0} V[c, k] -> tile.  lane -> row, warp -> (branch, 8 outputs)
-__device__ __noinline__ void conv2_backward_input(const float* __restrict__ sV, const uint32_t* __restrict__ sMaskZ, float* __restrict__ sOut, int n) {
+__device__ __noinline__ void conv2_backward_input(int v_off, int maskz_off, int out_off, int n) {
+  const float* sV = sm<float>(v_off);
+  const uint32_t* sMaskZ = sm<uint32_t>(maskz_off);
+  float* sOut = sm<float>(out_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int combo = warp & 3, br = combo >> 1, kh = combo & 1;
   const float* vb = sV + br * kF2 * kF1 + kh * 8;
   for (int r = (warp >> 2) * 32 + lane; r < n; r += 128) {
     const unsigned m = sMaskZ[r * 2 + br];
-    float o[8];
+    float2 o[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    for (int k = 0; k < 4; ++k) o[k] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < kF2; ++c) {
       const float4 v0 = *reinterpret_cast<const float4*>(vb + c * kF1);
       const float4 v1 = *reinterpret_cast<const float4*>(vb + c * kF1 + 4);
       if (m & (1u << c)) {
-        o[0] += v0.x; o[1] += v0.y; o[2] += v0.z; o[3] += v0.w;
-        o[4] += v1.x; o[5] += v1.y; o[6] += v1.z; o[7] += v1.w;
+        o[0] = __fadd2_rn(o[0], make_float2(v0.x, v0.y));
+        o[1] = __fadd2_rn(o[1], make_float2(v0.z, v0.w));
+        o[2] = __fadd2_rn(o[2], make_float2(v1.x, v1.y));
+        o[3] = __fadd2_rn(o[3], make_float2(v1.z, v1.w));
       }
     }
     float* out = sOut + r * kS1 + br * kF1 + kh * 8;
-    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<float4*>(out) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+    *reinterpret_cast<float4*>(out + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
   }
 }
 
 // dW1s[m, k] = sum_r Q[r, m] x[r, k]: lane -> (mg: 4 outputs m, kgl: 4 features k), warp -> (k block of 16, row split wn);
 // the four row-split partials go to sScr[wn][m][kp]
-__device__ __noinline__ void conv1_weight_grad(const float* __restrict__ sQ, const float* __restrict__ sX, float* __restrict__ sScr, int n, int kp) {
+__device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off, int n, int kp) {
+  const float* sQ = sm<float>(q_off);
+  const float* sX = sm<float>(x_off);
+  float* sScr = sm<float>(scr_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wk = warp & 3, wn = warp >> 2;
   const int mg = lane & 7, kgl = lane >> 3;
   const int k0 = wk * 16 + kgl * 4;
   if (k0 >= kp) return;  // kp is a multiple of 4: a float4 of features is all-in or all-out
-  float dw[4][4];
+  float2 dw[4][2];  // [m][k pair]
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dw[i][j] = 0.f;
+  for (int i = 0; i < 4; ++i) dw[i][0] = dw[i][1] = make_float2(0.f, 0.f);
   const float* qp = sQ + mg * 4;
   const float* xp = sX + k0;
   for (int r = wn; r < n; r += 4) {
     const float4 qa = *reinterpret_cast<const float4*>(qp + r * kS1);
     const float4 xb = *reinterpret_cast<const float4*>(xp + r * kp);
     const float qv[4] = {qa.x, qa.y, qa.z, qa.w};
-    const float xv[4] = {xb.x, xb.y, xb.z, xb.w};
+    const float2 x01 = make_float2(xb.x, xb.y), x23 = make_float2(xb.z, xb.w);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dw[i][j] = fmaf(qv[i], xv[j], dw[i][j]);
+    for (int i = 0; i < 4; ++i) {
+      const float2 qq = make_float2(qv[i], qv[i]);
+      dw[i][0] = __ffma2_rn(qq, x01, dw[i][0]);
+      dw[i][1] = __ffma2_rn(qq, x23, dw[i][1]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(sScr + (wn * kS1 + mg * 4 + i) * kp + k0) = make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]);
+    *reinterpret_cast<float4*>(sScr + (wn * kS1 + mg * 4 + i) * kp + k0) = make_float4(dw[i][0].x, dw[i][0].y, dw[i][1].x, dw[i][1].y);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
 template <bool TRAIN>
 __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* smem = g_smem;
   __shared__ int s_next;
   const Layout L = make_layout(a.fi, a.rows_cap, a.ent_cap);
   const int kp = L.kp;
@@ -522,21 +572,19 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
 
   IndexPlan plan;
   plan.cstride = a.rows_cap;
+  plan.cnt_r = L.t0;
+  plan.cnt_c = L.t0 + kNW * a.rows_cap * 2;
   if (!a.mode_b) {  // low degree: stash in tile 1, histograms + CSC staging in tile 0, x prefetched under the index build
-    plan.stash = reinterpret_cast<uint32_t*>(sT1);
-    plan.cnt_r = reinterpret_cast<uint16_t*>(sT0);
-    plan.cnt_c = plan.cnt_r + kNW * a.rows_cap;
-    plan.csc = plan.cnt_c + kNW * a.rows_cap;
+    plan.stash = L.t1;
+    plan.csc = plan.cnt_c + kNW * a.rows_cap * 2;
   } else {  // high degree: stash in the x region (x is loaded afterwards), CSC staging in tile 1
-    plan.stash = reinterpret_cast<uint32_t*>(sX);
-    plan.cnt_r = reinterpret_cast<uint16_t*>(sT0);
-    plan.cnt_c = plan.cnt_r + kNW * a.rows_cap;
-    plan.csc = reinterpret_cast<uint16_t*>(sT1);
+    plan.stash = L.x;
+    plan.csc = L.t1;
   }
-  plan.rinfo = sRinfo;
-  plan.cinfo = sCinfo;
-  plan.csr = sIdx;
-  plan.scan = reinterpret_cast<uint32_t*>(sHead + kHScan);
+  plan.rinfo = L.rinfo;
+  plan.cinfo = L.cinfo;
+  plan.csr = L.idx;
+  plan.scan = L.head + kHScan * 4;
 
   // ---- weights once per CTA.  W1 as [k/4][pos][4]: logical output m = 16*h + 4*cg + t sits at pos = 16*h + cg + 4*t, so the four
   // lanes cg = 0..3 of a quad read four consecutive 16-byte chunks (conflict-free)
@@ -575,7 +623,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status);
     uint16_t* spill = TRAIN ? a.csc_spill + (size_t)blockIdx.x * a.ent_cap : nullptr;
     if (TRAIN) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
-      const uint4* src = reinterpret_cast<const uint4*>(plan.csc);
+      const uint4* src = sm<uint4>(plan.csc);
       uint4* dst = reinterpret_cast<uint4*>(spill);
       for (int i = tid; i < (csc_entries + 7) / 8; i += kT) dst[i] = src[i];
     }
@@ -587,19 +635,19 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     cp_async_wait<0>();
     __syncthreads();
 
-    project_x(sX, sW1, sT0, n, a.rows_cap, kp);
+    project_x(L.x, L.w1, L.t0, n, a.rows_cap, kp);
     __syncthreads();
     // ---- H1 = relu(A P) -> tile 1 ; A2 = A H1 -> tile 0
-    aggregate<0>(sT0, sT1, sRinfo, sIdx, n);
+    aggregate<0>(L.t0, L.t1, L.rinfo, L.idx, n);
     __syncthreads();
-    aggregate<1>(sT1, sT0, sRinfo, sIdx, n);
+    aggregate<1>(L.t1, L.t0, L.rinfo, L.idx, n);
     __syncthreads();
     if (TRAIN) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
       const int chunks = (csc_entries + 7) / 8;
       for (int i = tid; i < chunks; i += kT) cp_async_cg16(sIdx + i * 8, spill + i * 8);  // L2 only: this CTA wrote it moments ago
       cp_async_commit();
     }
-    conv2_readout<TRAIN>(sT0, sW2, sMaskZ, sRed, n);
+    conv2_readout<TRAIN>(L.t0, L.w2, L.maskz, L.red, n);
     __syncthreads();
     float* hG = sHead + kHG;
     float* hDG = sHead + kHDG;
@@ -740,15 +788,15 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       sV[e] = dgc * sW2[e];
     }
     __syncthreads();
-    conv2_backward_input(sV, sMaskZ, sT0, n);
+    conv2_backward_input(L.v, L.maskz, L.t0, n);
     cp_async_wait<0>();  // the CSC is back in the index region
     __syncthreads();
     // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
-    aggregate<2>(sT0, sT1, sCinfo, sIdx, n);
+    aggregate<2>(L.t0, L.t1, L.cinfo, L.idx, n);
     __syncthreads();
-    aggregate<1>(sT1, sT0, sCinfo, sIdx, n);
+    aggregate<1>(L.t1, L.t0, L.cinfo, L.idx, n);
     __syncthreads();
-    conv1_weight_grad(sT0, sX, sT1, n, kp);
+    conv1_weight_grad(L.t0, L.x, L.t1, n, kp);
     __syncthreads();
     for (int e = tid; e < kS1 * kp; e += kT) {
       float s = 0.f;
@@ -824,7 +872,7 @@ struct BlockedIndexArgs {
 };
 
 __global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* smem = g_smem;
   // regions: stash [e_cap] u32 | cnt_r, cnt_c [kNW][rows_cap] u16 | degrees/starts [rows_cap] u32 x2 | scan
   uint32_t* stash = reinterpret_cast<uint32_t*>(smem);
   uint16_t* cnt_r = reinterpret_cast<uint16_t*>(stash + a.e_cap);
@@ -1038,7 +1086,8 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   DRK_REQUIRE(make_plan(fi, max_graph_nodes, max_graph_edges, p), DRK_EUNSUPPORTED,
               "ginet step: graphs of %d nodes / %d edges with %d features do not fit the shared-memory plan", max_graph_nodes, max_graph_edges, fi);
   if (num_graphs == 0) return DRK_OK;
-  DRK_REQUIRE(x && edge_index && graph_ptr && edge_ptr && w1a && w1b && w2a && w2b && fc1_w && fc1_b && fc2_w && fc2_b && pred, DRK_EINVAL,
+  DRK_REQUIRE(edge_index || num_edges == 0, DRK_EINVAL, "ginet step: null edge_index");
+  DRK_REQUIRE(x && graph_ptr && edge_ptr && w1a && w1b && w2a && w2b && fc1_w && fc1_b && fc2_w && fc2_b && pred, DRK_EINVAL,
               "ginet step: null pointer");
   DRK_REQUIRE(aligned16(fc1_w) && aligned16(fc2_w), DRK_EINVAL, "ginet step: head weights must be 16-byte aligned");
   if (train) {
