@@ -54,13 +54,14 @@ SIGNATURES = {
     "drk_edge_ptr": (c_int32, [_P, _I64, _P, _I32, _P, _P]),
     "drk_graph_index_blocked_supported": (c_int32, [_I32, _I32]),
     "drk_graph_index_build_blocked": (c_int32, [_P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "drk_ginet_step_ctas": (c_int32, [_I32]),
     "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
     "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),
     "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _I32, _I32,   # x .. max_graph_edges
                                  _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
                                  _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients
-                                 _P, _P, _P, c_size_t, _P]),                                 # counter, status, workspace, stream
+                                 _P, _P, c_size_t, _P]),                                     # status, workspace, stream
     "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),

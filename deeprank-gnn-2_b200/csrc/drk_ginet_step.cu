@@ -46,9 +46,9 @@ __host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
 
 // byte offsets of the shared-memory regions
 struct Layout {
-  int kp, t0, t1, x, idx, rinfo, cinfo, w1, w2, s, v, maskz, red, head, total;
+  int kp, t0, t1, x, idx, rinfo, cinfo, rperm, cperm, w1, w2, s, v, maskz, red, head, extra, total;
 };
-__host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap) {
+__host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap, int extra_bytes = 0) {
   Layout L;
   L.kp = pad_kp(fi);
   int o = 0;
@@ -58,23 +58,26 @@ __host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap)
   L.idx = o; o += align16(ent_cap * 2);
   L.rinfo = o; o += align16(rows_cap * 4);
   L.cinfo = o; o += align16(rows_cap * 4);
+  L.rperm = o; o += align16(rows_cap * 2);
+  L.cperm = o; o += align16(rows_cap * 2);
   L.w1 = o; o += kS1 * L.kp * 4;
   L.w2 = o; o += 2 * kF2 * kF1 * 4;
   L.s = o; o += kS2 * kF1 * 4;
   L.v = o; o += kS2 * kF1 * 4;
   L.maskz = o; o += align16(rows_cap * 8);
   L.red = o; o += 8 * kS2 * 4;
-  L.head = o; o += 704 * 4;
+  L.head = o; o += 832 * 4;
+  L.extra = o; o += align16(extra_bytes);  // index-build scratch that found no idle region
   L.total = o;
   return L;
 }
-// head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[32] ...
+// head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[32] degree bins / cursors [256]
 constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528;
 
 struct StepArgs {
   const float* x; int64_t ldx; int32_t fi;
   const int64_t* erow; const int64_t* ecol;
-  const int32_t* graph_ptr; const int32_t* edge_ptr; const int32_t* order; int32_t* counter; int32_t num_graphs;
+  const int32_t* graph_ptr; const int32_t* edge_ptr; const int32_t* order; int32_t num_graphs;
   const float* w1a; const float* w1b; const float* w2a; const float* w2b;
   const float* fc1_w; const float* fc1_b; const float* fc2_w; const float* fc2_b; int32_t out_dim;
   int32_t loss_kind; const float* y; const int64_t* y_cls; float dloss_scale;
@@ -82,7 +85,7 @@ struct StepArgs {
   float* pred; float* loss_terms; float* part; int32_t part_stride;
   float* gvec; float* hvec; float* dhvec; float* dpvec;
   uint16_t* csc_spill; int32_t* status;
-  int32_t rows_cap, e_cap, ent_cap, mode_b, x_vec;
+  int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;  // *_off: index-build scratch (bytes into shared memory)
 };
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -144,24 +147,33 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // copy rows [node0, node0+n) of a row-major global matrix (ld elements, width fi) into smem with row stride kp,
-// zero-filling the padding columns; asynchronous (cp.async), the caller commits / waits.
-__device__ __forceinline__ void stage_rows(float* __restrict__ s_dst, const float* __restrict__ src, int64_t ld, int fi, int kp, int node0,
-                                           int n, int vec) {
-  const int nv = fi / vec;
-  for (int e = threadIdx.x; e < n * nv; e += kT) {
-    const int r = e / nv;
-    const int v = e - r * nv;
-    const float* s = src + (int64_t)(node0 + r) * ld + v * vec;
-    float* d = s_dst + r * kp + v * vec;
-    if (vec == 4) cp_async<16>(d, s, true);
-    else if (vec == 2) cp_async<8>(d, s, true);
-    else cp_async<4>(d, s, true);
+// zero-filling the padding columns; asynchronous (cp.async), the caller commits / waits.  One warp per row, VEC floats per lane.
+template <int VEC>
+__device__ __forceinline__ void stage_rows_v(float* __restrict__ s_dst, const float* __restrict__ src, int64_t ld, int fi, int kp, int node0, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = fi / VEC, pad = kp - nv * VEC;
+  const float* s = src + (int64_t)(node0 + warp) * ld + lane * VEC;
+  float* d = s_dst + warp * kp + lane * VEC;
+  float* z = s_dst + warp * kp + nv * VEC + lane;
+  for (int r = warp; r < n; r += kNW) {
+    for (int v = lane; v < nv; v += 32) cp_async<4 * VEC>(d + (v - lane) * VEC, s + (v - lane) * VEC, true);
+    if (lane < pad) *z = 0.f;
+    s += kNW * ld;
+    d += kNW * kp;
+    z += kNW * kp;
   }
-  const int pv = kp - nv * vec;
-  for (int e = threadIdx.x; e < n * pv; e += kT) {
-    const int r = e / pv;
-    s_dst[r * kp + nv * vec + (e - r * pv)] = 0.f;
-  }
+}
+__device__ __forceinline__ void stage_rows(float* s_dst, const float* src, int64_t ld, int fi, int kp, int node0, int n, int vec) {
+  if (vec == 4) stage_rows_v<4>(s_dst, src, ld, fi, kp, node0, n);
+  else if (vec == 2) stage_rows_v<2>(s_dst, src, ld, fi, kp, node0, n);
+  else stage_rows_v<1>(s_dst, src, ld, fi, kp, node0, n);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// pull [p, p + bytes) into L2 (one prefetch per 128-byte line, spread over the CTA)
+__device__ __forceinline__ void prefetch_range_l2(const void* p, long long bytes) {
+  const char* c = static_cast<const char*>(p);
+  for (long long off = (long long)threadIdx.x * 128; off < bytes; off += (long long)kT * 128) prefetch_l2(c + off);
 }
 
 // ---------------------------------------------------------------------------------------------- graph index in shared memory
@@ -169,136 +181,182 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ s_dst, const floa
 // byte offset of the gathered 128-byte tile row divided by 16.  Same for the CSC (keyed by source, entries = destinations).
 struct IndexPlan {  // byte offsets into g_smem
   int stash;    // uint32 [e_cap] packed (r | c << 16) per edge, 0xffffffff = edge leaves the graph
-  int cnt_r;    // uint16 [kNW][cstride] per-warp-chunk histograms, then per-warp running offsets
+  int ranks;    // uint32 [e_cap] rank of the edge among the equal-destination (low half) / equal-source (high half) edges of its warp chunk
+  int cnt_r;    // uint16 [kNW][cstride] per-warp-chunk histograms, then the chunks' running offsets inside each segment
   int cnt_c;
   int cstride;
-  int rinfo;    // ushort2 [rows]
+  int rinfo;    // ushort2 [rows]: (segment start / 4, degree)
   int cinfo;
+  int rperm;    // uint16 [rows]: rows by decreasing in-degree (issue order of the aggregation)
+  int cperm;
   int csr;      // uint16 entries
   int csc;
-  int scan;     // kNW + 1 words
+  int scan;     // kNW + 1 words, then 4 x 64 words of degree histogram / cursors
 };
 
-// returns the number of CSC entries (padded), or -1 (uniformly) when the graph does not fit / is malformed
+constexpr int kDegBins = 64;
+
+// returns the number of CSC entries (padded)
 template <bool WANT_CSC>
 __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
                                         int node0, int n, int32_t* status) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = lanemask_lt();
-  struct {
-    uint32_t* stash; uint16_t* cnt_r; uint16_t* cnt_c; int cstride; ushort2* rinfo; ushort2* cinfo; uint16_t* csr; uint16_t* csc; uint32_t* scan;
-  } p = {sm<uint32_t>(pl.stash), sm<uint16_t>(pl.cnt_r), sm<uint16_t>(pl.cnt_c), pl.cstride, sm<ushort2>(pl.rinfo), sm<ushort2>(pl.cinfo),
-         sm<uint16_t>(pl.csr), sm<uint16_t>(pl.csc), sm<uint32_t>(pl.scan)};
+  uint32_t* stash = sm<uint32_t>(pl.stash);
+  uint32_t* ranks = sm<uint32_t>(pl.ranks);
+  uint16_t* cnt_r = sm<uint16_t>(pl.cnt_r);
+  uint16_t* cnt_c = sm<uint16_t>(pl.cnt_c);
+  const int cs = pl.cstride;
+  ushort2* rinfo = sm<ushort2>(pl.rinfo);
+  ushort2* cinfo = sm<ushort2>(pl.cinfo);
+  uint32_t* scan = sm<uint32_t>(pl.scan);
+  int* hist = reinterpret_cast<int*>(scan + 32);  // [0,64) in-degree bins, [64,128) out-degree bins, [128,256) their cursors
   // zero the histograms
   {
-    uint32_t* z = reinterpret_cast<uint32_t*>(p.cnt_r);
-    const int words = kNW * p.cstride / 2;
-    for (int i = threadIdx.x; i < words; i += kT) z[i] = 0u;
+    uint32_t* z = reinterpret_cast<uint32_t*>(cnt_r);
+    const int words = kNW * cs / 2;
+    for (int i = tid; i < words; i += kT) z[i] = 0u;
     if (WANT_CSC) {
-      z = reinterpret_cast<uint32_t*>(p.cnt_c);
-      for (int i = threadIdx.x; i < words; i += kT) z[i] = 0u;
+      z = reinterpret_cast<uint32_t*>(cnt_c);
+      for (int i = tid; i < words; i += kT) z[i] = 0u;
     }
+    if (tid < 2 * kDegBins) hist[tid] = 0;
   }
+  __syncthreads();
   const int chunk = ((ne + kNW - 1) / kNW + 31) & ~31;
   const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
-  // pass 1: stream the warp's chunk of the edge list (independent 8-byte loads, 4 edges in flight per lane)
-  bool bad = false;
-  for (int i0 = wb; i0 < we; i0 += 128) {
-    long long rr[4], cc[4];
+  // passes 1+2, software pipelined in groups of 8 batches (256 edges) per warp: the 8-byte loads of the next group are in flight
+  // while the current group is matched.
+  //   pass 1: local ids of the edge's endpoints -> stash (an edge leaving the graph is dropped and flagged);
+  //   pass 2: per-warp histograms of destinations / sources and every edge's rank among the equal keys of its warp chunk.
+  //           The histogram rows are warp-private: the first lane of each group of equal keys (MATCH.ANY) does a plain
+  //           read-modify-write.  MATCH serialises over the warp's distinct values (~32 cycles of a shared unit), which is
+  //           exactly the time the next group's global loads need.
+  {
+    uint16_t* my_r = cnt_r + warp * cs;
+    uint16_t* my_c = cnt_c + warp * cs;
+    bool bad = false;
+    long long rr[8], cc[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 32 + lane;
+    for (int u = 0; u < 8; ++u) {
+      const int i = wb + u * 32 + lane;
       rr[u] = i < we ? ld_stream_i64(erow + e0 + i) : 0;
       cc[u] = i < we ? ld_stream_i64(ecol + e0 + i) : 0;
     }
+    for (int i0 = wb; i0 < we; i0 += 256) {
+      unsigned pk[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 32 + lane;
-      if (i < we) {
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 32 + lane;
         const unsigned long long r = (unsigned long long)(rr[u] - node0), c = (unsigned long long)(cc[u] - node0);
-        const bool ok = r < (unsigned long long)n && c < (unsigned long long)n;
-        bad |= !ok;
-        p.stash[i] = ok ? ((unsigned)r | ((unsigned)c << 16)) : 0xffffffffu;
+        const bool ok = i < we && r < (unsigned long long)n && c < (unsigned long long)n;
+        bad |= i < we && !ok;
+        pk[u] = ok ? ((unsigned)r | ((unsigned)c << 16)) : 0xffffffffu;
+        if (i < we) stash[i] = pk[u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {  // next group's loads (predicated off past the end of the chunk)
+        const int i = i0 + 256 + u * 32 + lane;
+        rr[u] = i < we ? ld_stream_i64(erow + e0 + i) : 0;
+        cc[u] = i < we ? ld_stream_i64(ecol + e0 + i) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i0 + u * 32 >= we) break;  // warp-uniform
+        const bool ok = pk[u] != 0xffffffffu;
+        const unsigned r = pk[u] & 0xffffu, c = pk[u] >> 16;
+        const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
+        const unsigned mc = WANT_CSC ? __match_any_sync(kFull, ok ? c : 0x10000u + lane) : 0u;
+        unsigned base_r = 0, base_c = 0;
+        if (ok) {
+          base_r = my_r[r];
+          if (WANT_CSC) base_c = my_c[c];
+        }
+        if (i < we) ranks[i] = (base_r + __popc(mr & lt)) | ((base_c + __popc(mc & lt)) << 16);
+        __syncwarp();
+        if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(base_r + __popc(mr));
+        if (WANT_CSC && ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
+        __syncwarp();
       }
     }
-  }
-  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
-  __syncthreads();  // histograms are zero, the stash is complete
-  // pass 2: per-warp histograms of destinations / sources (warp-private rows: plain read-modify-write by one leader lane)
-  {
-    uint16_t* my_r = p.cnt_r + warp * p.cstride;
-    uint16_t* my_c = p.cnt_c + warp * p.cstride;
-    for (int i0 = wb; i0 < we; i0 += 32) {
-      const int i = i0 + lane;
-      const unsigned pk = i < we ? p.stash[i] : 0xffffffffu;
-      const bool ok = pk != 0xffffffffu;
-      const unsigned r = pk & 0xffffu, c = pk >> 16;
-      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
-      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(my_r[r] + __popc(mr));
-      if (WANT_CSC) {
-        const unsigned mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
-        if (ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(my_c[c] + __popc(mc));
-      }
-      __syncwarp();
-    }
+    if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
   }
   __syncthreads();
-  // pass 3: (node, warp)-ordered exclusive scan: running offset of every warp chunk inside its segment, padded segment starts
+  // pass 3: (node, warp)-ordered exclusive scan: offset of every warp chunk inside its segment, padded segment starts, degree bins
   uint32_t carry = 0;
   for (int vb = 0; vb < n; vb += kT) {
-    const int v = vb + threadIdx.x;
+    const int v = vb + tid;
     uint32_t dr = 0, dc = 0;
     if (v < n) {
 #pragma unroll
       for (int w = 0; w < kNW; ++w) {
-        const uint32_t t = p.cnt_r[w * p.cstride + v];
-        p.cnt_r[w * p.cstride + v] = (uint16_t)dr;
+        const uint32_t t = cnt_r[w * cs + v];
+        cnt_r[w * cs + v] = (uint16_t)dr;
         dr += t;
       }
       if (WANT_CSC) {
 #pragma unroll
         for (int w = 0; w < kNW; ++w) {
-          const uint32_t t = p.cnt_c[w * p.cstride + v];
-          p.cnt_c[w * p.cstride + v] = (uint16_t)dc;
+          const uint32_t t = cnt_c[w * cs + v];
+          cnt_c[w * cs + v] = (uint16_t)dc;
           dc += t;
         }
       }
+      atomicAdd(&hist[min((int)dr, kDegBins - 1)], 1);
+      if (WANT_CSC) atomicAdd(&hist[kDegBins + min((int)dc, kDegBins - 1)], 1);
     }
     const uint32_t packed = ((dr + 3u) & ~3u) | (((dc + 3u) & ~3u) << 16);
     uint32_t total;
-    const uint32_t ex = block_excl_scan(packed, p.scan, total) + carry;
+    const uint32_t ex = block_excl_scan(packed, scan, total) + carry;
     if (v < n) {
-      p.rinfo[v] = make_ushort2((unsigned short)((ex & 0xffffu) >> 2), (unsigned short)dr);
-      if (WANT_CSC) p.cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
+      rinfo[v] = make_ushort2((unsigned short)((ex & 0xffffu) >> 2), (unsigned short)dr);
+      if (WANT_CSC) cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
     }
     carry += total;
   }
   __syncthreads();
-  // pass 4: ordered placement.  Lanes hold consecutive edges; equal keys inside the 32-edge group are ranked by lane.
-  {
-    uint16_t* my_r = p.cnt_r + warp * p.cstride;
-    uint16_t* my_c = p.cnt_c + warp * p.cstride;
-    for (int i0 = wb; i0 < we; i0 += 32) {
-      const int i = i0 + lane;
-      const unsigned pk = i < we ? p.stash[i] : 0xffffffffu;
-      const bool ok = pk != 0xffffffffu;
-      const unsigned r = pk & 0xffffu, c = pk >> 16;
-      const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
-      unsigned mc = 0;
-      if (WANT_CSC) mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
-      int base_r = 0, base_c = 0;
-      if (ok) {
-        base_r = my_r[r];
-        p.csr[4 * p.rinfo[r].x + base_r + __popc(mr & lt)] = (uint16_t)(c * 8u);
-        if (WANT_CSC) {
-          base_c = my_c[c];
-          p.csc[4 * p.cinfo[c].x + base_c + __popc(mc & lt)] = (uint16_t)(r * 8u);
-        }
+  // rows by decreasing degree: cursor[bin] = number of rows with a larger degree bin (warp 0: in-degrees, warp 1: out-degrees)
+  if (warp < (WANT_CSC ? 2 : 1)) {
+    const int* h = hist + warp * kDegBins;
+    const int hi = h[kDegBins - 1 - lane], lo = h[kDegBins / 2 - 1 - lane];  // lane 0 holds the largest bins
+    int inc_hi = hi, inc_lo = lo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc_hi, o), u = __shfl_up_sync(kFull, inc_lo, o);
+      if (lane >= o) {
+        inc_hi += t;
+        inc_lo += u;
       }
-      __syncwarp();
-      if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(base_r + __popc(mr));
-      if (WANT_CSC && ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
-      __syncwarp();
+    }
+    const int total_hi = __shfl_sync(kFull, inc_hi, 31);
+    int* cur = hist + 2 * kDegBins + warp * kDegBins;
+    cur[kDegBins - 1 - lane] = inc_hi - hi;
+    cur[kDegBins / 2 - 1 - lane] = total_hi + inc_lo - lo;
+  }
+  __syncthreads();
+  {
+    uint16_t* rperm = sm<uint16_t>(pl.rperm);
+    uint16_t* cperm = sm<uint16_t>(pl.cperm);
+    int* cur = hist + 2 * kDegBins;
+    for (int v = tid; v < n; v += kT) {
+      rperm[atomicAdd(&cur[min((int)rinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;
+      if (WANT_CSC) cperm[atomicAdd(&cur[kDegBins + min((int)cinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;
+    }
+  }
+  // pass 4: placement, every edge independently: position = segment start + offset of its warp chunk + rank inside the chunk
+  {
+    uint16_t* csr = sm<uint16_t>(pl.csr);
+    uint16_t* csc = sm<uint16_t>(pl.csc);
+    const uint16_t* my_r = cnt_r + warp * cs;
+    const uint16_t* my_c = cnt_c + warp * cs;
+    for (int i = wb + lane; i < we; i += 32) {
+      const unsigned pk = stash[i];
+      if (pk == 0xffffffffu) continue;
+      const unsigned rk = ranks[i];
+      const unsigned r = pk & 0xffffu, c = pk >> 16;
+      csr[4 * rinfo[r].x + my_r[r] + (rk & 0xffffu)] = (uint16_t)(c * 8u);
+      if (WANT_CSC) csc[4 * cinfo[c].x + my_c[c] + (rk >> 16)] = (uint16_t)(r * 8u);
     }
   }
   __syncthreads();
@@ -310,20 +368,21 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
 // warp-uniform trip count, entries of a segment in CSR order (= ascending edge id).
 // MODE 0: relu ; MODE 1: none ; MODE 2: in place, dst = sum * (dst > 0)
 template <int MODE>
-__device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, int idx_off, int n) {
+__device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, int perm_off, int idx_off, int n) {
   const float* s_src = sm<float>(src_off);
   float* s_dst = sm<float>(dst_off);
   const ushort2* info = sm<ushort2>(info_off);
+  const uint16_t* perm = sm<uint16_t>(perm_off);
   const uint16_t* idx = sm<uint16_t>(idx_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
   const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
-  for (int rw = warp * 4; rw < n; rw += kNW * 4) {
-    const int r = rw + sub;
-    const bool row_ok = r < n;
-    int len = 0;
+  for (int rw = warp * 4; rw < n; rw += kNW * 4) {  // rows in order of decreasing degree: the warp's four rows are equally long
+    const bool row_ok = rw + sub < n;
+    int r = 0, len = 0;
     const uint16_t* seg = idx;
     if (row_ok) {
+      r = perm[rw + sub];
       const ushort2 inf = info[r];
       len = inf.y;
       seg = idx + 4 * (int)inf.x;
@@ -389,33 +448,35 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
 // Packed fp32 (FFMA2 / FADD2, sm_100): two independent fp32 operations per instruction, each rounded exactly like the scalar
 // one.  Dot products keep an (even k, odd k) pair of partial sums that is added once at the end.
 
-// P = x W1s^T -> tile.  warp tile = 32 rows x 16 outputs (one branch), lane = 4 rows (rg + 8j) x 4 outputs (4cg..4cg+3)
+// P = x W1s^T -> tile.  warp tile = 8J rows x 16 outputs (one branch), lane = J rows (rg + 8j) x 4 outputs (4cg..4cg+3).
+// J is chosen per graph so that the 2 * ceil(n / 8J) tiles fill the 16 warps evenly (n = 300: J = 5, 16 tiles of 40 rows).
+template <int J>
 __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp) {
   const float* sX = sm<float>(x_off);
   const float* sW1 = sm<float>(w1_off);
   float* sP = sm<float>(p_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane & 3, rg = lane >> 2;
-  const int n_tiles = 2 * ((n + 31) / 32);
+  const int n_tiles = 2 * ((n + 8 * J - 1) / (8 * J));
   for (int tl = warp; tl < n_tiles; tl += kNW) {
-    const int h = tl & 1, base = (tl >> 1) * 32;
-    float2 acc[4][4];
+    const int h = tl & 1, base = (tl >> 1) * (8 * J);
+    float2 acc[J][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < J; ++j)
 #pragma unroll
       for (int t = 0; t < 4; ++t) acc[j][t] = make_float2(0.f, 0.f);
-    const float* xr[4];
+    const float* xr[J];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) xr[j] = sX + min(base + rg + 8 * j, rows_cap - 1) * kp;  // rows beyond n: results are not stored
+    for (int j = 0; j < J; ++j) xr[j] = sX + min(base + rg + 8 * j, rows_cap - 1) * kp;  // rows beyond n: results are not stored
     const float* wb = sW1 + (h * 16 + cg) * 4;
     for (int k4 = 0; k4 < kp; k4 += 4) {
-      float4 av[4], bv[4];
+      float4 av[J], bv[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(xr[j] + k4);
+      for (int j = 0; j < J; ++j) av[j] = *reinterpret_cast<const float4*>(xr[j] + k4);
 #pragma unroll
       for (int t = 0; t < 4; ++t) bv[t] = *reinterpret_cast<const float4*>(wb + k4 * kS1 + 16 * t);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           acc[j][t] = __ffma2_rn(make_float2(av[j].x, av[j].y), make_float2(bv[t].x, bv[t].y), acc[j][t]);
@@ -423,13 +484,22 @@ __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, 
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int r = base + rg + 8 * j;
       if (r < n)
         *reinterpret_cast<float4*>(sP + r * kS1 + h * 16 + 4 * cg) =
             make_float4(acc[j][0].x + acc[j][0].y, acc[j][1].x + acc[j][1].y, acc[j][2].x + acc[j][2].y, acc[j][3].x + acc[j][3].y);
     }
   }
+}
+
+__device__ __forceinline__ void project_x_dispatch(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp) {
+  const int j = (n + 63) / 64;  // rows per lane that make one round of 16 tiles
+  if (j <= 2) project_x<2>(x_off, w1_off, p_off, n, rows_cap, kp);
+  else if (j == 3) project_x<3>(x_off, w1_off, p_off, n, rows_cap, kp);
+  else if (j == 4) project_x<4>(x_off, w1_off, p_off, n, rows_cap, kp);
+  else if (j == 5) project_x<5>(x_off, w1_off, p_off, n, rows_cap, kp);
+  else project_x<6>(x_off, w1_off, p_off, n, rows_cap, kp);
 }
 
 // Z2 = A2 W2^T per branch: column sums of relu(Z2) (readout) -> sRed[8][64]; when TRAIN also the sign mask of Z2 (one 32-bit word
@@ -552,7 +622,7 @@ __device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off
 template <bool TRAIN>
 __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   unsigned char* smem = g_smem;
-  __shared__ int s_next;
+  __shared__ int s_meta[2][8];
   const Layout L = make_layout(a.fi, a.rows_cap, a.ent_cap);
   const int kp = L.kp;
   float* sT0 = reinterpret_cast<float*>(smem + L.t0);
@@ -570,19 +640,18 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   float* sHead = reinterpret_cast<float*>(smem + L.head);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  // index-build scratch lives in regions that are idle until the projection: the x region (x is loaded afterwards) and the tiles
   IndexPlan plan;
   plan.cstride = a.rows_cap;
   plan.cnt_r = L.t0;
   plan.cnt_c = L.t0 + kNW * a.rows_cap * 2;
-  if (!a.mode_b) {  // low degree: stash in tile 1, histograms + CSC staging in tile 0, x prefetched under the index build
-    plan.stash = L.t1;
-    plan.csc = plan.cnt_c + kNW * a.rows_cap * 2;
-  } else {  // high degree: stash in the x region (x is loaded afterwards), CSC staging in tile 1
-    plan.stash = L.x;
-    plan.csc = L.t1;
-  }
+  plan.stash = a.stash_off;
+  plan.ranks = a.ranks_off;
+  plan.csc = a.csc_off;
   plan.rinfo = L.rinfo;
   plan.cinfo = L.cinfo;
+  plan.rperm = L.rperm;
+  plan.cperm = L.cperm;
   plan.csr = L.idx;
   plan.scan = L.head + kHScan * 4;
 
@@ -599,48 +668,78 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     sW2[kF2 * kF1 + e] = __ldg(a.w2b + e);
   }
 
-  int g_slot = blockIdx.x;
-  while (g_slot < a.num_graphs) {
-    const int g = a.order != nullptr ? __ldg(a.order + g_slot) : g_slot;
-    const int node0 = __ldg(a.graph_ptr + g);
-    const int n = __ldg(a.graph_ptr + g + 1) - node0;
-    const int e0 = __ldg(a.edge_ptr + g);
-    const int ne = __ldg(a.edge_ptr + g + 1) - e0;
-    __syncthreads();  // previous graph is finished with every region; weights are visible
-    if (tid == 0) s_next = a.counter != nullptr ? atomicAdd(a.counter, 1) + (int)gridDim.x : g_slot + (int)gridDim.x;
+  // Static schedule: CTA b processes slots b, b + grid, ... of `order` (the host lays the graphs out in snake order of
+  // decreasing size, so every CTA's total work is about equal).  The NEXT slot's offsets are fetched by one thread while the
+  // current graph is processed: {graph id, node0, n, e0, ne} go through shared memory one iteration ahead.
+  if (tid == 0) {
+    const int slot = blockIdx.x;
+    const int g0 = a.order != nullptr ? __ldg(a.order + slot) : slot;
+    s_meta[0][0] = g0;
+    s_meta[0][1] = __ldg(a.graph_ptr + g0);
+    s_meta[0][2] = __ldg(a.graph_ptr + g0 + 1) - s_meta[0][1];
+    s_meta[0][3] = __ldg(a.edge_ptr + g0);
+    s_meta[0][4] = __ldg(a.edge_ptr + g0 + 1) - s_meta[0][3];
+  }
+  int buf = 0;
+  for (int g_slot = blockIdx.x; g_slot < a.num_graphs; g_slot += gridDim.x, buf ^= 1) {
+    __syncthreads();  // previous graph is finished with every region; weights and this graph's offsets are visible
+    const int g = s_meta[buf][0], node0 = s_meta[buf][1], n = s_meta[buf][2], e0 = s_meta[buf][3], ne = s_meta[buf][4];
+    const int next_slot = g_slot + (int)gridDim.x;
+    const bool have_next = next_slot < a.num_graphs;
+    int gn = 0;
+    if (tid == 32 && have_next) gn = a.order != nullptr ? __ldg(a.order + next_slot) : next_slot;  // consumed after the index build
     const bool fits = n <= a.rows_cap && ne <= a.e_cap && ne + 3 * n <= a.ent_cap && n >= 0 && ne >= 0;
     if (!fits) {
       if (tid == 0 && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
-      __syncthreads();
-      g_slot = s_next;
+      if (tid == 32 && have_next) {
+        s_meta[buf ^ 1][0] = gn;
+        s_meta[buf ^ 1][1] = __ldg(a.graph_ptr + gn);
+        s_meta[buf ^ 1][2] = __ldg(a.graph_ptr + gn + 1) - s_meta[buf ^ 1][1];
+        s_meta[buf ^ 1][3] = __ldg(a.edge_ptr + gn);
+        s_meta[buf ^ 1][4] = __ldg(a.edge_ptr + gn + 1) - s_meta[buf ^ 1][3];
+      }
       continue;
     }
-    // ---- x rows (async) and the graph index
-    if (!a.mode_b) {
-      stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
-      cp_async_commit();
-    }
+    // ---- the graph index, then x rows (the index build uses the x region as scratch)
     const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status);
+    stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
+    cp_async_commit();
     uint16_t* spill = TRAIN ? a.csc_spill + (size_t)blockIdx.x * a.ent_cap : nullptr;
     if (TRAIN) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
       const uint4* src = sm<uint4>(plan.csc);
       uint4* dst = reinterpret_cast<uint4*>(spill);
       for (int i = tid; i < (csc_entries + 7) / 8; i += kT) dst[i] = src[i];
     }
-    if (a.mode_b) {
-      __syncthreads();  // stash (x region) and CSC staging are consumed
-      stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
-      cp_async_commit();
+    int nx[4] = {0, 0, 0, 0};
+    if (tid == 32 && have_next) {  // the graph id arrived during the index build; its four offsets arrive during the projection
+      nx[0] = __ldg(a.graph_ptr + gn);
+      nx[1] = __ldg(a.graph_ptr + gn + 1);
+      nx[2] = __ldg(a.edge_ptr + gn);
+      nx[3] = __ldg(a.edge_ptr + gn + 1);
     }
     cp_async_wait<0>();
     __syncthreads();
 
-    project_x(L.x, L.w1, L.t0, n, a.rows_cap, kp);
+    project_x_dispatch(L.x, L.w1, L.t0, n, a.rows_cap, kp);
+    if (tid == 32 && have_next) {
+      s_meta[buf ^ 1][0] = gn;
+      s_meta[buf ^ 1][1] = nx[0];
+      s_meta[buf ^ 1][2] = nx[1] - nx[0];
+      s_meta[buf ^ 1][3] = nx[2];
+      s_meta[buf ^ 1][4] = nx[3] - nx[2];
+    }
     __syncthreads();
+    if (have_next) {  // warm L2 with the next graph's edge slice and node rows while this one is being processed
+      const int node0n = s_meta[buf ^ 1][1], e0n = s_meta[buf ^ 1][3];
+      const long long nn = s_meta[buf ^ 1][2], nen = s_meta[buf ^ 1][4];
+      prefetch_range_l2(a.erow + e0n, nen * 8);
+      prefetch_range_l2(a.ecol + e0n, nen * 8);
+      prefetch_range_l2(a.x + (long long)node0n * a.ldx, nn * a.ldx * 4);
+    }
     // ---- H1 = relu(A P) -> tile 1 ; A2 = A H1 -> tile 0
-    aggregate<0>(L.t0, L.t1, L.rinfo, L.idx, n);
+    aggregate<0>(L.t0, L.t1, L.rinfo, L.rperm, L.idx, n);
     __syncthreads();
-    aggregate<1>(L.t1, L.t0, L.rinfo, L.idx, n);
+    aggregate<1>(L.t1, L.t0, L.rinfo, L.rperm, L.idx, n);
     __syncthreads();
     if (TRAIN) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
       const int chunks = (csc_entries + 7) / 8;
@@ -720,11 +819,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
         a.pred[(size_t)g * a.out_dim + warp] = pv;
       }
     }
-    if (!TRAIN) {
-      __syncthreads();
-      g_slot = s_next;
-      continue;
-    }
+    if (!TRAIN) continue;
     __syncthreads();
     // ---- loss term and d loss / d pred (thread 0: out_dim <= 8 values)
     if (tid == 0) {
@@ -792,9 +887,9 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     cp_async_wait<0>();  // the CSC is back in the index region
     __syncthreads();
     // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
-    aggregate<2>(L.t0, L.t1, L.cinfo, L.idx, n);
+    aggregate<2>(L.t0, L.t1, L.cinfo, L.cperm, L.idx, n);
     __syncthreads();
-    aggregate<1>(L.t1, L.t0, L.cinfo, L.idx, n);
+    aggregate<1>(L.t1, L.t0, L.cinfo, L.cperm, L.idx, n);
     __syncthreads();
     conv1_weight_grad(L.t0, L.x, L.t1, n, kp);
     __syncthreads();
@@ -804,61 +899,77 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int w4 = 0; w4 < 4; ++w4) s += sT1[w4 * kS1 * kp + e];
       part[e] = s;
     }
-    __syncthreads();
-    g_slot = s_next;
   }
 }
 
 // ---------------------------------------------------------------------------------------------- finalize
 // Sums the per-graph contributions in graph order (bit-reproducible), forms the head's weight gradients from the per-graph
-// vectors, reduces the loss, advances the dropout step counter and re-arms the work counter.
+// vectors, reduces the loss and advances the dropout step counter.
 struct FinalArgs {
   const float* part; int32_t part_stride; const float* gvec; const float* hvec; const float* dhvec; const float* dpvec; const float* loss_terms;
   int32_t num_graphs, fi, kp, out_dim;
   float* dw1a; float* dw1b; float* dw2a; float* dw2b; float* dfc1_w; float* dfc1_b; float* dfc2_w; float* dfc2_b; float* loss;
-  float loss_scale; int64_t* rng_step; int32_t* counter;
+  float loss_scale; int64_t* rng_step;
 };
 
+// Block = 32 outputs x 8 graph slices: thread (slice ty, output tx) adds the contributions of graphs ty, ty+8, ty+16, ... (loads are
+// independent and coalesced across tx), the 8 slice sums are combined in slice order through shared memory.  The association is
+// fixed by (num_graphs), never by scheduling: results are bit-reproducible.
+constexpr int kFinSlices = 8;
 __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_part[kFinSlices][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + tx;
   const int B = a.num_graphs;
   const int n1 = kS1 * a.fi, n2 = kS2 * kF1, n3 = kHid * kS2, n4 = kHid, n5 = a.out_dim * kHid, n6 = a.out_dim;
-  if (t == 0) {
-    if (a.rng_step != nullptr) *a.rng_step += 1;
-    if (a.counter != nullptr) *a.counter = 0;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.rng_step != nullptr) *a.rng_step += 1;
   int e = t;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc = 0.f;
   float* dst = nullptr;
+  float scale = 1.f;
   if (e < n1) {
     const int m = e / a.fi, k = e - m * a.fi;
     const float* p = a.part + m * a.kp + k;
-    for (int g = 0; g < B; ++g) acc[g & 3] += p[(size_t)g * a.part_stride];
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
     dst = m < kF1 ? a.dw1a + e : a.dw1b + (e - kF1 * a.fi);
   } else if ((e -= n1) < n2) {
     const float* p = a.part + kS1 * a.kp + e;
-    for (int g = 0; g < B; ++g) acc[g & 3] += p[(size_t)g * a.part_stride];
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
     dst = e < kF2 * kF1 ? a.dw2a + e : a.dw2b + (e - kF2 * kF1);
   } else if ((e -= n2) < n3) {
     const int j = e / kS2, c = e - j * kS2;
-    for (int g = 0; g < B; ++g) acc[g & 3] = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc[g & 3]);
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc);
     dst = a.dfc1_w + e;
   } else if ((e -= n3) < n4) {
-    for (int g = 0; g < B; ++g) acc[g & 3] += a.dhvec[(size_t)g * kHid + e];
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc += a.dhvec[(size_t)g * kHid + e];
     dst = a.dfc1_b + e;
   } else if ((e -= n4) < n5) {
     const int o = e / kHid, j = e - o * kHid;
-    for (int g = 0; g < B; ++g) acc[g & 3] = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc[g & 3]);
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc);
     dst = a.dfc2_w + e;
   } else if ((e -= n5) < n6) {
-    for (int g = 0; g < B; ++g) acc[g & 3] += a.dpvec[(size_t)g * a.out_dim + e];
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc += a.dpvec[(size_t)g * a.out_dim + e];
     dst = a.dfc2_b + e;
   } else if ((e -= n6) == 0) {
-    for (int g = 0; g < B; ++g) acc[g & 3] += a.loss_terms[g];
-    acc[0] *= a.loss_scale; acc[1] *= a.loss_scale; acc[2] *= a.loss_scale; acc[3] *= a.loss_scale;
+#pragma unroll 8
+    for (int g = ty; g < B; g += kFinSlices) acc += a.loss_terms[g];
+    scale = a.loss_scale;
     dst = a.loss;
   }
-  if (dst != nullptr) *dst = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  s_part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && dst != nullptr) {
+    float s = s_part[0][tx];
+#pragma unroll
+    for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
+    *dst = s * scale;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- standalone per-graph index build
@@ -1021,7 +1132,7 @@ __global__ void k_edge_ptr(const int64_t* __restrict__ erow, int64_t num_edges, 
 }
 
 struct PlanResult {
-  int rows_cap, e_cap, ent_cap, mode_b;
+  int rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, extra;
   size_t smem;
 };
 
@@ -1032,19 +1143,38 @@ static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
   p.e_cap = std::max(32, (max_edges + 31) / 32 * 32);
   p.ent_cap = (max_edges + 3 * max_nodes + 15) / 8 * 8;
   if (p.ent_cap > 65528 || p.rows_cap > 8184) return false;
-  const Layout L = make_layout(fi, p.rows_cap, p.ent_cap);
+  // index-build scratch (stash [e_cap] u32, ranks [e_cap] u32, CSC staging [ent_cap] u16) goes into regions that are idle until the
+  // projection -- the x region (x is loaded afterwards), tile 1, tile 0 behind the histograms -- and, if those are too small
+  // (few node features), into an extra region at the end
+  Layout L = make_layout(fi, p.rows_cap, p.ent_cap);
+  const int tile = p.rows_cap * kS1 * 4, cnt = 2 * kNW * p.rows_cap * 2;
+  if (cnt > tile) return false;
+  int base[3] = {L.x, L.t1, L.t0 + cnt};
+  int left[3] = {p.rows_cap * L.kp * 4, tile, tile - cnt};
+  const int need[3] = {align16(4 * p.e_cap), align16(4 * p.e_cap), align16(2 * p.ent_cap)};
+  int where[3];
+  int extra = 0;
+  for (int item = 0; item < 3; ++item) {
+    where[item] = -1;
+    // the CSC staging is still being copied out while x streams into the x region: it may only live in the tiles
+    for (int reg = (item == 2 ? 1 : 0); reg < 3 && where[item] < 0; ++reg)
+      if (need[item] <= left[reg]) {
+        where[item] = base[reg];
+        base[reg] += need[item];
+        left[reg] -= need[item];
+      }
+    if (where[item] < 0) {
+      where[item] = L.extra + extra;
+      extra += need[item];
+    }
+  }
+  L = make_layout(fi, p.rows_cap, p.ent_cap, extra);
+  p.extra = extra;
   p.smem = (size_t)L.total;
   if (p.smem > kSmemBudget) return false;
-  const size_t tile = (size_t)p.rows_cap * kS1 * 4;
-  const size_t cnt = (size_t)2 * kNW * p.rows_cap * 2;
-  const size_t xreg = (size_t)p.rows_cap * L.kp * 4;
-  if ((size_t)p.e_cap * 4 <= tile && cnt + (size_t)p.ent_cap * 2 <= tile) {
-    p.mode_b = 0;
-  } else if ((size_t)p.e_cap * 4 <= xreg && cnt <= tile && (size_t)p.ent_cap * 2 <= tile) {
-    p.mode_b = 1;
-  } else {
-    return false;
-  }
+  p.stash_off = where[0];
+  p.ranks_off = where[1];
+  p.csc_off = where[2];
   return true;
 }
 
@@ -1052,6 +1182,8 @@ static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
 }  // namespace drk
 
 extern "C" {
+
+int32_t drk_ginet_step_ctas(int32_t num_graphs) { return std::max(0, std::min(num_graphs, drk::kNumSM)); }
 
 int drk_ginet_step_supported(int32_t fi, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges) {
   drk::gs::PlanResult p;
@@ -1076,7 +1208,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
                    float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train, float* pred, float* loss, float* dw1a, float* dw1b,
-                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, int32_t* counter, int32_t* status,
+                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, int32_t* status,
                    void* workspace, size_t workspace_bytes, void* stream) {
   using namespace drk;
   using namespace drk::gs;
@@ -1100,7 +1232,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   StepArgs a{};
   a.x = x; a.ldx = ldx; a.fi = fi;
   a.erow = edge_index; a.ecol = edge_index + num_edges;
-  a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.counter = counter; a.num_graphs = num_graphs;
+  a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.num_graphs = num_graphs;
   a.w1a = w1a; a.w1b = w1b; a.w2a = w2a; a.w2b = w2b;
   a.fc1_w = fc1_w; a.fc1_b = fc1_b; a.fc2_w = fc2_w; a.fc2_b = fc2_b; a.out_dim = out_dim;
   a.loss_kind = loss_kind;
@@ -1109,7 +1241,8 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   a.dloss_scale = inv_loss_count;
   a.drop_p = dropout_p; a.seed = seed; a.rng_step = rng_step;
   a.pred = pred; a.status = status;
-  a.rows_cap = p.rows_cap; a.e_cap = p.e_cap; a.ent_cap = p.ent_cap; a.mode_b = p.mode_b;
+  a.rows_cap = p.rows_cap; a.e_cap = p.e_cap; a.ent_cap = p.ent_cap;
+  a.stash_off = p.stash_off; a.ranks_off = p.ranks_off; a.csc_off = p.csc_off;
   a.x_vec = 1;
   if (ldx % 4 == 0 && fi % 4 == 0 && aligned16(x)) a.x_vec = 4;
   else if (ldx % 2 == 0 && fi % 2 == 0 && aligned8(x)) a.x_vec = 2;
@@ -1138,15 +1271,14 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
     f.num_graphs = num_graphs; f.fi = fi; f.kp = kp; f.out_dim = out_dim;
     f.dw1a = dw1a; f.dw1b = dw1b; f.dw2a = dw2a; f.dw2b = dw2b; f.dfc1_w = dfc1_w; f.dfc1_b = dfc1_b; f.dfc2_w = dfc2_w; f.dfc2_b = dfc2_b; f.loss = loss;
     f.loss_scale = loss_kind == DRK_LOSS_MSE ? inv_loss_count : inv_loss_count;
-    f.rng_step = rng_step; f.counter = counter;
+    f.rng_step = rng_step;
     const int total = kS1 * fi + kS2 * kF1 + kHid * kS2 + kHid + out_dim * kHid + out_dim + 1;
-    k_step_finalize<<<ceil_div(total, 256), 256, 0, st>>>(f);
+    k_step_finalize<<<ceil_div(total, 32), 256, 0, st>>>(f);
     return finish_launch("ginet step", 2);
   }
   e = cudaFuncSetAttribute(k_ginet_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "ginet step: smem opt-in: %s", cudaGetErrorString(e));
   k_ginet_step<false><<<grid, kT, p.smem, st>>>(a);
-  if (counter != nullptr) cudaMemsetAsync(counter, 0, sizeof(int32_t), st);
   return finish_launch("ginet step (inference)", 1);
 }
 

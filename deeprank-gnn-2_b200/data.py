@@ -185,10 +185,24 @@ class Batch(Data):
             eptr[1:] = torch.cumsum(torch.tensor(e_sizes, dtype=torch.int64), 0)
             out.__dict__["_node_ptr32"] = ptr.to(torch.int32)
             out.__dict__["_edge_ptr32"] = eptr.to(torch.int32)
-            work = torch.tensor(e_sizes, dtype=torch.int64) + 8 * torch.tensor(sizes, dtype=torch.int64)
-            out.__dict__["_order32"] = torch.argsort(work, descending=True, stable=True).to(torch.int32)
+            out.__dict__["_order32"] = snake_order([e + 8 * n for e, n in zip(e_sizes, sizes)])
         out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(e_sizes), "num_edges_total": sum(e_sizes)}
         return out
+
+
+STEP_CTAS = 148  # CTAs of the per-graph kernels = SMs of a B200 (drk_ginet_step_ctas)
+
+
+def snake_order(work: list[int], ctas: int = STEP_CTAS) -> torch.Tensor:
+    """Slot -> graph id for the per-graph kernels: CTA b processes slots b, b + ctas, b + 2 ctas, ...  Graphs are sorted by
+    decreasing work and laid out boustrophedon (round 0 descending, round 1 ascending, ...), so the CTA that got the largest
+    graph of one round gets the smallest of the next and all CTAs finish at about the same time."""
+    idx = sorted(range(len(work)), key=lambda i: (-work[i], i))
+    order: list[int] = []
+    for k, start in enumerate(range(0, len(idx), ctas)):
+        chunk = idx[start : start + ctas]
+        order += chunk if k % 2 == 0 else chunk[::-1]
+    return torch.tensor(order, dtype=torch.int32)
 
 
 def collate(data_list: list[Data]) -> Batch:

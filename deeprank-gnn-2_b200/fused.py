@@ -128,7 +128,7 @@ def step_supported(model, data) -> bool:
     return bool(_lib.load().drk_ginet_step_supported(int(data.x.shape[1]), int(model.fc2.weight.shape[0]), info.max_nodes, info.max_edges))
 
 
-def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, rng_step, pred, loss, grads, counter):
+def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, rng_step, pred, loss, grads):
     lib = _lib.load()
     x = data.x
     fi = int(x.shape[1])
@@ -142,7 +142,7 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
             int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(rng_step), 1 if train else 0,
-            _p(pred), _p(loss), *[_p(g) for g in grads], _p(counter), _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
+            _p(pred), _p(loss), *[_p(g) for g in grads], _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
         )
     _lib.check(rc, "drk_ginet_step")
 
@@ -152,7 +152,7 @@ def ginet_infer(model, data) -> torch.Tensor:
     info = block_info(data)
     pred = torch.empty((info.num_graphs, int(model.fc2.weight.shape[0])), dtype=torch.float32, device=data.x.device)
     _call_step(model, data, info, train=False, loss_kind=_lib.LOSS_MSE, target=None, inv_loss_count=0.0, dropout_p=0.0, seed=0, rng_step=None,
-               pred=pred, loss=None, grads=[None] * 8, counter=None)
+               pred=pred, loss=None, grads=[None] * 8)
     return pred
 
 
@@ -186,7 +186,6 @@ class GINetFusedStep:
         m = model
         self.grads = [by_id[id(t)] for t in (m.conv1.fc.weight, m.conv1_ext.fc.weight, m.conv2.fc.weight, m.conv2_ext.fc.weight, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)]
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.seed = int(torch.initial_seed() if seed is None else seed)
         self._pred = {}
@@ -219,7 +218,7 @@ class GINetFusedStep:
                 p.grad = v
         drop = float(self.model.dropout) if self.model.training else 0.0
         _call_step(self.model, batch, info, train=True, loss_kind=self.kind, target=target, inv_loss_count=1.0 / max(count, 1), dropout_p=drop,
-                   seed=self.seed, rng_step=self.rng_step, pred=pred, loss=self.loss, grads=self.grads, counter=self.counter)
+                   seed=self.seed, rng_step=self.rng_step, pred=pred, loss=self.loss, grads=self.grads)
         if self.world > 1:
             import torch.distributed as dist
 

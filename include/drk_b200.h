@@ -237,8 +237,9 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  *   data-parallel ranks the summed gradients of all ranks then equal the single-process gradient.
  * dropout: keep-mask from Philox4x32-10(seed, *rng_step, graph, unit); rng_step (device int64) is advanced by the finalize
  *   kernel so CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.
- * order (may be NULL): graph ids in the order they should be issued (largest first balances the 148 CTAs); counter
- *   (device int32, zero before the first call, re-armed by the call; may be NULL = static round-robin).
+ * order (may be NULL = identity): slot -> graph id; CTA b of the G = drk_ginet_step_ctas(B) CTAs processes slots b, b+G, b+2G, ...
+ *   Laying the graphs out in snake order of decreasing size (round 0 descending, round 1 ascending, ...) gives every CTA about
+ *   the same total work; the result does not depend on the order (per-graph contributions are summed in graph order).
  * Outputs: pred [B,out]; loss [1]; gradients of conv1.fc.weight / conv1_ext.fc.weight [16,F], conv2.fc.weight /
  *   conv2_ext.fc.weight [32,16], fc1.{weight [128,64], bias [128]}, fc2.{weight [out,128], bias [out]}.
  * The gradients of fc_edge_attr / fc_attention are identically zero in the reference (softmax over a singleton axis,
@@ -246,6 +247,7 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  * drk_ginet_step_supported: 1 if graphs of that size fit the shared-memory plan (else use the layer kernels). */
 #define DRK_LOSS_MSE 0
 #define DRK_LOSS_CROSS_ENTROPY 1
+DRK_API int32_t drk_ginet_step_ctas(int32_t num_graphs);
 DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
                                       int32_t max_graph_nodes, int32_t max_graph_edges);
@@ -259,7 +261,7 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
                    float* pred, float* loss,
                    float* dw1a, float* dw1b, float* dw2a, float* dw2b,
                    float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
-                   int32_t* counter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -243,10 +243,9 @@ def test_fused_step_full_batch_properties():
     g1, l1, p1 = step.flat_grad.clone(), loss1.clone(), pred1.clone()
     loss2, pred2 = step.forward_backward(batch)
     assert torch.equal(g1, step.flat_grad) and torch.equal(l1, loss2) and torch.equal(p1, pred2)
-    # static round-robin schedule in collate order instead of size-sorted work stealing
+    # collate order instead of the size-sorted snake schedule
     info = block_info(batch)
     info.order = None
-    step.counter = None
     loss3, pred3 = step.forward_backward(batch)
     assert torch.equal(g1, step.flat_grad) and torch.equal(l1, loss3) and torch.equal(p1, pred3)
     check_status(info)
