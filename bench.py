@@ -177,6 +177,11 @@ def algorithmic_step_bytes(n_nodes: int, n_edges: int) -> int:
     return 2472 * n_nodes + 24 * n_edges
 
 
+def _trace(msg):
+    if os.environ.get("DRK_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -243,6 +248,7 @@ def run_ours(args):
             opt.step()
             return loss.detach(), pred.detach()
 
+    _trace("model and batches ready")
     # launches of OUR kernels in one eager step (what a graph replay re-issues)
     step(dev_batches[0])
     torch.cuda.synchronize()
@@ -251,6 +257,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - c0
 
+    _trace("eager steps done")
     if args.mode == "graph":
         graphed, pool = [], None
         for b in dev_batches:
@@ -266,9 +273,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    _trace("capture done")
     for i in range(max(args.warmup, 3)):
         run(i)
     barrier()
+    _trace("warmup done")
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -277,6 +286,7 @@ def run_ours(args):
             run(i)
         stop.record()
         barrier()
+    _trace("timed region done")
     ms = start.elapsed_time(stop)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if distributed:
@@ -295,22 +305,23 @@ def run_ours(args):
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches_per_step": int(launches_per_step)}), flush=True)
-        if distributed:
-            dist.destroy_process_group()
+        _finish(distributed)
         return
 
     # ---- end to end through the public API: pinned host batches -> device (copy stream, one batch ahead) -> step -> loss.item()
     e2e_steps = max(10, min(args.steps, 40))
-    h2d = batch_nbytes(host_batches[0])
+    fields = GINetFusedStep.FIELDS if args.path == "fused" else None
+    h2d = batch_nbytes(host_batches[0], fields)
 
     def e2e_pass(n_steps):
-        feed = DevicePrefetcher((host_batches[i % args.batches] for i in range(n_steps)), dev)
+        feed = DevicePrefetcher((host_batches[i % args.batches] for i in range(n_steps)), dev, depth=2, only=fields)
         last = None
         for b in feed:
             loss, _ = step(b)
             last = loss.item()  # D2H read of the step's result, every step (trainer.py:694)
         return last
 
+    _trace("e2e start")
     e2e_pass(4)
     barrier()
     t0 = time.perf_counter()
@@ -322,6 +333,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = GRAPHS_PER_BATCH * e2e_steps * world / float(te.item())
 
+    _trace("e2e done")
     # ---- roofline of the dominant kernel, timed per launch with CUDA events on this stream, L2 flushed before every launch
     roof = step_roofline(args, dev, dev_batches, model, loss_fn) if args.path == "fused" else aggregation_roofline(dev_batches, args, dev)
 
@@ -353,15 +365,27 @@ def run_ours(args):
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "mode": "eager launches; pinned host batch -> device on a copy stream one batch ahead; loss.item() every step"},
+                    "mode": "eager launches; pinned host batch (the tensors the step reads, reference dtypes) -> device on a copy stream two batches ahead; loss.item() every step"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+    _finish(distributed)
+
+
+def _finish(distributed):
+    """Leave without tearing NCCL down: destroy_process_group() blocks while captured CUDA graphs still hold collectives."""
     if distributed:
-        dist.destroy_process_group()
+        import torch
+        import torch.distributed as dist
+
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _peak():

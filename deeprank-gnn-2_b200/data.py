@@ -47,7 +47,11 @@ class Data:
 
     # -- introspection
     def _fields(self) -> Iterable[str]:
-        return [k for k in self.__dict__ if not k.startswith("_")]
+        names = [k for k in self.__dict__ if not k.startswith("_")]
+        pending = self.__dict__.get("_pending")
+        if pending is not None:
+            names += [k for k in pending[1] if not k.startswith("_")]
+        return names
 
     def meta(self, key: str, default=None):
         return self.__dict__.get(self._META_KEY, {}).get(key, default)
@@ -104,16 +108,44 @@ class Data:
         for k, v in self.__dict__.items():
             if k in self._DEVICE_CACHES:
                 continue
+            if k == "_pending":
+                new.__dict__[k] = (v[0], dict(v[1]))
+                continue
             new.__dict__[k] = v.clone() if isinstance(v, torch.Tensor) else copy.deepcopy(v)
         return new
 
-    def to(self, device, non_blocking: bool = False):
+    def to(self, device, non_blocking: bool = False, only=None):
+        """Move the tensors to ``device``.  With ``only`` (names) and a CUDA target, the other host tensors are NOT copied
+        now: they stay on the host and travel on first attribute access (a step that never reads ``edge_attr`` or ``pos``
+        never pays their PCIe time)."""
+        dev = torch.device(device)
+        stale = self.__dict__.pop("_pending", None)
+        pending = dict(stale[1]) if stale is not None else {}
+        lazy = only is not None and dev.type == "cuda"
         for k, v in list(self.__dict__.items()):
             if isinstance(v, torch.Tensor):
-                self.__dict__[k] = v.to(device, non_blocking=non_blocking)
+                if lazy and k not in only and not v.is_cuda:
+                    pending[k] = self.__dict__.pop(k)
+                else:
+                    self.__dict__[k] = v.to(dev, non_blocking=non_blocking)
             elif k in self._DEVICE_CACHES:
                 self.__dict__.pop(k)
+        if lazy:
+            if pending:
+                self.__dict__["_pending"] = (dev, pending)
+        else:
+            for k, v in pending.items():
+                self.__dict__[k] = v.to(dev, non_blocking=non_blocking)
         return self
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: a tensor whose host->device copy was deferred by to(..., only=...)
+        pending = self.__dict__.get("_pending")
+        if pending is not None and name in pending[1]:
+            value = pending[1].pop(name).to(pending[0], non_blocking=True)
+            self.__dict__[name] = value
+            return value
+        raise AttributeError(f"{type(self).__name__!r} object has no attribute {name!r}")
 
     def cuda(self, non_blocking: bool = False):
         return self.to("cuda", non_blocking=non_blocking)

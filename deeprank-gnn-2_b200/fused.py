@@ -166,6 +166,10 @@ class GINetFusedStep:
     ``target_fn(batch) -> tensor`` supplies the targets (float [B(,out)] for MSE, int64 class indices for cross entropy).
     """
 
+    #: the batch tensors a step reads (what an input pipeline has to copy ahead; GINet's attention is the identity, so
+    #: ``edge_attr`` is never read, and the readout uses the graph offsets instead of ``batch``)
+    FIELDS = ("x", "edge_index", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+
     def __init__(self, model, optimizer, loss_fn, target_fn=None, world_size: int = 1, group=None, seed: int | None = None):
         if not _standard_ginet(model):
             raise ValueError("GINetFusedStep needs the reference ginet_nocluster.GINet architecture on a CUDA device")

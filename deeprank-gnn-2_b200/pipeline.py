@@ -15,9 +15,9 @@ from typing import Iterable, Iterator
 import torch
 
 
-def batch_nbytes(batch) -> int:
-    """Bytes of every tensor a ``Batch.to(device)`` moves."""
-    return sum(v.numel() * v.element_size() for v in batch.__dict__.values() if isinstance(v, torch.Tensor))
+def batch_nbytes(batch, only=None) -> int:
+    """Bytes of the tensors a ``Batch.to(device, only=only)`` moves immediately."""
+    return sum(v.numel() * v.element_size() for k, v in batch.__dict__.items() if isinstance(v, torch.Tensor) and (only is None or k in only))
 
 
 def shallow_host_view(batch):
@@ -30,17 +30,18 @@ def shallow_host_view(batch):
 class DevicePrefetcher:
     """Iterate over host batches (pinned memory) as device batches, copying one batch ahead on a side stream."""
 
-    def __init__(self, batches: Iterable, device, depth: int = 1):
+    def __init__(self, batches: Iterable, device, depth: int = 1, only=None):
         self.batches = batches
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher needs a CUDA device: deeprank2_b200 has no CPU path")
         self.depth = max(1, int(depth))
+        self.only = tuple(only) if only is not None else None  # tensors copied ahead; the others travel on first access
         self.stream = torch.cuda.Stream(self.device)
 
     def _issue(self, host_batch):
         with torch.cuda.stream(self.stream):
-            dev_batch = shallow_host_view(host_batch).to(self.device, non_blocking=True)
+            dev_batch = shallow_host_view(host_batch).to(self.device, non_blocking=True, only=self.only)
             ready = torch.cuda.Event()
             ready.record(self.stream)
         return dev_batch, ready
