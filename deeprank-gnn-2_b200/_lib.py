@@ -61,7 +61,7 @@ SIGNATURES = {
                                  _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
                                  _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients
-                                 _P, _P, c_size_t, _P]),                                     # status, workspace, stream
+                                 _P, _P, _P, c_size_t, _P]),                                 # adam, status, workspace, stream
     "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),
@@ -71,6 +71,21 @@ SIGNATURES = {
     "drk_edge_msg_bwd_c_workspace_bytes": (c_size_t, []),
     "drk_edge_msg_bwd_c": (c_int32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _P, _I64, _I32, _P, c_size_t, _P]),
 }
+
+
+
+class AdamTensor(ctypes.Structure):
+    """``DrkAdamTensor`` of include/drk_b200.h"""
+
+    _fields_ = [("param", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("step", c_void_p), ("numel", c_int64)]
+
+
+class Adam(ctypes.Structure):
+    """``DrkAdam`` of include/drk_b200.h"""
+
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float), ("num_dead", c_int32),
+                ("live", AdamTensor * 8), ("dead", AdamTensor * 8)]
+
 
 _lib = None
 

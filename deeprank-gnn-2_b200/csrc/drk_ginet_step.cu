@@ -910,65 +910,113 @@ struct FinalArgs {
   int32_t num_graphs, fi, kp, out_dim;
   float* dw1a; float* dw1b; float* dw2a; float* dw2b; float* dfc1_w; float* dfc1_b; float* dfc2_w; float* dfc2_b; float* loss;
   float loss_scale; int64_t* rng_step;
+  // optional Adam update fused behind the reduction (adam_on): live[] in the order of the gradient outputs above
+  int32_t adam_on; DrkAdam adam; int32_t* done_counter; int32_t grad_blocks;
 };
+
+// torch.optim.Adam (L2 weight decay, no amsgrad, no maximize), the arithmetic of its fused CUDA implementation:
+//   g += wd * p ; m = lerp(m, g, 1 - b1) ; v = b2 v + (1 - b2) g^2 ; p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// with t = step + 1; the step scalars themselves are advanced by the last block of the grid, after every reader is done.
+__device__ __forceinline__ void adam_update(const DrkAdam& h, const DrkAdamTensor& t, int64_t i, float g) {
+  const float step = *t.step + 1.f;
+  const float p = t.param[i];
+  g = fmaf(h.weight_decay, p, g);
+  float m = t.exp_avg[i], v = t.exp_avg_sq[i];
+  m = fmaf(1.f - h.beta1, g - m, m);
+  v = fmaf(1.f - h.beta2, g * g, h.beta2 * v);
+  const float bc1 = 1.f - powf(h.beta1, step), bc2 = 1.f - powf(h.beta2, step);
+  const float denom = sqrtf(v) / sqrtf(bc2) + h.eps;
+  t.exp_avg[i] = m;
+  t.exp_avg_sq[i] = v;
+  t.param[i] = p - (h.lr / bc1) * (m / denom);
+}
 
 // Block = 32 outputs x 8 graph slices: thread (slice ty, output tx) adds the contributions of graphs ty, ty+8, ty+16, ... (loads are
 // independent and coalesced across tx), the 8 slice sums are combined in slice order through shared memory.  The association is
-// fixed by (num_graphs), never by scheduling: results are bit-reproducible.
+// fixed by (num_graphs), never by scheduling: results are bit-reproducible.  Blocks beyond grad_blocks apply Adam to the parameters
+// whose gradient is identically zero (weight decay still moves them).
 constexpr int kFinSlices = 8;
 __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
   __shared__ float s_part[kFinSlices][32];
+  __shared__ int s_last;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int t = blockIdx.x * 32 + tx;
   const int B = a.num_graphs;
-  const int n1 = kS1 * a.fi, n2 = kS2 * kF1, n3 = kHid * kS2, n4 = kHid, n5 = a.out_dim * kHid, n6 = a.out_dim;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.rng_step != nullptr) *a.rng_step += 1;
-  int e = t;
-  float acc = 0.f;
-  float* dst = nullptr;
-  float scale = 1.f;
-  if (e < n1) {
-    const int m = e / a.fi, k = e - m * a.fi;
-    const float* p = a.part + m * a.kp + k;
+  if ((int)blockIdx.x < a.grad_blocks) {
+    const int t = blockIdx.x * 32 + tx;
+    const int n1 = kS1 * a.fi, n2 = kS2 * kF1, n3 = kHid * kS2, n4 = kHid, n5 = a.out_dim * kHid, n6 = a.out_dim;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.rng_step != nullptr) *a.rng_step += 1;
+    int e = t;
+    float acc = 0.f;
+    float* dst = nullptr;
+    float scale = 1.f;
+    int live = -1;     // index into adam.live
+    int64_t li = 0;    // element inside that tensor
+    if (e < n1) {
+      const int m = e / a.fi, k = e - m * a.fi;
+      const float* p = a.part + m * a.kp + k;
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
-    dst = m < kF1 ? a.dw1a + e : a.dw1b + (e - kF1 * a.fi);
-  } else if ((e -= n1) < n2) {
-    const float* p = a.part + kS1 * a.kp + e;
+      for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
+      if (m < kF1) { dst = a.dw1a + e; live = 0; li = e; } else { dst = a.dw1b + (e - kF1 * a.fi); live = 1; li = e - kF1 * a.fi; }
+    } else if ((e -= n1) < n2) {
+      const float* p = a.part + kS1 * a.kp + e;
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
-    dst = e < kF2 * kF1 ? a.dw2a + e : a.dw2b + (e - kF2 * kF1);
-  } else if ((e -= n2) < n3) {
-    const int j = e / kS2, c = e - j * kS2;
+      for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
+      if (e < kF2 * kF1) { dst = a.dw2a + e; live = 2; li = e; } else { dst = a.dw2b + (e - kF2 * kF1); live = 3; li = e - kF2 * kF1; }
+    } else if ((e -= n2) < n3) {
+      const int j = e / kS2, c = e - j * kS2;
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc);
-    dst = a.dfc1_w + e;
-  } else if ((e -= n3) < n4) {
+      for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc);
+      dst = a.dfc1_w + e; live = 4; li = e;
+    } else if ((e -= n3) < n4) {
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc += a.dhvec[(size_t)g * kHid + e];
-    dst = a.dfc1_b + e;
-  } else if ((e -= n4) < n5) {
-    const int o = e / kHid, j = e - o * kHid;
+      for (int g = ty; g < B; g += kFinSlices) acc += a.dhvec[(size_t)g * kHid + e];
+      dst = a.dfc1_b + e; live = 5; li = e;
+    } else if ((e -= n4) < n5) {
+      const int o = e / kHid, j = e - o * kHid;
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc);
-    dst = a.dfc2_w + e;
-  } else if ((e -= n5) < n6) {
+      for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc);
+      dst = a.dfc2_w + e; live = 6; li = e;
+    } else if ((e -= n5) < n6) {
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc += a.dpvec[(size_t)g * a.out_dim + e];
-    dst = a.dfc2_b + e;
-  } else if ((e -= n6) == 0) {
+      for (int g = ty; g < B; g += kFinSlices) acc += a.dpvec[(size_t)g * a.out_dim + e];
+      dst = a.dfc2_b + e; live = 7; li = e;
+    } else if ((e -= n6) == 0) {
 #pragma unroll 8
-    for (int g = ty; g < B; g += kFinSlices) acc += a.loss_terms[g];
-    scale = a.loss_scale;
-    dst = a.loss;
-  }
-  s_part[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && dst != nullptr) {
-    float s = s_part[0][tx];
+      for (int g = ty; g < B; g += kFinSlices) acc += a.loss_terms[g];
+      scale = a.loss_scale;
+      dst = a.loss;
+    }
+    s_part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && dst != nullptr) {
+      float s = s_part[0][tx];
 #pragma unroll
-    for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
-    *dst = s * scale;
+      for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
+      s *= scale;
+      *dst = s;
+      if (a.adam_on && live >= 0) adam_update(a.adam, a.adam.live[live], li, s);
+    }
+  } else if (a.adam_on) {
+    // dead parameters (zero gradient): flat index over the concatenation of adam.dead[]
+    int64_t i = (int64_t)((int)blockIdx.x - a.grad_blocks) * 256 + threadIdx.x;
+    for (int d = 0; d < a.adam.num_dead; ++d) {
+      if (i < a.adam.dead[d].numel) {
+        adam_update(a.adam, a.adam.dead[d], i, 0.f);
+        break;
+      }
+      i -= a.adam.dead[d].numel;
+    }
+  }
+  if (!a.adam_on) return;
+  // every block has read the step scalars: the last one to finish advances them (and re-arms the counter)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.done_counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < 8) *a.adam.live[threadIdx.x].step += 1.f;
+    else if ((int)threadIdx.x - 8 < a.adam.num_dead) *a.adam.dead[threadIdx.x - 8].step += 1.f;
+    if (threadIdx.x == 0) *a.done_counter = 0;
   }
 }
 
@@ -1208,7 +1256,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
                    float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train, float* pred, float* loss, float* dw1a, float* dw1b,
-                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, int32_t* status,
+                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, const DrkAdam* adam, int32_t* status,
                    void* workspace, size_t workspace_bytes, void* stream) {
   using namespace drk;
   using namespace drk::gs;
@@ -1273,7 +1321,25 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
     f.loss_scale = loss_kind == DRK_LOSS_MSE ? inv_loss_count : inv_loss_count;
     f.rng_step = rng_step;
     const int total = kS1 * fi + kS2 * kF1 + kHid * kS2 + kHid + out_dim * kHid + out_dim + 1;
-    k_step_finalize<<<ceil_div(total, 32), 256, 0, st>>>(f);
+    f.grad_blocks = ceil_div(total, 32);
+    int blocks = f.grad_blocks;
+    if (adam != nullptr) {
+      DRK_REQUIRE(adam->num_dead >= 0 && adam->num_dead <= 8, DRK_EINVAL, "ginet step: adam.num_dead must be in [0, 8]");
+      int64_t dead_elems = 0;
+      for (int i = 0; i < 8; ++i)
+        DRK_REQUIRE(adam->live[i].param && adam->live[i].exp_avg && adam->live[i].exp_avg_sq && adam->live[i].step, DRK_EINVAL, "ginet step: adam.live[%d] has a null pointer", i);
+      for (int i = 0; i < adam->num_dead; ++i) {
+        DRK_REQUIRE(adam->dead[i].param && adam->dead[i].exp_avg && adam->dead[i].exp_avg_sq && adam->dead[i].step && adam->dead[i].numel >= 0, DRK_EINVAL,
+                    "ginet step: adam.dead[%d] is malformed", i);
+        dead_elems += adam->dead[i].numel;
+      }
+      f.adam_on = 1;
+      f.adam = *adam;
+      DRK_REQUIRE(rng_step != nullptr, DRK_EINVAL, "ginet step: the fused Adam update needs the int64[2] state buffer");
+      f.done_counter = reinterpret_cast<int32_t*>(rng_step + 1);
+      blocks += (int)ceil_div<int64_t>(dead_elems, 256);
+    }
+    k_step_finalize<<<blocks, 256, 0, st>>>(f);
     return finish_launch("ginet step", 2);
   }
   e = cudaFuncSetAttribute(k_ginet_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);

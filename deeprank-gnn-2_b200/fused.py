@@ -17,6 +17,8 @@ There is no CPU path: everything here raises if the extension is missing or a te
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 from torch import nn
 
@@ -128,7 +130,7 @@ def step_supported(model, data) -> bool:
     return bool(_lib.load().drk_ginet_step_supported(int(data.x.shape[1]), int(model.fc2.weight.shape[0]), info.max_nodes, info.max_edges))
 
 
-def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, rng_step, pred, loss, grads):
+def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, state, pred, loss, grads, adam=None):
     lib = _lib.load()
     x = data.x
     fi = int(x.shape[1])
@@ -141,8 +143,8 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
             _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), info.num_graphs, info.max_nodes, info.max_edges,
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
-            int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(rng_step), 1 if train else 0,
-            _p(pred), _p(loss), *[_p(g) for g in grads], _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
+            int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(state), 1 if train else 0,
+            _p(pred), _p(loss), *[_p(g) for g in grads], ctypes.byref(adam) if adam is not None else None, _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
         )
     _lib.check(rc, "drk_ginet_step")
 
@@ -151,7 +153,7 @@ def ginet_infer(model, data) -> torch.Tensor:
     """``model(data)`` for the reference GINet without autograd: one kernel, [B, out] predictions."""
     info = block_info(data)
     pred = torch.empty((info.num_graphs, int(model.fc2.weight.shape[0])), dtype=torch.float32, device=data.x.device)
-    _call_step(model, data, info, train=False, loss_kind=_lib.LOSS_MSE, target=None, inv_loss_count=0.0, dropout_p=0.0, seed=0, rng_step=None,
+    _call_step(model, data, info, train=False, loss_kind=_lib.LOSS_MSE, target=None, inv_loss_count=0.0, dropout_p=0.0, seed=0, state=None,
                pred=pred, loss=None, grads=[None] * 8)
     return pred
 
@@ -190,7 +192,8 @@ class GINetFusedStep:
         m = model
         self.grads = [by_id[id(t)] for t in (m.conv1.fc.weight, m.conv1_ext.fc.weight, m.conv2.fc.weight, m.conv2_ext.fc.weight, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)]
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)  # [0] steps done (dropout stream), [1] finalize-kernel scratch
+        self._adam = self._adam_descriptor() if self.world == 1 else None
         self.seed = int(torch.initial_seed() if seed is None else seed)
         self._pred = {}
 
@@ -198,7 +201,46 @@ class GINetFusedStep:
     def supports(model, loss_fn, batch=None) -> bool:
         return _standard_ginet(model) and _loss_kind(loss_fn) is not None and (batch is None or step_supported(model, batch))
 
-    def forward_backward(self, batch, global_size: int | None = None):
+    def _adam_descriptor(self):
+        """``DrkAdam`` over torch.optim.Adam's own state tensors, or None if the optimizer is anything else (then
+        ``optimizer.step()`` runs as usual).  Needs ``capturable=True`` or ``fused=True`` (step counters on the device)."""
+        opt = self.optimizer
+        if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+            return None
+        grp = opt.param_groups[0]
+        if grp.get("amsgrad") or grp.get("maximize") or grp.get("differentiable") or not (grp.get("capturable") or grp.get("fused")):
+            return None
+        if not isinstance(grp["lr"], float) or {id(p) for p in grp["params"]} != {id(p) for p in self.params}:
+            return None
+        for p in self.params:  # lazy state initialisation, as torch.optim.Adam._init_group does on the first step()
+            st = opt.state[p]
+            if len(st) == 0:
+                st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if not (st["step"].is_cuda and st["step"].dtype == torch.float32 and st["exp_avg"].is_contiguous() and st["exp_avg_sq"].is_contiguous()):
+                return None
+        desc = _lib.Adam()
+        desc.lr, (desc.beta1, desc.beta2), desc.eps, desc.weight_decay = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
+        m = self.model
+        live = [m.conv1.fc.weight, m.conv1_ext.fc.weight, m.conv2.fc.weight, m.conv2_ext.fc.weight, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+        live_ids = {id(p) for p in live}
+        dead = [p for p in self.params if id(p) not in live_ids]
+        if len(dead) > 8:
+            return None
+
+        def fill(slot, p):
+            st = opt.state[p]
+            slot.param, slot.exp_avg, slot.exp_avg_sq, slot.step, slot.numel = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["step"].data_ptr(), p.numel()
+
+        for i, p in enumerate(live):
+            fill(desc.live[i], p)
+        for i, p in enumerate(dead):
+            fill(desc.dead[i], p)
+        desc.num_dead = len(dead)
+        return desc
+
+    def forward_backward(self, batch, global_size: int | None = None, adam=None):
         """Everything but the optimizer: returns (loss, pred); ``p.grad`` of every parameter is set."""
         info = block_info(batch)
         out_dim = int(self.model.fc2.weight.shape[0])
@@ -222,7 +264,7 @@ class GINetFusedStep:
                 p.grad = v
         drop = float(self.model.dropout) if self.model.training else 0.0
         _call_step(self.model, batch, info, train=True, loss_kind=self.kind, target=target, inv_loss_count=1.0 / max(count, 1), dropout_p=drop,
-                   seed=self.seed, rng_step=self.rng_step, pred=pred, loss=self.loss, grads=self.grads)
+                   seed=self.seed, state=self.state, pred=pred, loss=self.loss, grads=self.grads, adam=adam)
         if self.world > 1:
             import torch.distributed as dist
 
@@ -230,6 +272,9 @@ class GINetFusedStep:
         return self.loss, pred
 
     def __call__(self, batch, global_size: int | None = None):
+        if self._adam is not None:  # Adam applied by the finalize kernel on torch's own optimizer state (2 launches per step)
+            self._adam.lr = self.optimizer.param_groups[0]["lr"]
+            return self.forward_backward(batch, global_size, adam=self._adam)
         loss, pred = self.forward_backward(batch, global_size)
         self.optimizer.step()
         return loss, pred

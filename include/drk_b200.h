@@ -235,8 +235,13 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  *            DRK_LOSS_CROSS_ENTROPY  target = int64 [B] class indices (CrossEntropyLoss without class weights)
  * inv_loss_count = 1 / (number of loss elements of the GLOBAL mini-batch): B_global*out for MSE, B_global for CE; with
  *   data-parallel ranks the summed gradients of all ranks then equal the single-process gradient.
- * dropout: keep-mask from Philox4x32-10(seed, *rng_step, graph, unit); rng_step (device int64) is advanced by the finalize
- *   kernel so CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.
+ * dropout: keep-mask from Philox4x32-10(seed, state[0], graph, unit); state (device int64[2], zero-initialised by the caller and
+ *   private to the calls: [0] = steps done, [1] = scratch of the finalize kernel) is advanced by the finalize kernel so
+ *   CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.
+ * adam (may be NULL = gradients only): torch.optim.Adam step (L2 weight decay, no amsgrad) applied by the finalize kernel right
+ *   behind the gradient reduction -- same arithmetic as torch's fused CUDA Adam, on torch's own state tensors:
+ *   live[0..7] = the tensors of the gradient outputs below, in that order; dead[0..num_dead) = parameters whose gradient is
+ *   identically zero (fc_edge_attr / fc_attention: weight decay still moves them); step = the float32 device scalar of each.
  * order (may be NULL = identity): slot -> graph id; CTA b of the G = drk_ginet_step_ctas(B) CTAs processes slots b, b+G, b+2G, ...
  *   Laying the graphs out in snake order of decreasing size (round 0 descending, round 1 ascending, ...) gives every CTA about
  *   the same total work; the result does not depend on the order (per-graph contributions are summed in graph order).
@@ -247,6 +252,19 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  * drk_ginet_step_supported: 1 if graphs of that size fit the shared-memory plan (else use the layer kernels). */
 #define DRK_LOSS_MSE 0
 #define DRK_LOSS_CROSS_ENTROPY 1
+typedef struct DrkAdamTensor {
+  float* param;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* step; /* device float32 scalar (torch.optim.Adam state["step"] with capturable/fused) */
+  int64_t numel;
+} DrkAdamTensor;
+typedef struct DrkAdam {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t num_dead;
+  DrkAdamTensor live[8];
+  DrkAdamTensor dead[8];
+} DrkAdam;
 DRK_API int32_t drk_ginet_step_ctas(int32_t num_graphs);
 DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
@@ -257,11 +275,11 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b,
                    const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, int32_t out_dim,
                    int32_t loss_kind, const void* target, float inv_loss_count,
-                   float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train,
+                   float dropout_p, uint64_t seed, int64_t* state, int32_t train,
                    float* pred, float* loss,
                    float* dw1a, float* dw1b, float* dw2a, float* dw2b,
                    float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
-                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                   const DrkAdam* adam, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -304,7 +304,7 @@ def test_fused_step_dropout_mask_replayed_through_oracle():
     torch.cuda.synchronize()
     hvec2 = ws[off + n_graphs * 64 : off + n_graphs * 192].view(n_graphs, 128).cpu()
     assert not torch.equal(h_first != 0, hvec2 != 0)
-    assert int(step.rng_step.item()) == 2
+    assert int(step.state[0].item()) == 2
     assert _lib.launch_count() > 0
 
 
@@ -340,3 +340,55 @@ def test_trainstep_graph_capture_of_fused_step():
         results.append(losses)
     assert results[0] == pytest.approx(results[1], rel=1e-6)
     assert results[0][-1] < results[0][0]
+
+
+def test_fused_adam_matches_torch_adam_on_its_own_state():
+    """The finalize kernel's Adam update (2 launches per step) against torch.optim.Adam fed with the same gradients: parameters,
+    exp_avg, exp_avg_sq and step after several steps, dead parameters (zero gradient, weight decay only) included."""
+    from deeprank2_b200.fused import GINetFusedStep
+
+    host = _synthetic(24, first=700)
+    batch = host.clone().to(DEV)
+    nets, opts, steps = [], [], []
+    for kind in ("kernel", "torch"):
+        net = _net(50, 1, 1, seed=8).eval()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=(kind == "torch"))
+        step = GINetFusedStep(net, opt, torch.nn.MSELoss())
+        if kind == "torch":
+            step._adam = None  # gradients from the kernels, update by torch
+        else:
+            assert step._adam is not None
+        nets.append(net), opts.append(opt), steps.append(step)
+    from deeprank2_b200 import _lib
+
+    for it in range(4):
+        before = _lib.launch_count()
+        l0, _ = steps[0](batch)
+        assert _lib.launch_count() - before == 2
+        l1, _ = steps[1](batch)
+        assert_close(l0, l1, f"loss at step {it}", rtol=1e-6, atol_scale=1e-6)
+    for (k, p0), p1 in zip(nets[0].named_parameters(), nets[1].parameters()):
+        s0, s1 = opts[0].state[p0], opts[1].state[p1]
+        assert float(s0["step"]) == float(s1["step"]) == 4.0
+        assert_close(p0, p1, f"param {k}", rtol=1e-6, atol_scale=1e-6)
+        assert_close(s0["exp_avg"], s1["exp_avg"], f"exp_avg {k}", rtol=1e-5, atol_scale=1e-6)
+        assert_close(s0["exp_avg_sq"], s1["exp_avg_sq"], f"exp_avg_sq {k}", rtol=1e-5, atol_scale=1e-6)
+    assert float(nets[0].conv1.fc_attention.weight.grad.abs().max()) == 0.0
+    w0 = _net(50, 1, 1, seed=8).conv1.fc_attention.weight
+    assert not torch.equal(nets[0].conv1.fc_attention.weight.detach().cpu(), w0.detach().cpu()), "weight decay moves the dead parameters"
+
+
+def test_fused_adam_one_step_vs_oracle():
+    from deeprank2_b200.fused import GINetFusedStep
+
+    host = _synthetic(6, first=900)
+    net = _net(50, 1, 1, seed=9).eval()
+    w_before = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    params, pred_ref, loss_ref = _oracle_step(net, host)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+    step = GINetFusedStep(net, opt, torch.nn.MSELoss())
+    assert step._adam is not None
+    loss, pred = step(host.clone().to(DEV))
+    assert_close(pred, pred_ref, "pred")
+    for (k, p_ref), p in zip(params.items(), net.parameters()):
+        assert_adam_close(p, p_ref, f"adam {k}", p_ref.grad, w_before[k])
