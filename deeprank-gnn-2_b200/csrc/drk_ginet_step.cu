@@ -60,7 +60,7 @@ __host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap,
   L.cinfo = o; o += align16(rows_cap * 4);
   L.rperm = o; o += align16(rows_cap * 2);
   L.cperm = o; o += align16(rows_cap * 2);
-  L.w1 = o; o += kS1 * L.kp * 4;
+  L.w1 = o; o += ((fi + 7) / 8) * 4 * 32 * 16;  // pre-split TF32 B fragments of W1s^T
   L.w2 = o; o += 2 * kF2 * kF1 * 4;
   L.s = o; o += kS2 * kF1 * 4;
   L.v = o; o += kS2 * kF1 * 4;
@@ -196,7 +196,7 @@ struct IndexPlan {  // byte offsets into g_smem
 
 constexpr int kDegBins = 64;
 
-// returns the number of CSC entries (padded)
+// returns the number of CSC entries (padded), or -1 when no source-sorted index was built (forward only, or symmetric adjacency)
 template <bool WANT_CSC>
 __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
                                         int node0, int n, int32_t* status) {
@@ -234,7 +234,6 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
   //           exactly the time the next group's global loads need.
   {
     uint16_t* my_r = cnt_r + warp * cs;
-    uint16_t* my_c = cnt_c + warp * cs;
     bool bad = false;
     long long rr[8], cc[8];
 #pragma unroll
@@ -267,22 +266,48 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
         const bool ok = pk[u] != 0xffffffffu;
         const unsigned r = pk[u] & 0xffffu, c = pk[u] >> 16;
         const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
-        const unsigned mc = WANT_CSC ? __match_any_sync(kFull, ok ? c : 0x10000u + lane) : 0u;
-        unsigned base_r = 0, base_c = 0;
-        if (ok) {
-          base_r = my_r[r];
-          if (WANT_CSC) base_c = my_c[c];
-        }
-        if (i < we) ranks[i] = (base_r + __popc(mr & lt)) | ((base_c + __popc(mc & lt)) << 16);
+        unsigned base_r = 0;
+        if (ok) base_r = my_r[r];
+        if (i < we) ranks[i] = base_r + __popc(mr & lt);
         __syncwarp();
         if (ok && (mr & lt) == 0u) my_r[r] = (uint16_t)(base_r + __popc(mr));
-        if (WANT_CSC && ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
         __syncwarp();
       }
     }
     if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
   }
   __syncthreads();
+  // Is the edge list the reference's doubled layout (dataset.py:944-948: all (i, j) first, then all (j, i) in the same order)?
+  // Then the adjacency is symmetric, A^T = A, and the backward pass can gather through the same CSR: no source-sorted index.
+  bool sym = false;
+  if (WANT_CSC) {
+    const int half = ne >> 1;
+    bool mine = (ne & 1) == 0;
+    for (int i = tid; i < half; i += kT) {
+      const unsigned a = stash[i], b = stash[i + half];
+      mine &= b == ((a << 16) | (a >> 16));  // dropped edges (0xffffffff) pair up only with dropped edges
+    }
+    sym = __syncthreads_and(mine);
+  }
+  const bool want_csc = WANT_CSC && !sym;
+  if (want_csc) {
+    // general edge lists: the same pass keyed by source (ranks into the high half)
+    uint16_t* my_c = cnt_c + warp * cs;
+    for (int i0 = wb; i0 < we; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned pk = i < we ? stash[i] : 0xffffffffu;
+      const bool ok = pk != 0xffffffffu;
+      const unsigned c = pk >> 16;
+      const unsigned mc = __match_any_sync(kFull, ok ? c : 0x10000u + lane);
+      unsigned base_c = 0;
+      if (ok) base_c = my_c[c];
+      if (i < we) ranks[i] |= (base_c + __popc(mc & lt)) << 16;
+      __syncwarp();
+      if (ok && (mc & lt) == 0u) my_c[c] = (uint16_t)(base_c + __popc(mc));
+      __syncwarp();
+    }
+    __syncthreads();
+  }
   // pass 3: (node, warp)-ordered exclusive scan: offset of every warp chunk inside its segment, padded segment starts, degree bins
   uint32_t carry = 0;
   for (int vb = 0; vb < n; vb += kT) {
@@ -295,7 +320,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
         cnt_r[w * cs + v] = (uint16_t)dr;
         dr += t;
       }
-      if (WANT_CSC) {
+      if (want_csc) {
 #pragma unroll
         for (int w = 0; w < kNW; ++w) {
           const uint32_t t = cnt_c[w * cs + v];
@@ -304,20 +329,20 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
         }
       }
       atomicAdd(&hist[min((int)dr, kDegBins - 1)], 1);
-      if (WANT_CSC) atomicAdd(&hist[kDegBins + min((int)dc, kDegBins - 1)], 1);
+      if (want_csc) atomicAdd(&hist[kDegBins + min((int)dc, kDegBins - 1)], 1);
     }
     const uint32_t packed = ((dr + 3u) & ~3u) | (((dc + 3u) & ~3u) << 16);
     uint32_t total;
     const uint32_t ex = block_excl_scan(packed, scan, total) + carry;
     if (v < n) {
       rinfo[v] = make_ushort2((unsigned short)((ex & 0xffffu) >> 2), (unsigned short)dr);
-      if (WANT_CSC) cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
+      if (want_csc) cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
     }
     carry += total;
   }
   __syncthreads();
   // rows by decreasing degree: cursor[bin] = number of rows with a larger degree bin (warp 0: in-degrees, warp 1: out-degrees)
-  if (warp < (WANT_CSC ? 2 : 1)) {
+  if (warp < (want_csc ? 2 : 1)) {
     const int* h = hist + warp * kDegBins;
     const int hi = h[kDegBins - 1 - lane], lo = h[kDegBins / 2 - 1 - lane];  // lane 0 holds the largest bins
     int inc_hi = hi, inc_lo = lo;
@@ -341,7 +366,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     int* cur = hist + 2 * kDegBins;
     for (int v = tid; v < n; v += kT) {
       rperm[atomicAdd(&cur[min((int)rinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;
-      if (WANT_CSC) cperm[atomicAdd(&cur[kDegBins + min((int)cinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;
+      if (want_csc) cperm[atomicAdd(&cur[kDegBins + min((int)cinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;
     }
   }
   // pass 4: placement, every edge independently: position = segment start + offset of its warp chunk + rank inside the chunk
@@ -356,11 +381,11 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
       const unsigned rk = ranks[i];
       const unsigned r = pk & 0xffffu, c = pk >> 16;
       csr[4 * rinfo[r].x + my_r[r] + (rk & 0xffffu)] = (uint16_t)(c * 8u);
-      if (WANT_CSC) csc[4 * cinfo[c].x + my_c[c] + (rk >> 16)] = (uint16_t)(r * 8u);
+      if (want_csc) csc[4 * cinfo[c].x + my_c[c] + (rk >> 16)] = (uint16_t)(r * 8u);
     }
   }
   __syncthreads();
-  return (int)(carry >> 16);
+  return want_csc ? (int)(carry >> 16) : -1;
 }
 
 // ---------------------------------------------------------------------------------------------- aggregation over a smem tile
@@ -448,58 +473,72 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
 // Packed fp32 (FFMA2 / FADD2, sm_100): two independent fp32 operations per instruction, each rounded exactly like the scalar
 // one.  Dot products keep an (even k, odd k) pair of partial sums that is added once at the end.
 
-// P = x W1s^T -> tile.  warp tile = 8J rows x 16 outputs (one branch), lane = J rows (rg + 8j) x 4 outputs (4cg..4cg+3).
-// J is chosen per graph so that the 2 * ceil(n / 8J) tiles fill the 16 warps evenly (n = 300: J = 5, 16 tiles of 40 rows).
-template <int J>
-__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp) {
-  const float* sX = sm<float>(x_off);
-  const float* sW1 = sm<float>(w1_off);
-  float* sP = sm<float>(p_off);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cg = lane & 3, rg = lane >> 2;
-  const int n_tiles = 2 * ((n + 8 * J - 1) / (8 * J));
-  for (int tl = warp; tl < n_tiles; tl += kNW) {
-    const int h = tl & 1, base = (tl >> 1) * (8 * J);
-    float2 acc[J][4];
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) acc[j][t] = make_float2(0.f, 0.f);
-    const float* xr[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) xr[j] = sX + min(base + rg + 8 * j, rows_cap - 1) * kp;  // rows beyond n: results are not stored
-    const float* wb = sW1 + (h * 16 + cg) * 4;
-    for (int k4 = 0; k4 < kp; k4 += 4) {
-      float4 av[J], bv[4];
-#pragma unroll
-      for (int j = 0; j < J; ++j) av[j] = *reinterpret_cast<const float4*>(xr[j] + k4);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) bv[t] = *reinterpret_cast<const float4*>(wb + k4 * kS1 + 16 * t);
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          acc[j][t] = __ffma2_rn(make_float2(av[j].x, av[j].y), make_float2(bv[t].x, bv[t].y), acc[j][t]);
-          acc[j][t] = __ffma2_rn(make_float2(av[j].z, av[j].w), make_float2(bv[t].z, bv[t].w), acc[j][t]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int r = base + rg + 8 * j;
-      if (r < n)
-        *reinterpret_cast<float4*>(sP + r * kS1 + h * 16 + 4 * cg) =
-            make_float4(acc[j][0].x + acc[j][0].y, acc[j][1].x + acc[j][1].y, acc[j][2].x + acc[j][2].y, acc[j][3].x + acc[j][3].y);
-    }
-  }
+// ---- tensor-core helpers: mma.sync m16n8k8 TF32 with error compensation ("3xTF32").
+// An fp32 operand is split as v = hi + lo with hi = tf32(v), lo = tf32(v - hi); a product is accumulated (fp32) as
+// lo_a*hi_b + hi_a*lo_b + hi_a*hi_b: the dropped lo*lo term is ~2^-22 relative, far inside the 1e-5 parity bar, while a plain
+// TF32 product (2^-11) would not be.  ncu showed the SIMT projections bound by shared-memory operand traffic (one LDS.128 =
+// 4 wavefronts feeds only 16 FFMA2 per lane); a fragment register feeds 8-32 MACs.
+// Fragment layout (PTX ISA, g = lane >> 2, t = lane & 3):  A 16x8 row-major: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B 8x8: b0 (k = t, n = g) b1 (k = t+4, n = g);  C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(v);
+  lo = to_tf32(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += a * b for fp32 a (already split) and fp32 b (already split)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint2 bhi, uint2 blo) {
+  mma_tf32(c, alo, bhi.x, bhi.y);
+  mma_tf32(c, ahi, blo.x, blo.y);
+  mma_tf32(c, ahi, bhi.x, bhi.y);
 }
 
-__device__ __forceinline__ void project_x_dispatch(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp) {
-  const int j = (n + 63) / 64;  // rows per lane that make one round of 16 tiles
-  if (j <= 2) project_x<2>(x_off, w1_off, p_off, n, rows_cap, kp);
-  else if (j == 3) project_x<3>(x_off, w1_off, p_off, n, rows_cap, kp);
-  else if (j == 4) project_x<4>(x_off, w1_off, p_off, n, rows_cap, kp);
-  else if (j == 5) project_x<5>(x_off, w1_off, p_off, n, rows_cap, kp);
-  else project_x<6>(x_off, w1_off, p_off, n, rows_cap, kp);
+// P = x W1s^T -> tile [n][32].  One warp per 16-row tile: 4 column tiles x ceil(F/8) k-steps of 3xTF32 MMAs.
+// sW holds the B fragments of W1s^T pre-split once per CTA: [k-step][column tile][lane] x (hi.b0, hi.b1, lo.b0, lo.b1).
+__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp, int ksteps) {
+  const float* sX = sm<float>(x_off);
+  const uint4* sW = sm<uint4>(w1_off);
+  float* sP = sm<float>(p_off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (n + 15) / 16;
+  for (int tl = warp; tl < n_tiles; tl += kNW) {
+    const int r0 = tl * 16;
+    const float* xa = sX + min(r0 + g, rows_cap - 1) * kp + t;      // rows beyond n: results are not stored
+    const float* xb = sX + min(r0 + g + 8, rows_cap - 1) * kp + t;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int k0 = ks * 8;
+      const bool in2 = k0 + t + 4 < kp;  // the last k-step may reach past the row: those products are zero, keep them finite
+      uint32_t ahi[4], alo[4];
+      split_tf32(xa[k0], ahi[0], alo[0]);
+      split_tf32(xb[k0], ahi[1], alo[1]);
+      split_tf32(in2 ? xa[k0 + 4] : 0.f, ahi[2], alo[2]);
+      split_tf32(in2 ? xb[k0 + 4] : 0.f, ahi[3], alo[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint4 w = sW[(ks * 4 + nt) * 32 + lane];
+        mma_3xtf32(acc[nt], ahi, alo, make_uint2(w.x, w.y), make_uint2(w.z, w.w));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (r0 + g < n) *reinterpret_cast<float2*>(sP + (r0 + g) * kS1 + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      if (r0 + g + 8 < n) *reinterpret_cast<float2*>(sP + (r0 + g + 8) * kS1 + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
 }
 
 // Z2 = A2 W2^T per branch: column sums of relu(Z2) (readout) -> sRed[8][64]; when TRAIN also the sign mask of Z2 (one 32-bit word
@@ -655,13 +694,21 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   plan.csr = L.idx;
   plan.scan = L.head + kHScan * 4;
 
-  // ---- weights once per CTA.  W1 as [k/4][pos][4]: logical output m = 16*h + 4*cg + t sits at pos = 16*h + cg + 4*t, so the four
-  // lanes cg = 0..3 of a quad read four consecutive 16-byte chunks (conflict-free)
-  for (int e = tid; e < kS1 * kp; e += kT) {
-    const int m = e / kp, k = e - m * kp;
-    const int pos = (m & 16) + ((m & 15) >> 2) + 4 * (m & 3);
-    const float* w = m < kF1 ? a.w1a + (size_t)m * a.fi : a.w1b + (size_t)(m - kF1) * a.fi;
-    sW1[((k >> 2) * kS1 + pos) * 4 + (k & 3)] = k < a.fi ? __ldg(w + k) : 0.f;
+  // ---- weights once per CTA.  W1s^T as pre-split TF32 B fragments: entry [(k-step * 4 + column tile) * 32 + lane] =
+  // (hi.b0, hi.b1, lo.b0, lo.b1) with b0 = W1s[8 nt + g][8 ks + t], b1 = W1s[8 nt + g][8 ks + t + 4] (zero beyond F)
+  {
+    uint4* sW = reinterpret_cast<uint4*>(sW1);
+    const int ksteps = (a.fi + 7) / 8;
+    for (int e = tid; e < ksteps * 4 * 32; e += kT) {
+      const int ln = e & 31, nt = (e >> 5) & 3, ks = e >> 7;
+      const int m = nt * 8 + (ln >> 2), k = ks * 8 + (ln & 3);
+      const float* w = m < kF1 ? a.w1a + (size_t)m * a.fi : a.w1b + (size_t)(m - kF1) * a.fi;
+      const float v0 = k < a.fi ? __ldg(w + k) : 0.f, v1 = k + 4 < a.fi ? __ldg(w + k + 4) : 0.f;
+      uint4 q;
+      split_tf32(v0, q.x, q.z);
+      split_tf32(v1, q.y, q.w);
+      sW[e] = q;
+    }
   }
   for (int e = tid; e < kF2 * kF1; e += kT) {
     sW2[e] = __ldg(a.w2a + e);
@@ -704,8 +751,9 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status);
     stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
+    const bool have_csc = TRAIN && csc_entries >= 0;  // false: symmetric adjacency, the backward pass gathers through the CSR
     uint16_t* spill = TRAIN ? a.csc_spill + (size_t)blockIdx.x * a.ent_cap : nullptr;
-    if (TRAIN) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
+    if (have_csc) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
       const uint4* src = sm<uint4>(plan.csc);
       uint4* dst = reinterpret_cast<uint4*>(spill);
       for (int i = tid; i < (csc_entries + 7) / 8; i += kT) dst[i] = src[i];
@@ -720,7 +768,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     cp_async_wait<0>();
     __syncthreads();
 
-    project_x_dispatch(L.x, L.w1, L.t0, n, a.rows_cap, kp);
+    project_x(L.x, L.w1, L.t0, n, a.rows_cap, kp, (a.fi + 7) / 8);
     if (tid == 32 && have_next) {
       s_meta[buf ^ 1][0] = gn;
       s_meta[buf ^ 1][1] = nx[0];
@@ -741,7 +789,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     __syncthreads();
     aggregate<1>(L.t1, L.t0, L.rinfo, L.rperm, L.idx, n);
     __syncthreads();
-    if (TRAIN) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
+    if (have_csc) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
       const int chunks = (csc_entries + 7) / 8;
       for (int i = tid; i < chunks; i += kT) cp_async_cg16(sIdx + i * 8, spill + i * 8);  // L2 only: this CTA wrote it moments ago
       cp_async_commit();
@@ -887,9 +935,9 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     cp_async_wait<0>();  // the CSC is back in the index region
     __syncthreads();
     // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
-    aggregate<2>(L.t0, L.t1, L.cinfo, L.cperm, L.idx, n);
+    aggregate<2>(L.t0, L.t1, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, n);
     __syncthreads();
-    aggregate<1>(L.t1, L.t0, L.cinfo, L.cperm, L.idx, n);
+    aggregate<1>(L.t1, L.t0, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, n);
     __syncthreads();
     conv1_weight_grad(L.t0, L.x, L.t1, n, kp);
     __syncthreads();
