@@ -271,6 +271,18 @@ class GINetFusedStep:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return self.loss, pred
 
+    def empty_step(self):
+        """A rank without graphs in this (ragged) global mini-batch still joins the all-reduce and steps the optimizer."""
+        self.flat_grad.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.optimizer.step()
+
     def __call__(self, batch, global_size: int | None = None):
         if self._adam is not None:  # Adam applied by the finalize kernel on torch's own optimizer state (2 launches per step)
             self._adam.lr = self.optimizer.param_groups[0]["lr"]

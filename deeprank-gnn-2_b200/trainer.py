@@ -108,6 +108,7 @@ class Trainer:
         self.shuffle = None
         self.model_load_state_dict = None
         self._grad_sync = None
+        self._fused = None
 
         if self.pretrained_model is None:
             if self.dataset_train is None:
@@ -257,8 +258,12 @@ class Trainer:
     # ------------------------------------------------------------------ public configuration
     def configure_optimizers(self, optimizer=None, lr: float = 0.001, weight_decay: float = 1e-05) -> None:
         self.lr, self.weight_decay = lr, weight_decay
+        self._fused = None
         if optimizer is None:
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
+            # same defaults as the reference (trainer.py:416); `fused` keeps the step counters on the device, which lets the
+            # per-graph step kernel's finalize apply the update itself (fused.GINetFusedStep)
+            on_gpu = next(self.model.parameters()).is_cuda
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay, **({"fused": True} if on_gpu else {}))
             return
         try:
             self.optimizer = optimizer(self.model.parameters(), lr=lr, weight_decay=weight_decay)
@@ -390,12 +395,20 @@ class Trainer:
         t0 = time()
         for batch, global_size in loader:
             if batch is None:
-                if train and self._grad_sync is not None:  # ragged tail: this rank has no graphs but must join the all-reduce
+                if train and self._fused is not None and self._fused is not False:
+                    self._fused.empty_step()
+                elif train and self._grad_sync is not None:  # ragged tail: this rank has no graphs but must join the all-reduce
                     self.optimizer.zero_grad()
                     self._grad_sync(local_weight=0.0)
                     self.optimizer.step()
                 continue
-            if train:
+            fused = self._fused_step(batch) if train else None
+            if fused is not None:
+                # whole step (index, forward, loss, backward, gradient all-reduce, optimizer) in the per-graph kernels
+                loss_, pred = fused(batch, global_size=global_size)
+                loss_ = loss_ * (global_size / pred.shape[0])  # the kernel scales by the global batch: back to this rank's mean
+                pred, y = self._format_output(pred.clone(), batch.y)
+            elif train:
                 self.optimizer.zero_grad()
                 pred = self.model(batch)
                 pred, y = self._format_output(pred, batch.y)
@@ -428,6 +441,23 @@ class Trainer:
         _log.info(f"{pass_name} loss {epoch_loss} | time {time() - t0}")
         return epoch_loss
 
+    def _fused_step(self, batch):
+        """The per-graph step kernels (``fused.GINetFusedStep``) when the model is the reference ``ginet_nocluster.GINet``, the
+        loss is MSELoss / unweighted CrossEntropyLoss and every graph of ``batch`` fits the kernel's plan; else None (the
+        layer kernels through autograd)."""
+        from .fused import GINetFusedStep, step_supported
+
+        if self._fused is None:
+            loss_fn = self.lossfunction
+            if isinstance(loss_fn, type) or not GINetFusedStep.supports(self.model, loss_fn):
+                self._fused = False
+            else:
+                world = dist.get_world_size() if self._distributed() else 1
+                self._fused = GINetFusedStep(self.model, self.optimizer, loss_fn, target_fn=lambda b: self._format_output(None, b.y)[1], world_size=world)
+        if self._fused is False or not step_supported(self.model, batch):
+            return None
+        return self._fused
+
     def _epoch(self, epoch_number: int, pass_name: str):
         return self._run_pass(self.train_loader, epoch_number, pass_name, train=True)
 
@@ -448,7 +478,7 @@ class Trainer:
                 raise ValueError("BCELoss and BCEWithLogitsLoss are currently not supported.\n\tFor further details see: https://github.com/DeepRank/deeprank2/issues/318")
             if isinstance(self.lossfunction, losses.classification_losses) and not isinstance(self.lossfunction, losses.classification_tested):
                 raise ValueError(f"{self.lossfunction} is currently not supported.\n\tSupported loss functions for classification: {losses.classification_tested}.")
-        elif self.task == targets.REGRESS:
+        elif self.task == targets.REGRESS and pred is not None:
             pred = pred.reshape(-1)
         if target is not None:
             target = target.to(self.device)

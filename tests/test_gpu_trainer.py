@@ -62,6 +62,13 @@ def test_trainer_trains_every_net_on_gpu(net_name, tmp_path):
     assert len(names) == 16 and len(sink.calls[0][3]) == 16 and len(sink.calls[0][4]) == 16
     trainer.test()
     assert sink.calls[-1][0] == "testing" and len(sink.calls[-1][2]) == 4
+    if net_name == "ginet_nocluster":
+        from deeprank2_b200.fused import GINetFusedStep
+
+        assert isinstance(trainer._fused, GINetFusedStep), "the Trainer must drive the reference GINet through the per-graph step kernels"
+        assert trainer._fused._adam is not None, "default optimizer: the Adam update runs in the finalize kernel"
+    else:
+        assert trainer._fused is False
 
 
 def test_trainer_epoch_matches_cpu_oracle_epoch():
