@@ -541,86 +541,174 @@ __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, 
   }
 }
 
-// Z2 = A2 W2^T per branch: column sums of relu(Z2) (readout) -> sRed[8][64]; when TRAIN also the sign mask of Z2 (one 32-bit word
-// per row and branch) and the masked column sums of A2 (dW2 = dG/n * those), left as 8 row-lane partials [rl][c][k] in the A2 tile.
+__device__ __forceinline__ uint32_t tf32_bit(uint32_t word, int pos) {  // 1.0 / 0.0 (exact in TF32) from bit `pos`
+  return (word >> pos) & 1u ? 0x3f800000u : 0u;
+}
+
+// conv2 of both branches on the tensor cores.  Warp w works on branch w & 1; the eight warps of a branch take 16-row tiles round-robin.
+//   Z2_br = A2_br W2_br^T (3xTF32): column sums of relu(Z2) (scatter_mean readout) -> sRed[8 warps][64]; when TRAIN also the
+//   sign mask of Z2, one 32-bit word per (row, branch) -> sMaskZ, and then
+//   S_br[c][k] = sum_r (Z2[r][c] > 0) A2[r][br*16 + k]  (dW2 = dG/n * S): a [32 x n] x [n x 16] product whose left operand is the
+//   0/1 mask (exact in TF32; A2 split hi + lo), left as 8 per-warp partials [warp][c][k] in the A2 tile.
 template <bool TRAIN>
-__device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off, int red_off, int n) {
+__device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off, int red_off, int n, int rows_cap) {
   float* sA2 = sm<float>(a2_off);
   const float* sW2 = sm<float>(w2_off);
   uint32_t* sMaskZ = sm<uint32_t>(maskz_off);
   float* sRed = sm<float>(red_off);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int c = tid & 63, rl = tid >> 6, br = c >> 5;
-  float2 w[kF1 / 2], s[kF1 / 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int br = warp & 1, slot = warp >> 1;
+  const float* a2b = sA2 + br * kF1;
+  {
+    // B fragments of W2_br^T, split once per call: b0 = W2[8nt + g][8ks + t], b1 = W2[8nt + g][8ks + t + 4]
+    uint2 bh[2][4], bl[2][4];
 #pragma unroll
-  for (int k = 0; k < kF1 / 2; ++k) {
-    w[k] = *reinterpret_cast<const float2*>(sW2 + (br * kF2 + (c & 31)) * kF1 + 2 * k);
-    s[k] = make_float2(0.f, 0.f);
-  }
-  float colsum = 0.f;
-  for (int r = rl; r < n; r += 8) {
-    const float* arow = sA2 + r * kS1 + br * kF1;
-    float2 av[kF1 / 2];
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int k4 = 0; k4 < kF1 / 4; ++k4) {
-      const float4 v = *reinterpret_cast<const float4*>(arow + 4 * k4);
-      av[2 * k4] = make_float2(v.x, v.y);
-      av[2 * k4 + 1] = make_float2(v.z, v.w);
-    }
-    float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < kF1 / 2; k += 2) {
-      z0 = __ffma2_rn(av[k], w[k], z0);
-      z1 = __ffma2_rn(av[k + 1], w[k + 1], z1);
-    }
-    const float z = (z0.x + z0.y) + (z1.x + z1.y);
-    const bool pos = z > 0.f;
-    if (pos) colsum += z;
-    if (TRAIN) {
-      if (pos) {
-#pragma unroll
-        for (int k = 0; k < kF1 / 2; ++k) s[k] = __fadd2_rn(s[k], av[k]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* w = sW2 + (br * kF2 + 8 * nt + g) * kF1 + 8 * ks + t;
+        split_tf32(w[0], bh[ks][nt].x, bl[ks][nt].x);
+        split_tf32(w[4], bh[ks][nt].y, bl[ks][nt].y);
       }
-      const unsigned word = __ballot_sync(kFull, pos);
-      if (lane == 0) sMaskZ[r * 2 + br] = word;
+    float cs[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) cs[nt][0] = cs[nt][1] = 0.f;
+    const int n_tiles = (n + 15) / 16;
+    for (int tl = slot; tl < n_tiles; tl += 8) {
+      const int r0 = tl * 16;
+      const float* ra = a2b + min(r0 + g, rows_cap - 1) * kS1 + t;  // rows beyond n: garbage in, masked out below
+      const float* rb = a2b + min(r0 + g + 8, rows_cap - 1) * kS1 + t;
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ahi[4], alo[4];
+        split_tf32(ra[8 * ks], ahi[0], alo[0]);
+        split_tf32(rb[8 * ks], ahi[1], alo[1]);
+        split_tf32(ra[8 * ks + 4], ahi[2], alo[2]);
+        split_tf32(rb[8 * ks + 4], ahi[3], alo[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_3xtf32(acc[nt], ahi, alo, bh[ks][nt], bl[ks][nt]);
+      }
+      const bool va = r0 + g < n, vb = r0 + g + 8 < n;
+      uint32_t wa = 0u, wb = 0u;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const bool p0 = va && acc[nt][0] > 0.f, p1 = va && acc[nt][1] > 0.f, p2 = vb && acc[nt][2] > 0.f, p3 = vb && acc[nt][3] > 0.f;
+        cs[nt][0] += (p0 ? acc[nt][0] : 0.f) + (p2 ? acc[nt][2] : 0.f);
+        cs[nt][1] += (p1 ? acc[nt][1] : 0.f) + (p3 ? acc[nt][3] : 0.f);
+        wa |= ((uint32_t)p0 << (8 * nt + 2 * t)) | ((uint32_t)p1 << (8 * nt + 2 * t + 1));
+        wb |= ((uint32_t)p2 << (8 * nt + 2 * t)) | ((uint32_t)p3 << (8 * nt + 2 * t + 1));
+      }
+      if (TRAIN) {
+        wa |= __shfl_xor_sync(kFull, wa, 1);
+        wa |= __shfl_xor_sync(kFull, wa, 2);
+        wb |= __shfl_xor_sync(kFull, wb, 1);
+        wb |= __shfl_xor_sync(kFull, wb, 2);
+        if (t == 0) {
+          if (va) sMaskZ[(r0 + g) * 2 + br] = wa;
+          if (vb) sMaskZ[(r0 + g + 8) * 2 + br] = wb;
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v = cs[nt][j];
+        v += __shfl_xor_sync(kFull, v, 4);
+        v += __shfl_xor_sync(kFull, v, 8);
+        v += __shfl_xor_sync(kFull, v, 16);
+        if (g == 0) sRed[slot * kS2 + br * kF2 + 8 * nt + 2 * t + j] = v;
+      }
+  }
+  if (!TRAIN) return;
+  __syncthreads();  // the sign masks of all rows are in place
+  float sacc[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sacc[mt][nt][i] = 0.f;
+  const int n_ks = (n + 7) / 8;
+  for (int ks = slot; ks < n_ks; ks += 8) {
+    const int r0 = ks * 8 + t, r1 = r0 + 4;
+    const bool v0 = r0 < n, v1 = r1 < n;
+    const uint32_t mw0 = v0 ? sMaskZ[r0 * 2 + br] : 0u, mw1 = v1 ? sMaskZ[r1 * 2 + br] : 0u;
+    uint2 bh[2], bl[2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {  // b0 = A2[r0][8nt + g], b1 = A2[r1][8nt + g]
+      split_tf32(v0 ? a2b[r0 * kS1 + 8 * nt + g] : 0.f, bh[nt].x, bl[nt].x);
+      split_tf32(v1 ? a2b[r1 * kS1 + 8 * nt + g] : 0.f, bh[nt].y, bl[nt].y);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t am[4] = {tf32_bit(mw0, 16 * mt + g), tf32_bit(mw0, 16 * mt + g + 8), tf32_bit(mw1, 16 * mt + g), tf32_bit(mw1, 16 * mt + g + 8)};
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        mma_tf32(sacc[mt][nt], am, bl[nt].x, bl[nt].y);
+        mma_tf32(sacc[mt][nt], am, bh[nt].x, bh[nt].y);
+      }
     }
   }
-  sRed[rl * kS2 + c] = colsum;
-  if (TRAIN) {
-    __syncthreads();  // every warp is done reading A2: reuse the tile as the 8-way reduction scratch
+  __syncthreads();  // every warp is done reading A2: reuse the tile as the reduction scratch [8 warps][64 c][16 k]
 #pragma unroll
-    for (int k4 = 0; k4 < kF1 / 4; ++k4)
-      *reinterpret_cast<float4*>(sA2 + ((rl * kS2 + c) * kF1 + 4 * k4)) = make_float4(s[2 * k4].x, s[2 * k4].y, s[2 * k4 + 1].x, s[2 * k4 + 1].y);
-  }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      float* d = sA2 + ((slot * kS2 + br * kF2 + 16 * mt + g) * kF1 + 8 * nt + 2 * t);
+      *reinterpret_cast<float2*>(d) = make_float2(sacc[mt][nt][0], sacc[mt][nt][1]);
+      *reinterpret_cast<float2*>(d + 8 * kF1) = make_float2(sacc[mt][nt][2], sacc[mt][nt][3]);
+    }
 }
 
-// dA2[r, br*16 + k] = sum_{c in branch, Z2[r,c] > 0} V[c, k] -> tile.  lane -> row, warp -> (branch, 8 outputs)
-__device__ __noinline__ void conv2_backward_input(int v_off, int maskz_off, int out_off, int n) {
-  const float* sV = sm<float>(v_off);
+// dA2_br [n x 16] = Mask_br [n x 32] V_br [32 x 16] with V[c][k] = dG[c]/n * W2[c][k]: the left operand is the 0/1 sign mask of Z2 (exact
+// in TF32), V is split hi + lo.  Same warp -> (branch, 16-row tile) assignment as conv2_readout.
+__device__ __noinline__ void conv2_backward_input(int w2_off, int dg_off, int maskz_off, int out_off, int n) {
+  const float* sW2 = sm<float>(w2_off);
+  const float* sDG = sm<float>(dg_off);
   const uint32_t* sMaskZ = sm<uint32_t>(maskz_off);
   float* sOut = sm<float>(out_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int combo = warp & 3, br = combo >> 1, kh = combo & 1;
-  const float* vb = sV + br * kF2 * kF1 + kh * 8;
-  for (int r = (warp >> 2) * 32 + lane; r < n; r += 128) {
-    const unsigned m = sMaskZ[r * 2 + br];
-    float2 o[4];
+  const int g = lane >> 2, t = lane & 3;
+  const int br = warp & 1, slot = warp >> 1;
+  uint2 vh[4][2], vl[4][2];  // b0 = V[8ks + t][8nt + g], b1 = V[8ks + t + 4][8nt + g]
 #pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = make_float2(0.f, 0.f);
+  for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-    for (int c = 0; c < kF2; ++c) {
-      const float4 v0 = *reinterpret_cast<const float4*>(vb + c * kF1);
-      const float4 v1 = *reinterpret_cast<const float4*>(vb + c * kF1 + 4);
-      if (m & (1u << c)) {
-        o[0] = __fadd2_rn(o[0], make_float2(v0.x, v0.y));
-        o[1] = __fadd2_rn(o[1], make_float2(v0.z, v0.w));
-        o[2] = __fadd2_rn(o[2], make_float2(v1.x, v1.y));
-        o[3] = __fadd2_rn(o[3], make_float2(v1.z, v1.w));
+    for (int nt = 0; nt < 2; ++nt) {
+      const int c0 = br * kF2 + 8 * ks + t, k = 8 * nt + g;
+      split_tf32(sDG[c0] * sW2[c0 * kF1 + k], vh[ks][nt].x, vl[ks][nt].x);
+      split_tf32(sDG[c0 + 4] * sW2[(c0 + 4) * kF1 + k], vh[ks][nt].y, vl[ks][nt].y);
+    }
+  const int n_tiles = (n + 15) / 16;
+  for (int tl = slot; tl < n_tiles; tl += 8) {
+    const int ra = tl * 16 + g, rb = ra + 8;
+    const uint32_t mwa = ra < n ? sMaskZ[ra * 2 + br] : 0u, mwb = rb < n ? sMaskZ[rb * 2 + br] : 0u;
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t am[4] = {tf32_bit(mwa, 8 * ks + t), tf32_bit(mwb, 8 * ks + t), tf32_bit(mwa, 8 * ks + t + 4), tf32_bit(mwb, 8 * ks + t + 4)};
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        mma_tf32(acc[nt], am, vl[ks][nt].x, vl[ks][nt].y);
+        mma_tf32(acc[nt], am, vh[ks][nt].x, vh[ks][nt].y);
       }
     }
-    float* out = sOut + r * kS1 + br * kF1 + kh * 8;
-    *reinterpret_cast<float4*>(out) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-    *reinterpret_cast<float4*>(out + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      if (ra < n) *reinterpret_cast<float2*>(sOut + ra * kS1 + br * kF1 + 8 * nt + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      if (rb < n) *reinterpret_cast<float2*>(sOut + rb * kS1 + br * kF1 + 8 * nt + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
   }
 }
 
@@ -673,7 +761,6 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   float* sW1 = reinterpret_cast<float*>(smem + L.w1);
   float* sW2 = reinterpret_cast<float*>(smem + L.w2);
   float* sS = reinterpret_cast<float*>(smem + L.s);
-  float* sV = reinterpret_cast<float*>(smem + L.v);
   uint32_t* sMaskZ = reinterpret_cast<uint32_t*>(smem + L.maskz);
   float* sRed = reinterpret_cast<float*>(smem + L.red);
   float* sHead = reinterpret_cast<float*>(smem + L.head);
@@ -794,7 +881,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int i = tid; i < chunks; i += kT) cp_async_cg16(sIdx + i * 8, spill + i * 8);  // L2 only: this CTA wrote it moments ago
       cp_async_commit();
     }
-    conv2_readout<TRAIN>(L.t0, L.w2, L.maskz, L.red, n);
+    conv2_readout<TRAIN>(L.t0, L.w2, L.maskz, L.red, n, a.rows_cap);
     __syncthreads();
     float* hG = sHead + kHG;
     float* hDG = sHead + kHDG;
@@ -928,10 +1015,8 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       const int c = e / kF1;
       const float dgc = hDG[c];
       part[kS1 * kp + e] = dgc * sS[e];
-      sV[e] = dgc * sW2[e];
     }
-    __syncthreads();
-    conv2_backward_input(L.v, L.maskz, L.t0, n);
+    conv2_backward_input(L.w2, L.head + kHDG * 4, L.maskz, L.t0, n);
     cp_async_wait<0>();  // the CSC is back in the index region
     __syncthreads();
     // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
