@@ -55,13 +55,14 @@ SIGNATURES = {
     "drk_graph_index_blocked_supported": (c_int32, [_I32, _I32]),
     "drk_graph_index_build_blocked": (c_int32, [_P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "drk_ginet_step_ctas": (c_int32, [_I32]),
+    "drk_ginet_step_exchange_floats": (c_int32, [_I32, _I32]),
     "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
     "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),
     "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _I32, _I32,   # x .. max_graph_edges
                                  _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
                                  _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients
-                                 _P, _P, _P, c_size_t, _P]),                                 # adam, status, workspace, stream
+                                 _P, _P, _P, _P, c_size_t, _P]),                             # adam, peers, status, workspace, stream
     "drk_segment_max": (c_int32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),
@@ -72,6 +73,12 @@ SIGNATURES = {
     "drk_edge_msg_bwd_c": (c_int32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _P, _I64, _I32, _P, c_size_t, _P]),
 }
 
+
+
+class Peers(ctypes.Structure):
+    """``DrkPeers`` of include/drk_b200.h"""
+
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("capacity", c_int64), ("flag_capacity", c_int64), ("grad_buf", c_void_p * 8), ("flags", c_void_p * 8)]
 
 
 class AdamTensor(ctypes.Structure):

@@ -1045,6 +1045,8 @@ struct FinalArgs {
   float loss_scale; int64_t* rng_step;
   // optional Adam update fused behind the reduction (adam_on): live[] in the order of the gradient outputs above
   int32_t adam_on; DrkAdam adam; int32_t* done_counter; int32_t grad_blocks;
+  // optional one-shot all-reduce over peer memory (peers.world > 1): see the exchange in k_step_finalize
+  DrkPeers peers; int32_t* epoch; int32_t total;
 };
 
 // torch.optim.Adam (L2 weight decay, no amsgrad, no maximize), the arithmetic of its fused CUDA implementation:
@@ -1062,6 +1064,18 @@ __device__ __forceinline__ void adam_update(const DrkAdam& h, const DrkAdamTenso
   t.exp_avg[i] = m;
   t.exp_avg_sq[i] = v;
   t.param[i] = p - (h.lr / bc1) * (m / denom);
+}
+
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // Block = 32 outputs x 8 graph slices: thread (slice ty, output tx) adds the contributions of graphs ty, ty+8, ty+16, ... (loads are
@@ -1126,8 +1140,48 @@ __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
 #pragma unroll
       for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
       s *= scale;
-      *dst = s;
-      if (a.adam_on && live >= 0) adam_update(a.adam, a.adam.live[live], li, s);
+      if (a.peers.world <= 1) {
+        *dst = s;
+        if (a.adam_on && live >= 0) adam_update(a.adam, a.adam.live[live], li, s);
+      }
+    }
+    if (a.peers.world > 1 && ty == 0) {
+      // One-shot all-reduce of this block's 32 values over NVLink peer memory, fused between the reduction and the optimizer:
+      // every rank publishes its partial sums in its own symmetric buffer, raises a flag in every peer's memory
+      // (release), waits for the same block of every peer (acquire) and adds all ranks' values IN RANK ORDER -- every
+      // rank computes bit-identical sums, no second exchange, no NCCL launch.  Buffers alternate with the epoch's parity:
+      // a rank can be at most one step ahead of a peer (it needs the peer's flag of the current step to finish it).
+      const DrkPeers& pr = a.peers;
+      const int32_t epoch = *a.epoch + 1;  // advanced by the last block of this launch, after everyone has read it
+      const size_t off = (size_t)(epoch & 1) * a.total + t;
+      float sum = 0.f;
+      {
+        float s = 0.f;
+        if (dst != nullptr) {
+          s = s_part[0][tx];
+#pragma unroll
+          for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
+          s *= scale;
+          pr.grad_buf[pr.rank][off] = s;
+        }
+        __threadfence_system();
+        __syncwarp();
+        const int nb = a.grad_blocks;
+        if (tx < pr.world && tx != pr.rank) {
+          st_release_sys(pr.flags[tx] + (size_t)pr.rank * nb + blockIdx.x, epoch);
+          const int32_t* mine = pr.flags[pr.rank] + (size_t)tx * nb + blockIdx.x;
+          while (ld_acquire_sys(mine) < epoch) {
+          }
+        }
+        __syncwarp();
+        if (dst != nullptr) {
+          for (int q = 0; q < pr.world; ++q) sum += q == pr.rank ? s : ld_relaxed_sys(pr.grad_buf[q] + off);
+        }
+      }
+      if (dst != nullptr) {
+        *dst = sum;
+        if (a.adam_on && live >= 0) adam_update(a.adam, a.adam.live[live], li, sum);
+      }
     }
   } else if (a.adam_on) {
     // dead parameters (zero gradient): flat index over the concatenation of adam.dead[]
@@ -1140,16 +1194,21 @@ __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
       i -= a.adam.dead[d].numel;
     }
   }
-  if (!a.adam_on) return;
-  // every block has read the step scalars: the last one to finish advances them (and re-arms the counter)
+  if (!a.adam_on && a.peers.world <= 1) return;
+  // every block has read the step scalars / the epoch: the last one to finish advances them (and re-arms the counter)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(a.done_counter, 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (s_last) {
-    if (threadIdx.x < 8) *a.adam.live[threadIdx.x].step += 1.f;
-    else if ((int)threadIdx.x - 8 < a.adam.num_dead) *a.adam.dead[threadIdx.x - 8].step += 1.f;
-    if (threadIdx.x == 0) *a.done_counter = 0;
+    if (a.adam_on) {
+      if (threadIdx.x < 8) *a.adam.live[threadIdx.x].step += 1.f;
+      else if ((int)threadIdx.x - 8 < a.adam.num_dead) *a.adam.dead[threadIdx.x - 8].step += 1.f;
+    }
+    if (threadIdx.x == 0) {
+      *a.done_counter = 0;
+      if (a.peers.world > 1) *a.epoch += 1;
+    }
   }
 }
 
@@ -1364,6 +1423,11 @@ static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
 
 extern "C" {
 
+int32_t drk_ginet_step_exchange_floats(int32_t fi, int32_t out_dim) {
+  using namespace drk::gs;
+  return kS1 * fi + kS2 * kF1 + kHid * kS2 + kHid + out_dim * kHid + out_dim + 1;
+}
+
 int32_t drk_ginet_step_ctas(int32_t num_graphs) { return std::max(0, std::min(num_graphs, drk::kNumSM)); }
 
 int drk_ginet_step_supported(int32_t fi, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges) {
@@ -1389,7 +1453,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
                    float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train, float* pred, float* loss, float* dw1a, float* dw1b,
-                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, const DrkAdam* adam, int32_t* status,
+                   float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, const DrkAdam* adam, const DrkPeers* peers, int32_t* status,
                    void* workspace, size_t workspace_bytes, void* stream) {
   using namespace drk;
   using namespace drk::gs;
@@ -1398,9 +1462,11 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   PlanResult p;
   DRK_REQUIRE(make_plan(fi, max_graph_nodes, max_graph_edges, p), DRK_EUNSUPPORTED,
               "ginet step: graphs of %d nodes / %d edges with %d features do not fit the shared-memory plan", max_graph_nodes, max_graph_edges, fi);
-  if (num_graphs == 0) return DRK_OK;
+  const bool exchange = train && peers != nullptr && peers->world > 1;  // a rank without graphs still takes part in the all-reduce
+  if (num_graphs == 0 && !exchange) return DRK_OK;
   DRK_REQUIRE(edge_index || num_edges == 0, DRK_EINVAL, "ginet step: null edge_index");
-  DRK_REQUIRE(x && graph_ptr && edge_ptr && w1a && w1b && w2a && w2b && fc1_w && fc1_b && fc2_w && fc2_b && pred, DRK_EINVAL,
+  DRK_REQUIRE(num_graphs == 0 || (x && graph_ptr && edge_ptr), DRK_EINVAL, "ginet step: null batch pointer");
+  DRK_REQUIRE(w1a && w1b && w2a && w2b && fc1_w && fc1_b && fc2_w && fc2_b && pred, DRK_EINVAL,
               "ginet step: null pointer");
   DRK_REQUIRE(aligned16(fc1_w) && aligned16(fc2_w), DRK_EINVAL, "ginet step: head weights must be 16-byte aligned");
   if (train) {
@@ -1446,7 +1512,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   if (train) {
     e = cudaFuncSetAttribute(k_ginet_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "ginet step: smem opt-in: %s", cudaGetErrorString(e));
-    k_ginet_step<true><<<grid, kT, p.smem, st>>>(a);
+    if (num_graphs > 0) k_ginet_step<true><<<grid, kT, p.smem, st>>>(a);
     FinalArgs f{};
     f.part = a.part; f.part_stride = a.part_stride; f.gvec = a.gvec; f.hvec = a.hvec; f.dhvec = a.dhvec; f.dpvec = a.dpvec; f.loss_terms = a.loss_terms;
     f.num_graphs = num_graphs; f.fi = fi; f.kp = kp; f.out_dim = out_dim;
@@ -1471,6 +1537,19 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
       DRK_REQUIRE(rng_step != nullptr, DRK_EINVAL, "ginet step: the fused Adam update needs the int64[2] state buffer");
       f.done_counter = reinterpret_cast<int32_t*>(rng_step + 1);
       blocks += (int)ceil_div<int64_t>(dead_elems, 256);
+    }
+    f.total = total;
+    f.peers.world = 1;
+    if (peers != nullptr && peers->world > 1) {
+      DRK_REQUIRE(peers->world <= 8 && peers->rank >= 0 && peers->rank < peers->world, DRK_EINVAL, "ginet step: peers.world must be <= 8 and rank inside it");
+      DRK_REQUIRE(rng_step != nullptr, DRK_EINVAL, "ginet step: the peer all-reduce needs the int64[4] state buffer");
+      for (int q = 0; q < peers->world; ++q)
+        DRK_REQUIRE(peers->grad_buf[q] && peers->flags[q], DRK_EINVAL, "ginet step: peers: null buffer of rank %d", q);
+      DRK_REQUIRE(peers->capacity >= 2 * (int64_t)total && peers->flag_capacity >= (int64_t)peers->world * f.grad_blocks, DRK_EINVAL,
+                  "ginet step: peer buffers too small (need %d floats and %d flags)", 2 * total, peers->world * f.grad_blocks);
+      f.peers = *peers;
+      f.done_counter = reinterpret_cast<int32_t*>(rng_step + 1);
+      f.epoch = reinterpret_cast<int32_t*>(rng_step + 2);
     }
     k_step_finalize<<<blocks, 256, 0, st>>>(f);
     return finish_launch("ginet step", 2);

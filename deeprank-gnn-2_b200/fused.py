@@ -130,7 +130,7 @@ def step_supported(model, data) -> bool:
     return bool(_lib.load().drk_ginet_step_supported(int(data.x.shape[1]), int(model.fc2.weight.shape[0]), info.max_nodes, info.max_edges))
 
 
-def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, state, pred, loss, grads, adam=None):
+def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, dropout_p, seed, state, pred, loss, grads, adam=None, peers=None):
     lib = _lib.load()
     x = data.x
     fi = int(x.shape[1])
@@ -144,7 +144,7 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
             int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(state), 1 if train else 0,
-            _p(pred), _p(loss), *[_p(g) for g in grads], ctypes.byref(adam) if adam is not None else None, _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
+            _p(pred), _p(loss), *[_p(g) for g in grads], ctypes.byref(adam) if adam is not None else None, ctypes.byref(peers) if peers is not None else None, _p(info.status), _p(ws), ws.numel() if ws is not None else 0, stream_ptr(),
         )
     _lib.check(rc, "drk_ginet_step")
 
@@ -192,14 +192,57 @@ class GINetFusedStep:
         m = model
         self.grads = [by_id[id(t)] for t in (m.conv1.fc.weight, m.conv1_ext.fc.weight, m.conv2.fc.weight, m.conv2_ext.fc.weight, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)]
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.state = torch.zeros(2, dtype=torch.int64, device=dev)  # [0] steps done (dropout stream), [1] finalize-kernel scratch
-        self._adam = self._adam_descriptor() if self.world == 1 else None
+        self.state = torch.zeros(4, dtype=torch.int64, device=dev)  # [0] steps done (dropout stream), [1] finalize scratch, [2] exchange epoch
+        self._peers = self._peer_exchange() if self.world > 1 else None
+        self._adam = self._adam_descriptor() if (self.world == 1 or self._peers is not None) else None
         self.seed = int(torch.initial_seed() if seed is None else seed)
         self._pred = {}
 
     @staticmethod
     def supports(model, loss_fn, batch=None) -> bool:
         return _standard_ginet(model) and _loss_kind(loss_fn) is not None and (batch is None or step_supported(model, batch))
+
+    def _peer_exchange(self):
+        """Symmetric buffers for the in-kernel gradient all-reduce (``DrkPeers``): every rank's gradient staging buffer and flag
+        array mapped into every process (``torch.distributed._symmetric_memory``: CUDA VMM handles over NVLink).  Returns None
+        -- and the step falls back to one NCCL all-reduce -- if the rendezvous is not available (``DRK_NO_PEER_EXCHANGE=1``
+        forces that)."""
+        import os
+
+        import torch.distributed as dist
+
+        if os.environ.get("DRK_NO_PEER_EXCHANGE") or self.world > 8:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            lib = _lib.load()
+            dev = self.flat_grad.device
+            fi, out_dim = int(self.model.conv1.fc.weight.shape[1]), int(self.model.fc2.weight.shape[0])
+            total = int(lib.drk_ginet_step_exchange_floats(fi, out_dim))
+            n_flags = self.world * ((total + 31) // 32)
+            group = self.group if self.group is not None else dist.group.WORLD
+            self._sym_grad = symm.empty(2 * total, dtype=torch.float32, device=dev)
+            self._sym_flags = symm.empty(n_flags, dtype=torch.int32, device=dev)
+            self._sym_grad.zero_()
+            self._sym_flags.zero_()
+            h_grad = symm.rendezvous(self._sym_grad, group)
+            h_flags = symm.rendezvous(self._sym_flags, group)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)  # everybody's flags are zero before anybody's first step
+            peers = _lib.Peers()
+            peers.world, peers.rank = self.world, int(h_grad.rank)
+            peers.capacity, peers.flag_capacity = 2 * total, n_flags
+            for q in range(self.world):
+                peers.grad_buf[q] = int(h_grad.buffer_ptrs[q])
+                peers.flags[q] = int(h_flags.buffer_ptrs[q])
+            self._sym_handles = (h_grad, h_flags)
+            return peers
+        except Exception as exc:  # noqa: BLE001 - any failure of the optional fast path means "use NCCL"
+            import warnings
+
+            warnings.warn(f"peer-memory gradient exchange unavailable ({type(exc).__name__}: {exc}); using one NCCL all-reduce per step", stacklevel=2)
+            return None
 
     def _adam_descriptor(self):
         """``DrkAdam`` over torch.optim.Adam's own state tensors, or None if the optimizer is anything else (then
@@ -264,19 +307,41 @@ class GINetFusedStep:
                 p.grad = v
         drop = float(self.model.dropout) if self.model.training else 0.0
         _call_step(self.model, batch, info, train=True, loss_kind=self.kind, target=target, inv_loss_count=1.0 / max(count, 1), dropout_p=drop,
-                   seed=self.seed, state=self.state, pred=pred, loss=self.loss, grads=self.grads, adam=adam)
-        if self.world > 1:
+                   seed=self.seed, state=self.state, pred=pred, loss=self.loss, grads=self.grads, adam=adam, peers=self._peers)
+        if self.world > 1 and self._peers is None:
             import torch.distributed as dist
 
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return self.loss, pred
 
     def empty_step(self):
-        """A rank without graphs in this (ragged) global mini-batch still joins the all-reduce and steps the optimizer."""
-        self.flat_grad.zero_()
+        """A rank without graphs in this (ragged) global mini-batch still joins the gradient exchange and steps the optimizer."""
         for p, v in zip(self.params, self.views):
             if p.grad is not v:
                 p.grad = v
+        if self._peers is not None:
+            # zero local contributions through the same finalize kernel: the peers wait for this rank's flags
+            m, lib, dev = self.model, _lib.load(), self.flat_grad.device
+            out_dim = int(m.fc2.weight.shape[0])
+            fi = int(m.conv1.fc.weight.shape[1])
+            pred = torch.empty((0, out_dim), dtype=torch.float32, device=dev)
+            if self._adam is not None:
+                self._adam.lr = self.optimizer.param_groups[0]["lr"]
+            with torch.cuda.device(dev):
+                ws = workspace(1 << 20, dev)
+                rc = lib.drk_ginet_step(
+                    None, fi, fi, None, 0, None, None, None, 0, 0, 0,
+                    _p(m.conv1.fc.weight), _p(m.conv1_ext.fc.weight), _p(m.conv2.fc.weight), _p(m.conv2_ext.fc.weight),
+                    _p(m.fc1.weight), _p(m.fc1.bias), _p(m.fc2.weight), _p(m.fc2.bias), out_dim,
+                    int(self.kind), _p(self.loss), 0.0, 0.0, int(self.seed) & (2**64 - 1), _p(self.state), 1,
+                    _p(pred) or _p(self.loss), _p(self.loss), *[_p(g) for g in self.grads],
+                    ctypes.byref(self._adam) if self._adam is not None else None, ctypes.byref(self._peers), None, _p(ws), ws.numel(), stream_ptr(),
+                )
+            _lib.check(rc, "drk_ginet_step (empty rank)")
+            if self._adam is None:
+                self.optimizer.step()
+            return
+        self.flat_grad.zero_()
         if self.world > 1:
             import torch.distributed as dist
 

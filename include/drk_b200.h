@@ -237,7 +237,9 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  *   data-parallel ranks the summed gradients of all ranks then equal the single-process gradient.
  * dropout: keep-mask from Philox4x32-10(seed, state[0], graph, unit); state (device int64[2], zero-initialised by the caller and
  *   private to the calls: [0] = steps done, [1] = scratch of the finalize kernel) is advanced by the finalize kernel so
- *   CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.
+ *   CUDA-graph replays draw fresh masks.  dropout_p == 0 disables it.  With `peers` the buffer is int64[4] ([2] = exchange epoch).
+ * peers (may be NULL = single rank): the per-rank gradients are summed over the ranks inside the finalize kernel (DrkPeers above);
+ *   the loss and every gradient output then hold the global values on every rank.
  * adam (may be NULL = gradients only): torch.optim.Adam step (L2 weight decay, no amsgrad) applied by the finalize kernel right
  *   behind the gradient reduction -- same arithmetic as torch's fused CUDA Adam, on torch's own state tensors:
  *   live[0..7] = the tensors of the gradient outputs below, in that order; dead[0..num_dead) = parameters whose gradient is
@@ -259,6 +261,18 @@ typedef struct DrkAdamTensor {
   float* step; /* device float32 scalar (torch.optim.Adam state["step"] with capturable/fused) */
   int64_t numel;
 } DrkAdamTensor;
+/* One-shot gradient all-reduce over NVLink peer memory, fused into the finalize kernel (data-parallel ranks, one process per GPU).
+ * grad_buf[q] / flags[q]: rank q's symmetric buffers as mapped in THIS process (e.g. torch.distributed._symmetric_memory):
+ * grad_buf holds 2 * drk_ginet_step_exchange_floats() floats (two epochs), flags world * ceil(that / 32) int32, zero before the
+ * first call.  All ranks must call drk_ginet_step the same number of times; the sums are formed in rank order, so every rank
+ * gets bit-identical gradients. */
+typedef struct DrkPeers {
+  int32_t world, rank;
+  int64_t capacity;      /* floats in each grad_buf */
+  int64_t flag_capacity; /* int32 in each flags array */
+  float* grad_buf[8];
+  int32_t* flags[8];
+} DrkPeers;
 typedef struct DrkAdam {
   float lr, beta1, beta2, eps, weight_decay;
   int32_t num_dead;
@@ -266,6 +280,7 @@ typedef struct DrkAdam {
   DrkAdamTensor dead[8];
 } DrkAdam;
 DRK_API int32_t drk_ginet_step_ctas(int32_t num_graphs);
+DRK_API int32_t drk_ginet_step_exchange_floats(int32_t num_node_features, int32_t out_dim);
 DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
                                       int32_t max_graph_nodes, int32_t max_graph_edges);
@@ -279,7 +294,7 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
                    float* pred, float* loss,
                    float* dw1a, float* dw1b, float* dw2a, float* dw2b,
                    float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
-                   const DrkAdam* adam, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                   const DrkAdam* adam, const DrkPeers* peers, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
