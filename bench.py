@@ -86,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self._nv is not None:
@@ -376,16 +376,27 @@ def run_ours(args):
 
 
 def _finish(distributed):
-    """Leave without tearing NCCL down: destroy_process_group() blocks while captured CUDA graphs still hold collectives."""
-    if distributed:
-        import torch
-        import torch.distributed as dist
+    """Orderly exit of a multi-rank run: flush, meet at a barrier, try a normal NCCL teardown and leave even if it blocks
+    (destroy_process_group() can wait forever while captured CUDA graphs still hold collectives)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if not distributed:
+        return
+    import torch
+    import torch.distributed as dist
 
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    worker = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    worker.start()
+    worker.join(10.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        os.fsync(sys.stdout.fileno())
+    except OSError:
+        pass
+    os._exit(0)
 
 
 def _peak():
