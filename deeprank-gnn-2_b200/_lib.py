@@ -12,7 +12,7 @@ import subprocess
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libdrk_b200.so")
+LIB_PATH = os.environ.get("DRK_B200_LIB") or os.path.join(PKG_DIR, "libdrk_b200.so")  # override: A/B builds of the kernels
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
 # constants mirrored from include/drk_b200.h

@@ -402,7 +402,10 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
   const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
-  for (int rw = warp * 4; rw < n; rw += kNW * 4) {  // rows in order of decreasing degree: the warp's four rows are equally long
+  // rows in order of decreasing degree: the four rows a warp takes together are equally long; rounds alternate the warp order
+  // (round 0: warp 0 gets the longest rows, round 1: warp 15 does) so every warp gathers about the same number of rows
+  for (int round = 0; round * kNW * 4 < n; ++round) {
+    const int rw = (round * kNW + ((round & 1) ? kNW - 1 - warp : warp)) * 4;
     const bool row_ok = rw + sub < n;
     int r = 0, len = 0;
     const uint16_t* seg = idx;
@@ -502,6 +505,8 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[
 }
 
 // P = x W1s^T -> tile [n][32].  One warp per 16-row tile: 4 column tiles x ceil(F/8) k-steps of 3xTF32 MMAs.
+// (Reading the A fragments straight from global/L2 so that the x tile could stream in under the forward pass was measured
+// 3 us per step SLOWER than staging x first: 28 dependent-latency loads per lane with 16 warps per SM are not hidden.)
 // sW holds the B fragments of W1s^T pre-split once per CTA: [k-step][column tile][lane] x (hi.b0, hi.b1, lo.b0, lo.b1).
 __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp, int ksteps) {
   const float* sX = sm<float>(x_off);
