@@ -365,7 +365,7 @@ def run_ours(args):
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "mode": "eager launches; pinned host batch (the tensors the step reads, reference dtypes) -> device on a copy stream two batches ahead; loss.item() every step"},
+                    "mode": "eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as int64 pairs -- the kernel rebuilds the reference's doubled edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof,

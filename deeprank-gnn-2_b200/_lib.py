@@ -24,6 +24,7 @@ STATUS_UNSORTED = 4
 ACT_NONE, ACT_RELU = 0, 1
 REDUCE_SUM, REDUCE_MEAN_CLAMP, REDUCE_MEAN_NAN = 0, 1, 2
 LOSS_MSE, LOSS_CROSS_ENTROPY = 0, 1
+EDGES_DIRECTED, EDGES_UNDIRECTED_PAIRS = 0, 1
 
 _P = c_void_p
 _I32 = c_int32
@@ -58,7 +59,7 @@ SIGNATURES = {
     "drk_ginet_step_exchange_floats": (c_int32, [_I32, _I32]),
     "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
     "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),
-    "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _I32, _I32,   # x .. max_graph_edges
+    "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32,   # x .. edge_layout .. max_graph_edges
                                  _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
                                  _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients

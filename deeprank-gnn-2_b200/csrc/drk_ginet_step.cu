@@ -86,6 +86,7 @@ struct StepArgs {
   float* gvec; float* hvec; float* dhvec; float* dpvec;
   uint16_t* csc_spill; int32_t* status;
   int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;  // *_off: index-build scratch (bytes into shared memory)
+  int32_t pairs;  // edge slices hold undirected pairs (edge_ptr counts pairs); each stands for both directions
 };
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -199,7 +200,7 @@ constexpr int kDegBins = 64;
 // returns the number of CSC entries (padded), or -1 when no source-sorted index was built (forward only, or symmetric adjacency)
 template <bool WANT_CSC>
 __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
-                                        int node0, int n, int32_t* status) {
+                                        int node0, int n, int32_t* status, bool pairs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = lanemask_lt();
   uint32_t* stash = sm<uint32_t>(pl.stash);
@@ -236,11 +237,15 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     uint16_t* my_r = cnt_r + warp * cs;
     bool bad = false;
     long long rr[8], cc[8];
+    // undirected-pairs layout: the slice holds P = ne/2 pairs; directed edge d < P is pair d, d >= P is pair d - P flipped
+    const int half = pairs ? ne >> 1 : ne;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = wb + u * 32 + lane;
-      rr[u] = i < we ? ld_stream_i64(erow + e0 + i) : 0;
-      cc[u] = i < we ? ld_stream_i64(ecol + e0 + i) : 0;
+      const bool flip = i >= half;
+      const int src = flip ? i - half : i;
+      rr[u] = i < we ? ld_stream_i64((flip ? ecol : erow) + e0 + src) : 0;
+      cc[u] = i < we ? ld_stream_i64((flip ? erow : ecol) + e0 + src) : 0;
     }
     for (int i0 = wb; i0 < we; i0 += 256) {
       unsigned pk[8];
@@ -256,8 +261,10 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
 #pragma unroll
       for (int u = 0; u < 8; ++u) {  // next group's loads (predicated off past the end of the chunk)
         const int i = i0 + 256 + u * 32 + lane;
-        rr[u] = i < we ? ld_stream_i64(erow + e0 + i) : 0;
-        cc[u] = i < we ? ld_stream_i64(ecol + e0 + i) : 0;
+        const bool flip = i >= half;
+        const int src = flip ? i - half : i;
+        rr[u] = i < we ? ld_stream_i64((flip ? ecol : erow) + e0 + src) : 0;
+        cc[u] = i < we ? ld_stream_i64((flip ? erow : ecol) + e0 + src) : 0;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -279,8 +286,8 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
   __syncthreads();
   // Is the edge list the reference's doubled layout (dataset.py:944-948: all (i, j) first, then all (j, i) in the same order)?
   // Then the adjacency is symmetric, A^T = A, and the backward pass can gather through the same CSR: no source-sorted index.
-  bool sym = false;
-  if (WANT_CSC) {
+  bool sym = pairs;  // pairs: symmetric by construction
+  if (WANT_CSC && !pairs) {
     const int half = ne >> 1;
     bool mine = (ne & 1) == 0;
     for (int i = tid; i < half; i += kT) {
@@ -822,7 +829,8 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   int buf = 0;
   for (int g_slot = blockIdx.x; g_slot < a.num_graphs; g_slot += gridDim.x, buf ^= 1) {
     __syncthreads();  // previous graph is finished with every region; weights and this graph's offsets are visible
-    const int g = s_meta[buf][0], node0 = s_meta[buf][1], n = s_meta[buf][2], e0 = s_meta[buf][3], ne = s_meta[buf][4];
+    const int g = s_meta[buf][0], node0 = s_meta[buf][1], n = s_meta[buf][2], e0 = s_meta[buf][3];
+    const int ne = a.pairs ? 2 * s_meta[buf][4] : s_meta[buf][4];  // directed edges of the graph
     const int next_slot = g_slot + (int)gridDim.x;
     const bool have_next = next_slot < a.num_graphs;
     int gn = 0;
@@ -840,7 +848,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       continue;
     }
     // ---- the graph index, then x rows (the index build uses the x region as scratch)
-    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status);
+    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs != 0);
     stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
     const bool have_csc = TRAIN && csc_entries >= 0;  // false: symmetric adjacency, the backward pass gathers through the CSR
@@ -1453,7 +1461,7 @@ size_t drk_ginet_step_workspace_bytes(int32_t fi, int32_t out_dim, int32_t num_g
   return b + 256;
 }
 
-int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_index, int64_t num_edges, const int32_t* graph_ptr,
+int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_index, int64_t num_edges, int32_t edge_layout, const int32_t* graph_ptr,
                    const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges,
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
@@ -1464,6 +1472,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   using namespace drk::gs;
   DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0, DRK_EINVAL, "ginet step: negative size");
   DRK_REQUIRE(out_dim >= 1 && out_dim <= kMaxOut, DRK_EUNSUPPORTED, "ginet step: 1 <= output_shape <= %d supported, got %d", kMaxOut, out_dim);
+  DRK_REQUIRE(edge_layout == DRK_EDGES_DIRECTED || edge_layout == DRK_EDGES_UNDIRECTED_PAIRS, DRK_EINVAL, "ginet step: unknown edge layout %d", edge_layout);
   PlanResult p;
   DRK_REQUIRE(make_plan(fi, max_graph_nodes, max_graph_edges, p), DRK_EUNSUPPORTED,
               "ginet step: graphs of %d nodes / %d edges with %d features do not fit the shared-memory plan", max_graph_nodes, max_graph_edges, fi);
@@ -1484,6 +1493,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   StepArgs a{};
   a.x = x; a.ldx = ldx; a.fi = fi;
   a.erow = edge_index; a.ecol = edge_index + num_edges;
+  a.pairs = edge_layout == DRK_EDGES_UNDIRECTED_PAIRS ? 1 : 0;
   a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.num_graphs = num_graphs;
   a.w1a = w1a; a.w1b = w1b; a.w2a = w2a; a.w2b = w2b;
   a.fc1_w = fc1_w; a.fc1_b = fc1_b; a.fc2_w = fc2_w; a.fc2_b = fc2_b; a.out_dim = out_dim;

@@ -218,6 +218,20 @@ class Batch(Data):
             out.__dict__["_node_ptr32"] = ptr.to(torch.int32)
             out.__dict__["_edge_ptr32"] = eptr.to(torch.int32)
             out.__dict__["_order32"] = snake_order([e + 8 * n for e, n in zip(e_sizes, sizes)])
+            # The reference stores every contact twice (dataset.py:944-948: all (i, j), then all (j, i) in the same order).  When
+            # every graph has that layout the contacts are also kept ONCE (`_pairs`, what the HDF5 files hold): the per-graph
+            # kernels rebuild the doubled list on the fly, so half of the edge bytes never cross PCIe.
+            halves = []
+            for d in data_list:
+                ei = d.__dict__.get("edge_index")
+                e = 0 if ei is None else int(ei.shape[1])
+                if ei is None or ei.dim() != 2 or e % 2 or not torch.equal(ei[:, e // 2 :], ei[:, : e // 2].flip(0)):
+                    halves = None
+                    break
+                halves.append(ei[:, : e // 2])
+            if halves is not None:
+                out.__dict__["_pairs"] = torch.cat([h + int(o) for h, o in zip(halves, ptr[:-1])], dim=1).contiguous()
+                out.__dict__["_pair_ptr32"] = (eptr // 2).to(torch.int32)
         out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(e_sizes), "num_edges_total": sum(e_sizes)}
         return out
 

@@ -31,37 +31,47 @@ def _p(t):
 
 
 class BlockInfo:
-    """Per-graph offsets of a collated batch on the device: ``node_ptr``/``edge_ptr`` int32 [B+1], issue ``order``
-    int32 [B] (or None), the largest graph's node / edge count, and the batch's status word."""
+    """Per-graph offsets of a collated batch on the device: ``node_ptr``/``edge_ptr`` int32 [B+1], issue ``order`` int32 [B]
+    (or None), the largest graph's node / (directed) edge count, the batch's status word, and the edge tensor the kernels read:
+    ``edges`` int64 [2, M] with ``layout`` EDGES_DIRECTED (= ``edge_index``) or EDGES_UNDIRECTED_PAIRS (each contact once)."""
 
-    __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status")
+    __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status", "edges", "layout")
 
 
 def block_info(data) -> BlockInfo:
     """The (cached) :class:`BlockInfo` of a device-resident ``Batch``.
 
-    Batches made by ``Batch.from_data_list`` carry the offsets (computed by the collate on the host, moved with the batch).
-    For any other batch they are derived on the device from ``batch`` and ``edge_index`` (``drk_batch_offsets`` +
+    Batches made by ``Batch.from_data_list`` carry the offsets (computed by the collate on the host, moved with the batch) and,
+    when every graph has the reference's doubled edge layout, the contacts once (``_pairs``): the kernels then read those.
+    For any other batch the offsets are derived on the device from ``batch`` and ``edge_index`` (``drk_batch_offsets`` +
     ``drk_edge_ptr``) with one host read-back of the largest graph size, remembered on the batch."""
     lib = _lib.load()
-    ei = data.edge_index
+    d = data.__dict__
+    pairs, pair_ptr = d.get("_pairs"), d.get("_pair_ptr32")
+    node_ptr, edge_ptr = d.get("_node_ptr32"), d.get("_edge_ptr32")
+    meta = d.get(data._META_KEY, {}) if hasattr(data, "_META_KEY") else {}
+    use_pairs = (
+        pairs is not None and pair_ptr is not None and node_ptr is not None and pairs.is_cuda and pair_ptr.is_cuda and node_ptr.is_cuda
+        and meta.get("num_edges_total") == 2 * int(pairs.shape[1]) and meta.get("max_graph_nodes") is not None
+    )
+    ei = pairs if use_pairs else data.edge_index  # (a lazily transferred edge_index is only touched when it is needed)
     if not ei.is_cuda:
         raise RuntimeError(f"the batch must live on a CUDA device: deeprank2_b200 has no CPU path (got {ei.device})")
-    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device))
-    cached = data.__dict__.get("_block_info")
+    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device), use_pairs)
+    cached = d.get("_block_info")
     if cached is not None and cached[0] == key:
         return cached[1]
     info = BlockInfo()
     dev = ei.device
-    node_ptr, edge_ptr = data.__dict__.get("_node_ptr32"), data.__dict__.get("_edge_ptr32")
-    meta = data.__dict__.get(data._META_KEY, {}) if hasattr(data, "_META_KEY") else {}
-    collated = (
+    info.edges = ei if ei.is_contiguous() else ei.contiguous()
+    info.layout = _lib.EDGES_UNDIRECTED_PAIRS if use_pairs else _lib.EDGES_DIRECTED
+    collated = use_pairs or (
         node_ptr is not None and edge_ptr is not None and node_ptr.is_cuda and edge_ptr.is_cuda
         and meta.get("num_edges_total") == int(ei.shape[1]) and meta.get("max_graph_nodes") is not None
     )
     if collated:
-        info.node_ptr, info.edge_ptr = node_ptr, edge_ptr
-        order = data.__dict__.get("_order32")
+        info.node_ptr, info.edge_ptr = node_ptr, (pair_ptr if use_pairs else edge_ptr)
+        order = d.get("_order32")
         info.order = order if order is not None and order.is_cuda else None
         info.num_graphs = int(node_ptr.numel()) - 1
         info.max_nodes, info.max_edges = int(meta["max_graph_nodes"]), int(meta["max_graph_edges"])
@@ -80,7 +90,7 @@ def block_info(data) -> BlockInfo:
         sizes = torch.stack([(info.node_ptr[1:] - info.node_ptr[:-1]).max(), (info.edge_ptr[1:] - info.edge_ptr[:-1]).max()]) if info.num_graphs else torch.zeros(2)
         info.max_nodes, info.max_edges = (int(v) for v in sizes.tolist())  # one host sync, remembered on the batch
     info.status = torch.zeros(1, dtype=torch.int32, device=dev)
-    data.__dict__["_block_info"] = (key, info)
+    d["_block_info"] = (key, info)
     return info
 
 
@@ -135,12 +145,12 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
     x = data.x
     fi = int(x.shape[1])
     out_dim = int(model.fc2.weight.shape[0])
-    ei = data.edge_index if data.edge_index.is_contiguous() else data.edge_index.contiguous()
+    ei = info.edges
     with torch.cuda.device(x.device):
         ws_bytes = lib.drk_ginet_step_workspace_bytes(fi, out_dim, info.num_graphs, info.max_nodes, info.max_edges) if train else 0
         ws = workspace(ws_bytes, x.device) if train else None
         rc = lib.drk_ginet_step(
-            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), info.num_graphs, info.max_nodes, info.max_edges,
+            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), int(info.layout), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), info.num_graphs, info.max_nodes, info.max_edges,
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
             int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(state), 1 if train else 0,
@@ -170,7 +180,9 @@ class GINetFusedStep:
 
     #: the batch tensors a step reads (what an input pipeline has to copy ahead; GINet's attention is the identity, so
     #: ``edge_attr`` is never read, and the readout uses the graph offsets instead of ``batch``)
-    FIELDS = ("x", "edge_index", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+    FIELDS = ("x", "_pairs", "_pair_ptr32", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+    #: the same for batches whose graphs are not in the doubled layout (no ``_pairs``): the full directed edge list
+    FIELDS_DIRECTED = ("x", "edge_index", "y", "_node_ptr32", "_edge_ptr32", "_order32")
 
     def __init__(self, model, optimizer, loss_fn, target_fn=None, world_size: int = 1, group=None, seed: int | None = None):
         if not _standard_ginet(model):
@@ -330,7 +342,7 @@ class GINetFusedStep:
             with torch.cuda.device(dev):
                 ws = workspace(1 << 20, dev)
                 rc = lib.drk_ginet_step(
-                    None, fi, fi, None, 0, None, None, None, 0, 0, 0,
+                    None, fi, fi, None, 0, 0, None, None, None, 0, 0, 0,
                     _p(m.conv1.fc.weight), _p(m.conv1_ext.fc.weight), _p(m.conv2.fc.weight), _p(m.conv2_ext.fc.weight),
                     _p(m.fc1.weight), _p(m.fc1.bias), _p(m.fc2.weight), _p(m.fc2.bias), out_dim,
                     int(self.kind), _p(self.loss), 0.0, 0.0, int(self.seed) & (2**64 - 1), _p(self.state), 1,

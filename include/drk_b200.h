@@ -252,6 +252,14 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  * The gradients of fc_edge_attr / fc_attention are identically zero in the reference (softmax over a singleton axis,
  * ginet_nocluster.py:48-51) and are not produced here.
  * drk_ginet_step_supported: 1 if graphs of that size fit the shared-memory plan (else use the layer kernels). */
+/* edge_layout: what edge_index [2, num_edges] and edge_ptr describe.
+ *   DRK_EDGES_DIRECTED          the reference's list of directed edges (dataset.py:944-948 stores every contact twice)
+ *   DRK_EDGES_UNDIRECTED_PAIRS  each contact ONCE, as the HDF5 files hold it (`edge_features/_index`, utils/graph.py:210-264);
+ *                               the kernel treats pair p of a graph with P pairs as directed edges p = (i,j) and P + p = (j,i),
+ *                               i.e. exactly the doubled list, without it ever crossing PCIe or HBM.  max_graph_edges still
+ *                               counts DIRECTED edges (2P). */
+#define DRK_EDGES_DIRECTED 0
+#define DRK_EDGES_UNDIRECTED_PAIRS 1
 #define DRK_LOSS_MSE 0
 #define DRK_LOSS_CROSS_ENTROPY 1
 typedef struct DrkAdamTensor {
@@ -284,7 +292,7 @@ DRK_API int32_t drk_ginet_step_exchange_floats(int32_t num_node_features, int32_
 DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
                                       int32_t max_graph_nodes, int32_t max_graph_edges);
-DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_features, const int64_t* edge_index, int64_t num_edges,
+DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_features, const int64_t* edge_index, int64_t num_edges, int32_t edge_layout,
                    const int32_t* graph_ptr, const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs,
                    int32_t max_graph_nodes, int32_t max_graph_edges,
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b,

@@ -49,6 +49,7 @@ def _blocked_index(batch):
     from deeprank2_b200.graph import stream_ptr
 
     lib = _lib.load()
+    batch.__dict__.pop("_pairs", None)  # the blocked index build takes the directed edge list: use its offsets, not the pairs'
     info = block_info(batch)
     n, e = batch.num_nodes, batch.num_edges
     out = {k: torch.full((n + 1 if k.endswith("ptr") else e,), -7, dtype=torch.int32, device=DEV) for k in ("rowptr", "colidx", "perm", "colptr", "rowidx", "permT")}
@@ -392,3 +393,36 @@ def test_fused_adam_one_step_vs_oracle():
     assert_close(pred, pred_ref, "pred")
     for (k, p_ref), p in zip(params.items(), net.parameters()):
         assert_adam_close(p, p_ref, f"adam {k}", p_ref.grad, w_before[k])
+
+
+def test_undirected_pairs_layout_is_bitwise_the_doubled_edge_list():
+    """Collated batches of doubled graphs also carry every contact once (`_pairs`); the step kernel rebuilds the doubled list on
+    the fly.  Same index, same sums: predictions, loss and gradients are bit-identical to reading the full `edge_index`."""
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.fused import GINetFusedStep, block_info, check_status
+
+    host = _synthetic(40, first=1200)
+    assert host._pairs.shape[1] * 2 == host.edge_index.shape[1]
+    results = []
+    for use_pairs in (True, False):
+        batch = host.clone().to(DEV)
+        if not use_pairs:
+            del batch.__dict__["_pairs"]
+        net = _net(50, 1, 1, seed=11).eval()
+        step = GINetFusedStep(net, torch.optim.SGD(net.parameters(), lr=0.0), torch.nn.MSELoss())
+        loss, pred = step.forward_backward(batch)
+        info = block_info(batch)
+        check_status(info)
+        assert info.layout == (_lib.EDGES_UNDIRECTED_PAIRS if use_pairs else _lib.EDGES_DIRECTED)
+        results.append((loss.clone(), pred.clone(), step.flat_grad.clone()))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+
+
+def test_collate_keeps_pairs_only_for_doubled_graphs():
+    from deeprank2_b200.data import Batch, Data
+
+    doubled = _synthetic(3, first=5)
+    assert "_pairs" in doubled.__dict__
+    odd = Data(x=torch.zeros(3, 4), edge_index=torch.tensor([[0, 1, 2], [1, 2, 0]]), edge_attr=torch.zeros(3, 1), y=torch.zeros(1))
+    assert "_pairs" not in Batch.from_data_list([odd, odd]).__dict__
