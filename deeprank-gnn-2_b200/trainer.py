@@ -51,6 +51,7 @@ class BatchLoader:
         self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), shuffle
         self.device, self.pin_memory = device, pin_memory
         self.rank, self.world_size = rank, world_size
+        self.only = None
         self._gen = torch.Generator()
         if seed is not None:
             self._gen.manual_seed(seed)
@@ -60,7 +61,7 @@ class BatchLoader:
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
-    def __iter__(self):
+    def _host_batches(self):
         from .parallel import shard_indices
 
         n = len(self.dataset)
@@ -76,9 +77,26 @@ class BatchLoader:
             batch = Batch.from_data_list([self.dataset.get(i) for i in ids])
             if self.pin_memory:
                 batch.pin_memory()
-            if self.device is not None and self.device.type == "cuda":
-                batch = batch.to(self.device, non_blocking=True)
             yield batch, global_size
+
+    def __iter__(self):
+        """Device batches, copied ONE BATCH AHEAD on a side stream (``pipeline.DevicePrefetcher``): the host collate and the PCIe
+        copy of batch i+1 overlap the step on batch i.  ``only`` (set by the Trainer when the per-graph step kernels are in use)
+        names the tensors to copy eagerly; everything else travels on first access."""
+        if self.device is None or self.device.type != "cuda":
+            yield from self._host_batches()
+            return
+        from .pipeline import DevicePrefetcher
+
+        feed = DevicePrefetcher((), self.device, only=self.only)
+        pending = None
+        for host_batch, global_size in self._host_batches():
+            issued = (feed._issue(host_batch) if host_batch is not None else None, global_size)
+            if pending is not None:
+                yield (feed._hand_out(pending[0]) if pending[0] is not None else None), pending[1]
+            pending = issued
+        if pending is not None:
+            yield (feed._hand_out(pending[0]) if pending[0] is not None else None), pending[1]
 
 
 class Trainer:
@@ -403,6 +421,8 @@ class Trainer:
                     self.optimizer.step()
                 continue
             fused = self._fused_step(batch) if train else None
+            if fused is not None and getattr(loader, "only", 0) is None:
+                loader.only = type(fused).FIELDS  # later batches: copy only what the step kernels read (the rest stays lazy)
             if fused is not None:
                 # whole step (index, forward, loss, backward, gradient all-reduce, optimizer) in the per-graph kernels
                 loss_, pred = fused(batch, global_size=global_size)

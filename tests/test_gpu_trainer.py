@@ -39,8 +39,15 @@ class _Collect:
 
 
 @pytest.mark.parametrize("net_name", ["ginet_nocluster", "vanilla", "ginet", "foutnet", "sgat"])
-def test_trainer_trains_every_net_on_gpu(net_name, tmp_path):
+def test_trainer_trains_every_net_on_gpu(net_name, tmp_path, monkeypatch):
+    import numpy as np
+
     from deeprank2_b200 import _lib
+
+    # the train/val/test split draws from an unseeded numpy generator (as the reference does): pin it, so that "the loss goes
+    # down over three epochs" is one deterministic trajectory instead of a coin with a small failure probability
+    seeded = np.random.Generator(np.random.PCG64(7))
+    monkeypatch.setattr(np.random, "default_rng", lambda *a, **k: seeded)
     from deeprank2_b200.dataset import InMemoryGraphDataset
     from deeprank2_b200.neuralnets.gnn import foutnet, ginet, ginet_nocluster, sgat, vanilla_gnn
     from deeprank2_b200.trainer import Trainer
