@@ -35,8 +35,8 @@ F_NODE, F_EDGE = 50, 1
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batches", type=int, default=6, help="distinct resident batches per rank (rotation defeats L2 reuse)")
     ap.add_argument("--mode", choices=["graph", "eager"], default="graph", help="replay a captured CUDA graph per batch, or launch eagerly")
@@ -399,6 +399,15 @@ def _finish(distributed):
     os._exit(0)
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_ginet_step launch on the C2 batch, from the committed ncu capture
+    (profiles/step_traffic.json; the input is deterministic, so the figure is a property of the build, not of the run)."""
+    path = os.path.join(ROOT, "profiles", "step_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("dram_bytes_per_launch")
+
+
 def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -416,7 +425,7 @@ def step_roofline(args, dev, dev_batches, model, loss_fn):
     peak, peak_src = _peak()
     opt = torch.optim.SGD(model.parameters(), lr=0.0)
     fused = GINetFusedStep(model, opt, loss_fn)
-    reps = max(args.steps, 30)
+    reps = max(min(args.steps, 200), 30)
     for i in range(6):
         fused.forward_backward(dev_batches[i % len(dev_batches)])
     torch.cuda.synchronize()
@@ -441,7 +450,7 @@ def step_roofline(args, dev, dev_batches, model, loss_fn):
         "peak_source": peak_src,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": _ncu_traffic(),
         "us_per_launch": 1e3 * ms / reps,
         "algorithmic_bytes_per_launch": total_bytes / reps,
         "algorithmic_model": "SURVEY 8(d): 2472*N + 24*E bytes per train step (every intermediate of the layer-by-layer path written and read once)",

@@ -55,7 +55,11 @@ class GraphIndex:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def build(cls, edge_index: torch.Tensor, num_nodes: int, batch: torch.Tensor | None = None, num_graphs: int | None = None, with_csc: bool = True) -> "GraphIndex":
+    def build(cls, edge_index: torch.Tensor, num_nodes: int, batch: torch.Tensor | None = None, num_graphs: int | None = None, with_csc: bool = True,
+              blocks: tuple | None = None) -> "GraphIndex":
+        """``blocks`` = (node_ptr int32 [B+1], edge_ptr int32 [B+1], max_graph_nodes, max_graph_edges) of a collated batch (the edges
+        of a graph are one contiguous slice of ``edge_index``): the index is then built per graph in shared memory
+        (``drk_graph_index_build_blocked``, ~10x faster than the global sort, bit-identical result)."""
         lib = _lib.load()
         _require_cuda(edge_index, "edge_index")
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -98,6 +102,23 @@ class GraphIndex:
             gi.graph_ptr, gi.batch32 = views[k][: b + 1], views[k + 1][:n]
         gi.status = views[-1][:1]
         gi.status.zero_()
+        use_blocks = (
+            blocks is not None and b > 0 and blocks[0].is_cuda and blocks[1].is_cuda and int(blocks[0].numel()) == b + 1
+            and bool(lib.drk_graph_index_blocked_supported(int(blocks[2]), int(blocks[3])))
+        )
+        if use_blocks:
+            with torch.cuda.device(dev):
+                rc = lib.drk_graph_index_build_blocked(
+                    edge_index.data_ptr(), e, n, blocks[0].data_ptr(), blocks[1].data_ptr(), b, int(blocks[2]), int(blocks[3]),
+                    gi.rowptr.data_ptr(), gi.colidx.data_ptr(), gi.perm.data_ptr(),
+                    gi.colptr.data_ptr() if with_csc else None, gi.rowidx.data_ptr() if with_csc else None, gi.permT.data_ptr() if with_csc else None,
+                    gi.status.data_ptr(), stream_ptr(),
+                )
+                _lib.check(rc, "drk_graph_index_build_blocked")
+                if batch is not None:
+                    rc = lib.drk_batch_offsets(batch.contiguous().data_ptr(), n, b, gi.graph_ptr.data_ptr(), gi.batch32.data_ptr(), gi.status.data_ptr(), stream_ptr())
+                    _lib.check(rc, "drk_batch_offsets")
+            return gi
         with torch.cuda.device(dev):
             ws_bytes = lib.drk_graph_index_workspace_bytes(e, n)
             ws = workspace(ws_bytes, dev)
@@ -142,7 +163,14 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
     num_graphs = int(ptr.numel()) - 1 if ptr is not None else data.__dict__.get("_num_graphs")
     if num_graphs is None and hasattr(data, "meta"):
         num_graphs = data.meta("num_graphs")
-    gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc)
+    # collated batches know where each graph's nodes and edges start: per-graph index build in shared memory
+    blocks = None
+    node_ptr, edge_ptr = data.__dict__.get("_node_ptr32"), data.__dict__.get("_edge_ptr32")
+    meta = data.__dict__.get(getattr(data, "_META_KEY", "_meta"), {})
+    if (node_ptr is not None and edge_ptr is not None and batch is not None and meta.get("num_edges_total") == int(ei.shape[1])
+            and meta.get("max_graph_nodes") is not None and meta.get("max_graph_edges") is not None):
+        blocks = (node_ptr, edge_ptr, meta["max_graph_nodes"], meta["max_graph_edges"])
+    gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc, blocks=blocks)
     gi._key = key
     data.__dict__["_graph_index"] = gi
     return gi

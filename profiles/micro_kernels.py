@@ -39,6 +39,8 @@ g = GraphIndex.build(b.edge_index, n, batch=b.batch, num_graphs=256)
 e = g.num_edges
 if what in ("index", "all"):
     timed("graph_index_build (CSR+CSC+offsets)", lambda: GraphIndex.build(b.edge_index, n, batch=b.batch, num_graphs=256), 16 * e + 16 * e + 8 * (n + 1))
+    blocks = (b._node_ptr32, b._edge_ptr32, b.meta("max_graph_nodes"), b.meta("max_graph_edges"))
+    timed("graph_index_build_blocked (same output)", lambda: GraphIndex.build(b.edge_index, n, batch=b.batch, num_graphs=256, blocks=blocks), 16 * e + 16 * e + 8 * (n + 1))
 if what in ("spmm", "all"):
     for w in (16, 32, 64):
         src = torch.randn(n, w, device=dev)
