@@ -271,7 +271,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
         const int i = i0 + u * 32 + lane;
         if (i0 + u * 32 >= we) break;  // warp-uniform
         const bool ok = pk[u] != 0xffffffffu;
-        const unsigned r = pk[u] & 0xffffu, c = pk[u] >> 16;
+        const unsigned r = pk[u] & 0xffffu;
         const unsigned mr = __match_any_sync(kFull, ok ? r : 0x10000u + lane);
         unsigned base_r = 0;
         if (ok) base_r = my_r[r];
@@ -768,12 +768,9 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   float* sT1 = reinterpret_cast<float*>(smem + L.t1);
   float* sX = reinterpret_cast<float*>(smem + L.x);
   uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.idx);
-  ushort2* sRinfo = reinterpret_cast<ushort2*>(smem + L.rinfo);
-  ushort2* sCinfo = reinterpret_cast<ushort2*>(smem + L.cinfo);
   float* sW1 = reinterpret_cast<float*>(smem + L.w1);
   float* sW2 = reinterpret_cast<float*>(smem + L.w2);
   float* sS = reinterpret_cast<float*>(smem + L.s);
-  uint32_t* sMaskZ = reinterpret_cast<uint32_t*>(smem + L.maskz);
   float* sRed = reinterpret_cast<float*>(smem + L.red);
   float* sHead = reinterpret_cast<float*>(smem + L.head);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -11,7 +11,14 @@ per = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 rows = []
 with open(path, newline="") as f:
     hdr = None
+    kernels = 0
     for rec in csv.reader(f):
+        if rec and rec[0] == "Kernel Name":
+            kernels += 1
+            if kernels > 1:
+                break  # only the first launch of the dump
+            print("kernel:", rec[1])
+            continue
         if rec and rec[0] == "Address":
             hdr = rec
             continue
