@@ -245,3 +245,28 @@ def test_vanilla_c2_batch_vs_oracle():
     assert_close(pred, pred_ref, "pred")
     for (k, p_ref), p in zip(params.items(), net.parameters()):
         assert_close(p.grad, p_ref.grad, f"grad:{k}")
+
+
+def test_atom_level_inference_vs_oracle_c3():
+    """Config C3: atom-level graphs (~3 k nodes, ~60 k directed edges each, 38 node features) are far beyond one CTA's shared
+    memory, so inference runs on the layer kernels (blocked index build, projection, aggregation, readout): predictions against
+    the CPU oracle, bit-reproducible, and the per-graph step kernel must report itself as not applicable."""
+    from deeprank2_b200.fused import step_supported
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.synthetic import ATOM, make_batch
+
+    batch = make_batch(3, first=50, n_node_features=38, n_edge_features=1, level=ATOM)
+    assert batch.num_nodes > 8000 and batch.num_edges > 150000
+    torch.manual_seed(0)
+    net = GINet(38, 1, 1).eval()
+    params = R.as_parameters(net.state_dict())
+    with torch.no_grad():
+        ref = R.ginet_nocluster_forward(params, batch)
+    net = net.to(DEV)
+    gb = batch.clone().to(DEV)
+    assert not step_supported(net, gb)
+    with torch.no_grad():
+        p1 = net(gb)
+        p2 = net(gb)
+    assert torch.equal(p1, p2)
+    assert_close(p1, ref, "atom-level inference")
