@@ -425,23 +425,40 @@ __global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float cn[4] = {0.f, 0.f, 0.f, 0.f};
     for (int off = 0; off < max_len; off += 8) {
+      // lane sl of the group fetches source, edge id and attributes of the chunk's sl-th edge: 8 edges in flight per group, the
+      // dependent loads (edge id -> attributes) happen once per chunk instead of once per edge
       int my_src = -1, my_eid = 0;
+      float my_attr[kMaxEdgeFeat];
+#pragma unroll
+      for (int k = 0; k < kMaxEdgeFeat; ++k) my_attr[k] = 0.f;
       if (off + sl < len) {
         my_src = ld_stream_i32(a.idx + beg + off + sl);
         my_eid = ld_stream_i32(a.perm + beg + off + sl);
+#pragma unroll
+        for (int k = 0; k < kMaxEdgeFeat; ++k)
+          if (k < a.fe) my_attr[k] = __ldg(a.attr + (size_t)my_eid * a.ld_attr + k);
+      }
+      float4 vv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // all gathers of the chunk before the first use
+        const int srow = __shfl_sync(kFull, my_src, group_base + j);
+        vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (srow >= 0) vv[j] = ld_gather_f4(a.uv + (size_t)srow * a.ld_uv + kMsg + c);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int srow = __shfl_sync(kFull, my_src, group_base + j);
         const int eid = __shfl_sync(kFull, my_eid, group_base + j);
         const bool on_edge = srow >= 0;  // uniform inside the 8-lane group; everything below is predicated, not branched
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on_edge) v = ld_gather_f4(a.uv + (size_t)srow * a.ld_uv + kMsg + c);
+        const float4 v = vv[j];
         float m[4] = {u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w};
-        for (int k = 0; k < a.fe; ++k) {
-          const float av = on_edge ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) m[q] = fmaf(cw[q][k], av, m[q]);
+        for (int k = 0; k < kMaxEdgeFeat; ++k) {
+          if (k < a.fe) {  // warp-uniform
+            const float av = __shfl_sync(kFull, my_attr[k], group_base + j);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = fmaf(cw[q][k], av, m[q]);
+          }
         }
         unsigned bits = 0;
 #pragma unroll
@@ -537,9 +554,12 @@ struct EdgeMsgBwdCArgs {
   int32_t n, fe;
 };
 
-__global__ void __launch_bounds__(256) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a) {
-  // thread -> channel c = threadIdx & 31; the 8 warps of the block stride over this block's rows
-  __shared__ float red[8][kMsg][kMaxEdgeFeat];
+constexpr int kBwdCWarps = 32;  // 1024 threads: the kernel is a chain of dependent global loads per row, it needs warps, not registers
+__global__ void __launch_bounds__(kBwdCWarps * 32) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a) {
+  // One warp per destination row, lane = channel c for the accumulation.  The row's edges are fetched LANE-PARALLEL (edge id, ReLU mask
+  // word and attributes of up to 32 edges in flight at once: three dependent global loads per 32 edges instead of per edge) and then
+  // broadcast to the channels with shuffles, in CSR order, so the sum keeps its fixed association.
+  __shared__ float red[kBwdCWarps][kMsg][kMaxEdgeFeat];
   const int c = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float acc[kMaxEdgeFeat];
@@ -548,18 +568,31 @@ __global__ void __launch_bounds__(256) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a)
   const int rows_per_block = (a.n + gridDim.x - 1) / gridDim.x;
   const int row0 = blockIdx.x * rows_per_block;
   const int row_end = min(row0 + rows_per_block, a.n);
-  for (int r = row0 + warp; r < row_end; r += 8) {
+  for (int r = row0 + warp; r < row_end; r += kBwdCWarps) {
     const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
     const float g = __ldg(a.ds + (size_t)r * a.ld_ds + c);
     float t[kMaxEdgeFeat];
 #pragma unroll
     for (int k = 0; k < kMaxEdgeFeat; ++k) t[k] = 0.f;
-    for (int s = beg; s < end; ++s) {
-      const int eid = __ldg(a.perm + s);  // warp-uniform
-      const bool on = (a.mask[eid] >> c) & 1u;
+    for (int s0 = beg; s0 < end; s0 += 32) {
+      const int s = s0 + c;
+      const bool valid = s < end;
+      const int eid = valid ? __ldg(a.perm + s) : 0;
+      const uint32_t m = valid ? __ldg(a.mask + eid) : 0u;
+      float av[kMaxEdgeFeat];
 #pragma unroll
-      for (int k = 0; k < kMaxEdgeFeat; ++k)
-        if (k < a.fe) t[k] += on ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
+      for (int k = 0; k < kMaxEdgeFeat; ++k) av[k] = (valid && k < a.fe) ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
+      const int cnt = min(32, end - s0);
+      for (int j = 0; j < cnt; ++j) {
+        const bool on = (__shfl_sync(0xffffffffu, m, j) >> c) & 1u;
+#pragma unroll
+        for (int k = 0; k < kMaxEdgeFeat; ++k) {
+          if (k < a.fe) {
+            const float v = __shfl_sync(0xffffffffu, av[k], j);
+            t[k] += on ? v : 0.f;
+          }
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < kMaxEdgeFeat; ++k) acc[k] = fmaf(g, t[k], acc[k]);
@@ -571,7 +604,7 @@ __global__ void __launch_bounds__(256) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a)
 #pragma unroll
     for (int k = 0; k < kMaxEdgeFeat; ++k) {
       float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w][c][k];
+      for (int w = 0; w < kBwdCWarps; ++w) s += red[w][c][k];
       a.partial[((size_t)blockIdx.x * kMsg + c) * kMaxEdgeFeat + k] = s;
     }
   }
@@ -636,7 +669,7 @@ int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const float* 
   DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_edge_msg_bwd_c_workspace_bytes(), DRK_EWORKSPACE, "edge msg bwd c: workspace too small");
   const int blocks = kNumSM * 2;
   EdgeMsgBwdCArgs a{rowptr, perm, ds, mask, edge_attr, static_cast<float*>(workspace), (uint32_t)ld_ds, (uint32_t)ld_attr, num_nodes, num_edge_features};
-  k_edge_msg_bwd_c<<<blocks, 256, 0, as_stream(stream)>>>(a);
+  k_edge_msg_bwd_c<<<blocks, kBwdCWarps * 32, 0, as_stream(stream)>>>(a);
   k_edge_msg_bwd_c_reduce<<<1, 32 * kMaxEdgeFeat, 0, as_stream(stream)>>>(static_cast<float*>(workspace), blocks, num_edge_features, dc, ld_dc);
   return finish_launch("edge msg bwd c", 2);
 }
