@@ -59,9 +59,16 @@ class Data:
     def set_meta(self, key: str, value) -> None:
         self.__dict__.setdefault(self._META_KEY, {})[key] = value
 
+    def _peek(self, key: str):
+        """The attribute's value without triggering a deferred host->device copy."""
+        if key in self.__dict__:
+            return self.__dict__[key]
+        pending = self.__dict__.get("_pending")
+        return pending[1].get(key) if pending is not None else None
+
     @property
     def keys(self):
-        return [k for k in self._fields() if self.__dict__[k] is not None]
+        return [k for k in self._fields() if self._peek(k) is not None]
 
     @property
     def num_nodes(self) -> int:
@@ -86,12 +93,12 @@ class Data:
         return 0 if self.edge_attr is None else (1 if self.edge_attr.dim() == 1 else int(self.edge_attr.shape[1]))
 
     def __contains__(self, key: str) -> bool:
-        return self.__dict__.get(key) is not None
+        return self._peek(key) is not None
 
     def __repr__(self) -> str:
         parts = []
         for k in self._fields():
-            v = self.__dict__[k]
+            v = self._peek(k)
             if isinstance(v, torch.Tensor):
                 parts.append(f"{k}={list(v.shape)}")
             elif v is not None:

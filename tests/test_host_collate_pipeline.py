@@ -1,0 +1,85 @@
+"""CPU: host-side logic added for the per-graph kernels -- collate extras (int32 offsets, snake schedule, contacts kept once for
+doubled graphs), the lazy / partial device transfer of a batch, the prefetching loader's bookkeeping."""
+from __future__ import annotations
+
+import torch
+
+from deeprank2_b200.data import Batch, Data, snake_order
+from deeprank2_b200.pipeline import batch_nbytes, shallow_host_view
+from deeprank2_b200.synthetic import make_batch, make_graph
+
+
+def test_collate_offsets_and_pairs_describe_the_same_edges():
+    graphs = [make_graph(g) for g in range(5)]
+    batch = Batch.from_data_list(graphs)
+    node_ptr, edge_ptr, pair_ptr = batch._node_ptr32, batch._edge_ptr32, batch._pair_ptr32
+    assert node_ptr.dtype == edge_ptr.dtype == pair_ptr.dtype == torch.int32
+    assert torch.equal(node_ptr.long(), batch.ptr)
+    assert int(edge_ptr[-1]) == batch.num_edges and torch.equal(edge_ptr, 2 * pair_ptr)
+    for g in range(5):
+        e0, e1 = int(edge_ptr[g]), int(edge_ptr[g + 1])
+        p0, p1 = int(pair_ptr[g]), int(pair_ptr[g + 1])
+        ei = batch.edge_index[:, e0:e1]
+        pairs = batch._pairs[:, p0:p1]
+        half = (e1 - e0) // 2
+        assert torch.equal(ei[:, :half], pairs) and torch.equal(ei[:, half:], pairs.flip(0))  # dataset.py:944-948 layout
+        lo, hi = int(node_ptr[g]), int(node_ptr[g + 1])
+        assert int(ei.min()) >= lo and int(ei.max()) < hi  # edges of a graph stay inside it and are contiguous
+    meta = batch.__dict__[Batch._META_KEY]
+    assert meta["num_edges_total"] == batch.num_edges and meta["max_graph_edges"] == int((edge_ptr[1:] - edge_ptr[:-1]).max())
+
+
+def test_pairs_are_dropped_when_a_graph_is_not_doubled():
+    doubled = make_graph(0, 4)
+    d = Data(x=torch.zeros(3, 4), edge_index=torch.tensor([[0, 1, 2, 0], [1, 2, 0, 2]]), edge_attr=torch.zeros(4, 1), y=torch.zeros(1),
+             pos=torch.zeros(3, 3))
+    d.entry_names = "hand-made"
+    mixed = Batch.from_data_list([doubled, d])
+    assert "_pairs" not in mixed.__dict__ and "_edge_ptr32" in mixed.__dict__
+
+
+def test_snake_order_balances_rounds():
+    work = [100 - i for i in range(10)]  # already descending
+    order = snake_order(work, ctas=4).tolist()
+    assert sorted(order) == list(range(10))
+    assert order[:4] == [0, 1, 2, 3] and order[4:8] == [7, 6, 5, 4] and order[8:] == [8, 9]
+    totals = [sum(work[order[s]] for s in range(b, 10, 4)) for b in range(4)]
+    assert max(totals[:2]) - min(totals[:2]) <= 2  # CTAs with the same number of graphs carry (almost) the same work
+    # ties keep graph order, any input order works
+    assert snake_order([5, 5, 5], ctas=2).tolist() == [0, 1, 2]
+    assert sorted(snake_order([3, 9, 1, 7], ctas=3).tolist()) == [0, 1, 2, 3]
+
+
+def test_partial_transfer_keeps_deferred_tensors_reachable():
+    host = make_batch(3)
+    view = shallow_host_view(host)
+    only = ("x", "_pairs", "y")
+    # a CPU "device" moves everything (the deferral only applies to CUDA targets) ...
+    moved = view.to("cpu", only=only)
+    assert "_pending" not in moved.__dict__ and moved.edge_attr.shape == host.edge_attr.shape
+    # ... so exercise the deferred bookkeeping directly
+    lazy = shallow_host_view(host)
+    pending = {k: lazy.__dict__.pop(k) for k in ("edge_attr", "pos", "batch")}
+    lazy.__dict__["_pending"] = (torch.device("cpu"), pending)
+    assert set(lazy.keys) >= {"x", "edge_index", "edge_attr", "pos", "batch", "y"}  # still listed
+    assert torch.equal(lazy.edge_attr, host.edge_attr)  # first access materialises it ...
+    assert "edge_attr" in lazy.__dict__ and "edge_attr" not in lazy.__dict__["_pending"][1]  # ... once
+    clone = lazy.clone()
+    assert torch.equal(clone.pos, host.pos) and torch.equal(lazy.pos, host.pos)
+    try:
+        lazy.no_such_attribute
+    except AttributeError:
+        pass
+    else:
+        raise AssertionError("unknown attributes must still raise AttributeError")
+    assert host.__dict__.get("_pending") is None  # the cached host batch is never modified
+
+
+def test_batch_nbytes_counts_what_a_partial_copy_moves():
+    host = make_batch(2)
+    full = batch_nbytes(host)
+    step_fields = ("x", "_pairs", "_pair_ptr32", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+    part = batch_nbytes(host, step_fields)
+    expected = sum(host.__dict__[k].numel() * host.__dict__[k].element_size() for k in step_fields)
+    assert part == expected < full
+    assert host._pairs.numel() * 2 == host.edge_index.numel()
