@@ -148,20 +148,27 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // copy rows [node0, node0+n) of a row-major global matrix (ld elements, width fi) into smem with row stride kp,
-// zero-filling the padding columns; asynchronous (cp.async), the caller commits / waits.  One warp per row, VEC floats per lane.
+// zero-filling the padding columns; asynchronous (cp.async), the caller commits / waits.  One warp per row, VEC floats per lane;
+// shared addresses are kept as 32-bit window offsets (no generic->shared conversion per copy).
 template <int VEC>
 __device__ __forceinline__ void stage_rows_v(float* __restrict__ s_dst, const float* __restrict__ src, int64_t ld, int fi, int kp, int node0, int n) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = fi / VEC, pad = kp - nv * VEC;
   const float* s = src + (int64_t)(node0 + warp) * ld + lane * VEC;
-  float* d = s_dst + warp * kp + lane * VEC;
-  float* z = s_dst + warp * kp + nv * VEC + lane;
+  unsigned d = (unsigned)__cvta_generic_to_shared(s_dst + warp * kp + lane * VEC);
+  unsigned z = (unsigned)__cvta_generic_to_shared(s_dst + warp * kp + nv * VEC + lane);
+  const unsigned d_step = (unsigned)(kNW * kp * 4);
+  const int64_t s_step = (int64_t)kNW * ld;
   for (int r = warp; r < n; r += kNW) {
-    for (int v = lane; v < nv; v += 32) cp_async<4 * VEC>(d + (v - lane) * VEC, s + (v - lane) * VEC, true);
-    if (lane < pad) *z = 0.f;
-    s += kNW * ld;
-    d += kNW * kp;
-    z += kNW * kp;
+    for (int v = lane; v < nv; v += 32) {
+      const unsigned dd = d + (unsigned)((v - lane) * VEC * 4);
+      const float* ss = s + (v - lane) * VEC;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dd), "l"(ss), "n"(4 * VEC) : "memory");
+    }
+    if (lane < pad) asm volatile("st.shared.f32 [%0], %1;" ::"r"(z), "f"(0.f) : "memory");
+    s += s_step;
+    d += d_step;
+    z += d_step;
   }
 }
 __device__ __forceinline__ void stage_rows(float* s_dst, const float* src, int64_t ld, int fi, int kp, int node0, int n, int vec) {

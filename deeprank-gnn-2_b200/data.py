@@ -247,14 +247,32 @@ STEP_CTAS = 148  # CTAs of the per-graph kernels = SMs of a B200 (drk_ginet_step
 
 
 def snake_order(work: list[int], ctas: int = STEP_CTAS) -> torch.Tensor:
-    """Slot -> graph id for the per-graph kernels: CTA b processes slots b, b + ctas, b + 2 ctas, ...  Graphs are sorted by
-    decreasing work and laid out boustrophedon (round 0 descending, round 1 ascending, ...), so the CTA that got the largest
-    graph of one round gets the smallest of the next and all CTAs finish at about the same time."""
-    idx = sorted(range(len(work)), key=lambda i: (-work[i], i))
-    order: list[int] = []
-    for k, start in enumerate(range(0, len(idx), ctas)):
-        chunk = idx[start : start + ctas]
-        order += chunk if k % 2 == 0 else chunk[::-1]
+    """Slot -> graph id for the per-graph kernels: CTA b processes slots b, b + ctas, b + 2 ctas, ...
+
+    Longest-processing-time-first: graphs are taken by decreasing work and each goes to the CTA with the least work so far, so
+    all CTAs finish at about the same time -- with 256 graphs on 148 CTAs the 40 largest graphs get a CTA of their own and the
+    other 216 are paired largest-with-smallest.  CTAs are then numbered by decreasing graph count (a CTA's k-th graph sits in
+    slot b + k * ctas, so the CTAs that run an extra round must be the first ones).  Ties keep graph order: deterministic."""
+    import heapq
+
+    n = len(work)
+    g = max(1, min(ctas, n))
+    idx = sorted(range(n), key=lambda i: (-work[i], i))
+    heap = [(0, b) for b in range(g)]  # (load, cta)
+    mine: list[list[int]] = [[] for _ in range(g)]
+    for i in idx:
+        load, b = heapq.heappop(heap)
+        mine[b].append(i)
+        heapq.heappush(heap, (load + work[i], b))
+    rank = sorted(range(g), key=lambda b: (-len(mine[b]), b))
+    order = [-1] * n
+    rounds = max((len(m) for m in mine), default=0)
+    slot_of_round = 0
+    for k in range(rounds):
+        members = [b for b in rank if len(mine[b]) > k]
+        for pos, b in enumerate(members):
+            order[slot_of_round + pos] = mine[b][k]
+        slot_of_round += len(members)
     return torch.tensor(order, dtype=torch.int32)
 
 
