@@ -74,7 +74,9 @@ class ClockSampler:
             "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
         }
-        while not self._stop.is_set():
+        first = True
+        while first or not self._stop.is_set():  # at least one sample even if the region is shorter than the thread's start-up
+            first = False
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
                 try:
