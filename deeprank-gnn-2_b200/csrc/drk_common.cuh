@@ -97,6 +97,33 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- tensor cores with fp32-level accuracy: mma.sync m16n8k8 TF32 with error compensation ("3xTF32").
+// An fp32 operand is split as v = hi + lo with hi = tf32(v), lo = tf32(v - hi); a product is accumulated (fp32) as
+// lo_a*hi_b + hi_a*lo_b + hi_a*hi_b: the dropped lo*lo term is ~2^-22 relative, far inside the 1e-5 parity bar, while a plain
+// TF32 product (2^-11) would not be.
+// Fragment layout (PTX ISA, g = lane >> 2, t = lane & 3):  A 16x8 row-major: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B 8x8: b0 (k = t, n = g) b1 (k = t+4, n = g);  C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(v);
+  lo = to_tf32(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += a * b for fp32 a (already split) and fp32 b (already split)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint2 bhi, uint2 blo) {
+  mma_tf32(c, alo, bhi.x, bhi.y);
+  mma_tf32(c, ahi, blo.x, blo.y);
+  mma_tf32(c, ahi, bhi.x, bhi.y);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace drk

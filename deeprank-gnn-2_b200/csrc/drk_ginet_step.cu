@@ -497,27 +497,6 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
 // 4 wavefronts feeds only 16 FFMA2 per lane); a fragment register feeds 8-32 MACs.
 // Fragment layout (PTX ISA, g = lane >> 2, t = lane & 3):  A 16x8 row-major: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
 // B 8x8: b0 (k = t, n = g) b1 (k = t+4, n = g);  C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(v);
-  lo = to_tf32(v - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// c += a * b for fp32 a (already split) and fp32 b (already split)
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint2 bhi, uint2 blo) {
-  mma_tf32(c, alo, bhi.x, bhi.y);
-  mma_tf32(c, ahi, blo.x, blo.y);
-  mma_tf32(c, ahi, bhi.x, bhi.y);
-}
-
 // P = x W1s^T -> tile [n][32].  One warp per 16-row tile: 4 column tiles x ceil(F/8) k-steps of 3xTF32 MMAs.
 // (Reading the A fragments straight from global/L2 so that the x tile could stream in under the forward pass was measured
 // 3 us per step SLOWER than staging x first: 28 dependent-latency loads per lane with 16 warps per SM are not hidden.)
