@@ -797,8 +797,8 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     sW2[kF2 * kF1 + e] = __ldg(a.w2b + e);
   }
 
-  // Static schedule: CTA b processes slots b, b + grid, ... of `order` (the host lays the graphs out in snake order of
-  // decreasing size, so every CTA's total work is about equal).  The NEXT slot's offsets are fetched by one thread while the
+  // Static schedule: CTA b processes slots b, b + grid, ... of `order` (the host lays the graphs out longest-processing-time-first,
+  // data.py:snake_order, so every CTA's total work is about equal).  The NEXT slot's offsets are fetched by one thread while the
   // current graph is processed: {graph id, node0, n, e0, ne} go through shared memory one iteration ahead.
   if (tid == 0) {
     const int slot = blockIdx.x;

@@ -245,8 +245,8 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  *   live[0..7] = the tensors of the gradient outputs below, in that order; dead[0..num_dead) = parameters whose gradient is
  *   identically zero (fc_edge_attr / fc_attention: weight decay still moves them); step = the float32 device scalar of each.
  * order (may be NULL = identity): slot -> graph id; CTA b of the G = drk_ginet_step_ctas(B) CTAs processes slots b, b+G, b+2G, ...
- *   Laying the graphs out in snake order of decreasing size (round 0 descending, round 1 ascending, ...) gives every CTA about
- *   the same total work; the result does not depend on the order (per-graph contributions are summed in graph order).
+ *   A longest-processing-time-first layout (largest graphs first, each to the least loaded CTA; CTAs numbered by decreasing
+ *   graph count) gives every CTA about the same total work; the result does not depend on the order (per-graph contributions are summed in graph order).
  * Outputs: pred [B,out]; loss [1]; gradients of conv1.fc.weight / conv1_ext.fc.weight [16,F], conv2.fc.weight /
  *   conv2_ext.fc.weight [32,16], fc1.{weight [128,64], bias [128]}, fc2.{weight [out,128], bias [out]}.
  * The gradients of fc_edge_attr / fc_attention are identically zero in the reference (softmax over a singleton axis,
