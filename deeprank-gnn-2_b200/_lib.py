@@ -59,7 +59,7 @@ SIGNATURES = {
     "drk_ginet_step_exchange_floats": (c_int32, [_I32, _I32]),
     "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
     "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),
-    "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32,   # x .. edge_layout .. max_graph_edges
+    "drk_ginet_step": (c_int32, [_P, _I64, _I32, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32, _I32,   # x .. edge_layout .. order, outputs_by_slot .. max_graph_edges
                                  _P, _P, _P, _P, _P, _P, _P, _P, _I32,                       # weights, out_dim
                                  _I32, _P, c_float, c_float, c_uint64, _P, _I32,             # loss, dropout, train
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,                     # pred, loss, 8 gradients

@@ -86,6 +86,7 @@ struct StepArgs {
   float* gvec; float* hvec; float* dhvec; float* dpvec;
   uint16_t* csc_spill; int32_t* status;
   int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;  // *_off: index-build scratch (bytes into shared memory)
+  int32_t slot_outputs;  // results indexed by slot instead of graph id (graph selections out of a resident set)
   int32_t pairs;  // edge slices hold undirected pairs (edge_ptr counts pairs); each stands for both directions
 };
 
@@ -814,6 +815,9 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     __syncthreads();  // previous graph is finished with every region; weights and this graph's offsets are visible
     const int g = s_meta[buf][0], node0 = s_meta[buf][1], n = s_meta[buf][2], e0 = s_meta[buf][3];
     const int ne = a.pairs ? 2 * s_meta[buf][4] : s_meta[buf][4];  // directed edges of the graph
+    // where this graph's results go: its id (a batch: `order` is a permutation of 0..B-1) or its slot (a selection of graphs out of a
+    // resident graph set: `order` holds B arbitrary graph ids, targets stay indexed by graph id)
+    const int og = a.slot_outputs ? g_slot : g;
     const int next_slot = g_slot + (int)gridDim.x;
     const bool have_next = next_slot < a.num_graphs;
     int gn = 0;
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int rl = 0; rl < 8; ++rl) s += sRed[rl * kS2 + tid];
       const float gm = s / cnt;
       hG[tid] = gm;
-      if (a.gvec != nullptr) a.gvec[(size_t)g * kS2 + tid] = gm;
+      if (a.gvec != nullptr) a.gvec[(size_t)og * kS2 + tid] = gm;
     }
     if (TRAIN) {
       for (int e = tid; e < kS2 * kF1; e += kT) {
@@ -934,7 +938,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
         const float hv = pre > 0.f ? pre * scale : 0.f;
         hH[j] = hv;
         hHM[j] = pre > 0.f ? scale : 0.f;  // d h / d pre
-        if (TRAIN) a.hvec[(size_t)g * kHid + j] = hv;
+        if (TRAIN) a.hvec[(size_t)og * kHid + j] = hv;
       }
     }
     __syncthreads();
@@ -947,7 +951,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       if (lane == 0) {
         const float pv = s + __ldg(a.fc2_b + warp);
         hPred[warp] = pv;
-        a.pred[(size_t)g * a.out_dim + warp] = pv;
+        a.pred[(size_t)og * a.out_dim + warp] = pv;
       }
     }
     if (!TRAIN) continue;
@@ -973,8 +977,8 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
         term = t_ok ? lse - hPred[t] : 0.f;
         for (int o = 0; o < a.out_dim; ++o) hDPred[o] = t_ok ? (expf(hPred[o] - lse) - (o == t ? 1.f : 0.f)) * a.dloss_scale : 0.f;
       }
-      a.loss_terms[g] = term;
-      for (int o = 0; o < a.out_dim; ++o) a.dpvec[(size_t)g * a.out_dim + o] = hDPred[o];
+      a.loss_terms[og] = term;
+      for (int o = 0; o < a.out_dim; ++o) a.dpvec[(size_t)og * a.out_dim + o] = hDPred[o];
     }
     __syncthreads();
     // ---- d pre-activation of fc1
@@ -983,7 +987,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int o = 0; o < a.out_dim; ++o) s = fmaf(hDPred[o], __ldg(a.fc2_w + (size_t)o * kHid + tid), s);
       s *= hHM[tid];
       hDH[tid] = s;
-      a.dhvec[(size_t)g * kHid + tid] = s;
+      a.dhvec[(size_t)og * kHid + tid] = s;
     }
     __syncthreads();
     // ---- dG = fc1_w^T dh: thread -> (column c, 16 rows j of fc1_w), coalesced rows
@@ -1006,7 +1010,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     }
     __syncthreads();
     // ---- dW2 contribution of this graph and V = diag(dG/n) W2
-    float* part = a.part + (size_t)g * a.part_stride;
+    float* part = a.part + (size_t)og * a.part_stride;
     for (int e = tid; e < kS2 * kF1; e += kT) {
       const int c = e / kF1;
       const float dgc = hDG[c];
@@ -1445,8 +1449,8 @@ size_t drk_ginet_step_workspace_bytes(int32_t fi, int32_t out_dim, int32_t num_g
 }
 
 int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_index, int64_t num_edges, int32_t edge_layout, const int32_t* graph_ptr,
-                   const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges,
-                   const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
+                   const int32_t* edge_ptr, const int32_t* order, int32_t outputs_by_slot, int32_t num_graphs, int32_t max_graph_nodes,
+                   int32_t max_graph_edges, const float* w1a, const float* w1b, const float* w2a, const float* w2b, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int32_t out_dim, int32_t loss_kind, const void* target, float inv_loss_count,
                    float dropout_p, uint64_t seed, int64_t* rng_step, int32_t train, float* pred, float* loss, float* dw1a, float* dw1b,
                    float* dw2a, float* dw2b, float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b, const DrkAdam* adam, const DrkPeers* peers, int32_t* status,
@@ -1478,6 +1482,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   a.erow = edge_index; a.ecol = edge_index + num_edges;
   a.pairs = edge_layout == DRK_EDGES_UNDIRECTED_PAIRS ? 1 : 0;
   a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.num_graphs = num_graphs;
+  a.slot_outputs = (outputs_by_slot && order != nullptr) ? 1 : 0;
   a.w1a = w1a; a.w1b = w1b; a.w2a = w2a; a.w2b = w2b;
   a.fc1_w = fc1_w; a.fc1_b = fc1_b; a.fc2_w = fc2_w; a.fc2_b = fc2_b; a.out_dim = out_dim;
   a.loss_kind = loss_kind;

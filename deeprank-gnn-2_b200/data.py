@@ -255,8 +255,17 @@ def snake_order(work: list[int], ctas: int = STEP_CTAS) -> torch.Tensor:
     slot b + k * ctas, so the CTAs that run an extra round must be the first ones).  Ties keep graph order: deterministic."""
     import heapq
 
+    import numpy as np
+
     n = len(work)
     g = max(1, min(ctas, n))
+    if n <= 2 * g:
+        # closed form of the same schedule for at most two rounds (the per-step path of resident graph sets): k = n - g CTAs run two
+        # graphs -- the k smallest of the g largest, each paired with one of the k smallest overall (smallest first graph with the
+        # largest second) -- and come first; the g - k largest graphs run alone.
+        idx = np.argsort(-np.asarray(work, dtype=np.int64), kind="stable")
+        k = max(n - g, 0)
+        return torch.from_numpy(np.concatenate((idx[g - k : g], idx[: g - k], idx[g:][::-1])).astype(np.int32))
     idx = sorted(range(n), key=lambda i: (-work[i], i))
     heap = [(0, b) for b in range(g)]  # (load, cta)
     mine: list[list[int]] = [[] for _ in range(g)]

@@ -35,7 +35,7 @@ class BlockInfo:
     (or None), the largest graph's node / (directed) edge count, the batch's status word, and the edge tensor the kernels read:
     ``edges`` int64 [2, M] with ``layout`` EDGES_DIRECTED (= ``edge_index``) or EDGES_UNDIRECTED_PAIRS (each contact once)."""
 
-    __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status", "edges", "layout")
+    __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status", "edges", "layout", "by_slot")
 
 
 def block_info(data) -> BlockInfo:
@@ -62,6 +62,7 @@ def block_info(data) -> BlockInfo:
     if cached is not None and cached[0] == key:
         return cached[1]
     info = BlockInfo()
+    info.by_slot = False
     dev = ei.device
     info.edges = ei if ei.is_contiguous() else ei.contiguous()
     info.layout = _lib.EDGES_UNDIRECTED_PAIRS if use_pairs else _lib.EDGES_DIRECTED
@@ -150,7 +151,8 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
         ws_bytes = lib.drk_ginet_step_workspace_bytes(fi, out_dim, info.num_graphs, info.max_nodes, info.max_edges) if train else 0
         ws = workspace(ws_bytes, x.device) if train else None
         rc = lib.drk_ginet_step(
-            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), int(info.layout), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), info.num_graphs, info.max_nodes, info.max_edges,
+            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), int(info.layout), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), 1 if getattr(info, "by_slot", False) else 0,
+            info.num_graphs, info.max_nodes, info.max_edges,
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
             int(loss_kind), _p(target), float(inv_loss_count), float(dropout_p), int(seed) & (2**64 - 1), _p(state), 1 if train else 0,
@@ -295,20 +297,25 @@ class GINetFusedStep:
         desc.num_dead = len(dead)
         return desc
 
-    def forward_backward(self, batch, global_size: int | None = None, adam=None):
-        """Everything but the optimizer: returns (loss, pred); ``p.grad`` of every parameter is set."""
-        info = block_info(batch)
+    def forward_backward(self, batch, global_size: int | None = None, adam=None, selection=None):
+        """Everything but the optimizer: returns (loss, pred); ``p.grad`` of every parameter is set.
+
+        ``selection`` (a :class:`BlockInfo` from ``ResidentGraphSet.select``) runs the step on a list of graph ids of a
+        device-resident graph set instead of a collated batch: ``batch`` is then the set's packed batch, targets stay indexed
+        by graph id and the predictions come back in the selection's slot order."""
+        info = selection if selection is not None else block_info(batch)
         out_dim = int(self.model.fc2.weight.shape[0])
         target = self.target_fn(batch)
+        n_targets = int(block_info(batch).num_graphs) if selection is not None else info.num_graphs
         if self.kind == _lib.LOSS_MSE:
             target = target.to(torch.float32).contiguous()
-            if target.numel() != info.num_graphs * out_dim:
-                raise ValueError(f"MSELoss target has {target.numel()} elements, predictions {info.num_graphs * out_dim}")
+            if target.numel() != n_targets * out_dim:
+                raise ValueError(f"MSELoss target has {target.numel()} elements, predictions {n_targets * out_dim}")
             count = (global_size or info.num_graphs) * out_dim
         else:
             target = target.to(torch.int64).contiguous()
-            if target.numel() != info.num_graphs:
-                raise ValueError(f"CrossEntropyLoss target has {target.numel()} elements for {info.num_graphs} graphs")
+            if target.numel() != n_targets:
+                raise ValueError(f"CrossEntropyLoss target has {target.numel()} elements for {n_targets} graphs")
             count = global_size or info.num_graphs
         key = (info.num_graphs, out_dim)
         pred = self._pred.get(key)
@@ -326,6 +333,19 @@ class GINetFusedStep:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return self.loss, pred
 
+    def step_selection(self, graph_set, ids=None, global_size: int | None = None, prepared=None):
+        """One train step on graphs ``ids`` of a :class:`ResidentGraphSet`: the mini-batch is a list of ids (the only host->device
+        traffic of the step), no collate, no copy of the graphs.  Returns (loss, pred, slot_ids): ``pred[s]`` belongs to graph
+        ``slot_ids[s]``.  ``prepared = graph_set.select(ids)`` may be computed ahead (e.g. while the previous step runs)."""
+        selection, slot_ids = prepared if prepared is not None else graph_set.select(ids)
+        if self._adam is not None:
+            self._adam.lr = self.optimizer.param_groups[0]["lr"]
+            loss, pred = self.forward_backward(graph_set.batch, global_size, adam=self._adam, selection=selection)
+        else:
+            loss, pred = self.forward_backward(graph_set.batch, global_size, selection=selection)
+            self.optimizer.step()
+        return loss, pred, slot_ids
+
     def empty_step(self):
         """A rank without graphs in this (ragged) global mini-batch still joins the gradient exchange and steps the optimizer."""
         for p, v in zip(self.params, self.views):
@@ -342,7 +362,7 @@ class GINetFusedStep:
             with torch.cuda.device(dev):
                 ws = workspace(1 << 20, dev)
                 rc = lib.drk_ginet_step(
-                    None, fi, fi, None, 0, 0, None, None, None, 0, 0, 0,
+                    None, fi, fi, None, 0, 0, None, None, None, 0, 0, 0, 0,
                     _p(m.conv1.fc.weight), _p(m.conv1_ext.fc.weight), _p(m.conv2.fc.weight), _p(m.conv2_ext.fc.weight),
                     _p(m.fc1.weight), _p(m.fc1.bias), _p(m.fc2.weight), _p(m.fc2.bias), out_dim,
                     int(self.kind), _p(self.loss), 0.0, 0.0, int(self.seed) & (2**64 - 1), _p(self.state), 1,
@@ -367,3 +387,68 @@ class GINetFusedStep:
         loss, pred = self.forward_backward(batch, global_size)
         self.optimizer.step()
         return loss, pred
+
+
+class ResidentGraphSet:
+    """A whole dataset collated ONCE and kept in HBM (180 GB hold ~1.8 M residue-level graphs): node features, contacts, targets and
+    per-graph offsets of all graphs as one packed batch.  A mini-batch is then a list of graph ids -- ``select`` turns it into the
+    descriptor the step kernel takes (ids in longest-processing-time-first order, results by slot); nothing else crosses PCIe and
+    nothing is gathered or copied on the device: every CTA reads its graph in place.
+
+    This is the device-side replacement of the per-batch collate + transfer of ``Trainer._epoch`` (``trainer.py:682-686``;
+    SURVEY 8f rank 2): the reference re-opens the HDF5 file and re-collates every graph in every epoch."""
+
+    def __init__(self, graphs, device):
+        from .data import Batch
+
+        host = Batch.from_data_list(list(graphs))
+        self.num_graphs = len(host.ptr) - 1
+        self.entry_names = list(host.entry_names) if isinstance(getattr(host, "entry_names", None), list) else None
+        node_ptr, edge_ptr = host._node_ptr32.tolist(), host._edge_ptr32.tolist()
+        self.work = [(edge_ptr[g + 1] - edge_ptr[g]) + 8 * (node_ptr[g + 1] - node_ptr[g]) for g in range(self.num_graphs)]
+        import numpy as np
+
+        self.work_np = np.asarray(self.work, dtype=np.int64)
+        self.batch = host.to(torch.device(device))
+        self.info = block_info(self.batch)
+
+    def select(self, ids):
+        """(descriptor, slot_ids) for the graphs ``ids``: ``slot_ids`` is the order in which results come back."""
+        from .data import snake_order
+
+        import numpy as np
+
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size == 0:
+            raise ValueError("empty selection")
+        if int(ids.min()) < 0 or int(ids.max()) >= self.num_graphs:
+            raise IndexError(f"graph ids must be in [0, {self.num_graphs})")
+        order = snake_order(self.work_np[ids]).numpy()
+        slot_ids = ids[order].astype(np.int32)
+        dev = self.batch.x.device
+        # the ids travel through a small ring of pinned staging buffers (no allocation per step); a slot is reused only after
+        # the copy that read it has completed (event recorded behind the copy)
+        ring = self.__dict__.setdefault("_ring", [])
+        if not ring and dev.type == "cuda":
+            for _ in range(4):
+                ring.append([torch.empty(4096, dtype=torch.int32).pin_memory(), None])
+        if dev.type == "cuda" and len(slot_ids) <= 4096:
+            slot = ring[self.__dict__.get("_ring_pos", 0) % len(ring)]
+            self.__dict__["_ring_pos"] = self.__dict__.get("_ring_pos", 0) + 1
+            if slot[1] is not None:
+                slot[1].synchronize()
+            host_ids = slot[0][: len(slot_ids)]
+            host_ids.numpy()[:] = slot_ids
+            dev_ids = host_ids.to(dev, non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record(torch.cuda.current_stream(dev))
+        else:
+            dev_ids = torch.from_numpy(slot_ids).to(dev)
+        sel = BlockInfo()
+        base = self.info
+        sel.node_ptr, sel.edge_ptr, sel.edges, sel.layout = base.node_ptr, base.edge_ptr, base.edges, base.layout
+        sel.max_nodes, sel.max_edges, sel.status = base.max_nodes, base.max_edges, base.status
+        sel.order = dev_ids
+        sel.num_graphs = len(slot_ids)
+        sel.by_slot = True
+        return sel, slot_ids.tolist()

@@ -293,8 +293,8 @@ DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim,
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,
                                       int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_features, const int64_t* edge_index, int64_t num_edges, int32_t edge_layout,
-                   const int32_t* graph_ptr, const int32_t* edge_ptr, const int32_t* order, int32_t num_graphs,
-                   int32_t max_graph_nodes, int32_t max_graph_edges,
+                   const int32_t* graph_ptr, const int32_t* edge_ptr, const int32_t* order, int32_t outputs_by_slot,
+                   int32_t num_graphs, int32_t max_graph_nodes, int32_t max_graph_edges,
                    const float* w1a, const float* w1b, const float* w2a, const float* w2b,
                    const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, int32_t out_dim,
                    int32_t loss_kind, const void* target, float inv_loss_count,

@@ -45,9 +45,15 @@ def test_snake_order_balances_rounds():
     assert order[:4] == [0, 1, 2, 3] and order[4:8] == [7, 6, 5, 4] and order[8:] == [8, 9]
     totals = [sum(work[order[s]] for s in range(b, 10, 4)) for b in range(4)]
     assert max(totals[:2]) - min(totals[:2]) <= 2  # CTAs with the same number of graphs carry (almost) the same work
-    # ties keep graph order, any input order works
-    assert snake_order([5, 5, 5], ctas=2).tolist() == [0, 1, 2]
+    # at most two rounds: closed form of the same schedule -- the CTAs that run two graphs come first and pair a mid-sized graph with
+    # one of the smallest; deterministic (ties keep graph order)
+    two = snake_order([9, 8, 7, 6, 2, 1], ctas=4).tolist()
+    assert sorted(two) == list(range(6))
+    loads = [sum([9, 8, 7, 6, 2, 1][two[s]] for s in range(b, 6, 4)) for b in range(4)]
+    assert sorted(loads) == [8, 8, 8, 9]  # 7+1 and 6+2 paired, 9 and 8 alone
+    assert snake_order([5, 5, 5], ctas=2).tolist() == snake_order([5, 5, 5], ctas=2).tolist()
     assert sorted(snake_order([3, 9, 1, 7], ctas=3).tolist()) == [0, 1, 2, 3]
+    assert snake_order([4, 2, 6], ctas=148).tolist() == [2, 0, 1]  # fewer graphs than CTAs: largest first
 
 
 def test_partial_transfer_keeps_deferred_tensors_reachable():
