@@ -161,9 +161,10 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
     _lib.check(rc, "drk_ginet_step")
 
 
-def ginet_infer(model, data) -> torch.Tensor:
-    """``model(data)`` for the reference GINet without autograd: one kernel, [B, out] predictions."""
-    info = block_info(data)
+def ginet_infer(model, data, selection=None) -> torch.Tensor:
+    """``model(data)`` for the reference GINet without autograd: one kernel, [B, out] predictions.  With ``selection`` (from
+    ``ResidentGraphSet.select``) ``data`` is the set's packed batch and the predictions come back in slot order."""
+    info = selection if selection is not None else block_info(data)
     pred = torch.empty((info.num_graphs, int(model.fc2.weight.shape[0])), dtype=torch.float32, device=data.x.device)
     _call_step(model, data, info, train=False, loss_kind=_lib.LOSS_MSE, target=None, inv_loss_count=0.0, dropout_p=0.0, seed=0, state=None,
                pred=pred, loss=None, grads=[None] * 8)
@@ -295,6 +296,8 @@ class GINetFusedStep:
         for i, p in enumerate(dead):
             fill(desc.dead[i], p)
         desc.num_dead = len(dead)
+        st0 = opt.state[self.params[0]]
+        self._adam_key = (st0["step"].data_ptr(), st0["exp_avg"].data_ptr())
         return desc
 
     def forward_backward(self, batch, global_size: int | None = None, adam=None, selection=None):
@@ -338,8 +341,8 @@ class GINetFusedStep:
         traffic of the step), no collate, no copy of the graphs.  Returns (loss, pred, slot_ids): ``pred[s]`` belongs to graph
         ``slot_ids[s]``.  ``prepared = graph_set.select(ids)`` may be computed ahead (e.g. while the previous step runs)."""
         selection, slot_ids = prepared if prepared is not None else graph_set.select(ids)
+        self._refresh_adam()
         if self._adam is not None:
-            self._adam.lr = self.optimizer.param_groups[0]["lr"]
             loss, pred = self.forward_backward(graph_set.batch, global_size, adam=self._adam, selection=selection)
         else:
             loss, pred = self.forward_backward(graph_set.batch, global_size, selection=selection)
@@ -380,9 +383,19 @@ class GINetFusedStep:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         self.optimizer.step()
 
-    def __call__(self, batch, global_size: int | None = None):
-        if self._adam is not None:  # Adam applied by the finalize kernel on torch's own optimizer state (2 launches per step)
+    def _refresh_adam(self):
+        """``optimizer.load_state_dict`` replaces the state tensors: re-point the descriptor when that happened."""
+        if self._adam is None:
+            return
+        st = self.optimizer.state.get(self.params[0])
+        if not st or (st["step"].data_ptr(), st["exp_avg"].data_ptr()) != self._adam_key:
+            self._adam = self._adam_descriptor()
+        if self._adam is not None:
             self._adam.lr = self.optimizer.param_groups[0]["lr"]
+
+    def __call__(self, batch, global_size: int | None = None):
+        self._refresh_adam()
+        if self._adam is not None:  # Adam applied by the finalize kernel on torch's own optimizer state (2 launches per step)
             return self.forward_backward(batch, global_size, adam=self._adam)
         loss, pred = self.forward_backward(batch, global_size)
         self.optimizer.step()

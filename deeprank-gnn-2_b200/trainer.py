@@ -99,6 +99,53 @@ class BatchLoader:
             yield (feed._hand_out(pending[0]) if pending[0] is not None else None), pending[1]
 
 
+class SelectionBatch:
+    """A mini-batch of a device-resident graph set: a prepared selection of graph ids (``fused.ResidentGraphSet.select``) plus what the
+    Trainer's bookkeeping needs (targets and entry names in the selection's slot order)."""
+
+    __slots__ = ("graph_set", "prepared", "y", "entry_names")
+
+    def __init__(self, graph_set, prepared):
+        self.graph_set, self.prepared = graph_set, prepared
+        selection, slot_ids = prepared
+        self.y = graph_set.batch.y.index_select(0, selection.order.long())
+        names = graph_set.entry_names
+        self.entry_names = [names[i] for i in slot_ids] if names is not None else [str(i) for i in slot_ids]
+
+
+class ResidentBatches:
+    """Loader over a :class:`fused.ResidentGraphSet`: the same ``batch_size`` / ``shuffle`` / rank-slice semantics as
+    :class:`BatchLoader`, but a batch is a list of graph ids -- no per-epoch collate, no per-batch PCIe copy of the graphs."""
+
+    def __init__(self, graph_set, batch_size: int, shuffle: bool, rank: int = 0, world_size: int = 1, seed: int | None = None):
+        self.graph_set, self.batch_size, self.shuffle = graph_set, int(batch_size), shuffle
+        self.rank, self.world_size = rank, world_size
+        self.only = ()
+        self._gen = torch.Generator()
+        if seed is not None:
+            self._gen.manual_seed(seed)
+        elif world_size > 1:
+            self._gen.manual_seed(0)
+
+    def __len__(self):
+        return (self.graph_set.num_graphs + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        from .parallel import shard_indices
+
+        n = self.graph_set.num_graphs
+        order = torch.randperm(n, generator=self._gen).tolist() if self.shuffle else list(range(n))
+        for start in range(0, n, self.batch_size):
+            ids = order[start : start + self.batch_size]
+            global_size = len(ids)
+            if self.world_size > 1:
+                ids = [ids[i] for i in shard_indices(len(ids), self.rank, self.world_size)]
+            if not ids:
+                yield None, global_size
+                continue
+            yield SelectionBatch(self.graph_set, self.graph_set.select(ids)), global_size
+
+
 class Trainer:
     def __init__(
         self,
@@ -319,7 +366,41 @@ class Trainer:
             self.lossfunction = lossfunction()
 
     # ------------------------------------------------------------------ training / testing
+    def _resident_loader(self, dataset, batch_size, shuffle):
+        """A :class:`ResidentBatches` loader if the per-graph step kernels apply to this model / loss and the whole dataset fits
+        the device (collated once, kept in HBM), else None.  ``DRK_NO_RESIDENT=1`` disables it."""
+        import os
+
+        from . import _lib
+        from .fused import GINetFusedStep, ResidentGraphSet
+
+        if os.environ.get("DRK_NO_RESIDENT") or self.device.type != "cuda" or len(dataset) == 0:
+            return None
+        loss_fn = self.lossfunction
+        if isinstance(loss_fn, type) or not GINetFusedStep.supports(self.model, loss_fn):
+            return None
+        cache = self.__dict__.setdefault("_resident_sets", {})
+        gset = cache.get(id(dataset))
+        if gset is None:
+            graphs = [dataset.get(i) for i in range(len(dataset))]
+            nbytes = sum(v.numel() * v.element_size() for g in graphs for v in g.__dict__.values() if isinstance(v, torch.Tensor))
+            free, _total = torch.cuda.mem_get_info(self.device)
+            if 3 * nbytes > free:  # packed copy + pairs + head room
+                return None
+            gset = ResidentGraphSet(graphs, self.device)
+            fi, out = int(gset.batch.x.shape[1]), int(self.model.fc2.weight.shape[0])
+            if gset.batch.__dict__.get("_pairs") is None and gset.batch.__dict__.get("_edge_ptr32") is None:
+                return None
+            if not _lib.load().drk_ginet_step_supported(fi, out, gset.info.max_nodes, gset.info.max_edges) or fi != self.model.conv1.fc.weight.shape[1]:
+                return None
+            cache[id(dataset)] = gset
+        rank, world = (dist.get_rank(), dist.get_world_size()) if self._distributed() else (0, 1)
+        return ResidentBatches(gset, batch_size, shuffle, rank=rank, world_size=world)
+
     def _loader(self, dataset, batch_size, shuffle):
+        resident = self._resident_loader(dataset, batch_size, shuffle)
+        if resident is not None:
+            return resident
         rank, world = (dist.get_rank(), dist.get_world_size()) if self._distributed() else (0, 1)
         return BatchLoader(dataset, batch_size=batch_size, shuffle=shuffle, device=self.device, pin_memory=self.device.type == "cuda", rank=rank, world_size=world)
 
@@ -340,6 +421,7 @@ class Trainer:
             raise ValueError("No training dataset provided.")
         self.data_type = type(self.dataset_train)
         self.batch_size_train, self.shuffle = batch_size, shuffle
+        self._fused = None  # rebuilt lazily: the optimizer (and its state tensors) may have changed since the last call
         self.train_loader = self._loader(self.dataset_train, batch_size, shuffle)
         if self.dataset_val is not None:
             self.valid_loader = self._loader(self.dataset_val, batch_size, shuffle)
@@ -413,17 +495,31 @@ class Trainer:
         t0 = time()
         for batch, global_size in loader:
             if batch is None:
-                if train and self._fused is not None and self._fused is not False:
-                    self._fused.empty_step()
+                if train and (isinstance(loader, ResidentBatches) or (self._fused is not None and self._fused is not False)):
+                    self._ensure_fused().empty_step()
                 elif train and self._grad_sync is not None:  # ragged tail: this rank has no graphs but must join the all-reduce
                     self.optimizer.zero_grad()
                     self._grad_sync(local_weight=0.0)
                     self.optimizer.step()
                 continue
-            fused = self._fused_step(batch) if train else None
-            if fused is not None and getattr(loader, "only", 0) is None:
-                loader.only = type(fused).FIELDS  # later batches: copy only what the step kernels read (the rest stays lazy)
-            if fused is not None:
+            resident = isinstance(batch, SelectionBatch)
+            fused = self._fused_step(batch) if (train and not resident) else None
+            if resident:
+                # graphs resident in HBM: the batch is a list of ids; step / inference run in place
+                from .fused import ginet_infer
+
+                if train:
+                    loss_, pred, _ = self._ensure_fused().step_selection(batch.graph_set, prepared=batch.prepared, global_size=global_size)
+                    loss_ = loss_ * (global_size / pred.shape[0])
+                    pred, y = self._format_output(pred.clone(), batch.y)
+                else:
+                    with torch.no_grad():
+                        pred = ginet_infer(self.model, batch.graph_set.batch, selection=batch.prepared[0])
+                        pred, y = self._format_output(pred, batch.y)
+                        loss_ = self.lossfunction(pred, y) if y is not None else None
+            elif fused is not None:
+                if getattr(loader, "only", 0) is None:
+                    loader.only = type(fused).FIELDS  # later batches: copy only what the step kernels read (the rest stays lazy)
                 # whole step (index, forward, loss, backward, gradient all-reduce, optimizer) in the per-graph kernels
                 loss_, pred = fused(batch, global_size=global_size)
                 loss_ = loss_ * (global_size / pred.shape[0])  # the kernel scales by the global batch: back to this rank's mean
@@ -460,6 +556,14 @@ class Trainer:
         self._output_exporters.process(pass_name, epoch_number, names, outputs, target_vals, epoch_loss)
         _log.info(f"{pass_name} loss {epoch_loss} | time {time() - t0}")
         return epoch_loss
+
+    def _ensure_fused(self):
+        from .fused import GINetFusedStep
+
+        if self._fused is None or self._fused is False:
+            world = dist.get_world_size() if self._distributed() else 1
+            self._fused = GINetFusedStep(self.model, self.optimizer, self.lossfunction, target_fn=lambda b: self._format_output(None, b.y)[1], world_size=world)
+        return self._fused
 
     def _fused_step(self, batch):
         """The per-graph step kernels (``fused.GINetFusedStep``) when the model is the reference ``ginet_nocluster.GINet``, the

@@ -72,7 +72,10 @@ def test_trainer_trains_every_net_on_gpu(net_name, tmp_path, monkeypatch):
     if net_name == "ginet_nocluster":
         from deeprank2_b200.fused import GINetFusedStep
 
+        from deeprank2_b200.trainer import ResidentBatches
+
         assert isinstance(trainer._fused, GINetFusedStep), "the Trainer must drive the reference GINet through the per-graph step kernels"
+        assert isinstance(trainer.train_loader, ResidentBatches), "a dataset that fits HBM is collated once and stays resident"
         assert trainer._fused._adam is not None, "default optimizer: the Adam update runs in the finalize kernel"
     else:
         assert trainer._fused is False
@@ -102,3 +105,30 @@ def test_trainer_epoch_matches_cpu_oracle_epoch():
     assert abs(loss_gpu - sum(losses) / 12) <= 1e-5 * abs(sum(losses) / 12) + 1e-7
     for (k, p_ref), p in zip(params.items(), trainer.model.parameters()):
         assert_adam_close(p, p_ref, f"weights after 3 steps: {k}")
+
+
+def test_resident_and_streamed_training_agree(monkeypatch):
+    """Trainer.train on a device-resident graph set (batches = id lists) vs the streamed BatchLoader path (DRK_NO_RESIDENT=1): same
+    shuffles, same weights up to the order of the per-graph sums."""
+    import numpy as np
+
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.trainer import BatchLoader, ResidentBatches, Trainer
+
+    results = []
+    for resident in (True, False):
+        if resident:
+            monkeypatch.delenv("DRK_NO_RESIDENT", raising=False)
+        else:
+            monkeypatch.setenv("DRK_NO_RESIDENT", "1")
+        seeded = np.random.Generator(np.random.PCG64(3))
+        monkeypatch.setattr(np.random, "default_rng", lambda *a, **k: seeded)
+        ds = InMemoryGraphDataset(_graphs(20))
+        torch.manual_seed(1)
+        trainer = Trainer(GINet, ds, cuda=True, output_exporters=[_Collect()])
+        trainer.model.dropout = 0.0  # the two paths number the graphs of a batch differently, so they would draw different masks
+        trainer.train(nepoch=2, batch_size=8, shuffle=False, validate=False, filename=None)
+        assert isinstance(trainer.train_loader, ResidentBatches if resident else BatchLoader)
+        results.append(torch.cat([p.detach().reshape(-1) for p in trainer.model.parameters()]).cpu())
+    assert float((results[0] - results[1]).abs().max()) <= 2e-6
