@@ -344,21 +344,32 @@ def run_ours(args):
     # the only per-step host->device traffic, nothing is collated or copied.  Reported next to `e2e`, not instead of it.
     e2e_resident = None
     if args.path == "fused":
-        import random
-
         from deeprank2_b200.fused import ResidentGraphSet
         from deeprank2_b200.synthetic import make_graph
 
         n_set = GRAPHS_PER_BATCH * args.batches
         gset = ResidentGraphSet([make_graph(rank * n_set + g, n_node_features=F_NODE, n_edge_features=F_EDGE) for g in range(n_set)], dev)
-        rnd = random.Random(rank)
+
+        from deeprank2_b200.fused import CapturedSelectionStep
+
+        replay = CapturedSelectionStep(fused, gset, GRAPHS_PER_BATCH, global_size=global_graphs)
+
+        import numpy as np
+
+        np_rng = np.random.default_rng(rank)
+
+        def epochs():  # a loader's shuffle: one permutation of the set per epoch, consecutive slices of 256 ids
+            while True:
+                perm = np_rng.permutation(n_set)
+                for s0 in range(0, n_set - GRAPHS_PER_BATCH + 1, GRAPHS_PER_BATCH):
+                    yield perm[s0 : s0 + GRAPHS_PER_BATCH]
+
+        id_batches = epochs()
 
         def resident_pass(n_steps):
             last = None
-            prepared = gset.select(rnd.sample(range(n_set), GRAPHS_PER_BATCH))
             for _ in range(n_steps):
-                loss, _, _ = fused.step_selection(gset, prepared=prepared, global_size=global_graphs)
-                prepared = gset.select(rnd.sample(range(n_set), GRAPHS_PER_BATCH))  # next step's ids, chosen while this one runs
+                loss, _, _ = replay(next(id_batches))
                 last = loss.item()
             return last
 
@@ -372,7 +383,7 @@ def run_ours(args):
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         e2e_resident = {"value": GRAPHS_PER_BATCH * e2e_steps * world / float(tr.item()), "unit": "graphs/s", "h2d_bytes_per_step": 4 * GRAPHS_PER_BATCH,
                         "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                        "mode": f"{n_set} graphs per rank collated once and resident in HBM; every step draws 256 random graph ids on the host (LPT-ordered), uploads the ids, runs the two-launch step in place, loss.item()"}
+                        "mode": f"{n_set} graphs per rank collated once and resident in HBM; every step takes the next 256 ids of the epoch's permutation (LPT-ordered on the host), uploads the ids, replays the captured two-launch step in place, loss.item()"}
         del gset
     _trace("e2e done")
     # ---- roofline of the dominant kernel, timed per launch with CUDA events on this stream, L2 flushed before every launch

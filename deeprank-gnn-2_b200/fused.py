@@ -465,3 +465,84 @@ class ResidentGraphSet:
         sel.num_graphs = len(slot_ids)
         sel.by_slot = True
         return sel, slot_ids.tolist()
+
+
+class CapturedSelectionStep:
+    """The two-launch train step on a :class:`ResidentGraphSet`, captured ONCE into a CUDA graph for a fixed batch size: a step is
+    then "write the graph ids into a static device buffer, replay".  The host's share of a step drops to the LPT ordering of the ids
+    (numpy) and one small copy; everything else -- index build, forward, loss, backward, gradient exchange, Adam -- replays.
+
+    Capturing does not disturb training: parameters and optimizer state are restored after the warm-up run."""
+
+    def __init__(self, step: "GINetFusedStep", graph_set: "ResidentGraphSet", batch_size: int, global_size: int | None = None):
+        import numpy as np
+
+        if batch_size < 1 or batch_size > 4096:
+            raise ValueError("batch_size must be in [1, 4096]")
+        self.step, self.graph_set, self.batch_size, self.global_size = step, graph_set, int(batch_size), global_size
+        dev = graph_set.batch.x.device
+        self.ids_dev = torch.zeros(self.batch_size, dtype=torch.int32, device=dev)
+        base = graph_set.info
+        sel = BlockInfo()
+        sel.node_ptr, sel.edge_ptr, sel.edges, sel.layout = base.node_ptr, base.edge_ptr, base.edges, base.layout
+        sel.max_nodes, sel.max_edges, sel.status = base.max_nodes, base.max_edges, base.status
+        sel.order, sel.num_graphs, sel.by_slot = self.ids_dev, self.batch_size, True
+        self.selection = sel
+        self._ring = [[torch.empty(self.batch_size, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
+        self._pos = 0
+        self._np = np
+        # warm-up + capture on a side stream, then put parameters and optimizer state back
+        params = [p.detach().clone() for p in step.params]
+        opt_state = {k: {n: (v.clone() if isinstance(v, torch.Tensor) else v) for n, v in st.items()} for k, st in step.optimizer.state.items()}
+        state = step.state.clone()
+        self._write_ids(np.arange(self.batch_size) % graph_set.num_graphs)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.pred = self._run()
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for p, saved in zip(step.params, params):
+                p.copy_(saved)
+            for k, st in step.optimizer.state.items():
+                for n, v in st.items():
+                    if isinstance(v, torch.Tensor) and k in opt_state and n in opt_state[k]:
+                        v.copy_(opt_state[k][n])
+            step.state.copy_(state)
+
+    def _run(self):
+        st = self.step
+        st._refresh_adam()
+        if st._adam is not None:
+            return st.forward_backward(self.graph_set.batch, self.global_size, adam=st._adam, selection=self.selection)
+        out = st.forward_backward(self.graph_set.batch, self.global_size, selection=self.selection)
+        st.optimizer.step()
+        return out
+
+    def _write_ids(self, slot_ids):
+        slot = self._ring[self._pos % len(self._ring)]
+        self._pos += 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0].numpy()[:] = slot_ids
+        self.ids_dev.copy_(slot[0], non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(self.ids_dev.device))
+
+    def __call__(self, ids):
+        """One train step on exactly ``batch_size`` graph ids.  Returns (loss, pred, slot_ids) -- views of static buffers, valid until
+        the next call."""
+        from .data import snake_order
+
+        np = self._np
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size != self.batch_size:
+            raise ValueError(f"this step was captured for {self.batch_size} graphs, got {ids.size}")
+        slot_ids = ids[snake_order(self.graph_set.work_np[ids]).numpy()]
+        self._write_ids(slot_ids)
+        self.graph.replay()
+        return self.loss, self.pred, slot_ids

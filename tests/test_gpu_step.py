@@ -469,3 +469,27 @@ def test_resident_graph_set_selection_matches_collated_batch():
     for _ in range(5):
         l1, _, _ = step.step_selection(rset, ids)
     assert float(l1) < l0
+
+
+def test_captured_selection_step_equals_eager_selection_steps():
+    """The CUDA-graph replay of the step on a resident graph set: same loss sequence and weights as the eager id-list steps, and the
+    capture itself leaves parameters and optimizer state untouched."""
+    from deeprank2_b200.fused import CapturedSelectionStep, GINetFusedStep, ResidentGraphSet
+    from deeprank2_b200.synthetic import make_graph
+
+    rset = ResidentGraphSet([make_graph(g) for g in range(200, 248)], DEV)
+    batches = [list(range(0, 16)), list(range(16, 32)), [47, 3, 9, 21, 33, 40, 41, 42, 5, 6, 7, 8, 30, 31, 32, 2], list(range(32, 48))]
+    outs = []
+    for captured in (False, True):
+        net = _net(50, 1, 1, seed=13).eval()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        step = GINetFusedStep(net, opt, torch.nn.MSELoss())
+        before = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+        run = CapturedSelectionStep(step, rset, 16) if captured else (lambda ids: step.step_selection(rset, ids))
+        if captured:
+            assert torch.equal(before, torch.cat([p.detach().reshape(-1) for p in net.parameters()])), "capture must not train"
+            assert all(float(opt.state[p]["step"]) == 0.0 for p in net.parameters())
+        losses = [float(run(ids)[0]) for ids in batches]
+        outs.append((losses, torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()))
+    assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6)
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-7
