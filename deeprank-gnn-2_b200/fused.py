@@ -512,7 +512,7 @@ class CapturedSelectionStep:
                 for n, v in st.items():
                     if isinstance(v, torch.Tensor) and k in opt_state and n in opt_state[k]:
                         v.copy_(opt_state[k][n])
-            step.state.copy_(state)
+            step.state[0:1].copy_(state[0:1])  # the dropout step counter; the exchange epoch ([2]) must keep counting: the peers' flags did
 
     def _run(self):
         st = self.step
