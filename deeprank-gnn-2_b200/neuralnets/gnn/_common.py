@@ -26,12 +26,20 @@ class GINetConvLayer(nn.Module):
     ``attention="reference"`` reproduces the reference bit-for-bit in structure: its ``softmax(alpha,
     dim=1)`` runs over a singleton axis, so the layer is ``z = scatter_sum(fc(x[col]), row)`` and the
     two attention weights get exact-zero gradients.
+
+    ``attention="segment_softmax"`` (opt-in, not the reference's arithmetic) normalises the same logit over the edges of
+    each destination node -- the operator the layer's name and BASELINE.json's north_star describe
+    (``ops.GINetAttentionConvFunction``, ``csrc/drk_attention.cu``); all three weights then receive real gradients.
     """
+
+    ATTENTION_MODES = ("reference", "segment_softmax")
 
     def __init__(self, in_channels, out_channels, number_edge_features=1, bias=False, attention="reference"):
         super().__init__()
-        if attention != "reference":
-            raise NotImplementedError("only attention='reference' (the behaviour of the reference code) is implemented")
+        if attention not in self.ATTENTION_MODES:
+            raise ValueError(f"attention must be one of {self.ATTENTION_MODES}, got {attention!r}")
+        if attention == "segment_softmax" and bias:
+            raise NotImplementedError("attention='segment_softmax' is implemented for bias=False (the only setting the reference nets use)")
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.attention = attention
@@ -53,6 +61,10 @@ class GINetConvLayer(nn.Module):
             from ...graph import GraphIndex
 
             graph = GraphIndex.build(edge_index, x.shape[0])
+        if self.attention == "segment_softmax":
+            if edge_attr is None:
+                raise ValueError("attention='segment_softmax' needs edge_attr")
+            return ops.ginet_attention_conv(x, edge_attr, self.fc.weight, self.fc_edge_attr.weight, self.fc_attention.weight, graph, relu=relu)
         # biases of the attention branch (bias=True) are dead parameters as well: they get no grad, like
         # any parameter torch autograd sees only through a softmax over one element ... the reference
         # gives them zeros too, but bias=True is never used by the reference nets.

@@ -14,13 +14,16 @@ from ._common import GINetConvLayer, num_graphs_of  # noqa: F401
 
 
 class GINet(nn.Module):
-    def __init__(self, input_shape, output_shape=1, input_shape_edge=1):
+    def __init__(self, input_shape, output_shape=1, input_shape_edge=1, attention="reference"):
+        """``attention``: "reference" (the reference's arithmetic: every coefficient is 1) or "segment_softmax" (opt-in:
+        the logit normalised over each destination's edges, see ``_common.GINetConvLayer``)."""
         super().__init__()
-        self.conv1 = GINetConvLayer(input_shape, 16, input_shape_edge)
-        self.conv2 = GINetConvLayer(16, 32, input_shape_edge)
+        self.attention = attention
+        self.conv1 = GINetConvLayer(input_shape, 16, input_shape_edge, attention=attention)
+        self.conv2 = GINetConvLayer(16, 32, input_shape_edge, attention=attention)
 
-        self.conv1_ext = GINetConvLayer(input_shape, 16, input_shape_edge)
-        self.conv2_ext = GINetConvLayer(16, 32, input_shape_edge)
+        self.conv1_ext = GINetConvLayer(input_shape, 16, input_shape_edge, attention=attention)
+        self.conv2_ext = GINetConvLayer(16, 32, input_shape_edge, attention=attention)
 
         self.fc1 = nn.Linear(2 * 32, 128)
         self.fc2 = nn.Linear(128, output_shape)

@@ -20,13 +20,16 @@ class GINet(nn.Module):
     graph, per-graph mean readout, ``fc1`` 64->128, ReLU, dropout 0.4, ``fc2`` 128->out
     (``ginet_nocluster.py:72-111``)."""
 
-    def __init__(self, input_shape, output_shape=1, input_shape_edge=1):
+    def __init__(self, input_shape, output_shape=1, input_shape_edge=1, attention="reference"):
+        """``attention``: "reference" (the reference's arithmetic: every coefficient is 1) or "segment_softmax" (opt-in:
+        the logit normalised over each destination's edges, see ``_common.GINetConvLayer``)."""
         super().__init__()
-        self.conv1 = GINetConvLayer(input_shape, 16, input_shape_edge)
-        self.conv2 = GINetConvLayer(16, 32, input_shape_edge)
+        self.attention = attention
+        self.conv1 = GINetConvLayer(input_shape, 16, input_shape_edge, attention=attention)
+        self.conv2 = GINetConvLayer(16, 32, input_shape_edge, attention=attention)
 
-        self.conv1_ext = GINetConvLayer(input_shape, 16, input_shape_edge)
-        self.conv2_ext = GINetConvLayer(16, 32, input_shape_edge)
+        self.conv1_ext = GINetConvLayer(input_shape, 16, input_shape_edge, attention=attention)
+        self.conv2_ext = GINetConvLayer(16, 32, input_shape_edge, attention=attention)
 
         self.fc1 = nn.Linear(2 * 32, 128)
         self.fc2 = nn.Linear(128, output_shape)
@@ -38,7 +41,7 @@ class GINet(nn.Module):
         for the reference architecture; a user-modified net falls back to layer-by-layer)."""
         convs = (self.conv1, self.conv1_ext, self.conv2, self.conv2_ext)
         return (
-            all(c.fc.bias is None for c in convs)
+            all(c.fc.bias is None and c.attention == "reference" for c in convs)
             and self.conv1.fc.weight.shape == self.conv1_ext.fc.weight.shape
             and self.conv2.fc.weight.shape == self.conv2_ext.fc.weight.shape
             and self.conv2.fc.weight.shape[1] == self.conv1.fc.weight.shape[0]

@@ -219,6 +219,104 @@ def ginet_conv(x, weight, graph, bias=None, relu=False, dead_params=(None, None)
     return GINetConvFunction.apply(x, weight, bias, dead_params[0], dead_params[1], graph, relu)
 
 
+LEAKY_SLOPE = 0.01  # torch.nn.functional.leaky_relu default, ginet.py:52
+
+
+class GINetAttentionConvFunction(torch.autograd.Function):
+    """``GINetConvLayer`` with the attention normalised per destination node (``attention="segment_softmax"``).
+
+    The logit is the reference's (``ginet.py:45-52``): ``q_e = fc_attention([fc(x)[row_e], fc(x)[col_e], fc_edge_attr(edge_attr_e)])``,
+    ``leaky_relu``; the softmax then runs over the edges that share ``row_e`` instead of the reference's singleton axis
+    (``ginet.py:54``), and ``z[i] = sum_e alpha_e fc(x)[col_e]``.  With ``fc_attention.weight = [a_r | a_c | a_e]`` the logit
+    splits into two per-node scalars ``s = P [a_r a_c]^T`` and ``u . edge_attr_e`` with ``u = We^T a_e``, so nothing of size
+    ``[E, F]`` is formed.  Oracle: ``oracle/restate.py:ginet_conv_segment_softmax`` (+ torch autograd).
+    """
+
+    @staticmethod
+    def forward(ctx, x, edge_attr, weight, w_edge, w_att, graph: GraphIndex, relu: bool):
+        lib = _lib.load()
+        x = _f32_cuda(x, "x")
+        fo = weight.shape[0]
+        if edge_attr.dim() == 1:
+            edge_attr = edge_attr.unsqueeze(-1)  # ginet.py:43
+        edge_attr = _f32_cuda(edge_attr, "edge_attr")
+        fe = edge_attr.shape[1]
+        n, e = x.shape[0], graph.num_edges
+        if edge_attr.shape[0] != e:
+            raise ValueError(f"edge_attr has {edge_attr.shape[0]} rows for {e} edges")
+        if tuple(w_att.shape) != (1, 2 * fo + fe) or tuple(w_edge.shape) != (fe, fe):
+            raise ValueError(f"attention weights {tuple(w_att.shape)} / {tuple(w_edge.shape)} do not match {fo} channels and {fe} edge features")
+        if not lib.drk_attn_supported(fo, fe):
+            raise NotImplementedError(f"segment-softmax attention needs out_channels % 4 == 0, <= 128 and <= 32 edge features (got {fo}, {fe})")
+        ctx.graph, ctx.relu, ctx.no_edges = graph, relu, e == 0
+        if e == 0:  # scatter into zeros with nothing to scatter (ginet.py:57-58)
+            ctx.save_for_backward(x, edge_attr, weight, w_edge, w_att)
+            return torch.zeros((n, fo), dtype=torch.float32, device=x.device)
+        p = node_linear(x, weight, True)
+        att = w_att[0, : 2 * fo].reshape(2, fo).contiguous()
+        s = node_linear(p, att, True)  # [n, 2]: a_r.P[i], a_c.P[i]
+        a_e = w_att[0, 2 * fo :]
+        u = (a_e @ w_edge).contiguous()  # u[l] = sum_k a_e[k] We[k,l]
+        z = torch.empty((n, fo), dtype=torch.float32, device=x.device)
+        alpha = torch.empty(e, dtype=torch.float32, device=x.device)
+        salpha = torch.empty(e, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.drk_attn_fwd(_p(graph.rowptr), _p(graph.colidx), _p(graph.perm), _p(p), _ld(p), _p(s), _p(edge_attr), _ld(edge_attr), fe,
+                                  _p(u), LEAKY_SLOPE, _p(z), _ld(z), _p(alpha), _p(salpha), n, fo, ACT_RELU if relu else ACT_NONE, stream_ptr())
+        _lib.check(rc, "drk_attn_fwd")
+        ctx.save_for_backward(x, edge_attr, weight, w_edge, w_att, p, z, alpha, salpha)
+        return z
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        if ctx.no_edges:
+            x, edge_attr, weight, w_edge, w_att = ctx.saved_tensors
+            grads = [torch.zeros_like(t) if need else None for t, need in zip((x, edge_attr, weight, w_edge, w_att), ctx.needs_input_grad[:5])]
+            grads[1] = None
+            return (*grads, None, None)
+        x, edge_attr, weight, w_edge, w_att, p, z, alpha, salpha = ctx.saved_tensors
+        g = ctx.graph
+        if g.colptr is None:
+            raise RuntimeError("backward needs the CSC half of the graph index (build it with with_csc=True)")
+        dy = _f32_cuda(dy, "grad_output")
+        n, fo = z.shape
+        fe = edge_attr.shape[1]
+        e = g.num_edges
+        dev = x.device
+        dq = torch.empty(e, dtype=torch.float32, device=dev)
+        ds = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        dz = torch.empty_like(z) if ctx.relu else None
+        dp = torch.empty_like(p)
+        att = w_att[0, : 2 * fo].contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.drk_attn_bwd_dst(_p(g.rowptr), _p(g.colidx), _p(g.perm), _p(p), _ld(p), _p(dy), _ld(dy), _p(z), _ld(z), _p(salpha), _p(dq), _p(ds),
+                                      _p(dz), _ld(dz) if dz is not None else 0, n, fo, ACT_RELU if ctx.relu else ACT_NONE, stream_ptr())
+            _lib.check(rc, "drk_attn_bwd_dst")
+            grad_rows = dz if ctx.relu else dy
+            rc = lib.drk_attn_bwd_src(_p(g.colptr), _p(g.rowidx), _p(g.permT), _p(grad_rows), _ld(grad_rows), _p(alpha), _p(dq), _p(ds), _p(att),
+                                      _p(dp), _ld(dp), n, fo, stream_ptr())
+            _lib.check(rc, "drk_attn_bwd_src")
+        dx = dw = dwe = dwa = None
+        if ctx.needs_input_grad[2]:
+            dw = weight_grad(dp, x)
+        if ctx.needs_input_grad[0]:
+            dx = node_linear(dp, weight, False)
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            a_e = w_att[0, 2 * fo :]
+            gsum = weight_grad(dq.unsqueeze(1), edge_attr).reshape(fe) if fe > 0 else dq.new_zeros(0)  # sum_e dq_e attr_e, fixed order
+            if ctx.needs_input_grad[3]:
+                dwe = torch.outer(a_e, gsum)  # q_e = a_e^T We attr_e
+            if ctx.needs_input_grad[4]:
+                d_rc = weight_grad(ds, p).reshape(1, 2 * fo)  # d[a_r | a_c] = ds^T P
+                dwa = torch.cat([d_rc, (w_edge @ gsum).reshape(1, fe)], dim=1)
+        return dx, None, dw, dwe, dwa, None, None
+
+
+def ginet_attention_conv(x, edge_attr, weight, w_edge, w_att, graph, relu=False):
+    return GINetAttentionConvFunction.apply(x, edge_attr, weight, w_edge, w_att, graph, relu)
+
+
 class MeanReadoutFunction(torch.autograd.Function):
     """``scatter_mean(x, batch, dim=0)`` over the sorted batch vector (``ginet_nocluster.py:103``)."""
 

@@ -304,6 +304,34 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
                    float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
                    const DrkAdam* adam, const DrkPeers* peers, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ GINet attention with a segment softmax per destination
+ * The operator the reference's GINetConvLayer sets up (ginet.py:45-52: logit = leaky_relu(fc_attention([fc(x)[row], fc(x)[col],
+ * fc_edge_attr(edge_attr)]))) normalised over the edges of each destination node -- BASELINE.json north_star, SURVEY 8f rank 4.
+ * The reference itself normalises over a singleton axis (softmax(alpha, dim=1), ginet.py:54 => alpha == 1), which is what
+ * drk_spmm / drk_ginet_step implement; this is the opt-in `attention="segment_softmax"` mode of the layer.
+ *   p [n,width] = fc(x);  s [n,2] = (a_r.p[i], a_c.p[i]) with fc_attention.weight = [a_r | a_c | a_e];  u [fe] = We^T a_e;
+ *   edge_attr [E,fe] in edge-id order;  rowptr/colidx/perm = CSR of drk_graph_index_build (perm = edge id of a slot).
+ *   z[i,:] = act( sum_{e in seg i} alpha_e p[col_e,:] ),  alpha = softmax_seg(leaky_relu(s_r[i] + s_c[col_e] + u.attr_e, slope))
+ *   alpha [E], salpha [E] (= alpha * leaky_relu'(q)) are stored by edge id for the backward.
+ * One sub-warp per destination, edges in CSR order, no atomics.  width % 4 == 0, width <= 128, fe <= 32. */
+DRK_API int drk_attn_supported(int32_t width, int32_t fe);
+DRK_API int drk_attn_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
+                 const float* p, int64_t ldp, const float* s, const float* edge_attr, int64_t ld_attr, int32_t fe,
+                 const float* u, float slope, float* z, int64_t ldz, float* alpha, float* salpha,
+                 int32_t n, int32_t width, int32_t act, void* stream);
+/* Backward, destinations (CSR): dz = dy [* (y > 0) if act == RELU, written to `dz`]; dq[e] = salpha_e (dz[row_e].p[col_e] - dz[i].y[i])
+ * by edge id (the gradient of the logit before the leaky ReLU); ds[i,0] = sum_{e in seg i} dq_e. */
+DRK_API int drk_attn_bwd_dst(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
+                     const float* p, int64_t ldp, const float* dy, int64_t ld_dy, const float* y, int64_t ld_y,
+                     const float* salpha, float* dq, float* ds, float* dz, int64_t ld_dz,
+                     int32_t n, int32_t width, int32_t act, void* stream);
+/* Backward, sources (CSC): ds[j,1] = sum_{e: col_e = j} dq_e;  dp[j,:] = sum_{e: col_e = j} alpha_e dz[row_e,:] + ds[j,0] a_r + ds[j,1] a_c
+ * (att = [a_r | a_c], 2*width floats).  The remaining gradients are dense contractions of these outputs:
+ * d fc.weight = dp^T x (drk_weight_grad), d[a_r|a_c] = ds^T p, sum_e dq_e attr_e -> d a_e and d fc_edge_attr.weight. */
+DRK_API int drk_attn_bwd_src(const int32_t* colptr, const int32_t* rowidx, const int32_t* permT,
+                     const float* dz, int64_t ld_dz, const float* alpha, const float* dq, float* ds, const float* att,
+                     float* dp, int64_t ld_dp, int32_t n, int32_t width, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,14 +189,17 @@ def _ginet_head(g, p, training, dropout_p, keep=None):
     return F.linear(g, p["fc2.weight"], p["fc2.bias"])
 
 
-def ginet_nocluster_forward(p, data, training=False, dropout_p=0.4, keep=None):
+def ginet_nocluster_forward(p, data, training=False, dropout_p=0.4, keep=None, conv=None):
     """``ginet_nocluster.GINet.forward`` (``ginet_nocluster.py:84-111``): two branches of
-    conv(50->16) -> ReLU -> conv(16->32) -> ReLU on the same graph, per-graph mean, MLP head."""
+    conv(50->16) -> ReLU -> conv(16->32) -> ReLU on the same graph, per-graph mean, MLP head.
+    ``conv``: the convolution restatement to use (default ``ginet_conv``, the reference's; ``ginet_conv_segment_softmax`` for the
+    opt-in attention mode)."""
+    conv = conv or ginet_conv
     x, ei, ea = data.x, data.edge_index, data.edge_attr
-    a = F.relu(ginet_conv(x, ei, ea, p, "conv1."))
-    a = F.relu(ginet_conv(a, ei, ea, p, "conv2."))
-    b = F.relu(ginet_conv(x, ei, ea, p, "conv1_ext."))
-    b = F.relu(ginet_conv(b, ei, ea, p, "conv2_ext."))
+    a = F.relu(conv(x, ei, ea, p, "conv1."))
+    a = F.relu(conv(a, ei, ea, p, "conv2."))
+    b = F.relu(conv(x, ei, ea, p, "conv1_ext."))
+    b = F.relu(conv(b, ei, ea, p, "conv2_ext."))
     g = torch.cat([mean_readout(a, data.batch), mean_readout(b, data.batch)], dim=1)
     return _ginet_head(g, p, training, dropout_p, keep)
 
@@ -240,22 +243,23 @@ def ginet_init(input_shape, output_shape=1, input_shape_edge=1, generator=None):
     return _ginet_init(input_shape, output_shape, input_shape_edge, generator)
 
 
-def _ginet_cluster_branch(p, names, data):
+def _ginet_cluster_branch(p, names, data, conv=None):
+    conv = conv or ginet_conv
     c1, c2 = names
     d = SimpleNamespace(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in vars(data).items()})
-    d.x = F.relu(ginet_conv(d.x, d.edge_index, d.edge_attr, p, c1))
+    d.x = F.relu(conv(d.x, d.edge_index, d.edge_attr, p, c1))
     d = community_pool(preloaded_cluster(d.cluster0, d.batch), d)
-    d.x = F.relu(ginet_conv(d.x, d.edge_index, d.edge_attr, p, c2))
+    d.x = F.relu(conv(d.x, d.edge_index, d.edge_attr, p, c2))
     x, batch = tp.max_pool_x(preloaded_cluster(d.cluster1, d.batch), d.x, d.batch)
     return tp.scatter_mean(x, batch, dim=0)
 
 
-def ginet_forward(p, data, training=False, dropout_p=0.4):
+def ginet_forward(p, data, training=False, dropout_p=0.4, conv=None):
     """clustered ``ginet.GINet.forward`` (``ginet.py:90-125``).  Both branches start from
     their own deep copy (``data.clone()`` at ``:92``), so the in-place cluster-offset edits of
-    one branch do not leak into the other."""
+    one branch do not leak into the other.  ``conv``: see ``ginet_nocluster_forward``."""
     ns = data if isinstance(data, SimpleNamespace) else SimpleNamespace(**{k: v for k, v in vars(data).items()})
-    g = torch.cat([_ginet_cluster_branch(p, ("conv1.", "conv2."), ns), _ginet_cluster_branch(p, ("conv1_ext.", "conv2_ext."), ns)], dim=1)
+    g = torch.cat([_ginet_cluster_branch(p, ("conv1.", "conv2."), ns, conv), _ginet_cluster_branch(p, ("conv1_ext.", "conv2_ext."), ns, conv)], dim=1)
     return _ginet_head(g, p, training, dropout_p)
 
 
