@@ -46,7 +46,7 @@ class GraphIndex:
     __slots__ = (
         "num_nodes", "num_edges", "num_graphs", "device",
         "rowptr", "colidx", "perm", "colptr", "rowidx", "permT",
-        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree",
+        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree", "_slot_map", "_attr_csr",
     )
 
     def __init__(self):
@@ -141,6 +141,30 @@ class GraphIndex:
         if self._degree is None:
             self._degree = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
         return self._degree
+
+    def slot_map(self) -> torch.Tensor:
+        """int32 [E]: CSR slot of the edge in every CSC slot (cached; ``drk_attn_slot_map``).  Per-edge state kept in CSR order by
+        the destination kernels is reached through it by the source kernels."""
+        if self._slot_map is None:
+            if self.colptr is None:
+                raise RuntimeError("the slot map needs the CSC half of the graph index (build it with with_csc=True)")
+            out = torch.empty(2 * max(self.num_edges, 1), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = _lib.load().drk_attn_slot_map(self.perm.data_ptr(), self.permT.data_ptr(), self.num_edges, out[self.num_edges :].data_ptr(),
+                                                   out.data_ptr(), stream_ptr())
+            _lib.check(rc, "drk_attn_slot_map")
+            self._slot_map = out[: self.num_edges]
+        return self._slot_map
+
+    def attr_in_slot_order(self, edge_attr: torch.Tensor) -> torch.Tensor:
+        """``edge_attr[perm]`` (float32 [E, Fe], rows in CSR-slot order), cached per edge_attr tensor: the four convolutions of a
+        GINet and their backward passes share one gather per batch."""
+        key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape))
+        if self._attr_csr is None or self._attr_csr[0] != key:
+            from . import ops
+
+            self._attr_csr = (key, ops.gather_rows(edge_attr, self.perm))
+        return self._attr_csr[1]
 
     # ------------------------------------------------------------------ validation (host sync: call it off the hot path)
     def check(self) -> None:

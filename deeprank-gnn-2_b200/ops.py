@@ -257,14 +257,15 @@ class GINetAttentionConvFunction(torch.autograd.Function):
         s = node_linear(p, att, True)  # [n, 2]: a_r.P[i], a_c.P[i]
         a_e = w_att[0, 2 * fo :]
         u = (a_e @ w_edge).contiguous()  # u[l] = sum_k a_e[k] We[k,l]
+        attr = graph.attr_in_slot_order(edge_attr)
         z = torch.empty((n, fo), dtype=torch.float32, device=x.device)
-        alpha = torch.empty(e, dtype=torch.float32, device=x.device)
-        salpha = torch.empty(e, dtype=torch.float32, device=x.device)
+        adq = torch.empty((e, 2), dtype=torch.float32, device=x.device)  # per CSR slot: (signed alpha, dq)
         with torch.cuda.device(x.device):
-            rc = lib.drk_attn_fwd(_p(graph.rowptr), _p(graph.colidx), _p(graph.perm), _p(p), _ld(p), _p(s), _p(edge_attr), _ld(edge_attr), fe,
-                                  _p(u), LEAKY_SLOPE, _p(z), _ld(z), _p(alpha), _p(salpha), n, fo, ACT_RELU if relu else ACT_NONE, stream_ptr())
+            scratch = workspace(4 * e, x.device)
+            rc = lib.drk_attn_fwd(_p(graph.rowptr), _p(graph.colidx), _p(p), _ld(p), _p(s), _p(attr), _ld(attr), fe, _p(u), LEAKY_SLOPE,
+                                  _p(z), _ld(z), _p(adq), _p(scratch), n, fo, ACT_RELU if relu else ACT_NONE, stream_ptr())
         _lib.check(rc, "drk_attn_fwd")
-        ctx.save_for_backward(x, edge_attr, weight, w_edge, w_att, p, z, alpha, salpha)
+        ctx.save_for_backward(x, attr, weight, w_edge, w_att, p, z, adq)
         return z
 
     @staticmethod
@@ -275,26 +276,26 @@ class GINetAttentionConvFunction(torch.autograd.Function):
             grads = [torch.zeros_like(t) if need else None for t, need in zip((x, edge_attr, weight, w_edge, w_att), ctx.needs_input_grad[:5])]
             grads[1] = None
             return (*grads, None, None)
-        x, edge_attr, weight, w_edge, w_att, p, z, alpha, salpha = ctx.saved_tensors
+        x, attr, weight, w_edge, w_att, p, z, adq = ctx.saved_tensors
         g = ctx.graph
         if g.colptr is None:
             raise RuntimeError("backward needs the CSC half of the graph index (build it with with_csc=True)")
         dy = _f32_cuda(dy, "grad_output")
         n, fo = z.shape
-        fe = edge_attr.shape[1]
+        fe = attr.shape[1]
         e = g.num_edges
         dev = x.device
-        dq = torch.empty(e, dtype=torch.float32, device=dev)
         ds = torch.empty((n, 2), dtype=torch.float32, device=dev)
         dz = torch.empty_like(z) if ctx.relu else None
         dp = torch.empty_like(p)
         att = w_att[0, : 2 * fo].contiguous()
+        slot_map = g.slot_map()
         with torch.cuda.device(dev):
-            rc = lib.drk_attn_bwd_dst(_p(g.rowptr), _p(g.colidx), _p(g.perm), _p(p), _ld(p), _p(dy), _ld(dy), _p(z), _ld(z), _p(salpha), _p(dq), _p(ds),
+            rc = lib.drk_attn_bwd_dst(_p(g.rowptr), _p(g.colidx), _p(p), _ld(p), _p(dy), _ld(dy), _p(z), _ld(z), _p(adq), LEAKY_SLOPE, _p(ds),
                                       _p(dz), _ld(dz) if dz is not None else 0, n, fo, ACT_RELU if ctx.relu else ACT_NONE, stream_ptr())
             _lib.check(rc, "drk_attn_bwd_dst")
             grad_rows = dz if ctx.relu else dy
-            rc = lib.drk_attn_bwd_src(_p(g.colptr), _p(g.rowidx), _p(g.permT), _p(grad_rows), _ld(grad_rows), _p(alpha), _p(dq), _p(ds), _p(att),
+            rc = lib.drk_attn_bwd_src(_p(g.colptr), _p(g.rowidx), _p(slot_map), _p(grad_rows), _ld(grad_rows), _p(adq), _p(ds), _p(att),
                                       _p(dp), _ld(dp), n, fo, stream_ptr())
             _lib.check(rc, "drk_attn_bwd_src")
         dx = dw = dwe = dwa = None
@@ -304,7 +305,12 @@ class GINetAttentionConvFunction(torch.autograd.Function):
             dx = node_linear(dp, weight, False)
         if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
             a_e = w_att[0, 2 * fo :]
-            gsum = weight_grad(dq.unsqueeze(1), edge_attr).reshape(fe) if fe > 0 else dq.new_zeros(0)  # sum_e dq_e attr_e, fixed order
+            gsum = torch.empty(fe, dtype=torch.float32, device=dev)  # sum_e dq_e attr_e, fixed order
+            with torch.cuda.device(dev):
+                ws_bytes = lib.drk_attn_edge_grad_workspace_bytes(fe)
+                ws = workspace(ws_bytes, dev)
+                rc = lib.drk_attn_edge_grad(_p(adq), _p(attr), _ld(attr), e, fe, _p(gsum), _p(ws), ws.numel(), stream_ptr())
+            _lib.check(rc, "drk_attn_edge_grad")
             if ctx.needs_input_grad[3]:
                 dwe = torch.outer(a_e, gsum)  # q_e = a_e^T We attr_e
             if ctx.needs_input_grad[4]:

@@ -310,27 +310,34 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
  * The reference itself normalises over a singleton axis (softmax(alpha, dim=1), ginet.py:54 => alpha == 1), which is what
  * drk_spmm / drk_ginet_step implement; this is the opt-in `attention="segment_softmax"` mode of the layer.
  *   p [n,width] = fc(x);  s [n,2] = (a_r.p[i], a_c.p[i]) with fc_attention.weight = [a_r | a_c | a_e];  u [fe] = We^T a_e;
- *   edge_attr [E,fe] in edge-id order;  rowptr/colidx/perm = CSR of drk_graph_index_build (perm = edge id of a slot).
+ *   attr_csr [E,fe] = edge_attr in CSR-slot order (drk_gather_rows with perm, once per batch);  rowptr/colidx of drk_graph_index_build.
  *   z[i,:] = act( sum_{e in seg i} alpha_e p[col_e,:] ),  alpha = softmax_seg(leaky_relu(s_r[i] + s_c[col_e] + u.attr_e, slope))
- *   alpha [E], salpha [E] (= alpha * leaky_relu'(q)) are stored by edge id for the backward.
+ *   adq [E,2] (CSR-slot order): column 0 = alpha_e with the sign bit set where the logit is <= 0 (written by fwd), column 1 = the
+ *   gradient of the logit (written by bwd_dst);  logit_scratch [E] is scratch between the two sweeps of the forward kernel.
  * One sub-warp per destination, edges in CSR order, no atomics.  width % 4 == 0, width <= 128, fe <= 32. */
 DRK_API int drk_attn_supported(int32_t width, int32_t fe);
-DRK_API int drk_attn_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
-                 const float* p, int64_t ldp, const float* s, const float* edge_attr, int64_t ld_attr, int32_t fe,
-                 const float* u, float slope, float* z, int64_t ldz, float* alpha, float* salpha,
+DRK_API int drk_attn_fwd(const int32_t* rowptr, const int32_t* colidx,
+                 const float* p, int64_t ldp, const float* s, const float* attr_csr, int64_t ld_attr, int32_t fe,
+                 const float* u, float slope, float* z, int64_t ldz, float* adq, float* logit_scratch,
                  int32_t n, int32_t width, int32_t act, void* stream);
-/* Backward, destinations (CSR): dz = dy [* (y > 0) if act == RELU, written to `dz`]; dq[e] = salpha_e (dz[row_e].p[col_e] - dz[i].y[i])
- * by edge id (the gradient of the logit before the leaky ReLU); ds[i,0] = sum_{e in seg i} dq_e. */
-DRK_API int drk_attn_bwd_dst(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
+/* Backward, destinations (CSR): dz = dy [* (y > 0) if act == RELU, written to `dz`]; adq[s,1] = dq_e = alpha_e lrelu'(q_e) (dz[i].p[col_e] - dz[i].y[i])
+ * (the gradient of the logit before the leaky ReLU); ds[i,0] = sum_{e in seg i} dq_e. */
+DRK_API int drk_attn_bwd_dst(const int32_t* rowptr, const int32_t* colidx,
                      const float* p, int64_t ldp, const float* dy, int64_t ld_dy, const float* y, int64_t ld_y,
-                     const float* salpha, float* dq, float* ds, float* dz, int64_t ld_dz,
+                     float* adq, float slope, float* ds, float* dz, int64_t ld_dz,
                      int32_t n, int32_t width, int32_t act, void* stream);
+/* CSC slot -> CSR slot of the same edge (perm/permT of drk_graph_index_build; inverse_scratch int32 [E]); once per batch. */
+DRK_API int drk_attn_slot_map(const int32_t* perm, const int32_t* permT, int64_t num_edges, int32_t* inverse_scratch, int32_t* slot_map, void* stream);
 /* Backward, sources (CSC): ds[j,1] = sum_{e: col_e = j} dq_e;  dp[j,:] = sum_{e: col_e = j} alpha_e dz[row_e,:] + ds[j,0] a_r + ds[j,1] a_c
  * (att = [a_r | a_c], 2*width floats).  The remaining gradients are dense contractions of these outputs:
- * d fc.weight = dp^T x (drk_weight_grad), d[a_r|a_c] = ds^T p, sum_e dq_e attr_e -> d a_e and d fc_edge_attr.weight. */
-DRK_API int drk_attn_bwd_src(const int32_t* colptr, const int32_t* rowidx, const int32_t* permT,
-                     const float* dz, int64_t ld_dz, const float* alpha, const float* dq, float* ds, const float* att,
+ * d fc.weight = dp^T x (drk_weight_grad), d[a_r|a_c] = ds^T p, and g below -> d a_e = We g, d fc_edge_attr.weight = a_e (x) g. */
+DRK_API int drk_attn_bwd_src(const int32_t* colptr, const int32_t* rowidx, const int32_t* slot_map,
+                     const float* dz, int64_t ld_dz, const float* adq, float* ds, const float* att,
                      float* dp, int64_t ld_dp, int32_t n, int32_t width, void* stream);
+/* g[k] = sum_s adq[s,1] attr_csr[s,k]  (two-stage fixed-order reduction). */
+DRK_API size_t drk_attn_edge_grad_workspace_bytes(int32_t fe);
+DRK_API int drk_attn_edge_grad(const float* adq, const float* attr_csr, int64_t ld_attr, int64_t num_edges, int32_t fe,
+                       float* g, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
