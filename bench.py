@@ -443,7 +443,7 @@ def run_ours(args):
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "mode": "eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as int64 pairs -- the kernel rebuilds the reference's doubled edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
+                    "mode": "eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as one packed word of graph-local ids, 4 bytes -- the kernel rebuilds the reference's doubled int64 edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
             "e2e_resident": e2e_resident,
             "e2e_trainer": e2e_trainer,
             "gpu_launches": int(launches_per_step * args.steps),

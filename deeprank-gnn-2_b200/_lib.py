@@ -24,7 +24,7 @@ STATUS_UNSORTED = 4
 ACT_NONE, ACT_RELU = 0, 1
 REDUCE_SUM, REDUCE_MEAN_CLAMP, REDUCE_MEAN_NAN = 0, 1, 2
 LOSS_MSE, LOSS_CROSS_ENTROPY = 0, 1
-EDGES_DIRECTED, EDGES_UNDIRECTED_PAIRS = 0, 1
+EDGES_DIRECTED, EDGES_UNDIRECTED_PAIRS, EDGES_LOCAL_PAIRS16 = 0, 1, 2
 
 _P = c_void_p
 _I32 = c_int32

@@ -87,7 +87,7 @@ struct StepArgs {
   uint16_t* csc_spill; int32_t* status;
   int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;  // *_off: index-build scratch (bytes into shared memory)
   int32_t slot_outputs;  // results indexed by slot instead of graph id (graph selections out of a resident set)
-  int32_t pairs;  // edge slices hold undirected pairs (edge_ptr counts pairs); each stands for both directions
+  int32_t pairs;  // edge layout (DRK_EDGES_*); != 0: the slices hold undirected pairs (edge_ptr counts pairs), each stands for both directions
 };
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -208,7 +208,8 @@ constexpr int kDegBins = 64;
 // returns the number of CSC entries (padded), or -1 when no source-sorted index was built (forward only, or symmetric adjacency)
 template <bool WANT_CSC>
 __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
-                                        int node0, int n, int32_t* status, bool pairs) {
+                                        int node0, int n, int32_t* status, int layout) {
+  const bool pairs = layout != DRK_EDGES_DIRECTED;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = lanemask_lt();
   uint32_t* stash = sm<uint32_t>(pl.stash);
@@ -247,14 +248,26 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     long long rr[8], cc[8];
     // undirected-pairs layout: the slice holds P = ne/2 pairs; directed edge d < P is pair d, d >= P is pair d - P flipped
     const int half = pairs ? ne >> 1 : ne;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = wb + u * 32 + lane;
+    // packed layout: one 32-bit word per pair, (i | j << 16) with ids local to the graph
+    const int32_t* words = reinterpret_cast<const int32_t*>(erow);
+    auto load_edge = [&](int i, long long& r, long long& c) {
+      r = 0;
+      c = 0;
+      if (i >= we) return;
       const bool flip = i >= half;
       const int src = flip ? i - half : i;
-      rr[u] = i < we ? ld_stream_i64((flip ? ecol : erow) + e0 + src) : 0;
-      cc[u] = i < we ? ld_stream_i64((flip ? erow : ecol) + e0 + src) : 0;
-    }
+      if (layout == DRK_EDGES_LOCAL_PAIRS16) {
+        const unsigned w = (unsigned)ld_stream_i32(words + e0 + src);
+        const unsigned lo = w & 0xffffu, hi = w >> 16;
+        r = node0 + (long long)(flip ? hi : lo);
+        c = node0 + (long long)(flip ? lo : hi);
+      } else {
+        r = ld_stream_i64((flip ? ecol : erow) + e0 + src);
+        c = ld_stream_i64((flip ? erow : ecol) + e0 + src);
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < 8; ++u) load_edge(wb + u * 32 + lane, rr[u], cc[u]);
     for (int i0 = wb; i0 < we; i0 += 256) {
       unsigned pk[8];
 #pragma unroll
@@ -267,13 +280,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
         if (i < we) stash[i] = pk[u];
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {  // next group's loads (predicated off past the end of the chunk)
-        const int i = i0 + 256 + u * 32 + lane;
-        const bool flip = i >= half;
-        const int src = flip ? i - half : i;
-        rr[u] = i < we ? ld_stream_i64((flip ? ecol : erow) + e0 + src) : 0;
-        cc[u] = i < we ? ld_stream_i64((flip ? erow : ecol) + e0 + src) : 0;
-      }
+      for (int u = 0; u < 8; ++u) load_edge(i0 + 256 + u * 32 + lane, rr[u], cc[u]);  // next group's loads (predicated off past the end of the chunk)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * 32 + lane;
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       continue;
     }
     // ---- the graph index, then x rows (the index build uses the x region as scratch)
-    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs != 0);
+    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs);
     stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
     const bool have_csc = TRAIN && csc_entries >= 0;  // false: symmetric adjacency, the backward pass gathers through the CSR
@@ -867,8 +874,12 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     if (have_next) {  // warm L2 with the next graph's edge slice and node rows while this one is being processed
       const int node0n = s_meta[buf ^ 1][1], e0n = s_meta[buf ^ 1][3];
       const long long nn = s_meta[buf ^ 1][2], nen = s_meta[buf ^ 1][4];
-      prefetch_range_l2(a.erow + e0n, nen * 8);
-      prefetch_range_l2(a.ecol + e0n, nen * 8);
+      if (a.pairs == DRK_EDGES_LOCAL_PAIRS16) {
+        prefetch_range_l2(reinterpret_cast<const int32_t*>(a.erow) + e0n, nen * 4);
+      } else {
+        prefetch_range_l2(a.erow + e0n, nen * 8);
+        prefetch_range_l2(a.ecol + e0n, nen * 8);
+      }
       prefetch_range_l2(a.x + (long long)node0n * a.ldx, nn * a.ldx * 4);
     }
     // ---- H1 = relu(A P) -> tile 1 ; A2 = A H1 -> tile 0
@@ -1459,7 +1470,8 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   using namespace drk::gs;
   DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0, DRK_EINVAL, "ginet step: negative size");
   DRK_REQUIRE(out_dim >= 1 && out_dim <= kMaxOut, DRK_EUNSUPPORTED, "ginet step: 1 <= output_shape <= %d supported, got %d", kMaxOut, out_dim);
-  DRK_REQUIRE(edge_layout == DRK_EDGES_DIRECTED || edge_layout == DRK_EDGES_UNDIRECTED_PAIRS, DRK_EINVAL, "ginet step: unknown edge layout %d", edge_layout);
+  DRK_REQUIRE(edge_layout == DRK_EDGES_DIRECTED || edge_layout == DRK_EDGES_UNDIRECTED_PAIRS || edge_layout == DRK_EDGES_LOCAL_PAIRS16, DRK_EINVAL,
+              "ginet step: unknown edge layout %d", edge_layout);
   PlanResult p;
   DRK_REQUIRE(make_plan(fi, max_graph_nodes, max_graph_edges, p), DRK_EUNSUPPORTED,
               "ginet step: graphs of %d nodes / %d edges with %d features do not fit the shared-memory plan", max_graph_nodes, max_graph_edges, fi);
@@ -1480,7 +1492,7 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   StepArgs a{};
   a.x = x; a.ldx = ldx; a.fi = fi;
   a.erow = edge_index; a.ecol = edge_index + num_edges;
-  a.pairs = edge_layout == DRK_EDGES_UNDIRECTED_PAIRS ? 1 : 0;
+  a.pairs = edge_layout;
   a.graph_ptr = graph_ptr; a.edge_ptr = edge_ptr; a.order = order; a.num_graphs = num_graphs;
   a.slot_outputs = (outputs_by_slot && order != nullptr) ? 1 : 0;
   a.w1a = w1a; a.w1b = w1b; a.w2a = w2a; a.w2b = w2b;

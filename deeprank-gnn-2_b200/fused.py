@@ -33,7 +33,8 @@ def _p(t):
 class BlockInfo:
     """Per-graph offsets of a collated batch on the device: ``node_ptr``/``edge_ptr`` int32 [B+1], issue ``order`` int32 [B]
     (or None), the largest graph's node / (directed) edge count, the batch's status word, and the edge tensor the kernels read:
-    ``edges`` int64 [2, M] with ``layout`` EDGES_DIRECTED (= ``edge_index``) or EDGES_UNDIRECTED_PAIRS (each contact once)."""
+    ``edges`` int64 [2, M] with ``layout`` EDGES_DIRECTED (= ``edge_index``) or EDGES_UNDIRECTED_PAIRS (each contact once), or int32 [M]
+    with EDGES_LOCAL_PAIRS16 (each contact once as one packed word of graph-local ids)."""
 
     __slots__ = ("node_ptr", "edge_ptr", "order", "num_graphs", "max_nodes", "max_edges", "status", "edges", "layout", "by_slot")
 
@@ -47,17 +48,21 @@ def block_info(data) -> BlockInfo:
     ``drk_edge_ptr``) with one host read-back of the largest graph size, remembered on the batch."""
     lib = _lib.load()
     d = data.__dict__
-    pairs, pair_ptr = d.get("_pairs"), d.get("_pair_ptr32")
+    pairs, pair_ptr = d.get("_pairs16"), d.get("_pair_ptr32")
+    packed = pairs is not None and pairs.is_cuda
+    if not packed:
+        pairs = d.get("_pairs")
     node_ptr, edge_ptr = d.get("_node_ptr32"), d.get("_edge_ptr32")
     meta = d.get(data._META_KEY, {}) if hasattr(data, "_META_KEY") else {}
     use_pairs = (
         pairs is not None and pair_ptr is not None and node_ptr is not None and pairs.is_cuda and pair_ptr.is_cuda and node_ptr.is_cuda
-        and meta.get("num_edges_total") == 2 * int(pairs.shape[1]) and meta.get("max_graph_nodes") is not None
+        and meta.get("num_edges_total") == 2 * int(pairs.shape[-1]) and meta.get("max_graph_nodes") is not None
     )
+    packed = packed and use_pairs
     ei = pairs if use_pairs else data.edge_index  # (a lazily transferred edge_index is only touched when it is needed)
     if not ei.is_cuda:
         raise RuntimeError(f"the batch must live on a CUDA device: deeprank2_b200 has no CPU path (got {ei.device})")
-    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device), use_pairs)
+    key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device), use_pairs, packed)
     cached = d.get("_block_info")
     if cached is not None and cached[0] == key:
         return cached[1]
@@ -65,10 +70,10 @@ def block_info(data) -> BlockInfo:
     info.by_slot = False
     dev = ei.device
     info.edges = ei if ei.is_contiguous() else ei.contiguous()
-    info.layout = _lib.EDGES_UNDIRECTED_PAIRS if use_pairs else _lib.EDGES_DIRECTED
+    info.layout = (_lib.EDGES_LOCAL_PAIRS16 if packed else _lib.EDGES_UNDIRECTED_PAIRS) if use_pairs else _lib.EDGES_DIRECTED
     collated = use_pairs or (
         node_ptr is not None and edge_ptr is not None and node_ptr.is_cuda and edge_ptr.is_cuda
-        and meta.get("num_edges_total") == int(ei.shape[1]) and meta.get("max_graph_nodes") is not None
+        and meta.get("num_edges_total") == int(ei.shape[-1]) and meta.get("max_graph_nodes") is not None
     )
     if collated:
         info.node_ptr, info.edge_ptr = node_ptr, (pair_ptr if use_pairs else edge_ptr)
@@ -151,7 +156,7 @@ def _call_step(model, data, info, *, train, loss_kind, target, inv_loss_count, d
         ws_bytes = lib.drk_ginet_step_workspace_bytes(fi, out_dim, info.num_graphs, info.max_nodes, info.max_edges) if train else 0
         ws = workspace(ws_bytes, x.device) if train else None
         rc = lib.drk_ginet_step(
-            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[1]), int(info.layout), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), 1 if getattr(info, "by_slot", False) else 0,
+            _p(x), x.stride(0), fi, _p(ei), int(ei.shape[-1]), int(info.layout), _p(info.node_ptr), _p(info.edge_ptr), _p(info.order), 1 if getattr(info, "by_slot", False) else 0,
             info.num_graphs, info.max_nodes, info.max_edges,
             _p(model.conv1.fc.weight), _p(model.conv1_ext.fc.weight), _p(model.conv2.fc.weight), _p(model.conv2_ext.fc.weight),
             _p(model.fc1.weight), _p(model.fc1.bias), _p(model.fc2.weight), _p(model.fc2.bias), out_dim,
@@ -183,7 +188,7 @@ class GINetFusedStep:
 
     #: the batch tensors a step reads (what an input pipeline has to copy ahead; GINet's attention is the identity, so
     #: ``edge_attr`` is never read, and the readout uses the graph offsets instead of ``batch``)
-    FIELDS = ("x", "_pairs", "_pair_ptr32", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+    FIELDS = ("x", "_pairs16", "_pair_ptr32", "y", "_node_ptr32", "_edge_ptr32", "_order32")
     #: the same for batches whose graphs are not in the doubled layout (no ``_pairs``): the full directed edge list
     FIELDS_DIRECTED = ("x", "edge_index", "y", "_node_ptr32", "_edge_ptr32", "_order32")
 

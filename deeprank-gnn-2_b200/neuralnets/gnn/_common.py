@@ -76,7 +76,7 @@ class GINetConvLayer(nn.Module):
 
 
 def mean_readout(x, data):
-    return ops.mean_readout(x, graph_index(data))
+    return ops.mean_readout(x, graph_index(data, with_csc=False))  # any cached index serves: the readout only needs the graph offsets
 
 
 def num_graphs_of(data):

@@ -54,7 +54,8 @@ class GINet(nn.Module):
 
             if data.x.is_cuda and _fused.step_supported(self, data):
                 return _fused.ginet_infer(self, data)  # inference: the whole forward pass as one per-graph kernel
-        g = graph_index(data)  # CSR/CSC + graph offsets, built once on the device and shared by all layers
+        # CSR/CSC + graph offsets, built once on the device and shared by all layers; the CSC half only serves the backward pass
+        g = graph_index(data, with_csc=torch.is_grad_enabled())
         # the reference deep-copies the batch (data.clone(), :86) and overwrites data.x in place (:90,:93);
         # neither has a numerical effect, so no copy is made here.
         if self._stackable():

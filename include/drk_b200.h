@@ -257,9 +257,14 @@ DRK_API int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num
  *   DRK_EDGES_UNDIRECTED_PAIRS  each contact ONCE, as the HDF5 files hold it (`edge_features/_index`, utils/graph.py:210-264);
  *                               the kernel treats pair p of a graph with P pairs as directed edges p = (i,j) and P + p = (j,i),
  *                               i.e. exactly the doubled list, without it ever crossing PCIe or HBM.  max_graph_edges still
- *                               counts DIRECTED edges (2P). */
+ *                               counts DIRECTED edges (2P).
+ *   DRK_EDGES_LOCAL_PAIRS16     the same contacts, one 32-bit word each: (i - node0) | (j - node0) << 16 with node0 the first node of
+ *                               the pair's graph (a graph of the step kernel has < 65536 nodes).  `edge_index` then points at
+ *                               num_edges such words (pass it as the pointer; only its first num_edges*4 bytes are read).  This is
+ *                               the form the host collate ships over PCIe: 4 bytes per contact instead of 16. */
 #define DRK_EDGES_DIRECTED 0
 #define DRK_EDGES_UNDIRECTED_PAIRS 1
+#define DRK_EDGES_LOCAL_PAIRS16 2
 #define DRK_LOSS_MSE 0
 #define DRK_LOSS_CROSS_ENTROPY 1
 typedef struct DrkAdamTensor {

@@ -59,20 +59,31 @@ with torch.no_grad():
         return net(batches[i[0] % len(batches)])
 
     t = event_time(infer, reps)
-    print(f"GINet inference, eager, L2 flushed: {t:8.1f} us per batch  {graphs / t * 1e6:9.0f} graphs/s  {e / t * 1e-3:7.2f} G edges/s  ({launches} launches of ours)", flush=True)
-    # the same forward replayed from a CUDA graph (no launch gaps); input rotates through a static batch
+    print(f"(index cached on the batch) GINet inference, eager, L2 flushed: {t:8.1f} us per batch  {graphs / t * 1e6:9.0f} graphs/s  {e / t * 1e-3:7.2f} G edges/s  ({launches} launches of ours)", flush=True)
+
+    def infer_fresh():  # what a loader delivers: a batch nobody has indexed yet
+        i[0] += 1
+        bt = batches[i[0] % len(batches)]
+        bt.__dict__.pop("_graph_index", None)
+        return net(bt)
+
+    t = event_time(infer_fresh, reps)
+    print(f"GINet inference incl. index build (CSR only), eager, L2 flushed: {t:8.1f} us per batch  {graphs / t * 1e6:9.0f} graphs/s  {e / t * 1e-3:7.2f} G edges/s", flush=True)
+    # the same forward replayed from a CUDA graph (no launch gaps)
     static = batches[0]
+    static.__dict__.pop("_graph_index", None)
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         net(static)
     torch.cuda.current_stream().wait_stream(s)
+    static.__dict__.pop("_graph_index", None)
     with torch.cuda.graph(g):
-        out = net(static)
+        out = net(static)  # index build + forward
     t = event_time(g.replay, reps)
     fwd_bytes = 4 * n * 38 + 16 * e + 980 * n  # x + int64 contacts + the layer path's forward intermediates (F_in=38 -> close)
-    print(f"GINet inference, graph replay, L2 flushed: {t:8.1f} us per batch  {graphs / t * 1e6:9.0f} graphs/s  {e / t * 1e-3:7.2f} G edges/s", flush=True)
+    print(f"GINet inference incl. index build, graph replay, L2 flushed: {t:8.1f} us per batch  {graphs / t * 1e6:9.0f} graphs/s  {e / t * 1e-3:7.2f} G edges/s", flush=True)
 
 gi = GraphIndex.build(static.edge_index, n, batch=static.batch, num_graphs=graphs)
 for w in (16, 32, 64):
@@ -91,3 +102,6 @@ except Exception as exc:  # noqa: BLE001
     print("blocked index build not applicable:", str(exc)[:100])
 t = event_time(lambda: GraphIndex.build(static.edge_index, n, batch=static.batch, num_graphs=graphs), reps)
 print(f"graph index build (general): {t:7.1f} us  {by / t / 1e3:7.1f} GB/s = {by / t / 1e3 / peak:5.3f} of peak", flush=True)
+by = 16 * e + 12 * e + 4 * (n + 1)
+t = event_time(lambda: GraphIndex.build(static.edge_index, n, batch=static.batch, num_graphs=graphs, with_csc=False), reps)
+print(f"graph index build (general, CSR only): {t:7.1f} us  {by / t / 1e3:7.1f} GB/s = {by / t / 1e3 / peak:5.3f} of peak", flush=True)

@@ -193,3 +193,31 @@ def test_clustered_ginet_with_segment_softmax_runs_and_matches_layerwise_oracle(
         ref = R.ginet_forward(params, copy.copy(batch).clone(), conv=R.ginet_conv_segment_softmax)
         out = net.to(DEV)(copy.copy(batch).clone().to(DEV))
     assert_close(out, ref, "clustered prediction")
+
+
+def test_trainer_trains_ginet_with_segment_softmax(tmp_path, monkeypatch):
+    """The Trainer API with the opt-in attention (``functools.partial`` as ``neuralnet``): runs on the layer kernels, the loss goes
+    down, and the attention weights -- dead parameters in the reference arithmetic -- move."""
+    import functools
+
+    import numpy as np
+
+    seeded = np.random.Generator(np.random.PCG64(7))
+    monkeypatch.setattr(np.random, "default_rng", lambda *a, **k: seeded)
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.synthetic import RESIDUE, make_graph
+    from deeprank2_b200.trainer import Trainer
+
+    level = dict(RESIDUE, n_lo=30, n_hi=60)
+    ds = InMemoryGraphDataset([make_graph(g, 50, 1, level=level) for g in range(24)])
+    torch.manual_seed(0)
+    trainer = Trainer(functools.partial(GINet, attention="segment_softmax"), ds, val_size=4, test_size=4, cuda=True, output_exporters=[])
+    assert trainer.model.attention == "segment_softmax"
+    w0 = {k: v.detach().clone() for k, v in trainer.model.state_dict().items()}
+    trainer.train(nepoch=3, batch_size=8, validate=True, filename=str(tmp_path / "m.pth.tar"))
+    assert trainer._fused is None or not trainer._fused, "the per-graph step kernel implements the reference arithmetic only"
+    w1 = trainer.model.state_dict()
+    for k in ("conv1.fc_attention.weight", "conv2.fc_attention.weight", "conv1_ext.fc_edge_attr.weight"):
+        assert not torch.equal(w0[k], w1[k]), f"{k} must receive a gradient in segment_softmax mode"
+    assert all(bool(torch.isfinite(v).all()) for v in w1.values())

@@ -50,6 +50,7 @@ def _blocked_index(batch):
 
     lib = _lib.load()
     batch.__dict__.pop("_pairs", None)  # the blocked index build takes the directed edge list: use its offsets, not the pairs'
+    batch.__dict__.pop("_pairs16", None)
     info = block_info(batch)
     n, e = batch.num_nodes, batch.num_edges
     out = {k: torch.full((n + 1 if k.endswith("ptr") else e,), -7, dtype=torch.int32, device=DEV) for k in ("rowptr", "colidx", "perm", "colptr", "rowidx", "permT")}
@@ -403,29 +404,33 @@ def test_undirected_pairs_layout_is_bitwise_the_doubled_edge_list():
 
     host = _synthetic(40, first=1200)
     assert host._pairs.shape[1] * 2 == host.edge_index.shape[1]
+    assert host._pairs16.numel() == host._pairs.shape[1] and host._pairs16.dtype == torch.int32
     results = []
-    for use_pairs in (True, False):
+    for layout in (_lib.EDGES_LOCAL_PAIRS16, _lib.EDGES_UNDIRECTED_PAIRS, _lib.EDGES_DIRECTED):
         batch = host.clone().to(DEV)
-        if not use_pairs:
+        if layout != _lib.EDGES_LOCAL_PAIRS16:
+            del batch.__dict__["_pairs16"]  # packed graph-local words (4 bytes per contact) are what the collate ships by default
+        if layout == _lib.EDGES_DIRECTED:
             del batch.__dict__["_pairs"]
         net = _net(50, 1, 1, seed=11).eval()
         step = GINetFusedStep(net, torch.optim.SGD(net.parameters(), lr=0.0), torch.nn.MSELoss())
         loss, pred = step.forward_backward(batch)
         info = block_info(batch)
         check_status(info)
-        assert info.layout == (_lib.EDGES_UNDIRECTED_PAIRS if use_pairs else _lib.EDGES_DIRECTED)
+        assert info.layout == layout
         results.append((loss.clone(), pred.clone(), step.flat_grad.clone()))
-    for a, b in zip(*results):
-        assert torch.equal(a, b)
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert torch.equal(a, b)
 
 
 def test_collate_keeps_pairs_only_for_doubled_graphs():
     from deeprank2_b200.data import Batch, Data
 
     doubled = _synthetic(3, first=5)
-    assert "_pairs" in doubled.__dict__
+    assert "_pairs" in doubled.__dict__ and "_pairs16" in doubled.__dict__
     odd = Data(x=torch.zeros(3, 4), edge_index=torch.tensor([[0, 1, 2], [1, 2, 0]]), edge_attr=torch.zeros(3, 1), y=torch.zeros(1))
-    assert "_pairs" not in Batch.from_data_list([odd, odd]).__dict__
+    assert "_pairs" not in Batch.from_data_list([odd, odd]).__dict__ and "_pairs16" not in Batch.from_data_list([odd, odd]).__dict__
 
 
 def test_resident_graph_set_selection_matches_collated_batch():

@@ -23,6 +23,9 @@ def test_collate_offsets_and_pairs_describe_the_same_edges():
         pairs = batch._pairs[:, p0:p1]
         half = (e1 - e0) // 2
         assert torch.equal(ei[:, :half], pairs) and torch.equal(ei[:, half:], pairs.flip(0))  # dataset.py:944-948 layout
+        words = batch._pairs16[p0:p1].long() & 0xFFFFFFFF  # the same contacts as one packed word of graph-local ids
+        lo_node = int(node_ptr[g])
+        assert torch.equal((words & 0xFFFF) + lo_node, pairs[0]) and torch.equal((words >> 16) + lo_node, pairs[1])
         lo, hi = int(node_ptr[g]), int(node_ptr[g + 1])
         assert int(ei.min()) >= lo and int(ei.max()) < hi  # edges of a graph stay inside it and are contiguous
     meta = batch.__dict__[Batch._META_KEY]
@@ -35,7 +38,7 @@ def test_pairs_are_dropped_when_a_graph_is_not_doubled():
              pos=torch.zeros(3, 3))
     d.entry_names = "hand-made"
     mixed = Batch.from_data_list([doubled, d])
-    assert "_pairs" not in mixed.__dict__ and "_edge_ptr32" in mixed.__dict__
+    assert "_pairs" not in mixed.__dict__ and "_pairs16" not in mixed.__dict__ and "_edge_ptr32" in mixed.__dict__
 
 
 def test_snake_order_balances_rounds():
@@ -84,8 +87,11 @@ def test_partial_transfer_keeps_deferred_tensors_reachable():
 def test_batch_nbytes_counts_what_a_partial_copy_moves():
     host = make_batch(2)
     full = batch_nbytes(host)
-    step_fields = ("x", "_pairs", "_pair_ptr32", "y", "_node_ptr32", "_edge_ptr32", "_order32")
+    from deeprank2_b200.fused import GINetFusedStep
+
+    step_fields = GINetFusedStep.FIELDS
+    assert "_pairs16" in step_fields and "_pairs" not in step_fields and "edge_index" not in step_fields
     part = batch_nbytes(host, step_fields)
     expected = sum(host.__dict__[k].numel() * host.__dict__[k].element_size() for k in step_fields)
     assert part == expected < full
-    assert host._pairs.numel() * 2 == host.edge_index.numel()
+    assert host._pairs.numel() * 2 == host.edge_index.numel() and host._pairs16.numel() * 2 == host._pairs.numel()
