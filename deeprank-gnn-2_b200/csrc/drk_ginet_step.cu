@@ -206,10 +206,11 @@ struct IndexPlan {  // byte offsets into g_smem
 constexpr int kDegBins = 64;
 
 // returns the number of CSC entries (padded), or -1 when no source-sorted index was built (forward only, or symmetric adjacency)
-template <bool WANT_CSC>
+// PACKED: the edge slice holds one 32-bit word per undirected pair, (i | j << 16) with graph-local ids (DRK_EDGES_LOCAL_PAIRS16)
+template <bool WANT_CSC, bool PACKED>
 __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int e0, int ne,
                                         int node0, int n, int32_t* status, int layout) {
-  const bool pairs = layout != DRK_EDGES_DIRECTED;
+  const bool pairs = PACKED || layout != DRK_EDGES_DIRECTED;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = lanemask_lt();
   uint32_t* stash = sm<uint32_t>(pl.stash);
@@ -245,25 +246,18 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
   {
     uint16_t* my_r = cnt_r + warp * cs;
     bool bad = false;
-    long long rr[8], cc[8];
+    long long rr[8], cc[8];  // PACKED: rr holds the raw word, cc is unused
     // undirected-pairs layout: the slice holds P = ne/2 pairs; directed edge d < P is pair d, d >= P is pair d - P flipped
     const int half = pairs ? ne >> 1 : ne;
-    // packed layout: one 32-bit word per pair, (i | j << 16) with ids local to the graph
     const int32_t* words = reinterpret_cast<const int32_t*>(erow);
     auto load_edge = [&](int i, long long& r, long long& c) {
-      r = 0;
-      c = 0;
-      if (i >= we) return;
       const bool flip = i >= half;
       const int src = flip ? i - half : i;
-      if (layout == DRK_EDGES_LOCAL_PAIRS16) {
-        const unsigned w = (unsigned)ld_stream_i32(words + e0 + src);
-        const unsigned lo = w & 0xffffu, hi = w >> 16;
-        r = node0 + (long long)(flip ? hi : lo);
-        c = node0 + (long long)(flip ? lo : hi);
+      if constexpr (PACKED) {
+        r = i < we ? (long long)(unsigned)ld_stream_i32(words + e0 + src) : 0;
       } else {
-        r = ld_stream_i64((flip ? ecol : erow) + e0 + src);
-        c = ld_stream_i64((flip ? erow : ecol) + e0 + src);
+        r = i < we ? ld_stream_i64((flip ? ecol : erow) + e0 + src) : 0;
+        c = i < we ? ld_stream_i64((flip ? erow : ecol) + e0 + src) : 0;
       }
     };
 #pragma unroll
@@ -273,10 +267,19 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * 32 + lane;
-        const unsigned long long r = (unsigned long long)(rr[u] - node0), c = (unsigned long long)(cc[u] - node0);
-        const bool ok = i < we && r < (unsigned long long)n && c < (unsigned long long)n;
+        bool ok;
+        if constexpr (PACKED) {
+          const unsigned w = (unsigned)rr[u];
+          const unsigned swapped = (w >> 16) | (w << 16);
+          pk[u] = i >= half ? swapped : w;  // low half = destination, high half = source of directed edge i
+          ok = i < we && (pk[u] & 0xffffu) < (unsigned)n && (pk[u] >> 16) < (unsigned)n;
+        } else {
+          const unsigned long long r = (unsigned long long)(rr[u] - node0), c = (unsigned long long)(cc[u] - node0);
+          ok = i < we && r < (unsigned long long)n && c < (unsigned long long)n;
+          pk[u] = (unsigned)r | ((unsigned)c << 16);
+        }
         bad |= i < we && !ok;
-        pk[u] = ok ? ((unsigned)r | ((unsigned)c << 16)) : 0xffffffffu;
+        if (!ok) pk[u] = 0xffffffffu;
         if (i < we) stash[i] = pk[u];
       }
 #pragma unroll
@@ -842,7 +845,8 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       continue;
     }
     // ---- the graph index, then x rows (the index build uses the x region as scratch)
-    const int csc_entries = build_index<TRAIN>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs);
+    const int csc_entries = a.pairs == DRK_EDGES_LOCAL_PAIRS16 ? build_index<TRAIN, true>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs)
+                                                               : build_index<TRAIN, false>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs);
     stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
     cp_async_commit();
     const bool have_csc = TRAIN && csc_entries >= 0;  // false: symmetric adjacency, the backward pass gathers through the CSR
