@@ -427,8 +427,91 @@ class ResidentGraphSet:
         import numpy as np
 
         self.work_np = np.asarray(self.work, dtype=np.int64)
+        # per-graph extent of every collated tensor (what `collate` needs to cut a mini-batch out of the packed set)
+        from .data import _takes_node_offset
+
+        graphs = list(graphs)
+        self._extents = {}
+        for k, v in host.__dict__.items():
+            if k.startswith("_") or k in ("batch", "ptr") or not isinstance(v, torch.Tensor):
+                continue
+            dim = 1 if _takes_node_offset(k) else 0
+            sizes = np.fromiter(((1 if g.__dict__[k].dim() == 0 else g.__dict__[k].shape[dim]) for g in graphs), dtype=np.int64, count=len(graphs))
+            starts = np.zeros(len(graphs) + 1, dtype=np.int64)
+            np.cumsum(sizes, out=starts[1:])
+            self._extents[k] = (dim, sizes, starts)
+        self._lists = {k: v for k, v in host.__dict__.items() if not k.startswith("_") and isinstance(v, list)}
         self.batch = host.to(torch.device(device))
-        self.info = block_info(self.batch)
+        self._info = None
+
+    @property
+    def info(self) -> BlockInfo:
+        """Descriptor of the packed set for the per-graph step kernel (built on first use; needs a CUDA device)."""
+        if self._info is None:
+            self._info = block_info(self.batch)
+        return self._info
+
+    def collate(self, ids):
+        """The mini-batch of graphs ``ids`` as a device ``Batch`` -- what ``Batch.from_data_list([dataset.get(i) for i in ids]).to(device)``
+        returns, bit for bit, but cut out of the packed resident set by a handful of device gathers: no per-graph Python, no
+        host tensors, no PCIe traffic beyond one small block of offsets (the reference re-collates on the host every epoch,
+        ``trainer.py:541-557``).  Used by the Trainer for every network the per-graph step kernel does not cover."""
+        import numpy as np
+
+        from .data import Batch, _takes_node_offset
+
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size == 0:
+            raise ValueError("empty selection")
+        if int(ids.min()) < 0 or int(ids.max()) >= self.num_graphs:
+            raise IndexError(f"graph ids must be in [0, {self.num_graphs})")
+        dev = self.batch.x.device
+        b = int(ids.size)
+        # tensors with the same per-graph extents (node-aligned, edge-aligned, one row per graph, ...) share one gather index
+        plans, plan_of, seen = [], {}, {}
+        for k, (_dim, sizes, starts) in self._extents.items():
+            sel, old = sizes[ids], starts[ids]
+            key = (sel.tobytes(), old.tobytes())
+            if key not in seen:
+                new = np.zeros(b + 1, dtype=np.int64)
+                np.cumsum(sel, out=new[1:])
+                seen[key] = len(plans)
+                plans.append((sel, old, new))
+            plan_of[k] = seen[key]
+        # every small host array in ONE pinned block: ids | per plan: sizes, old starts, new starts
+        staging = torch.from_numpy(np.concatenate([ids] + [a for plan in plans for a in plan]))
+        block = (staging.pin_memory() if dev.type == "cuda" else staging).to(dev, non_blocking=True)
+        arange_b = torch.arange(b, device=dev)
+        gathers, off = [], b
+        for sel, _old, new in plans:
+            sizes_dev, old_dev, new_dev = block[off : off + b], block[off + b : off + 2 * b], block[off + 2 * b : off + 3 * b + 1]
+            off += 3 * b + 1
+            total = int(new[-1])
+            if bool((sel == 1).all()):  # one row per graph: the old starts are the gather index
+                gathers.append((old_dev, arange_b, old_dev, new_dev))
+                continue
+            owner = torch.repeat_interleave(arange_b, sizes_dev, output_size=total)
+            src = torch.arange(total, device=dev) + (old_dev - new_dev[:-1])[owner]
+            gathers.append((src, owner, old_dev, new_dev))
+        node = gathers[plan_of["x"]]
+        node_shift = node[3][:-1] - node[2]  # new first node - old first node, per graph
+        out = Batch()
+        packed = self.batch.__dict__
+        for k, pi in plan_of.items():
+            src, owner = gathers[pi][0], gathers[pi][1]
+            out.__dict__[k] = packed[k].index_select(1, src) + node_shift[owner] if _takes_node_offset(k) else packed[k].index_select(0, src)
+        for k, column in self._lists.items():
+            out.__dict__[k] = [column[i] for i in ids.tolist()]
+        out.batch = node[1]
+        out.ptr = node[3]
+        if "edge_index" in plan_of:
+            n_plan, e_plan = plans[plan_of["x"]], plans[plan_of["edge_index"]]
+            if n_plan[2][-1] < 2**31 and e_plan[2][-1] < 2**31:
+                out.__dict__["_node_ptr32"] = node[3].to(torch.int32)
+                out.__dict__["_edge_ptr32"] = gathers[plan_of["edge_index"]][3].to(torch.int32)
+            out.__dict__[Batch._META_KEY] = {"num_graphs": b, "max_graph_nodes": int(n_plan[0].max()), "max_graph_edges": int(e_plan[0].max()),
+                                             "num_edges_total": int(e_plan[2][-1])}
+        return out
 
     def select(self, ids):
         """(descriptor, slot_ids) for the graphs ``ids``: ``slot_ids`` is the order in which results come back."""

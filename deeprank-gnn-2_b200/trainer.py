@@ -117,9 +117,12 @@ class ResidentBatches:
     """Loader over a :class:`fused.ResidentGraphSet`: the same ``batch_size`` / ``shuffle`` / rank-slice semantics as
     :class:`BatchLoader`, but a batch is a list of graph ids -- no per-epoch collate, no per-batch PCIe copy of the graphs."""
 
-    def __init__(self, graph_set, batch_size: int, shuffle: bool, rank: int = 0, world_size: int = 1, seed: int | None = None):
+    def __init__(self, graph_set, batch_size: int, shuffle: bool, rank: int = 0, world_size: int = 1, seed: int | None = None, collate: bool = False):
+        """``collate=False``: batches are :class:`SelectionBatch` (ids for the per-graph step kernel, graphs read in place);
+        ``collate=True``: batches are device ``Batch`` objects gathered out of the resident set (any network)."""
         self.graph_set, self.batch_size, self.shuffle = graph_set, int(batch_size), shuffle
         self.rank, self.world_size = rank, world_size
+        self.collate = collate
         self.only = ()
         self._gen = torch.Generator()
         if seed is not None:
@@ -143,7 +146,10 @@ class ResidentBatches:
             if not ids:
                 yield None, global_size
                 continue
-            yield SelectionBatch(self.graph_set, self.graph_set.select(ids)), global_size
+            if self.collate:
+                yield self.graph_set.collate(ids), global_size
+            else:
+                yield SelectionBatch(self.graph_set, self.graph_set.select(ids)), global_size
 
 
 class Trainer:
@@ -367,17 +373,16 @@ class Trainer:
 
     # ------------------------------------------------------------------ training / testing
     def _resident_loader(self, dataset, batch_size, shuffle):
-        """A :class:`ResidentBatches` loader if the per-graph step kernels apply to this model / loss and the whole dataset fits
-        the device (collated once, kept in HBM), else None.  ``DRK_NO_RESIDENT=1`` disables it."""
+        """A :class:`ResidentBatches` loader if the whole dataset fits the device (collated once, kept in HBM), else None.  When the
+        per-graph step kernels apply to this model / loss a mini-batch is a list of graph ids the kernels read in place; for every
+        other network it is a ``Batch`` cut out of the resident set on the device (``ResidentGraphSet.collate``) -- either way
+        there is no per-epoch host collate and no per-batch PCIe copy of the graphs.  ``DRK_NO_RESIDENT=1`` disables it."""
         import os
 
         from . import _lib
         from .fused import GINetFusedStep, ResidentGraphSet
 
         if os.environ.get("DRK_NO_RESIDENT") or self.device.type != "cuda" or len(dataset) == 0:
-            return None
-        loss_fn = self.lossfunction
-        if isinstance(loss_fn, type) or not GINetFusedStep.supports(self.model, loss_fn):
             return None
         cache = self.__dict__.setdefault("_resident_sets", {})
         gset = cache.get(id(dataset))
@@ -388,14 +393,17 @@ class Trainer:
             if 3 * nbytes > free:  # packed copy + pairs + head room
                 return None
             gset = ResidentGraphSet(graphs, self.device)
+            cache[id(dataset)] = gset
+        loss_fn = self.lossfunction
+        in_place = not isinstance(loss_fn, type) and GINetFusedStep.supports(self.model, loss_fn)
+        if in_place:
             fi, out = int(gset.batch.x.shape[1]), int(self.model.fc2.weight.shape[0])
             if gset.batch.__dict__.get("_pairs") is None and gset.batch.__dict__.get("_edge_ptr32") is None:
-                return None
-            if not _lib.load().drk_ginet_step_supported(fi, out, gset.info.max_nodes, gset.info.max_edges) or fi != self.model.conv1.fc.weight.shape[1]:
-                return None
-            cache[id(dataset)] = gset
+                in_place = False
+            elif not _lib.load().drk_ginet_step_supported(fi, out, gset.info.max_nodes, gset.info.max_edges) or fi != self.model.conv1.fc.weight.shape[1]:
+                in_place = False
         rank, world = (dist.get_rank(), dist.get_world_size()) if self._distributed() else (0, 1)
-        return ResidentBatches(gset, batch_size, shuffle, rank=rank, world_size=world)
+        return ResidentBatches(gset, batch_size, shuffle, rank=rank, world_size=world, collate=not in_place)
 
     def _loader(self, dataset, batch_size, shuffle):
         resident = self._resident_loader(dataset, batch_size, shuffle)
@@ -495,7 +503,7 @@ class Trainer:
         t0 = time()
         for batch, global_size in loader:
             if batch is None:
-                if train and (isinstance(loader, ResidentBatches) or (self._fused is not None and self._fused is not False)):
+                if train and ((isinstance(loader, ResidentBatches) and not loader.collate) or (self._fused is not None and self._fused is not False)):
                     self._ensure_fused().empty_step()
                 elif train and self._grad_sync is not None:  # ragged tail: this rank has no graphs but must join the all-reduce
                     self.optimizer.zero_grad()

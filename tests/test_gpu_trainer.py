@@ -78,7 +78,64 @@ def test_trainer_trains_every_net_on_gpu(net_name, tmp_path, monkeypatch):
         assert isinstance(trainer.train_loader, ResidentBatches), "a dataset that fits HBM is collated once and stays resident"
         assert trainer._fused._adam is not None, "default optimizer: the Adam update runs in the finalize kernel"
     else:
+        from deeprank2_b200.trainer import ResidentBatches
+
         assert trainer._fused is False
+        assert isinstance(trainer.train_loader, ResidentBatches) and trainer.train_loader.collate, "other networks: batches are cut out of the resident set on the device"
+
+
+def test_device_collate_equals_host_collate():
+    """ResidentGraphSet.collate(ids) on the GPU == Batch.from_data_list([...]).to(device), tensor by tensor and bit for bit
+    (clustered graphs: node-, edge-, graph- and cluster-aligned attributes), and the nets give identical outputs on both."""
+    from deeprank2_b200.data import Batch
+    from deeprank2_b200.fused import ResidentGraphSet
+    from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
+
+    graphs = _graphs(16, clusters=True)
+    gset = ResidentGraphSet(graphs, "cuda")
+    for ids in ([5, 2, 2, 15, 0, 9], [7], list(range(16))):
+        got = gset.collate(ids)
+        ref = Batch.from_data_list([graphs[i] for i in ids]).to("cuda")
+        for k in ("x", "edge_index", "edge_attr", "y", "pos", "cluster0", "cluster1", "batch", "ptr", "_node_ptr32", "_edge_ptr32"):
+            a, b = got.__dict__[k], ref.__dict__[k]
+            assert a.is_cuda and a.dtype == b.dtype and torch.equal(a, b), k
+        assert got.entry_names == ref.entry_names and got.__dict__[Batch._META_KEY] == ref.__dict__[Batch._META_KEY]
+        assert got.num_graphs == len(ids) and got.num_nodes == ref.num_nodes and got.num_edges == ref.num_edges
+    torch.manual_seed(0)
+    net = VanillaNetwork(50, 1, 1).to("cuda").eval()
+    with torch.no_grad():
+        assert torch.equal(net(gset.collate([3, 1, 4])), net(Batch.from_data_list([graphs[i] for i in (3, 1, 4)]).to("cuda")))
+
+
+@pytest.mark.parametrize("net_name", ["vanilla", "ginet"])
+def test_device_collated_and_streamed_training_are_identical(net_name, monkeypatch):
+    """Trainer.train of a network outside the per-graph step kernel: batches gathered on the device out of the resident set vs
+    batches collated on the host and copied (DRK_NO_RESIDENT=1).  The batches are bit-identical, so are the trained weights."""
+    import numpy as np
+
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn import ginet, vanilla_gnn
+    from deeprank2_b200.trainer import BatchLoader, ResidentBatches, Trainer
+
+    net = {"vanilla": vanilla_gnn.VanillaNetwork, "ginet": ginet.GINet}[net_name]
+    clustered = net_name == "ginet"
+    results = []
+    for resident in (True, False):
+        if resident:
+            monkeypatch.delenv("DRK_NO_RESIDENT", raising=False)
+        else:
+            monkeypatch.setenv("DRK_NO_RESIDENT", "1")
+        seeded = np.random.Generator(np.random.PCG64(3))
+        monkeypatch.setattr(np.random, "default_rng", lambda *a, **k: seeded)
+        ds = InMemoryGraphDataset(_graphs(20, clusters=clustered), clustering_method="mcl" if clustered else None)
+        torch.manual_seed(1)
+        trainer = Trainer(net, ds, cuda=True, output_exporters=[_Collect()])
+        if hasattr(trainer.model, "dropout"):
+            trainer.model.dropout = 0.0  # torch's dropout RNG advances identically anyway; keep the comparison about the batches
+        trainer.train(nepoch=2, batch_size=8, shuffle=True, validate=False, filename=None)
+        assert isinstance(trainer.train_loader, ResidentBatches if resident else BatchLoader)
+        results.append(torch.cat([p.detach().reshape(-1) for p in trainer.model.parameters()]).cpu())
+    assert torch.equal(results[0], results[1])
 
 
 def test_trainer_epoch_matches_cpu_oracle_epoch():

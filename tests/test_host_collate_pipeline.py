@@ -95,3 +95,34 @@ def test_batch_nbytes_counts_what_a_partial_copy_moves():
     expected = sum(host.__dict__[k].numel() * host.__dict__[k].element_size() for k in step_fields)
     assert part == expected < full
     assert host._pairs.numel() * 2 == host.edge_index.numel() and host._pairs16.numel() * 2 == host._pairs.numel()
+
+
+def test_resident_set_collate_is_the_host_collate():
+    """``ResidentGraphSet.collate`` (gathers out of the packed set; runs on the GPU in production) against ``Batch.from_data_list``
+    on the same ids: every tensor, dtype, list attribute and the collate metadata -- here on CPU tensors, which exercises the
+    same index arithmetic."""
+    from deeprank2_b200.fused import ResidentGraphSet
+
+    graphs = [make_graph(g, 6, 2, with_clusters=True, n=7 + 3 * g) for g in range(9)]
+    gset = ResidentGraphSet(graphs, "cpu")
+    for ids in ([4, 0, 8, 8, 1], [2], list(range(9)), [8, 7, 6]):
+        got = gset.collate(ids)
+        ref = Batch.from_data_list([graphs[i] for i in ids])
+        for k in ("x", "edge_index", "edge_attr", "y", "pos", "cluster0", "cluster1", "batch", "ptr", "_node_ptr32", "_edge_ptr32"):
+            a, b = got.__dict__[k], ref.__dict__[k]
+            assert a.dtype == b.dtype and torch.equal(a, b), k
+        assert got.entry_names == ref.entry_names
+        assert got.__dict__[Batch._META_KEY] == ref.__dict__[Batch._META_KEY]
+        assert sorted(got.keys) == sorted(ref.keys)
+    try:
+        gset.collate([9])
+    except IndexError:
+        pass
+    else:
+        raise AssertionError("an id outside the set must raise IndexError")
+    try:
+        gset.collate([])
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("an empty selection must raise ValueError")
