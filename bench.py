@@ -329,15 +329,19 @@ def run_ours(args):
 
     _trace("e2e start")
     e2e_pass(24)  # warm the copy stream's allocator pool and the pinned-memory path
-    barrier()
-    t0 = time.perf_counter()
-    e2e_pass(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = GRAPHS_PER_BATCH * e2e_steps * world / float(te.item())
+    # three timed passes, the median is reported (the host side of this loop -- PCIe, Python, the VM's neighbours -- is the noisy
+    # part: the same box gives 0.46-0.67 M graphs/s run to run while the device-timed value moves by 0.03 %); all three are listed
+    e2e_passes = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pass(e2e_steps)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_passes.append(GRAPHS_PER_BATCH * e2e_steps * world / float(te.item()))
+    e2e_value = sorted(e2e_passes)[1]
 
     _trace("e2e done")
     # ---- the same loop with the graphs resident in HBM (fused.ResidentGraphSet): a mini-batch is a list of 256 graph ids, the ids are
@@ -442,8 +446,8 @@ def run_ours(args):
             "config": dict(workload_config(args, world), nodes_per_batch=nodes[0], edges_per_batch=edges[0]),
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "mode": "eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as one packed word of graph-local ids, 4 bytes -- the kernel rebuilds the reference's doubled int64 edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps, "passes": e2e_passes,
+                    "mode": "median of three timed passes; eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as one packed word of graph-local ids, 4 bytes -- the kernel rebuilds the reference's doubled int64 edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
             "e2e_resident": e2e_resident,
             "e2e_trainer": e2e_trainer,
             "gpu_launches": int(launches_per_step * args.steps),
