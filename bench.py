@@ -160,7 +160,7 @@ def run_reference(args):
         "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -310,7 +310,7 @@ def run_ours(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches_per_step": int(launches_per_step)}), flush=True)
+            _emit({"profile_run": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches_per_step": int(launches_per_step)})
         _finish(distributed)
         return
 
@@ -455,7 +455,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     _finish(distributed)
 
 
@@ -476,10 +476,12 @@ def _finish(distributed):
     worker.join(10.0)
     sys.stdout.flush()
     sys.stderr.flush()
-    try:
-        os.fsync(sys.stdout.fileno())
-    except OSError:
-        pass
+    for fd in (_RESULT_FD, sys.stdout.fileno()):
+        try:
+            if fd is not None:
+                os.fsync(fd)
+        except OSError:
+            pass
     os._exit(0)
 
 
@@ -587,8 +589,31 @@ def aggregation_roofline(dev_batches, args, dev):
     }
 
 
+_RESULT_FD = None
+
+
+def _emit(line: dict) -> None:
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout."""
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text)
+
+
+def _reserve_stdout() -> None:
+    """Keep stdout for the result line: anything a library prints there (NCCL's "NCCL version ..." banner on the first
+    communicator, warnings of the reference arm) goes to stderr instead."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
