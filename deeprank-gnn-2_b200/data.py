@@ -29,6 +29,19 @@ import torch
 _OFFSET_KEYS = ("index", "face")
 
 
+def _is_doubled(d, ei) -> bool:
+    """Does the graph's edge list have the reference's layout (``dataset.py:944-948``: all (i, j) first, then all (j, i) in the same
+    order)?  Remembered on the graph: datasets hand out the same ``Data`` objects epoch after epoch."""
+    key = (ei.data_ptr(), ei._version, tuple(ei.shape))
+    cached = d.__dict__.get("_doubled")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    e = int(ei.shape[1]) if ei.dim() == 2 else -1
+    ok = ei.dim() == 2 and e % 2 == 0 and bool(torch.equal(ei[:, e // 2 :], ei[:, : e // 2].flip(0)))
+    d.__dict__["_doubled"] = (key, ok)
+    return ok
+
+
 def _takes_node_offset(key: str) -> bool:
     return any(tag in key for tag in _OFFSET_KEYS)
 
@@ -194,9 +207,22 @@ class Batch(Data):
             for k in d._fields():
                 if k not in names:
                     names.append(k)
+        import numpy as np
+
         sizes = [d.num_nodes for d in data_list]
-        ptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
-        ptr[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0)
+        ptr_np = np.zeros(len(sizes) + 1, dtype=np.int64)
+        np.cumsum(np.asarray(sizes, dtype=np.int64), out=ptr_np[1:])
+        ptr = torch.from_numpy(ptr_np)
+
+        def with_node_offsets(column):
+            """cat(dim=1) of per-graph index tensors with each graph's first node id added: one cat + one vectorised add."""
+            widths = np.fromiter((int(v.shape[1]) for v in column), dtype=np.int64, count=len(column))
+            merged = torch.cat(column, dim=1)
+            if merged.dtype == torch.int64 and merged.numel():
+                merged += torch.from_numpy(np.repeat(ptr_np[:-1], widths))
+                return merged
+            return torch.cat([v + int(o) for v, o in zip(column, ptr_np[:-1])], dim=1)
+
         out = cls()
         for k in names:
             column = [d.__dict__.get(k) for d in data_list]
@@ -207,21 +233,22 @@ class Batch(Data):
                 if len(present) != len(column):
                     raise ValueError(f"attribute {k!r} is missing on some graphs of the batch")
                 if _takes_node_offset(k):
-                    setattr(out, k, torch.cat([v + int(o) for v, o in zip(column, ptr[:-1])], dim=1))
+                    setattr(out, k, with_node_offsets(column))
                 else:
                     column = [v.unsqueeze(0) if v.dim() == 0 else v for v in column]
                     setattr(out, k, torch.cat(column, dim=0))
             else:
                 setattr(out, k, list(column))
-        out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int64), torch.tensor(sizes, dtype=torch.int64))
+        out.batch = torch.from_numpy(np.repeat(np.arange(len(sizes), dtype=np.int64), np.asarray(sizes, dtype=np.int64)))
         out.ptr = ptr
         # what the per-graph kernels need and PyG's Batch does not keep: int32 node / edge offsets of every graph (the edges of a
         # graph are a contiguous slice of edge_index) and the graphs sorted by size, largest first (issue order of the CTAs).
         # Private attributes: they follow the batch through clone()/to()/pin_memory() but are not part of `keys`.
         e_sizes = [d.num_edges for d in data_list]
-        if ptr[-1] < 2**31 and sum(e_sizes) < 2**31:
-            eptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
-            eptr[1:] = torch.cumsum(torch.tensor(e_sizes, dtype=torch.int64), 0)
+        if ptr_np[-1] < 2**31 and sum(e_sizes) < 2**31:
+            eptr_np = np.zeros(len(sizes) + 1, dtype=np.int64)
+            np.cumsum(np.asarray(e_sizes, dtype=np.int64), out=eptr_np[1:])
+            eptr = torch.from_numpy(eptr_np)
             out.__dict__["_node_ptr32"] = ptr.to(torch.int32)
             out.__dict__["_edge_ptr32"] = eptr.to(torch.int32)
             out.__dict__["_order32"] = snake_order([e + 8 * n for e, n in zip(e_sizes, sizes)])
@@ -231,20 +258,23 @@ class Batch(Data):
             halves = []
             for d in data_list:
                 ei = d.__dict__.get("edge_index")
-                e = 0 if ei is None else int(ei.shape[1])
-                if ei is None or ei.dim() != 2 or e % 2 or not torch.equal(ei[:, e // 2 :], ei[:, : e // 2].flip(0)):
+                if ei is None or not _is_doubled(d, ei):
                     halves = None
                     break
-                halves.append(ei[:, : e // 2])
+                halves.append(ei[:, : int(ei.shape[1]) // 2])
             if halves is not None:
-                out.__dict__["_pairs"] = torch.cat([h + int(o) for h, o in zip(halves, ptr[:-1])], dim=1).contiguous()
-                out.__dict__["_pair_ptr32"] = (eptr // 2).to(torch.int32)
+                local = torch.cat(halves, dim=1)
                 if max(sizes) <= 65536:
                     # ... and packed: one 32-bit word per contact, (i | j << 16) with ids local to the graph -- what the per-graph step
                     # kernel needs and all it reads (DRK_EDGES_LOCAL_PAIRS16): 4 bytes per contact over PCIe instead of 16 (32 doubled)
-                    local = torch.cat(halves, dim=1)
                     words = (local[0] | (local[1] << 16)).numpy().astype("uint32").view("int32")
                     out.__dict__["_pairs16"] = torch.from_numpy(words.copy())
+                if local.dtype == torch.int64:
+                    local = local + torch.from_numpy(np.repeat(ptr_np[:-1], np.asarray(e_sizes, dtype=np.int64) // 2))
+                else:
+                    local = torch.cat([h + int(o) for h, o in zip(halves, ptr_np[:-1])], dim=1)
+                out.__dict__["_pairs"] = local.contiguous()
+                out.__dict__["_pair_ptr32"] = (eptr // 2).to(torch.int32)
         out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(e_sizes), "num_edges_total": sum(e_sizes)}
         return out
 
