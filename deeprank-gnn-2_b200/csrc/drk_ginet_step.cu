@@ -1161,39 +1161,39 @@ __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
       }
     }
     if (a.peers.world > 1 && ty == 0) {
-      // One-shot all-reduce of this block's 32 values over NVLink peer memory, fused between the reduction and the optimizer:
-      // every rank publishes its partial sums in its own symmetric buffer, raises a flag in every peer's memory
-      // (release), waits for the same block of every peer (acquire) and adds all ranks' values IN RANK ORDER -- every
-      // rank computes bit-identical sums, no second exchange, no NCCL launch.  Buffers alternate with the epoch's parity:
-      // a rank can be at most one step ahead of a peer (it needs the peer's flag of the current step to finish it).
+      // One-shot all-reduce of this block's 32 values over NVLink peer memory, fused between the reduction and the optimizer.
+      // Every value travels together with the step's epoch in ONE 8-byte store into the receiving rank's memory (the pairing the
+      // low-latency protocols of collective libraries use): the receiver polls its OWN memory until the word carries the
+      // current epoch, so there is no separate flag, no fence and no remote load on the critical path -- one NVLink store
+      // latency per step.  All ranks add the values IN RANK ORDER: bit-identical sums everywhere, no second exchange, no NCCL
+      // launch.  Slots alternate with the epoch's parity: a rank can be at most one step ahead of a peer (it needs the peer's
+      // words of the current step to finish it), so a slot is never overwritten before it has been read.
       const DrkPeers& pr = a.peers;
       const int32_t epoch = *a.epoch + 1;  // advanced by the last block of this launch, after everyone has read it
-      const size_t off = (size_t)(epoch & 1) * a.total + t;
-      float sum = 0.f;
-      {
-        float s = 0.f;
-        if (dst != nullptr) {
-          s = s_part[0][tx];
-#pragma unroll
-          for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
-          s *= scale;
-          pr.grad_buf[pr.rank][off] = s;
-        }
-        __threadfence_system();
-        __syncwarp();
-        const int nb = a.grad_blocks;
-        if (tx < pr.world && tx != pr.rank) {
-          st_release_sys(pr.flags[tx] + (size_t)pr.rank * nb + blockIdx.x, epoch);
-          const int32_t* mine = pr.flags[pr.rank] + (size_t)tx * nb + blockIdx.x;
-          while (ld_acquire_sys(mine) < epoch) {
-          }
-        }
-        __syncwarp();
-        if (dst != nullptr) {
-          for (int q = 0; q < pr.world; ++q) sum += q == pr.rank ? s : ld_relaxed_sys(pr.grad_buf[q] + off);
-        }
-      }
       if (dst != nullptr) {
+        float s = s_part[0][tx];
+#pragma unroll
+        for (int y = 1; y < kFinSlices; ++y) s += s_part[y][tx];
+        s *= scale;
+        const size_t par = (size_t)(epoch & 1) * pr.world;
+        for (int q = 0; q < pr.world; ++q) {
+          if (q == pr.rank) continue;
+          uint2* slot = reinterpret_cast<uint2*>(pr.grad_buf[q]) + (par + pr.rank) * a.total + t;
+          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(__float_as_uint(s)), "r"((uint32_t)epoch) : "memory");
+        }
+        float sum = 0.f;
+        for (int q = 0; q < pr.world; ++q) {
+          if (q == pr.rank) {
+            sum += s;
+            continue;
+          }
+          const uint2* slot = reinterpret_cast<const uint2*>(pr.grad_buf[pr.rank]) + (par + q) * a.total + t;
+          uint32_t v, e;
+          do {
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(slot) : "memory");
+          } while (e != (uint32_t)epoch);
+          sum += __uint_as_float(v);
+        }
         *dst = sum;
         if (a.adam_on && live >= 0) adam_update(a.adam, a.adam.live[live], li, sum);
       }
@@ -1563,9 +1563,9 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
       DRK_REQUIRE(peers->world <= 8 && peers->rank >= 0 && peers->rank < peers->world, DRK_EINVAL, "ginet step: peers.world must be <= 8 and rank inside it");
       DRK_REQUIRE(rng_step != nullptr, DRK_EINVAL, "ginet step: the peer all-reduce needs the int64[4] state buffer");
       for (int q = 0; q < peers->world; ++q)
-        DRK_REQUIRE(peers->grad_buf[q] && peers->flags[q], DRK_EINVAL, "ginet step: peers: null buffer of rank %d", q);
-      DRK_REQUIRE(peers->capacity >= 2 * (int64_t)total && peers->flag_capacity >= (int64_t)peers->world * f.grad_blocks, DRK_EINVAL,
-                  "ginet step: peer buffers too small (need %d floats and %d flags)", 2 * total, peers->world * f.grad_blocks);
+        DRK_REQUIRE(peers->grad_buf[q] && aligned8(peers->grad_buf[q]), DRK_EINVAL, "ginet step: peers: null or misaligned buffer of rank %d", q);
+      DRK_REQUIRE(peers->capacity >= 4 * (int64_t)peers->world * total, DRK_EINVAL, "ginet step: peer buffers too small (need %lld floats)",
+                  (long long)(4 * (int64_t)peers->world * total));
       f.peers = *peers;
       f.done_counter = reinterpret_cast<int32_t*>(rng_step + 1);
       f.epoch = reinterpret_cast<int32_t*>(rng_step + 2);

@@ -242,7 +242,8 @@ class GINetFusedStep:
             total = int(lib.drk_ginet_step_exchange_floats(fi, out_dim))
             n_flags = self.world * ((total + 31) // 32)
             group = self.group if self.group is not None else dist.group.WORLD
-            self._sym_grad = symm.empty(2 * total, dtype=torch.float32, device=dev)
+            n_words = 4 * self.world * total  # two epochs x one slot array per sending rank x (value, epoch)
+            self._sym_grad = symm.empty(n_words, dtype=torch.float32, device=dev)
             self._sym_flags = symm.empty(n_flags, dtype=torch.int32, device=dev)
             self._sym_grad.zero_()
             self._sym_flags.zero_()
@@ -252,7 +253,7 @@ class GINetFusedStep:
             dist.barrier(group=group)  # everybody's flags are zero before anybody's first step
             peers = _lib.Peers()
             peers.world, peers.rank = self.world, int(h_grad.rank)
-            peers.capacity, peers.flag_capacity = 2 * total, n_flags
+            peers.capacity, peers.flag_capacity = n_words, n_flags
             for q in range(self.world):
                 peers.grad_buf[q] = int(h_grad.buffer_ptrs[q])
                 peers.flags[q] = int(h_flags.buffer_ptrs[q])

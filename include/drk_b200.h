@@ -275,10 +275,11 @@ typedef struct DrkAdamTensor {
   int64_t numel;
 } DrkAdamTensor;
 /* One-shot gradient all-reduce over NVLink peer memory, fused into the finalize kernel (data-parallel ranks, one process per GPU).
- * grad_buf[q] / flags[q]: rank q's symmetric buffers as mapped in THIS process (e.g. torch.distributed._symmetric_memory):
- * grad_buf holds 2 * drk_ginet_step_exchange_floats() floats (two epochs), flags world * ceil(that / 32) int32, zero before the
- * first call.  All ranks must call drk_ginet_step the same number of times; the sums are formed in rank order, so every rank
- * gets bit-identical gradients. */
+ * grad_buf[q]: rank q's symmetric buffer as mapped in THIS process (e.g. torch.distributed._symmetric_memory), 8-byte aligned,
+ * 4 * world * drk_ginet_step_exchange_floats() floats (two epochs x one slot array per sending rank x (value, epoch) words), zero
+ * before the first call.  Every rank stores its partial sums together with the step's epoch straight into the receivers' memory
+ * (one 8-byte store per value) and polls its own.  All ranks must call drk_ginet_step the same number of times; the sums are
+ * formed in rank order, so every rank gets bit-identical gradients.  `flags` / `flag_capacity` are reserved (unused). */
 typedef struct DrkPeers {
   int32_t world, rank;
   int64_t capacity;      /* floats in each grad_buf */
