@@ -223,8 +223,9 @@ class GINetFusedStep:
         return _standard_ginet(model) and _loss_kind(loss_fn) is not None and (batch is None or step_supported(model, batch))
 
     def _peer_exchange(self):
-        """Symmetric buffers for the in-kernel gradient all-reduce (``DrkPeers``): every rank's gradient staging buffer and flag
-        array mapped into every process (``torch.distributed._symmetric_memory``: CUDA VMM handles over NVLink).  Returns None
+        """Symmetric buffers for the in-kernel gradient all-reduce (``DrkPeers``): every rank's slot buffer (one (value, epoch) word
+        per gradient element, sending rank and epoch parity; the flag array is reserved and no longer read by the kernel)
+        mapped into every process (``torch.distributed._symmetric_memory``: CUDA VMM handles over NVLink).  Returns None
         -- and the step falls back to one NCCL all-reduce -- if the rendezvous is not available (``DRK_NO_PEER_EXCHANGE=1``
         forces that)."""
         import os
