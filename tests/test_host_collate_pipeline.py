@@ -126,3 +126,40 @@ def test_resident_set_collate_is_the_host_collate():
         pass
     else:
         raise AssertionError("an empty selection must raise ValueError")
+
+
+def test_resident_batches_shard_like_the_streamed_loader():
+    """``ResidentBatches(collate=True)`` hands every rank the same slice of every global mini-batch as ``BatchLoader`` does
+    (``parallel.shard_indices``), ragged tail included; the union over ranks is the global batch, in order."""
+    from deeprank2_b200.fused import ResidentGraphSet
+    from deeprank2_b200.trainer import BatchLoader, ResidentBatches
+
+    class _ListDataset:
+        def __init__(self, graphs):
+            self.graphs = graphs
+
+        def __len__(self):
+            return len(self.graphs)
+
+        def get(self, i):
+            return self.graphs[i]
+
+    graphs = [make_graph(g, 5, 1, n=6 + g) for g in range(11)]
+    gset = ResidentGraphSet(graphs, "cpu")
+    world = 2
+    per_rank = []
+    for rank in range(world):
+        resident = list(ResidentBatches(gset, batch_size=4, shuffle=True, rank=rank, world_size=world, collate=True))
+        streamed = list(BatchLoader(_ListDataset(graphs), batch_size=4, shuffle=True, device=None, rank=rank, world_size=world))
+        assert len(resident) == len(streamed) == 3
+        for (rb, rg), (sb, sg) in zip(resident, streamed):
+            assert rg == sg
+            assert (rb is None) == (sb is None)
+            if rb is not None:
+                assert rb.entry_names == sb.entry_names
+                assert torch.equal(rb.x, sb.x) and torch.equal(rb.edge_index, sb.edge_index) and torch.equal(rb.batch, sb.batch)
+        per_rank.append(resident)
+    # union over ranks == the global mini-batches of the shared permutation
+    seen = [name for step in range(3) for rank in range(world) if per_rank[rank][step][0] is not None for name in per_rank[rank][step][0].entry_names]
+    assert sorted(seen) == sorted(g.entry_names for g in graphs)
+    assert [per_rank[0][s][1] for s in range(3)] == [4, 4, 3]
