@@ -173,9 +173,10 @@ class Data:
     def cpu(self):
         return self.to("cpu")
 
-    def pin_memory(self):
+    def pin_memory(self, only=None):
+        """Page-lock the host tensors (all of them, or the names in ``only``: the ones an input pipeline copies ahead)."""
         for k, v in list(self.__dict__.items()):
-            if isinstance(v, torch.Tensor) and not v.is_cuda:
+            if isinstance(v, torch.Tensor) and not v.is_cuda and (only is None or k in only):
                 self.__dict__[k] = v.pin_memory()
         return self
 

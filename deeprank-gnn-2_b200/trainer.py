@@ -76,7 +76,7 @@ class BatchLoader:
                 continue
             batch = Batch.from_data_list([self.dataset.get(i) for i in ids])
             if self.pin_memory:
-                batch.pin_memory()
+                batch.pin_memory(only=self.only)  # with `only` set, the other tensors travel lazily (if ever): no need to page-lock them
             yield batch, global_size
 
     def __iter__(self):
