@@ -47,11 +47,17 @@ class BatchLoader:
     rank receives the ``rank``-th contiguous slice of every global mini-batch (``parallel.shard_indices``).
     """
 
-    def __init__(self, dataset, batch_size: int = 1, shuffle: bool = False, device=None, pin_memory: bool = False, rank: int = 0, world_size: int = 1, seed: int | None = None):
+    def __init__(self, dataset, batch_size: int = 1, shuffle: bool = False, device=None, pin_memory: bool = False, rank: int = 0, world_size: int = 1, seed: int | None = None,
+                 num_workers: int | None = None):
+        """``num_workers``: threads that collate (and page-lock) batches ahead of the consumer, in order (the big concatenations
+        release the GIL); ``None`` picks min(4, cores / 2), 0 collates in the calling thread like the reference's default."""
         self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), shuffle
         self.device, self.pin_memory = device, pin_memory
         self.rank, self.world_size = rank, world_size
         self.only = None
+        import os
+
+        self.num_workers = min(4, max(1, (os.cpu_count() or 2) // 2)) if num_workers is None else max(0, int(num_workers))
         self._gen = torch.Generator()
         if seed is not None:
             self._gen.manual_seed(seed)
@@ -66,18 +72,39 @@ class BatchLoader:
 
         n = len(self.dataset)
         order = torch.randperm(n, generator=self._gen).tolist() if self.shuffle else list(range(n))
-        for start in range(0, n, self.batch_size):
-            ids = order[start : start + self.batch_size]
-            global_size = len(ids)
-            if self.world_size > 1:
-                ids = [ids[i] for i in shard_indices(len(ids), self.rank, self.world_size)]
-            if not ids:
-                yield None, global_size
-                continue
-            batch = Batch.from_data_list([self.dataset.get(i) for i in ids])
+
+        def collate(graphs):
+            batch = Batch.from_data_list(graphs)
             if self.pin_memory:
                 batch.pin_memory(only=self.only)  # with `only` set, the other tensors travel lazily (if ever): no need to page-lock them
-            yield batch, global_size
+            return batch
+
+        def jobs():
+            for start in range(0, n, self.batch_size):
+                ids = order[start : start + self.batch_size]
+                global_size = len(ids)
+                if self.world_size > 1:
+                    ids = [ids[i] for i in shard_indices(len(ids), self.rank, self.world_size)]
+                # the dataset is read in the calling thread (its parse-once cache and h5py are not meant for concurrent use)
+                yield ([self.dataset.get(i) for i in ids] if ids else None), global_size
+
+        if self.num_workers == 0:
+            for graphs, global_size in jobs():
+                yield (collate(graphs) if graphs is not None else None), global_size
+            return
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=self.num_workers, thread_name_prefix="drk-collate") as pool:
+            pending: deque = deque()
+            for graphs, global_size in jobs():
+                pending.append((pool.submit(collate, graphs) if graphs is not None else None, global_size))
+                if len(pending) > self.num_workers:  # results leave in submission order
+                    fut, gs = pending.popleft()
+                    yield (fut.result() if fut is not None else None), gs
+            while pending:
+                fut, gs = pending.popleft()
+                yield (fut.result() if fut is not None else None), gs
 
     def __iter__(self):
         """Device batches, copied ONE BATCH AHEAD on a side stream (``pipeline.DevicePrefetcher``): the host collate and the PCIe
@@ -410,7 +437,9 @@ class Trainer:
         if resident is not None:
             return resident
         rank, world = (dist.get_rank(), dist.get_world_size()) if self._distributed() else (0, 1)
-        return BatchLoader(dataset, batch_size=batch_size, shuffle=shuffle, device=self.device, pin_memory=self.device.type == "cuda", rank=rank, world_size=world)
+        workers = getattr(self, "_num_workers", 0) or None  # DataLoader's num_workers=0 means "no helpers asked for": pick a default
+        return BatchLoader(dataset, batch_size=batch_size, shuffle=shuffle, device=self.device, pin_memory=self.device.type == "cuda", rank=rank, world_size=world,
+                           num_workers=workers)
 
     def train(
         self,
@@ -421,7 +450,7 @@ class Trainer:
         earlystop_maxgap: float | None = None,
         min_epoch: int = 10,
         validate: bool = False,
-        num_workers: int = 0,  # noqa: ARG002  (kept for signature compatibility: batches come from the in-memory cache)
+        num_workers: int = 0,  # collate threads of the streamed loader (0 = default: min(4, cores / 2)); unused when the dataset is resident in HBM
         best_model: bool = True,
         filename: str | None = "model.pth.tar",
     ) -> None:
@@ -429,6 +458,7 @@ class Trainer:
             raise ValueError("No training dataset provided.")
         self.data_type = type(self.dataset_train)
         self.batch_size_train, self.shuffle = batch_size, shuffle
+        self._num_workers = int(num_workers)
         self._fused = None  # rebuilt lazily: the optimizer (and its state tensors) may have changed since the last call
         self.train_loader = self._loader(self.dataset_train, batch_size, shuffle)
         if self.dataset_val is not None:

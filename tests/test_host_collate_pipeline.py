@@ -163,3 +163,33 @@ def test_resident_batches_shard_like_the_streamed_loader():
     seen = [name for step in range(3) for rank in range(world) if per_rank[rank][step][0] is not None for name in per_rank[rank][step][0].entry_names]
     assert sorted(seen) == sorted(g.entry_names for g in graphs)
     assert [per_rank[0][s][1] for s in range(3)] == [4, 4, 3]
+
+
+def test_threaded_collate_keeps_order_and_content():
+    """The streamed loader's collate threads hand the batches out in submission order: identical to collating in the calling thread."""
+    from deeprank2_b200.trainer import BatchLoader
+
+    class _ListDataset:
+        def __init__(self, graphs):
+            self.graphs = graphs
+
+        def __len__(self):
+            return len(self.graphs)
+
+        def get(self, i):
+            return self.graphs[i]
+
+    ds = _ListDataset([make_graph(g, 5, 1, n=5 + (g * 7) % 11) for g in range(23)])
+    runs = []
+    for workers in (0, 3, None):
+        loader = BatchLoader(ds, batch_size=4, shuffle=True, device=None, seed=5, num_workers=workers)
+        runs.append([(b.entry_names, b.x.clone(), b.edge_index.clone(), gs) for b, gs in loader])
+    assert len(runs[0]) == 6
+    for other in runs[1:]:
+        assert len(other) == len(runs[0])
+        for (n0, x0, e0, g0), (n1, x1, e1, g1) in zip(runs[0], other):
+            assert n0 == n1 and g0 == g1 and torch.equal(x0, x1) and torch.equal(e0, e1)
+    # an abandoned iteration shuts the pool down cleanly
+    it = iter(BatchLoader(ds, batch_size=2, shuffle=False, device=None, num_workers=2))
+    next(it)
+    it.close()
