@@ -132,7 +132,8 @@ def ginet_conv_effective(x, edge_index, w):
 def ginet_conv_segment_softmax(x, edge_index, edge_attr, p, prefix=""):
     """The *intended* operator of BASELINE.json north_star (softmax of the attention logit
     over the edges of each destination).  The reference never computes this (it uses
-    ``dim=1``): PARITY UNPINNED, restatement only."""
+    ``dim=1``): PARITY UNPINNED for the normalisation; the logit itself is pinned to the reference's own modules
+    through ``tests/golden/attention_segment_softmax.npz`` (``oracle/make_golden_attention.py``)."""
     row, col = edge_index[0], edge_index[1]
     if edge_attr.dim() == 1:
         edge_attr = edge_attr.unsqueeze(-1)

@@ -77,3 +77,31 @@ def test_attention_switch_arguments():
         assert all(c.attention == "segment_softmax" for c in (net.conv1, net.conv2, net.conv1_ext, net.conv2_ext))
     assert not ginet_nocluster.GINet(7, 2, 3, attention="segment_softmax")._stackable()
     assert ginet_nocluster.GINet(7, 2, 3)._stackable()
+
+
+def _attention_golden(case):
+    import os
+
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "attention_segment_softmax.npz"))
+    pre = case + "/"
+    return {k[len(pre):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_segment_softmax_restatement_vs_golden(case):
+    """``tests/golden/attention_segment_softmax.npz`` (``oracle/make_golden_attention.py``): logits computed by the REFERENCE'S OWN
+    module up to ``ginet.py:52``, normalisation per destination and gradients in float64.  The fp32 restatement must reproduce
+    the logits' consequences -- output and every gradient -- at the path's tolerance."""
+    from conftest import assert_close
+
+    g = _attention_golden(case)
+    p = {k[2:]: v.clone().requires_grad_(True) for k, v in g.items() if k.startswith("w/")}
+    x = g["in/x"].clone().requires_grad_(True)
+    z = R.ginet_conv_segment_softmax(x, g["in/edge_index"], g["in/edge_attr"], p)
+    assert_close(z, g["out/z"], "z")
+    (z * g["gout/z"]).sum().backward()
+    assert_close(x.grad, g["grad/x"], "dx")
+    for k, v in p.items():
+        assert_close(v.grad, g["grad/" + k], f"grad {k}")

@@ -221,3 +221,29 @@ def test_trainer_trains_ginet_with_segment_softmax(tmp_path, monkeypatch):
     for k in ("conv1.fc_attention.weight", "conv2.fc_attention.weight", "conv1_ext.fc_edge_attr.weight"):
         assert not torch.equal(w0[k], w1[k]), f"{k} must receive a gradient in segment_softmax mode"
     assert all(bool(torch.isfinite(v).all()) for v in w1.values())
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_attention_layer_vs_golden(case):
+    """CUDA layer against ``tests/golden/attention_segment_softmax.npz``: logits from the reference's own module (``ginet.py:45-52``),
+    per-destination normalisation and gradients recorded in float64 (``oracle/make_golden_attention.py``)."""
+    import os
+
+    import numpy as np
+
+    from deeprank2_b200.neuralnets.gnn._common import GINetConvLayer
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "attention_segment_softmax.npz"))
+    g = {k[len(case) + 1:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(case + "/")}
+    fo, fi = g["w/fc.weight"].shape
+    fe = g["in/edge_attr"].shape[1]
+    layer = GINetConvLayer(fi, fo, fe, attention="segment_softmax")
+    layer.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("w/")})
+    layer = layer.to(DEV)
+    x = g["in/x"].to(DEV).requires_grad_(True)
+    out = layer(x, g["in/edge_index"].to(DEV), g["in/edge_attr"].to(DEV))
+    assert_close(out, g["out/z"], "z")
+    (out * g["gout/z"].to(DEV)).sum().backward()
+    assert_close(x.grad, g["grad/x"], "dx")
+    for k, v in layer.named_parameters():
+        assert_close(v.grad, g["grad/" + k], f"grad {k}")
