@@ -557,6 +557,39 @@ class ResidentGraphSet:
         return sel, slot_ids.tolist()
 
 
+    def select_epoch(self, id_lists):
+        """``select`` for every mini-batch of an epoch at once: the slot-ordered ids of ALL batches travel in one host->device copy and
+        every selection's ``order`` is a view of that one buffer.  Returns ``(all_ids_dev, [(descriptor, slot_ids), ...])`` with
+        ``descriptor.order = all_ids_dev[offset : offset + len]``."""
+        from .data import snake_order
+
+        import numpy as np
+
+        chunks = []
+        for ids in id_lists:
+            ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+            if ids.size == 0:
+                raise ValueError("empty selection")
+            if int(ids.min()) < 0 or int(ids.max()) >= self.num_graphs:
+                raise IndexError(f"graph ids must be in [0, {self.num_graphs})")
+            chunks.append(ids[snake_order(self.work_np[ids]).numpy()].astype(np.int32))
+        dev = self.batch.x.device
+        flat = torch.from_numpy(np.concatenate(chunks)) if chunks else torch.zeros(0, dtype=torch.int32)
+        all_ids = (flat.pin_memory() if dev.type == "cuda" else flat).to(dev, non_blocking=True)
+        base = self.info
+        out, off = [], 0
+        for slot_ids in chunks:
+            sel = BlockInfo()
+            sel.node_ptr, sel.edge_ptr, sel.edges, sel.layout = base.node_ptr, base.edge_ptr, base.edges, base.layout
+            sel.max_nodes, sel.max_edges, sel.status = base.max_nodes, base.max_edges, base.status
+            sel.order = all_ids[off : off + len(slot_ids)]
+            sel.num_graphs = len(slot_ids)
+            sel.by_slot = True
+            out.append((sel, slot_ids.tolist()))
+            off += len(slot_ids)
+        return all_ids, out
+
+
 class CapturedSelectionStep:
     """The two-launch train step on a :class:`ResidentGraphSet`, captured ONCE into a CUDA graph for a fixed batch size: a step is
     then "write the graph ids into a static device buffer, replay".  The host's share of a step drops to the LPT ordering of the ids

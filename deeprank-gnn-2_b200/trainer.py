@@ -132,10 +132,11 @@ class SelectionBatch:
 
     __slots__ = ("graph_set", "prepared", "y", "entry_names")
 
-    def __init__(self, graph_set, prepared):
+    def __init__(self, graph_set, prepared, y=None):
         self.graph_set, self.prepared = graph_set, prepared
         selection, slot_ids = prepared
-        self.y = graph_set.batch.y.index_select(0, selection.order.long())
+        y_all = graph_set.batch.__dict__.get("y")
+        self.y = y if y is not None else (y_all.index_select(0, selection.order.long()) if y_all is not None else None)
         names = graph_set.entry_names
         self.entry_names = [names[i] for i in slot_ids] if names is not None else [str(i) for i in slot_ids]
 
@@ -165,18 +166,30 @@ class ResidentBatches:
 
         n = self.graph_set.num_graphs
         order = torch.randperm(n, generator=self._gen).tolist() if self.shuffle else list(range(n))
+        plan = []
         for start in range(0, n, self.batch_size):
             ids = order[start : start + self.batch_size]
             global_size = len(ids)
             if self.world_size > 1:
                 ids = [ids[i] for i in shard_indices(len(ids), self.rank, self.world_size)]
+            plan.append((ids, global_size))
+        if self.collate:
+            for ids, global_size in plan:
+                yield (self.graph_set.collate(ids) if ids else None), global_size
+            return
+        # ids in place: the whole epoch's selections in ONE upload, the targets of the epoch in ONE gather; a batch is two views
+        all_ids, prepared = self.graph_set.select_epoch([ids for ids, _ in plan if ids])
+        y_all = self.graph_set.batch.__dict__.get("y")
+        y_epoch = y_all.index_select(0, all_ids.long()) if y_all is not None and all_ids.numel() else None
+        k = off = 0
+        for ids, global_size in plan:
             if not ids:
                 yield None, global_size
                 continue
-            if self.collate:
-                yield self.graph_set.collate(ids), global_size
-            else:
-                yield SelectionBatch(self.graph_set, self.graph_set.select(ids)), global_size
+            sel = prepared[k]
+            y = y_epoch[off : off + len(ids)] if y_epoch is not None else None
+            k, off = k + 1, off + len(ids)
+            yield SelectionBatch(self.graph_set, sel, y=y), global_size
 
 
 class Trainer:
@@ -548,7 +561,8 @@ class Trainer:
 
                 if train:
                     loss_, pred, _ = self._ensure_fused().step_selection(batch.graph_set, prepared=batch.prepared, global_size=global_size)
-                    loss_ = loss_ * (global_size / pred.shape[0])
+                    if global_size != pred.shape[0]:  # the kernel scales by the global batch: back to this rank's mean
+                        loss_ = loss_ * (global_size / pred.shape[0])  # (else: the step's own loss buffer, consumed below before the next step overwrites it)
                     pred, y = self._format_output(pred.clone(), batch.y)
                 else:
                     with torch.no_grad():
@@ -578,7 +592,7 @@ class Trainer:
                     loss_ = self.lossfunction(pred, y) if y is not None else None
             n_here = pred.shape[0]
             if y is not None:
-                loss_sum += loss_.detach().double() * n_here  # "convert mean back to sum" (trainer.py:694)
+                loss_sum.add_(loss_.detach(), alpha=float(n_here))  # "convert mean back to sum" (trainer.py:694), accumulated in float64
                 count += n_here
                 ys.append(y.detach())
             else:
