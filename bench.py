@@ -606,9 +606,13 @@ def _reserve_stdout() -> None:
     """Keep stdout for the result line: anything a library prints there (NCCL's "NCCL version ..." banner on the first
     communicator, warnings of the reference arm) goes to stderr instead."""
     global _RESULT_FD
-    sys.stdout.flush()
-    _RESULT_FD = os.dup(1)
-    os.dup2(2, 1)
+    try:
+        sys.stdout.flush()
+        fd = os.dup(1)
+        os.dup2(2, 1)
+        _RESULT_FD = fd
+    except OSError:  # no usable stdout/stderr pair (unusual launchers): print the line the ordinary way
+        _RESULT_FD = None
 
 
 def main():
