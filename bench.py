@@ -394,27 +394,30 @@ def run_ours(args):
     # accumulation for the exporters) is included, the single device->host read-back happens at the end of every epoch.
     e2e_trainer = None
     if args.path == "fused" and world == 1:
-        from deeprank2_b200.dataset import InMemoryGraphDataset
-        from deeprank2_b200.synthetic import make_graph
-        from deeprank2_b200.trainer import Trainer
+        try:  # an auxiliary figure: it must never cost the contract line
+            from deeprank2_b200.dataset import InMemoryGraphDataset
+            from deeprank2_b200.synthetic import make_graph
+            from deeprank2_b200.trainer import Trainer
 
-        n_set = GRAPHS_PER_BATCH * args.batches
-        ds = InMemoryGraphDataset([make_graph(g, n_node_features=F_NODE, n_edge_features=F_EDGE) for g in range(n_set)])
-        torch.manual_seed(0)
-        trainer = Trainer(GINet, ds, cuda=True, output_exporters=[])
-        trainer.train(nepoch=1, batch_size=GRAPHS_PER_BATCH, validate=False, filename=None)  # builds the resident set, warms up
-        torch.cuda.synchronize()
-        epochs = 10
-        t0 = time.perf_counter()
-        for e in range(epochs):
-            trainer.model.train()
-            trainer._epoch(e + 2, "training")
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e_trainer = {"value": epochs * n_set / dt, "unit": "graphs/s", "epochs": epochs, "graphs_per_epoch": n_set, "batch_size": GRAPHS_PER_BATCH,
-                       "loader": type(trainer.train_loader).__name__,
-                       "mode": "deeprank2_b200.trainer.Trainer._epoch (the reference's Trainer API) on an in-memory dataset: collated once, resident in HBM, one read-back per epoch"}
-        del trainer, ds
+            n_set = GRAPHS_PER_BATCH * args.batches
+            ds = InMemoryGraphDataset([make_graph(g, n_node_features=F_NODE, n_edge_features=F_EDGE) for g in range(n_set)])
+            torch.manual_seed(0)
+            trainer = Trainer(GINet, ds, cuda=True, output_exporters=[])
+            trainer.train(nepoch=1, batch_size=GRAPHS_PER_BATCH, validate=False, filename=None)  # builds the resident set, warms up
+            torch.cuda.synchronize()
+            epochs = 10
+            t0 = time.perf_counter()
+            for e in range(epochs):
+                trainer.model.train()
+                trainer._epoch(e + 2, "training")
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e_trainer = {"value": epochs * n_set / dt, "unit": "graphs/s", "epochs": epochs, "graphs_per_epoch": n_set, "batch_size": GRAPHS_PER_BATCH,
+                           "loader": type(trainer.train_loader).__name__,
+                           "mode": "deeprank2_b200.trainer.Trainer._epoch (the reference's Trainer API) on an in-memory dataset: collated once, resident in HBM, one read-back per epoch"}
+            del trainer, ds
+        except Exception as exc:  # noqa: BLE001
+            e2e_trainer = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     _trace("e2e done")
     # ---- roofline of the dominant kernel, timed per launch with CUDA events on this stream, L2 flushed before every launch
     roof = step_roofline(args, dev, dev_batches, model, loss_fn) if args.path == "fused" else aggregation_roofline(dev_batches, args, dev)
