@@ -12,6 +12,7 @@
 // every 128-bit shared-memory load feeds 16 FMAs per thread and the tile strides are chosen
 // so that the 8 (resp. 4) distinct float4 a warp reads per instruction fall in distinct banks.
 #include <algorithm>
+#include <cstdlib>
 
 #include "drk_common.cuh"
 
@@ -54,6 +55,105 @@ struct LinearArgs {
   int32_t k2;
   int32_t a2_vec;
 };
+
+// ---------------------------------------------------------------- tensor-core variant for wide outputs (M > 32)
+// Same contract as k_node_linear, products on mma.sync m16n8k8 TF32 with error compensation (3xTF32, drk_common.cuh: fp32-level
+// accuracy, profiles/tf32_emulation.py).  OPT-IN (DRK_LINEAR_TC=1), see the dispatcher.  A CTA owns a 64-column slab of the output: the weights of that slab are split into
+// hi/lo B fragments ONCE per CTA (shared memory, [k-step][column tile][lane]), then the CTA walks 64-row tiles of A (4 warps x 16
+// rows): rows staged in shared memory with a stride = 4 (mod 8) floats (conflict-free fragment loads), 8 accumulator tiles per
+// warp.  The SIMT kernel spends 2.5 instructions per FFMA on these shapes (~10 % of the fp32 peak); here the inner loop is
+// 3 MMAs per 1024 products.
+constexpr int kTcThreads = 128;
+constexpr int kTcRows = 64;
+constexpr int kTcCols = 64;
+
+__global__ void __launch_bounds__(kTcThreads) k_node_linear_tc(const LinearArgs p, int num_tiles) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  const int ks1 = (p.k + 7) / 8, ks2 = (p.k2 + 7) / 8, ks = ks1 + ks2;
+  const int kpad = (ks1 > ks2 ? ks1 : ks2) * 8 + 4;
+  uint4* sW = reinterpret_cast<uint4*>(tc_smem);            // [ks][8][32]: (hi.b0, hi.b1, lo.b0, lo.b1)
+  float* sA = reinterpret_cast<float*>(sW + ks * 8 * 32);   // [kTcRows][kpad]
+  const int lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * kTcCols;
+  const int nt_count = min(8, (p.m - m0 + 7) / 8);
+  // B fragments: b0 = W[m0 + 8 nt + g][8 s + t], b1 = W[m0 + 8 nt + g][8 s + t + 4]  (W = op(B) as [M, K]; zero beyond M / K)
+  for (int e = threadIdx.x; e < ks * 8 * 32; e += kTcThreads) {
+    const int ln = e & 31, nt = (e >> 5) & 7, step = e >> 8;
+    const bool second = step >= ks1;
+    const int kk = (second ? step - ks1 : step) * 8 + (ln & 3);
+    const int ktot = second ? p.k2 : p.k;
+    const float* __restrict__ pb = second ? p.b2 : p.b;
+    const int64_t ldb = second ? p.ldb2 : p.ldb;
+    const int gm = m0 + nt * 8 + (ln >> 2);
+    float w0 = 0.f, w1 = 0.f;
+    if (gm < p.m) {
+      if (kk < ktot) w0 = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk) : __ldg(pb + (int64_t)kk * ldb + gm);
+      if (kk + 4 < ktot) w1 = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk + 4) : __ldg(pb + (int64_t)(kk + 4) * ldb + gm);
+    }
+    uint4 q;
+    split_tf32(w0, q.x, q.z);
+    split_tf32(w1, q.y, q.w);
+    sW[e] = q;
+  }
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = (int64_t)tile * kTcRows;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    for (int op = 0; op < (p.k2 > 0 ? 2 : 1); ++op) {
+      const float* __restrict__ pa = op ? p.a2 : p.a;
+      const int64_t lda = op ? p.lda2 : p.lda;
+      const int ktot = op ? p.k2 : p.k;
+      const int steps = op ? ks2 : ks1, step0 = op ? ks1 : 0;
+      __syncthreads();  // the previous tile / operand is done with sA (first trip: the B fragments are complete)
+      for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
+        const int64_t gr = row0 + r;
+        const float* src = pa + (gr < p.n ? gr : 0) * lda;
+        for (int kk = lane; kk < steps * 8; kk += 32) sA[r * kpad + kk] = (gr < p.n && kk < ktot) ? __ldg(src + kk) : 0.f;
+      }
+      __syncthreads();
+      const float* xa = sA + (warp * 16 + g) * kpad + t;
+      const float* xb = xa + 8 * kpad;
+      for (int s = 0; s < steps; ++s) {
+        uint32_t ahi[4], alo[4];
+        split_tf32(xa[s * 8], ahi[0], alo[0]);
+        split_tf32(xb[s * 8], ahi[1], alo[1]);
+        split_tf32(xa[s * 8 + 4], ahi[2], alo[2]);
+        split_tf32(xb[s * 8 + 4], ahi[3], alo[3]);
+        const uint4* wrow = sW + (size_t)(step0 + s) * 8 * 32 + lane;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (nt < nt_count) {  // warp-uniform
+            const uint4 w = wrow[nt * 32];
+            mma_3xtf32(acc[nt], ahi, alo, make_uint2(w.x, w.y), make_uint2(w.z, w.w));
+          }
+        }
+      }
+    }
+    // epilogue: bias, activation, relu-mask, store.  c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt >= nt_count) continue;
+      const int col = m0 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t gr = row0 + warp * 16 + g + 8 * h;
+        if (gr >= p.n) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (col + j >= p.m) continue;
+          float v = acc[nt][2 * h + j];
+          if (p.bias != nullptr) v += __ldg(p.bias + col + j);
+          if (p.act == DRK_ACT_RELU) v = v < 0.f ? 0.f : v;
+          if (p.mask != nullptr) v = p.mask[gr * p.ld_mask + col + j] <= 0.f ? 0.f : v;
+          p.c[gr * p.ldc + col + j] = v;
+        }
+      }
+    }
+  }
+}
 
 // CT = output columns per thread (4, 8 or 16) -> CTA column tile of 4*CT = 16 / 32 / 64.
 template <int CT>
@@ -436,6 +536,23 @@ int drk_node_linear2(const float* a, int64_t lda, const float* b, int64_t ldb, i
     kernel<<<grid, kLinThreads, smem, st>>>(p);
     return DRK_OK;
   };
+  // Opt-in (DRK_LINEAR_TC=1): wide outputs of large row counts on the tensor cores (3xTF32).  Parity-green
+  // (tests/test_gpu_kernels.py), but this single-buffered version is 7 % SLOWER than the SIMT kernel on the VanillaNetwork step
+  // (1.48 vs 1.38 ms): the A tiles need cp.async double buffering before it can become the default.
+  const char* tc_env = std::getenv("DRK_LINEAR_TC");
+  const bool tc_on = tc_env != nullptr && tc_env[0] == '1';
+  if (tc_on && m > 32 && n >= 2048 && k <= 128 && k2 <= 128) {
+    const int ks = (k + 7) / 8 + (k2 + 7) / 8;
+    const int kpad = std::max((k + 7) / 8, (k2 + 7) / 8) * 8 + 4;
+    const size_t smem = (size_t)ks * 8 * 32 * sizeof(uint4) + (size_t)kTcRows * kpad * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k_node_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "node linear: smem opt-in: %s", cudaGetErrorString(e));
+    const int num_tiles = (int)ceil_div<int64_t>(n, kTcRows);
+    const int per_sm = std::max(1, std::min(3, (int)((220 * 1024) / (smem + 1024))));
+    dim3 grid((unsigned)std::min(num_tiles, kNumSM * per_sm), (unsigned)ceil_div(m, kTcCols));
+    k_node_linear_tc<<<grid, kTcThreads, smem, st>>>(p, num_tiles);
+    return finish_launch("node linear (tensor cores)");
+  }
   int rc;
   if (m <= 16) rc = launch(k_node_linear<4>, 16);
   else if (m <= 32 || (m > 64 && m % 64 != 0 && m % 32 == 0)) rc = launch(k_node_linear<8>, 32);

@@ -121,6 +121,53 @@ def test_node_linear(n, k, m, trans_b):
     assert_close(got, torch.where(mask <= 0, torch.zeros_like(ref), ref).float(), "mask")
 
 
+@pytest.mark.parametrize("n,k,m", [(5000, 50, 64), (4097, 82, 50), (2048, 64, 50), (3000, 13, 40), (2500, 128, 128), (2300, 96, 200), (2049, 1, 33)])
+@pytest.mark.parametrize("trans_b", [True, False])
+def test_node_linear_wide_outputs_tensor_core_path(n, k, m, trans_b, monkeypatch):
+    """With ``DRK_LINEAR_TC=1`` M > 32 on >= 2048 rows runs on the tensor cores (3xTF32, ``k_node_linear_tc``; opt-in until it is
+    faster than the SIMT kernel): same contract, same fp32 parity bar -- plain, bias + ReLU, ReLU-mask, ragged last row tile, K not
+    a multiple of 8, several 64-column slabs."""
+    from deeprank2_b200 import _lib
+
+    monkeypatch.setenv("DRK_LINEAR_TC", "1")
+    ops = _ops()
+    before = _lib.launch_count()
+    gen = torch.Generator().manual_seed(n + 31 * k + 7 * m)
+    a = torch.randn(n, k, generator=gen) * 3.0
+    b = torch.randn(m, k, generator=gen) if trans_b else torch.randn(k, m, generator=gen)
+    bias = torch.randn(m, generator=gen)
+    mask = torch.randn(n, m, generator=gen)
+    ref = a.double() @ (b.double().T if trans_b else b.double())
+    assert_close(ops.node_linear(a.to(DEV), b.to(DEV), trans_b), ref.float(), "plain")
+    assert_close(ops.node_linear(a.to(DEV), b.to(DEV), trans_b, bias=bias.to(DEV), act=ops.ACT_RELU), torch.relu(ref + bias.double()).float(), "bias+relu")
+    assert_close(ops.node_linear(a.to(DEV), b.to(DEV), trans_b, mask=mask.to(DEV)), torch.where(mask <= 0, torch.zeros_like(ref), ref).float(), "mask")
+    r1 = ops.node_linear(a.to(DEV), b.to(DEV), trans_b)
+    assert torch.equal(r1, ops.node_linear(a.to(DEV), b.to(DEV), trans_b)), "bit-reproducible"
+    assert _lib.launch_count() - before == 5
+    # the default (SIMT) kernel agrees with it inside the same bar
+    monkeypatch.setenv("DRK_LINEAR_TC", "0")
+    assert_close(ops.node_linear(a.to(DEV), b.to(DEV), trans_b), ref.float(), "plain, SIMT")
+
+
+def test_node_linear2_wide_outputs_tensor_core_path(monkeypatch):
+    """The concat-free two-operand Linear (``vanilla_gnn.py:37-38``: [x | message sums] -> node MLP) on the opt-in tensor-core path."""
+    monkeypatch.setenv("DRK_LINEAR_TC", "1")
+    ops = _ops()
+    gen = torch.Generator().manual_seed(9)
+    n = 4500
+    a, a2 = torch.randn(n, 50, generator=gen), torch.randn(n, 32, generator=gen) * 5.0
+    for trans_b in (True, False):
+        b = torch.randn(50, 50, generator=gen)
+        b2 = torch.randn(50, 32, generator=gen) if trans_b else torch.randn(32, 50, generator=gen)
+        bias = torch.randn(50, generator=gen)
+        mask = torch.randn(n, 50, generator=gen)
+        ref = a.double() @ (b.double().T if trans_b else b.double()) + a2.double() @ (b2.double().T if trans_b else b2.double()) + bias.double()
+        ref = torch.relu(ref)
+        ref = torch.where(mask <= 0, torch.zeros_like(ref), ref)
+        got = ops.node_linear2(a.to(DEV), b.to(DEV), a2.to(DEV), b2.to(DEV), trans_b, bias=bias.to(DEV), mask=mask.to(DEV), act=ops.ACT_RELU)
+        assert_close(got, ref.float(), f"two operands, trans_b={trans_b}")
+
+
 def test_node_linear_strided_views():
     ops = _ops()
     gen = torch.Generator().manual_seed(3)
