@@ -13,7 +13,16 @@ Each rank owns ``--batches`` distinct pre-collated batches resident in HBM and r
 inputs of a step were last touched (batches-1) steps and > 126 MB of L2 traffic ago.
 
 One JSON line on stdout (rank 0).  Under torchrun (N > 1) ranks shard the graphs (weak scaling: 256
-graphs per GPU per step), gradients are all-reduced with NCCL every step.
+graphs per GPU per step); the gradient all-reduce is fused into the step's finalize kernel (value+epoch words pushed
+into every peer's memory over NVLink, `grad_exchange: "peer_push"`), or one NCCL all-reduce per step when the
+symmetric-memory rendezvous is unavailable (`"nccl"`).  At N > 1 the line carries `multi_gpu_check`: the ranks'
+weights after a few data-parallel steps compared bit for bit with each other and against a single-process run over
+the union of the ranks' batches.
+
+`--config` selects the BASELINE.json configuration: c2 (default, the contract line: GINet train step), c3 (atom-level
+GINet inference), c4-vanilla / c4-fout / c4-ginet (VanillaNetwork, FoutNet, clustered GINet train steps on the C2 batch).
+The default c2 line also carries short measurements of the other configurations under `configs` and the reference
+modules on the same GPU with stock eager ATen kernels under `gpu_torch_baseline`.
 """
 from __future__ import annotations
 
@@ -44,7 +53,9 @@ def parse_args():
                     help="fused: whole step as one per-graph kernel; fused2: per-graph forward and backward kernels through autograd; layers: one kernel per layer op")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="only the timed steps (no e2e / roofline / cpu legs): the command ncu wraps")
-    ap.add_argument("--ref-graphs", type=int, default=64, help="graphs per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-graphs", type=int, default=GRAPHS_PER_BATCH, help="graphs per step of the CPU reference arm (default: the full 256-graph batch)")
+    ap.add_argument("--config", choices=["c2", "c3", "c4-vanilla", "c4-fout", "c4-ginet"], default="c2", help="BASELINE.json configuration the line is quoted on")
+    ap.add_argument("--no-extras", action="store_true", help="c2 only: skip the `configs` sub-records (c3 / c4) and the gpu_torch_baseline leg")
     return ap.parse_args()
 
 
@@ -107,42 +118,53 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_steps(n_graphs: int, steps: int, warmup: int, first_graph: int = 0, budget_s: float | None = None):
-    """The reference's CPU implementation of the step (oracle port: same ATen op sequence as
-    deeprank2/neuralnets/gnn/ginet_nocluster.py + trainer.py:682-694), all host threads."""
-    import torch
+C3_GRAPHS, C3_F_NODE = 64, 38
+CONFIG_NET = {"c2": "ginet", "c3": "ginet", "c4-vanilla": "vanilla", "c4-fout": "fout", "c4-ginet": "ginet_clustered"}
+CONFIG_METRIC = {"c2": "ginet_train_step_graphs_per_s", "c3": "ginet_atom_level_inference_graphs_per_s", "c4-vanilla": "vanilla_network_train_step_graphs_per_s",
+                 "c4-fout": "foutnet_train_step_graphs_per_s", "c4-ginet": "ginet_clustered_train_step_graphs_per_s"}
 
-    from deeprank2_b200.synthetic import make_batch
-    from oracle import restate as R
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    batch = make_batch(n_graphs, first=first_graph, n_node_features=F_NODE, n_edge_features=F_EDGE)
-    torch.manual_seed(0)
-    params = R.as_parameters(R.ginet_nocluster_init(F_NODE, 1, F_EDGE))
-    opt = R.make_adam(params)
-    t0 = time.perf_counter()
-    for _ in range(warmup):
-        R.train_step(R.ginet_nocluster_forward, params, opt, batch, training=True)
-    if warmup > 0 and budget_s is not None:  # bounded sample: as many of the requested steps as fit the time budget
-        per_step = (time.perf_counter() - t0) / warmup
-        steps = max(3, min(steps, int(budget_s / max(per_step, 1e-6))))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        R.train_step(R.ginet_nocluster_forward, params, opt, batch, training=True)
-    dt = time.perf_counter() - t0
-    return dict(seconds=dt, steps=steps, graphs=n_graphs, nodes=batch.num_nodes, edges=batch.num_edges, threads=torch.get_num_threads())
+def config_host_batch(config: str, n_graphs: int | None = None, first: int = 0):
+    """The synthetic host batch of a BASELINE configuration."""
+    from deeprank2_b200.synthetic import ATOM, make_batch
+
+    if config == "c3":
+        return make_batch(n_graphs or C3_GRAPHS, first=first, n_node_features=C3_F_NODE, n_edge_features=F_EDGE, level=ATOM)
+    clustered = config in ("c4-fout", "c4-ginet")
+    return make_batch(n_graphs or GRAPHS_PER_BATCH, first=first, n_node_features=F_NODE, n_edge_features=F_EDGE, with_clusters=clustered)
+
+
+def workload_text(config: str, n_graphs: int) -> str:
+    if config == "c3":
+        return f"C3: synthetic atom-level PPI graphs, {n_graphs} graphs x ~3000 nodes, 4.5 A contacts (~60 k directed edges each), GINet(no-cluster) F_in={C3_F_NODE} F_e=1, inference (eval, no_grad)"
+    net = {"c2": "GINet(no-cluster)", "c4-vanilla": "VanillaNetwork (NaiveNetwork)", "c4-fout": "FoutNet (two-level synthetic clusters)", "c4-ginet": "GINet (clustered, two-level synthetic clusters)"}[config]
+    return f"{config.upper()}: synthetic residue-level PPI batch, {n_graphs} graphs x ~300 nodes, 8.5 A contacts (degree ~20), {net} F_in={F_NODE} F_e=1, fwd+bwd+Adam, MSELoss"
+
+
+def cpu_reference_steps(config: str, n_graphs: int, steps: int, warmup: int, budget_s: float | None = None):
+    """The reference's own CPU implementation of the step on all host threads: the unmodified deeprank2 module executed from
+    oracle/_ref (or /root/reference) -- kind "reference" -- or, if those files are missing, the oracle port -- kind "port"."""
+    from oracle.reference_step import reference_train_steps
+
+    batch = config_host_batch(config, n_graphs)
+    if config == "c4-fout":
+        # FoutLayer is an O(N*E) Python loop (foutnet.py:56-58): 256 graphs would take hours; time a 4-graph batch (SURVEY 8d)
+        batch = config_host_batch(config, min(n_graphs, 4))
+    return reference_train_steps(batch, CONFIG_NET[config], steps=steps, warmup=warmup, budget_s=budget_s, train=config != "c3")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_steps(args.ref_graphs, args.steps, max(1, min(args.warmup, 2)), budget_s=60.0)  # at most ~1 min of CPU steps
+    n_graphs = args.ref_graphs if args.config != "c3" else min(args.ref_graphs, 8)
+    r = cpu_reference_steps(args.config, n_graphs, args.steps, max(1, min(args.warmup, 2)), budget_s=60.0)  # at most ~1 min of CPU steps
     gps = r["graphs"] * r["steps"] / r["seconds"]
-    sample = f"{r['steps']} steps of a {r['graphs']}-graph slice of the C2 batch ({r['nodes']} nodes, {r['edges']} directed edges)"
+    what = "the unmodified deeprank2 module (oracle/_ref) under the oracle's torch_scatter / torch_geometric restatements" if r["kind"] == "reference" else "oracle port of the reference's CPU path"
+    sample = f"{r['steps']} steps of a {r['graphs']}-graph batch ({r['nodes']} nodes, {r['edges']} directed edges), {what}, {r['threads']} host threads"
     line = {
         "impl": "reference",
-        "metric": "ginet_train_step_graphs_per_s",
+        "metric": CONFIG_METRIC[args.config],
         "value": gps,
         "unit": "graphs/s",
         "n_gpus": args.gpus,
@@ -154,9 +176,10 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": {"workload": workload_text(args.config, r["graphs"]), "graphs_per_step": r["graphs"], "nodes_per_batch": r["nodes"], "edges_per_batch": r["edges"],
+                   "device": "host CPU", "threads": r["threads"], "implementation": what},
         "edges_per_s": r["edges"] * r["steps"] / r["seconds"],
-        "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": r["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": r["threads"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -165,12 +188,15 @@ def run_reference(args):
 
 def workload_config(args, world):
     return {
-        "workload": "C2: synthetic residue-level PPI batch, 256 graphs x ~300 nodes, 8.5 A contacts (degree ~20), GINet(no-cluster) F_in=50 F_e=1, fwd+bwd+Adam, MSELoss",
+        "workload": workload_text("c2", GRAPHS_PER_BATCH),
         "graphs_per_step_per_gpu": GRAPHS_PER_BATCH,
         "global_graphs_per_step": GRAPHS_PER_BATCH * world,
         "parallelism": f"dp{world}",
         "l2_policy": f"rotation over {args.batches} distinct resident batches per rank (> L2 between reuses)",
         "index_build": "inside every step",
+        "edge_input_layout": "_pairs16: every contact once as one packed 32-bit word of graph-local ids (i | j << 16), made once by the host collate / dataset cache "
+                             "from the reference's int64 edge_index [2,E]; the kernel rebuilds the doubled directed list and its CSR on the fly "
+                             "(the int64 edge_index path is the same kernel, tests/test_gpu_step.py::test_undirected_pairs_layout_is_bitwise_the_doubled_edge_list)",
         "mode": args.mode,
         "path": getattr(args, "path", "fused"),
     }
@@ -186,6 +212,311 @@ def algorithmic_step_bytes(n_nodes: int, n_edges: int) -> int:
 def _trace(msg):
     if os.environ.get("DRK_BENCH_TRACE"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+def cpu_baseline_record(config: str, n_graphs: int):
+    r = cpu_reference_steps(config, n_graphs, 3, 1, budget_s=20.0)
+    what = "the unmodified deeprank2 module (oracle/_ref)" if r["kind"] == "reference" else "oracle port of the reference's CPU path"
+    unit = "train steps" if config != "c3" else "inference passes"
+    return {"value": r["graphs"] * r["steps"] / r["seconds"], "unit": "graphs/s", "cores": r["threads"], "kind": r["kind"],
+            "sample": f"{r['steps']} {unit} of a {r['graphs']}-graph batch ({r['nodes']} nodes, {r['edges']} directed edges), {what}"}
+
+
+def gpu_torch_baseline(dev, config: str = "c2", steps: int = 20):
+    """The reference modules themselves on this GPU with stock eager ATen kernels (SURVEY 8d last row / BASELINE.md 4.6): what the
+    hand-written kernels buy over `model.to('cuda')`.  Device-timed, same synthetic batch, same optimizer."""
+    import torch
+
+    from oracle.reference_step import reference_train_steps
+
+    try:
+        batch = config_host_batch(config, 4 if config == "c4-fout" else None)
+        r = reference_train_steps(batch, CONFIG_NET[config], steps=steps, warmup=5, device=str(dev), train=config != "c3")
+        if r is None:
+            return {"unavailable": "reference modules not found (oracle/_ref missing)"}
+        torch.cuda.synchronize(dev)
+        return {"value": r["graphs"] * r["steps"] / r["seconds"], "unit": "graphs/s", "ms_per_step": 1e3 * r["seconds"] / r["steps"], "graphs_per_step": r["graphs"],
+                "kind": r["kind"], "what": "unmodified deeprank2 module on cuda, eager ATen kernels (index_select / scatter_add_ / mm), torch.optim.Adam, wall clock around synchronised steps"}
+    except Exception as exc:  # noqa: BLE001 - an auxiliary figure must never cost the contract line
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+
+def _event_ms(fn, reps, flush=None):
+    import torch
+
+    total = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    return total / reps
+
+
+def measure_c3(dev, steps: int = 40, n_batches: int = 3):
+    """Config C3: GINet inference (eval, no_grad) on atom-level graphs -- index build (CSR only) + forward, replayed from a CUDA graph,
+    rotating over `n_batches` resident batches; and the aggregation kernel (drk_spmm) on the C3 adjacency against the HBM peak."""
+    import torch
+
+    from deeprank2_b200 import _lib, ops
+    from deeprank2_b200.graph import GraphIndex
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+
+    host = [config_host_batch("c3", first=b * C3_GRAPHS) for b in range(n_batches)]
+    batches = [h.clone().to(dev) for h in host]
+    n, e = host[0].num_nodes, host[0].num_edges
+    torch.manual_seed(0)
+    net = GINet(C3_F_NODE, 1, F_EDGE).to(dev).eval()
+    graphs, out = [], None
+    with torch.no_grad():
+        for b in batches:
+            net(b)
+        torch.cuda.synchronize()
+        c0 = _lib.launch_count()
+        batches[0].__dict__.pop("_graph_index", None)
+        net(batches[0])
+        launches = _lib.launch_count() - c0
+        pool = None
+        for b in batches:
+            b.__dict__.pop("_graph_index", None)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                net(b)
+            torch.cuda.current_stream().wait_stream(side)
+            b.__dict__.pop("_graph_index", None)
+            with torch.cuda.graph(g, pool=pool):
+                out = net(b)  # index build + forward
+            pool = g.pool()
+            graphs.append(g)
+    for i in range(6):
+        graphs[i % n_batches].replay()
+    torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        graphs[i % n_batches].replay()
+    c.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(c) / steps
+    # the aggregation kernel alone, L2 flushed
+    peak, peak_src = _peak()
+    gi = GraphIndex.build(batches[0].edge_index, n, batch=batches[0].batch, num_graphs=C3_GRAPHS)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    roof = {}
+    for width in (16, 32):
+        src = torch.randn(n, width, device=dev)
+        dst = torch.empty_like(src)
+        ops.spmm(gi.rowptr, gi.colidx, src, n, act=ops.ACT_RELU, out=dst)
+        t = _event_ms(lambda: ops.spmm(gi.rowptr, gi.colidx, src, n, act=ops.ACT_RELU, out=dst), 20, flush)
+        by = 8 * n * width + 4 * e + 4 * (n + 1)
+        roof[f"width{width}"] = {"bound": "hbm", "kernel": f"drk_spmm width {width}, ReLU epilogue, C3 adjacency, L2 flushed", "achieved": by / (t * 1e-3) / 1e9, "peak": peak,
+                                 "peak_source": peak_src, "unit": "GB/s", "frac": by / (t * 1e-3) / 1e9 / peak, "us_per_launch": 1e3 * t, "algorithmic_bytes_per_launch": by,
+                                 "traffic": None}
+    return {"metric": CONFIG_METRIC["c3"], "value": C3_GRAPHS / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "edges_per_s": e / (ms * 1e-3), "steps": steps,
+            "mode": "CUDA-graph replay of index build (CSR only) + forward, rotation over 3 resident batches", "gpu_launches_per_step": int(launches),
+            "config": {"workload": workload_text("c3", C3_GRAPHS), "graphs_per_step": C3_GRAPHS, "nodes_per_batch": n, "edges_per_batch": e},
+            "roofline": roof["width16"], "roofline_width32": roof["width32"]}
+
+
+def measure_c4(dev, config: str, steps: int = 40):
+    """Config C4: a train step (index build, forward, MSELoss, backward, Adam) of VanillaNetwork / FoutNet / clustered GINet on the C2
+    batch; CUDA-graph replay when the network's step can be captured, eager launches otherwise."""
+    import copy
+
+    import torch
+
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.neuralnets.gnn import foutnet, ginet, vanilla_gnn
+    from deeprank2_b200.step import GraphedTrainStep, TrainStep
+
+    cls = {"c4-vanilla": vanilla_gnn.VanillaNetwork, "c4-fout": foutnet.FoutNet, "c4-ginet": ginet.GINet}[config]
+    host = config_host_batch(config)
+    batch = host.clone().to(dev)
+    torch.manual_seed(0)
+    net = cls(F_NODE, 1, F_EDGE).to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+    inner = TrainStep(net, opt, torch.nn.MSELoss())
+
+    def step(b):
+        view = copy.copy(b)  # the clustered networks overwrite data.x and pool the batch in place (foutnet.py:104): a loader hands out fresh views
+        view.__dict__ = dict(b.__dict__)
+        return inner(view)
+
+    for _ in range(3):
+        step(batch)
+    torch.cuda.synchronize()
+    c0 = _lib.launch_count()
+    step(batch)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - c0
+    mode = "CUDA-graph replay"
+    if getattr(net, "capturable", config == "c4-vanilla"):
+        g = GraphedTrainStep(step, batch, warmup=1)
+        run = g.replay
+    else:  # the pooled batch is sized on the host (as the reference does): not capturable
+        mode = "eager launches (host-sized pooling)"
+        run = lambda: step(batch)  # noqa: E731
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        run()
+    c.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(c) / steps
+    return {"metric": CONFIG_METRIC[config], "value": GRAPHS_PER_BATCH / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "edges_per_s": host.num_edges / (ms * 1e-3),
+            "steps": steps, "mode": mode, "gpu_launches_per_step": int(launches),
+            "config": {"workload": workload_text(config, GRAPHS_PER_BATCH), "graphs_per_step": GRAPHS_PER_BATCH, "nodes_per_batch": host.num_nodes, "edges_per_batch": host.num_edges}}
+
+
+def measure_extra(dev, config: str, steps: int = 40):
+    try:
+        return measure_c3(dev, steps) if config == "c3" else measure_c4(dev, config, steps)
+    except Exception as exc:  # noqa: BLE001 - an auxiliary figure must never cost the contract line
+        import traceback
+
+        traceback.print_exc(file=sys.stderr)
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+
+def run_config(args):
+    """`--config c3 | c4-*` as the primary line (single GPU; under torchrun every rank measures its own replica, rank 0 reports
+    the sum: these configurations are N independent replicas, no exchange)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    with ClockSampler(local_rank) as clocks:
+        rec = measure_c3(dev, max(args.steps, 20)) if args.config == "c3" else measure_c4(dev, args.config, max(args.steps, 20))
+    t = torch.tensor([rec["ms_per_step"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    per_step = rec["config"]["graphs_per_step"]
+    # end to end: pinned host batch -> device -> step -> read-back, eager
+    from deeprank2_b200.pipeline import batch_nbytes
+
+    e2e = None
+    try:
+        e2e = e2e_generic(dev, args.config, 20)
+    except Exception as exc:  # noqa: BLE001
+        e2e = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    if rank == 0:
+        line = {"metric": rec["metric"], "value": per_step * world / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world, "steps": rec["steps"], "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(rec["config"], parallelism=f"{world} independent replicas", mode=rec["mode"]), "edges_per_s": rec["edges_per_s"] * world,
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": rec["gpu_launches_per_step"] * rec["steps"], "gpu_launches_per_step": rec["gpu_launches_per_step"],
+                "roofline": rec.get("roofline"), "roofline_width32": rec.get("roofline_width32"),
+                "cpu_baseline": None if args.no_cpu_baseline or world > 1 else cpu_baseline_record(args.config, 8 if args.config == "c3" else GRAPHS_PER_BATCH)}
+        _emit(line)
+    _finish(world > 1)
+
+
+def e2e_generic(dev, config: str, steps: int):
+    """Host-fed loop of a non-benchmark configuration: pinned host batch -> device (all tensors) -> step -> loss/pred read-back."""
+    import copy
+
+    import torch
+
+    from deeprank2_b200.neuralnets.gnn import foutnet, ginet, ginet_nocluster, vanilla_gnn
+    from deeprank2_b200.pipeline import batch_nbytes
+    from deeprank2_b200.step import TrainStep
+
+    host = config_host_batch(config).pin_memory()
+    torch.manual_seed(0)
+    if config == "c3":
+        net = ginet_nocluster.GINet(C3_F_NODE, 1, F_EDGE).to(dev).eval()
+
+        def run(b):
+            with torch.no_grad():
+                return net(b).sum()
+    else:
+        cls = {"c4-vanilla": vanilla_gnn.VanillaNetwork, "c4-fout": foutnet.FoutNet, "c4-ginet": ginet.GINet}[config]
+        net = cls(F_NODE, 1, F_EDGE).to(dev).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        inner = TrainStep(net, opt, torch.nn.MSELoss())
+
+        def run(b):
+            return inner(b)[0]
+
+    for _ in range(3):
+        float(run(host.clone().to(dev, non_blocking=True)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        float(run(host.clone().to(dev, non_blocking=True)))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": host.num_graphs * steps / dt, "unit": "graphs/s", "h2d_bytes_per_step": batch_nbytes(host), "d2h_bytes_per_step": 4, "steps": steps,
+            "mode": "eager launches; pinned host batch (every tensor, reference dtypes: int64 edge_index) -> device -> step -> scalar read-back every step"}
+
+
+def multi_gpu_check(rank, world, dev, n_steps: int = 3):
+    """Data-parallel correctness, measured in the benchmark process itself: every rank takes `n_steps` train steps (dropout off) on its
+    own 256-graph batches with the gradient exchange the timed region uses; then (a) the ranks' flat weights are all-gathered and
+    compared bit for bit, (b) rank 0 repeats the steps single-process on the union of all ranks' batches (one 256*N-graph batch per
+    step) and reports max |w_dp - w_single|."""
+    import torch
+    import torch.distributed as dist
+
+    from deeprank2_b200.data import Batch
+    from deeprank2_b200.fused import GINetFusedStep
+    from deeprank2_b200.neuralnets.gnn.ginet_nocluster import GINet
+    from deeprank2_b200.synthetic import make_graph
+
+    first = 10_000_000  # graphs nobody else in this run uses
+    loss_fn = torch.nn.MSELoss()
+
+    def graphs_of(r, s):
+        base = first + (r * n_steps + s) * GRAPHS_PER_BATCH
+        return [make_graph(base + g, n_node_features=F_NODE, n_edge_features=F_EDGE) for g in range(GRAPHS_PER_BATCH)]
+
+    def fresh(world_size):
+        torch.manual_seed(0)
+        model = GINet(F_NODE, 1, F_EDGE).to(dev).eval()  # eval: dropout masks are keyed by batch-local graph ids, which differ between the two runs
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=True)
+        return model, GINetFusedStep(model, opt, loss_fn, world_size=world_size)
+
+    model, fused = fresh(world)
+    for s in range(n_steps):
+        fused(Batch.from_data_list(graphs_of(rank, s)).to(dev), global_size=GRAPHS_PER_BATCH * world)
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    identical = all(bool(torch.equal(gathered[0], g)) for g in gathered[1:])
+    exchange = "peer_push" if fused._peers is not None else "nccl"
+    result = None
+    if rank == 0:
+        model1, fused1 = fresh(1)
+        for s in range(n_steps):
+            union = [g for r in range(world) for g in graphs_of(r, s)]
+            fused1(Batch.from_data_list(union).to(dev), global_size=GRAPHS_PER_BATCH * world)
+        torch.cuda.synchronize()
+        flat1 = torch.cat([p.detach().reshape(-1) for p in model1.parameters()])
+        torch.manual_seed(0)
+        w0 = torch.cat([p.detach().reshape(-1) for p in GINet(F_NODE, 1, F_EDGE).parameters()]).to(dev)
+        result = {"ranks_bit_identical": identical, "vs_single_process_max_abs": float((flat - flat1).abs().max()), "max_abs_weight": float(flat1.abs().max()),
+                  "max_abs_update": float((flat1 - w0).abs().max()), "steps": n_steps, "graphs_per_step": GRAPHS_PER_BATCH * world,
+                  "what": "weights after data-parallel Adam steps vs one process on the union of the ranks' batches (dropout off); ranks compared bit for bit"}
+    dist.barrier()
+    return result, exchange
 
 
 def run_ours(args):
@@ -254,6 +585,14 @@ def run_ours(args):
             opt.step()
             return loss.detach(), pred.detach()
 
+    mgpu, exchange = None, "none"
+    if distributed and args.path == "fused" and not args.profile:
+        mgpu, exchange = multi_gpu_check(rank, world, dev)
+        _trace("multi-GPU check done")
+    elif distributed and args.path == "fused":
+        exchange = "peer_push" if fused._peers is not None else "nccl"
+    elif distributed:
+        exchange = "nccl"
     _trace("model and batches ready")
     # launches of OUR kernels in one eager step (what a graph replay re-issues)
     step(dev_batches[0])
@@ -425,14 +764,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_steps(args.ref_graphs, 3, 1)
-            cpu = {
-                "value": r["graphs"] * r["steps"] / r["seconds"],
-                "unit": "graphs/s",
-                "cores": r["threads"],
-                "kind": "port",
-                "sample": f"{r['steps']} train steps of a {r['graphs']}-graph slice of the C2 batch ({r['nodes']} nodes, {r['edges']} edges), oracle port of the reference's CPU path",
-            }
+            cpu = cpu_baseline_record("c2", args.ref_graphs)
         line = {
             "metric": "ginet_train_step_graphs_per_s",
             "value": value,
@@ -457,7 +789,13 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "grad_exchange": exchange,
         }
+        if mgpu is not None:
+            line["multi_gpu_check"] = mgpu
+        if world == 1 and not args.no_extras:
+            line["gpu_torch_baseline"] = gpu_torch_baseline(dev, "c2")
+            line["configs"] = {c: measure_extra(dev, c) for c in ("c3", "c4-vanilla", "c4-fout", "c4-ginet")}
         _emit(line)
     _finish(distributed)
 
@@ -623,6 +961,8 @@ def main():
     _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c2":
+        run_config(args)
     else:
         run_ours(args)
 

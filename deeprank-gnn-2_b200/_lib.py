@@ -56,6 +56,7 @@ SIGNATURES = {
     "drk_graph_index_blocked_supported": (c_int32, [_I32, _I32]),
     "drk_graph_index_build_blocked": (c_int32, [_P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "drk_ginet_step_ctas": (c_int32, [_I32]),
+    "drk_ginet_step_set_phase_clocks": (c_int32, [_P, _I32]),
     "drk_ginet_step_exchange_floats": (c_int32, [_I32, _I32]),
     "drk_ginet_step_supported": (c_int32, [_I32, _I32, _I32, _I32]),
     "drk_ginet_step_workspace_bytes": (c_size_t, [_I32, _I32, _I32, _I32, _I32]),

@@ -97,6 +97,37 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk: SASS UBLKCP) tracked by an mbarrier in shared memory.  One thread issues a copy of
+// any multiple of 16 bytes (16-byte aligned on both sides); the copy engine moves it without occupying the LSU or any register, and
+// signals completion by transaction bytes on the barrier.  Waiters spin on the barrier's phase parity (acquire: the data is visible).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DRK_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DRK_MBAR_DONE;\n"
+      "bra DRK_MBAR_WAIT;\n"
+      "DRK_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// generic-proxy accesses to shared memory made so far are ordered before async-proxy (bulk copy) accesses issued afterwards
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- tensor cores with fp32-level accuracy: mma.sync m16n8k8 TF32 with error compensation ("3xTF32").
 // An fp32 operand is split as v = hi + lo with hi = tf32(v), lo = tf32(v - hi); a product is accumulated (fp32) as
 // lo_a*hi_b + hi_a*lo_b + hi_a*hi_b: the dropped lo*lo term is ~2^-22 relative, far inside the 1e-5 parity bar, while a plain

@@ -26,8 +26,14 @@
 namespace drk {
 namespace gs {
 
-constexpr int kT = 512;  // threads per CTA
+#ifndef DRK_STEP_THREADS
+#define DRK_STEP_THREADS 512
+#endif
+constexpr int kT = DRK_STEP_THREADS;  // threads per CTA of the step kernel.  1024 (-DDRK_STEP_THREADS=1024: 32 warps, 64 registers per thread) is supported and
+                                    // parity-green but measured 33 % slower on B200 (0.161 vs 0.121 ms per step): the register cap costs more than the warps hide
 constexpr int kNW = kT / 32;
+constexpr int kTI = 512, kNWI = 16;  // the standalone index kernel, and the warp chunks of the general in-kernel builder
+static_assert(kT == 512 || kT == 1024, "the step kernel's phase layouts are written for 16 or 32 warps");
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kS1 = 32;   // stacked conv1 outputs (2 x 16)
 constexpr int kF1 = 16;   // conv1 outputs per branch = conv2 inputs per branch
@@ -35,7 +41,8 @@ constexpr int kS2 = 64;   // stacked conv2 outputs (2 x 32)
 constexpr int kF2 = 32;
 constexpr int kHid = 128;  // fc1 outputs
 constexpr int kMaxOut = 8;
-constexpr size_t kSmemBudget = 227 * 1024 - 64;  // 64 B for the kernels' static shared variables
+constexpr size_t kSmemBudget = 227 * 1024 - 128;  // 128 B for the kernels' static shared variables
+constexpr int kHW1B = 0, kHW2B = kHid, kHW2 = kHid + kMaxOut, kHeadWeights = kHid + kMaxOut + kMaxOut * kHid;  // floats in the head-weight region
 
 __host__ __device__ inline int pad_kp(int fi) {  // smem row stride of the x tile: multiple of 4 with (kp/4) odd -> conflict-free float4 rows
   int kp = (fi + 3) / 4 * 4;
@@ -46,7 +53,7 @@ __host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
 
 // byte offsets of the shared-memory regions
 struct Layout {
-  int kp, t0, t1, x, idx, rinfo, cinfo, rperm, cperm, w1, w2, s, v, maskz, red, head, extra, total;
+  int kp, t0, t1, x, idx, rinfo, cinfo, rperm, cperm, w1, w2, s, hw, hmask, maskz, red, head, extra, total;
 };
 __host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap, int extra_bytes = 0) {
   Layout L;
@@ -63,16 +70,17 @@ __host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap,
   L.w1 = o; o += ((fi + 7) / 8) * 4 * 32 * 16;  // pre-split TF32 B fragments of W1s^T
   L.w2 = o; o += 2 * kF2 * kF1 * 4;
   L.s = o; o += kS2 * kF1 * 4;
-  L.v = o; o += kS2 * kF1 * 4;
+  L.hw = o; o += kHeadWeights * 4;         // fc1 bias, fc2 weight and bias: once per CTA
+  L.hmask = o; o += align16(rows_cap * 4);  // sign of H1, one 32-bit word per row (what the backward pass needs of H1)
   L.maskz = o; o += align16(rows_cap * 8);
-  L.red = o; o += 8 * kS2 * 4;
-  L.head = o; o += 832 * 4;
+  L.red = o; o += (kNW / 2) * kS2 * 4;
+  L.head = o; o += 848 * 4;
   L.extra = o; o += align16(extra_bytes);  // index-build scratch that found no idle region
   L.total = o;
   return L;
 }
-// head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[32] degree bins / cursors [256]
-constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528;
+// head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[40] degree bins / cursors [256] y[8] class[1]
+constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528, kHY = 824, kHCls = 832;  // scan 40 + 256 words; y[8]; class index
 
 struct StepArgs {
   const float* x; int64_t ldx; int32_t fi;
@@ -85,10 +93,17 @@ struct StepArgs {
   float* pred; float* loss_terms; float* part; int32_t part_stride;
   float* gvec; float* hvec; float* dhvec; float* dpvec;
   uint16_t* csc_spill; int32_t* status;
-  int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;  // *_off: index-build scratch (bytes into shared memory)
+  int32_t rows_cap, e_cap, ent_cap, stash_off, ranks_off, csc_off, x_vec;
+  int32_t x_bulk;  // x rows are contiguous (ldx == fi) and 16-byte aligned as a whole: one bulk copy (TMA) per graph  // *_off: index-build scratch (bytes into shared memory)
   int32_t slot_outputs;  // results indexed by slot instead of graph id (graph selections out of a resident set)
   int32_t pairs;  // edge layout (DRK_EDGES_*); != 0: the slices hold undirected pairs (edge_ptr counts pairs), each stands for both directions
+  long long* clk;  // profiling only (drk_ginet_step_set_phase_clocks): [slot][kClkMarks] SM clock at the phase boundaries, or null
 };
+constexpr int kClkMarks = 16;
+#define DRK_MARK(i)                                                                                     \
+  do {                                                                                                  \
+    if (a.clk != nullptr && threadIdx.x == 0) a.clk[(size_t)g_slot * kClkMarks + (i)] = clock64();      \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------- small helpers
 // One dynamic shared-memory array for every kernel of this file.  The phase functions below are __noinline__ (each gets its own
@@ -106,7 +121,8 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-// exclusive scan of one value per thread over the CTA; `scratch` has kNW + 1 words; returns the exclusive prefix, `total` = CTA sum
+// exclusive scan of one value per thread over a CTA of NW warps; `scratch` has NW + 1 words; returns the exclusive prefix, `total` = CTA sum
+template <int NW>
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t val, uint32_t* scratch, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = val;
@@ -118,18 +134,18 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t val, uint32_t* scra
   if (lane == 31) scratch[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    const uint32_t w = lane < kNW ? scratch[lane] : 0u;
+    const uint32_t w = lane < NW ? scratch[lane] : 0u;
     uint32_t winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(kFull, winc, o);
       if (lane >= o) winc += t;
     }
-    if (lane < kNW) scratch[lane] = winc - w;
-    if (lane == kNW - 1) scratch[kNW] = winc;
+    if (lane < NW) scratch[lane] = winc - w;
+    if (lane == NW - 1) scratch[NW] = winc;
   }
   __syncthreads();
-  total = scratch[kNW];
+  total = scratch[NW];
   const uint32_t res = scratch[warp] + inc - val;
   __syncthreads();
   return res;
@@ -200,7 +216,7 @@ struct IndexPlan {  // byte offsets into g_smem
   int cperm;
   int csr;      // uint16 entries
   int csc;
-  int scan;     // kNW + 1 words, then 4 x 64 words of degree histogram / cursors
+  int scan;     // 40 words for the block scan (kNW + 1 used), then 4 x 64 words of degree histogram / cursors
 };
 
 constexpr int kDegBins = 64;
@@ -221,11 +237,11 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
   ushort2* rinfo = sm<ushort2>(pl.rinfo);
   ushort2* cinfo = sm<ushort2>(pl.cinfo);
   uint32_t* scan = sm<uint32_t>(pl.scan);
-  int* hist = reinterpret_cast<int*>(scan + 32);  // [0,64) in-degree bins, [64,128) out-degree bins, [128,256) their cursors
+  int* hist = reinterpret_cast<int*>(scan + 40);  // [0,64) in-degree bins, [64,128) out-degree bins, [128,256) their cursors
   // zero the histograms
   {
     uint32_t* z = reinterpret_cast<uint32_t*>(cnt_r);
-    const int words = kNW * cs / 2;
+    const int words = kNWI * cs / 2;
     for (int i = tid; i < words; i += kT) z[i] = 0u;
     if (WANT_CSC) {
       z = reinterpret_cast<uint32_t*>(cnt_c);
@@ -234,7 +250,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     if (tid < 2 * kDegBins) hist[tid] = 0;
   }
   __syncthreads();
-  const int chunk = ((ne + kNW - 1) / kNW + 31) & ~31;
+  const int chunk = ((ne + kNWI - 1) / kNWI + 31) & ~31;  // the first kNWI warps take the edge chunks (warps beyond find wb == we == ne)
   const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
   // passes 1+2, software pipelined in groups of 8 batches (256 edges) per warp: the 8-byte loads of the next group are in flight
   // while the current group is matched.
@@ -340,14 +356,14 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     uint32_t dr = 0, dc = 0;
     if (v < n) {
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) {
+      for (int w = 0; w < kNWI; ++w) {
         const uint32_t t = cnt_r[w * cs + v];
         cnt_r[w * cs + v] = (uint16_t)dr;
         dr += t;
       }
       if (want_csc) {
 #pragma unroll
-        for (int w = 0; w < kNW; ++w) {
+        for (int w = 0; w < kNWI; ++w) {
           const uint32_t t = cnt_c[w * cs + v];
           cnt_c[w * cs + v] = (uint16_t)dc;
           dc += t;
@@ -358,7 +374,7 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
     }
     const uint32_t packed = ((dr + 3u) & ~3u) | (((dc + 3u) & ~3u) << 16);
     uint32_t total;
-    const uint32_t ex = block_excl_scan(packed, scan, total) + carry;
+    const uint32_t ex = block_excl_scan<kNW>(packed, scan, total) + carry;
     if (v < n) {
       rinfo[v] = make_ushort2((unsigned short)((ex & 0xffffu) >> 2), (unsigned short)dr);
       if (want_csc) cinfo[v] = make_ushort2((unsigned short)((ex >> 16) >> 2), (unsigned short)dc);
@@ -413,17 +429,170 @@ __device__ __noinline__ int build_index(const IndexPlan pl, const int64_t* __res
   return want_csc ? (int)(carry >> 16) : -1;
 }
 
+// Fast index build for graphs whose adjacency is a SET (no repeated edge, no self loop stored twice) and symmetric -- every graph the
+// reference's dataset produces (dataset.py:944-948 doubles a list of unique contacts).  The graph's adjacency goes into a dense
+// bitmap in shared memory (n x ceil(n/32) words: 16 KB for 360 nodes) with one atomicOr per directed edge -- OR is commutative, so
+// the result does not depend on the order in which the threads arrive -- and row r of the CSR is then the list of set bits of
+// bitmap row r: sources in ASCENDING NODE ORDER, a pure function of the graph (bit-reproducible, identical for the three edge
+// layouts).  A repeated edge shows up as an atomicOr that finds its bit already set, a one-directional edge as a missing mirror
+// bit: either makes the whole CTA return false and the caller runs the general stable builder (build_index) instead.
+// No MATCH, no per-warp histograms, no ranks: ~4 k cycles per 6 k-edge graph instead of ~18 k.
+template <bool CHECK_SYMMETRY>
+__device__ __noinline__ bool build_index_bitmap(const IndexPlan pl, int bm_off, int bm_bytes, const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol,
+                                                int e0, int items, int node0, int n, int32_t* status, int layout, long long* clk) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = (n + 31) >> 5;
+  if ((long long)n * W * 6 > bm_bytes) return false;  // bitmap + per-word prefix counts; CTA-uniform
+  uint32_t* bm = sm<uint32_t>(bm_off);
+  ushort2* rinfo = sm<ushort2>(pl.rinfo);
+  uint32_t* scan = sm<uint32_t>(pl.scan);
+  int* hist = reinterpret_cast<int*>(scan + 40);
+  const int32_t* words = reinterpret_cast<const int32_t*>(erow);
+  const bool undirected = layout != DRK_EDGES_DIRECTED;  // one item = one contact = both directions
+  // the thread's first kBatch items are requested before anything else: their latency hides behind the zeroing of the bitmap
+  constexpr int kBatch = 8;
+  uint32_t pk[kBatch];  // (r | c << 16) local ids, 0xffffffff = edge leaves the graph
+  auto fetch = [&](int i) -> uint32_t {
+    if (i >= items) return 0xfffffffeu;  // no item
+    if (layout == DRK_EDGES_LOCAL_PAIRS16) {
+      const unsigned w = (unsigned)ld_stream_i32(words + e0 + i);
+      return ((w & 0xffffu) < (unsigned)n && (w >> 16) < (unsigned)n) ? w : 0xffffffffu;
+    }
+    const unsigned long long rr = (unsigned long long)(ld_stream_i64(erow + e0 + i) - node0), cc = (unsigned long long)(ld_stream_i64(ecol + e0 + i) - node0);
+    return (rr < (unsigned long long)n && cc < (unsigned long long)n) ? ((unsigned)rr | ((unsigned)cc << 16)) : 0xffffffffu;
+  };
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) pk[u] = fetch(tid + u * kT);
+  {
+    uint4* z = reinterpret_cast<uint4*>(bm);
+    const int chunks = (n * W + 3) >> 2;
+    for (int i = tid; i < chunks; i += kT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < kDegBins) hist[tid] = 0;
+  }
+  __syncthreads();
+  bool bad = false, reject = false;
+  auto mark = [&](uint32_t w) {
+    if (w == 0xfffffffeu) return;
+    if (w == 0xffffffffu) {
+      bad = true;  // an edge that leaves the graph is dropped and flagged, as in build_index
+      return;
+    }
+    const unsigned r = w & 0xffffu, c = w >> 16;
+    const unsigned bit_c = 1u << (c & 31), bit_r = 1u << (r & 31);
+    reject |= (atomicOr(&bm[r * W + (c >> 5)], bit_c) & bit_c) != 0u;
+    if (undirected) reject |= (atomicOr(&bm[c * W + (r >> 5)], bit_r) & bit_r) != 0u;
+  };
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) mark(pk[u]);
+  for (int i0 = kBatch * kT; i0 < items; i0 += kBatch * kT) {  // graphs with more than 4096 items
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) pk[u] = fetch(i0 + tid + u * kT);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) mark(pk[u]);
+  }
+  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
+  if (__syncthreads_or(reject)) return false;
+  if (CHECK_SYMMETRY && !undirected) {
+    for (int i0 = 0; i0 < items; i0 += kBatch * kT) {
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) pk[u] = fetch(i0 + tid + u * kT);
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (pk[u] < 0xfffffffeu) {
+          const unsigned r = pk[u] & 0xffffu, c = pk[u] >> 16;
+          reject |= ((bm[c * W + (r >> 5)] >> (r & 31)) & 1u) == 0u;
+        }
+    }
+    if (__syncthreads_or(reject)) return false;
+    if (items <= kBatch * kT) {
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) pk[u] = fetch(tid + u * kT);
+    }
+  }
+  // degrees and, per bitmap word, the number of set bits in the row's earlier words (thread per row)
+  uint16_t* pref = reinterpret_cast<uint16_t*>(bm + n * W);
+  uint32_t carry = 0;
+  for (int vb = 0; vb < n; vb += kT) {
+    const int v = vb + tid;
+    uint32_t dr = 0;
+    if (v < n) {
+      for (int w = 0; w < W; ++w) {
+        pref[v * W + w] = (uint16_t)dr;
+        dr += __popc(bm[v * W + w]);
+      }
+      atomicAdd(&hist[min((int)dr, kDegBins - 1)], 1);
+    }
+    uint32_t total;
+    const uint32_t ex = block_excl_scan<kNW>((dr + 3u) & ~3u, scan, total) + carry;
+    if (v < n) rinfo[v] = make_ushort2((unsigned short)(ex >> 2), (unsigned short)dr);
+    carry += total;
+  }
+  __syncthreads();
+  if (warp == 0) {  // cursor[bin] = number of rows in a larger degree bin (lane 0 holds the largest bins)
+    const int hi = hist[kDegBins - 1 - lane], lo = hist[kDegBins / 2 - 1 - lane];
+    int inc_hi = hi, inc_lo = lo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc_hi, o), u = __shfl_up_sync(kFull, inc_lo, o);
+      if (lane >= o) {
+        inc_hi += t;
+        inc_lo += u;
+      }
+    }
+    const int total_hi = __shfl_sync(kFull, inc_hi, 31);
+    int* cur = hist + 2 * kDegBins;
+    cur[kDegBins - 1 - lane] = inc_hi - hi;
+    cur[kDegBins / 2 - 1 - lane] = total_hi + inc_lo - lo;
+  }
+  // placement, every directed edge on its own: slot = segment start + set bits of the row below the edge's column
+  {
+    uint16_t* csr = sm<uint16_t>(pl.csr);
+    auto place = [&](uint32_t w) {
+      if (w >= 0xfffffffeu) return;
+      const unsigned r = w & 0xffffu, c = w >> 16;
+      {
+        const unsigned word = bm[r * W + (c >> 5)];
+        csr[4 * (int)rinfo[r].x + pref[r * W + (c >> 5)] + __popc(word & ((1u << (c & 31)) - 1u))] = (uint16_t)(c * 8u);
+      }
+      if (undirected) {
+        const unsigned word = bm[c * W + (r >> 5)];
+        csr[4 * (int)rinfo[c].x + pref[c * W + (r >> 5)] + __popc(word & ((1u << (r & 31)) - 1u))] = (uint16_t)(r * 8u);
+      }
+    };
+    if (items <= kBatch * kT) {  // the thread's items are still in registers
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) place(pk[u]);
+    } else {
+      for (int i0 = 0; i0 < items; i0 += kBatch * kT) {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) pk[u] = fetch(i0 + tid + u * kT);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) place(pk[u]);
+      }
+    }
+  }
+  __syncthreads();  // the cursors are in place
+  {
+    uint16_t* rperm = sm<uint16_t>(pl.rperm);
+    int* cur = hist + 2 * kDegBins;
+    for (int v = tid; v < n; v += kT) rperm[atomicAdd(&cur[min((int)rinfo[v].y, kDegBins - 1)], 1)] = (uint16_t)v;  // rows by decreasing degree
+  }
+  __syncthreads();
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------- aggregation over a smem tile
 // dst[i] = epi( sum_{s in segment i} src[entry s] ), tiles are [rows][32] floats.  8 lanes per row (float4 each), 4 rows per warp,
 // warp-uniform trip count, entries of a segment in CSR order (= ascending edge id).
-// MODE 0: relu ; MODE 1: none ; MODE 2: in place, dst = sum * (dst > 0)
+// MODE 0: relu, and the sign of every output as one bit -> hmask[row] ; MODE 1: none ; MODE 2: dst = sum * (hmask bit)
 template <int MODE>
-__device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, int perm_off, int idx_off, int n) {
+__device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, int perm_off, int idx_off, int hmask_off, int n) {
   const float* s_src = sm<float>(src_off);
   float* s_dst = sm<float>(dst_off);
   const ushort2* info = sm<ushort2>(info_off);
   const uint16_t* perm = sm<uint16_t>(perm_off);
   const uint16_t* idx = sm<uint16_t>(idx_off);
+  uint32_t* hmask = sm<uint32_t>(hmask_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
   const char* lane_base = reinterpret_cast<const char*>(s_src) + sl * 16;
@@ -478,20 +647,27 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
           a23 = __fadd2_rn(a23, make_float2(v[j].z, v[j].w));
         }
     }
-    if (!row_ok) continue;
     float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
-    float4* out = reinterpret_cast<float4*>(s_dst + r * kS1 + sl * 4);
     if (MODE == 0) {
       acc.x = acc.x < 0.f ? 0.f : acc.x;
       acc.y = acc.y < 0.f ? 0.f : acc.y;
       acc.z = acc.z < 0.f ? 0.f : acc.z;
       acc.w = acc.w < 0.f ? 0.f : acc.w;
-    } else if (MODE == 2) {
-      const float4 m = *out;
-      acc.x = m.x <= 0.f ? 0.f : acc.x;
-      acc.y = m.y <= 0.f ? 0.f : acc.y;
-      acc.z = m.z <= 0.f ? 0.f : acc.z;
-      acc.w = m.w <= 0.f ? 0.f : acc.w;
+      // which outputs are positive: 4 bits per lane, 32 per row (all lanes take part in the shuffles)
+      uint32_t bits = ((acc.x > 0.f ? 1u : 0u) | (acc.y > 0.f ? 2u : 0u) | (acc.z > 0.f ? 4u : 0u) | (acc.w > 0.f ? 8u : 0u)) << (sl * 4);
+      bits |= __shfl_xor_sync(kFull, bits, 1);
+      bits |= __shfl_xor_sync(kFull, bits, 2);
+      bits |= __shfl_xor_sync(kFull, bits, 4);
+      if (row_ok && sl == 0) hmask[r] = bits;
+    }
+    if (!row_ok) continue;
+    float4* out = reinterpret_cast<float4*>(s_dst + r * kS1 + sl * 4);
+    if (MODE == 2) {
+      const uint32_t m = hmask[r] >> (sl * 4);
+      acc.x = (m & 1u) ? acc.x : 0.f;
+      acc.y = (m & 2u) ? acc.y : 0.f;
+      acc.z = (m & 4u) ? acc.z : 0.f;
+      acc.w = (m & 8u) ? acc.w : 0.f;
     }
     *out = acc;
   }
@@ -512,7 +688,7 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
 // (Reading the A fragments straight from global/L2 so that the x tile could stream in under the forward pass was measured
 // 3 us per step SLOWER than staging x first: 28 dependent-latency loads per lane with 16 warps per SM are not hidden.)
 // sW holds the B fragments of W1s^T pre-split once per CTA: [k-step][column tile][lane] x (hi.b0, hi.b1, lo.b0, lo.b1).
-__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int rows_cap, int kp, int ksteps) {
+__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int fi, int ksteps) {
   const float* sX = sm<float>(x_off);
   const uint4* sW = sm<uint4>(w1_off);
   float* sP = sm<float>(p_off);
@@ -521,8 +697,8 @@ __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, 
   const int n_tiles = (n + 15) / 16;
   for (int tl = warp; tl < n_tiles; tl += kNW) {
     const int r0 = tl * 16;
-    const float* xa = sX + min(r0 + g, rows_cap - 1) * kp + t;      // rows beyond n: results are not stored
-    const float* xb = sX + min(r0 + g + 8, rows_cap - 1) * kp + t;
+    const float* xa = sX + min(r0 + g, n - 1) * fi + t;      // rows beyond n: results are not stored
+    const float* xb = sX + min(r0 + g + 8, n - 1) * fi + t;
     float acc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -530,10 +706,10 @@ __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, 
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     for (int ks = 0; ks < ksteps; ++ks) {
       const int k0 = ks * 8;
-      const bool in2 = k0 + t + 4 < kp;  // the last k-step may reach past the row: those products are zero, keep them finite
+      const bool in1 = k0 + t < fi, in2 = k0 + t + 4 < fi;  // the last k-step reaches past the (unpadded) row: those operands are zero
       uint32_t ahi[4], alo[4];
-      split_tf32(xa[k0], ahi[0], alo[0]);
-      split_tf32(xb[k0], ahi[1], alo[1]);
+      split_tf32(in1 ? xa[k0] : 0.f, ahi[0], alo[0]);
+      split_tf32(in1 ? xb[k0] : 0.f, ahi[1], alo[1]);
       split_tf32(in2 ? xa[k0 + 4] : 0.f, ahi[2], alo[2]);
       split_tf32(in2 ? xb[k0 + 4] : 0.f, ahi[3], alo[3]);
 #pragma unroll
@@ -584,7 +760,7 @@ __device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) cs[nt][0] = cs[nt][1] = 0.f;
     const int n_tiles = (n + 15) / 16;
-    for (int tl = slot; tl < n_tiles; tl += 8) {
+    for (int tl = slot; tl < n_tiles; tl += kNW / 2) {
       const int r0 = tl * 16;
       const float* ra = a2b + min(r0 + g, rows_cap - 1) * kS1 + t;  // rows beyond n: garbage in, masked out below
       const float* rb = a2b + min(r0 + g + 8, rows_cap - 1) * kS1 + t;
@@ -645,7 +821,7 @@ __device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off
 #pragma unroll
       for (int i = 0; i < 4; ++i) sacc[mt][nt][i] = 0.f;
   const int n_ks = (n + 7) / 8;
-  for (int ks = slot; ks < n_ks; ks += 8) {
+  for (int ks = slot; ks < n_ks; ks += kNW / 2) {
     const int r0 = ks * 8 + t, r1 = r0 + 4;
     const bool v0 = r0 < n, v1 = r1 < n;
     const uint32_t mw0 = v0 ? sMaskZ[r0 * 2 + br] : 0u, mw1 = v1 ? sMaskZ[r1 * 2 + br] : 0u;
@@ -665,15 +841,26 @@ __device__ __noinline__ void conv2_readout(int a2_off, int w2_off, int maskz_off
       }
     }
   }
-  __syncthreads();  // every warp is done reading A2: reuse the tile as the reduction scratch [8 warps][64 c][16 k]
+  __syncthreads();  // every warp is done reading A2: reuse the tile as the reduction scratch [8 slots][64 c][16 k]
+  // slots 0..7 store their partials; with 32 warps slots 8..15 then add theirs on top (fixed order: deterministic)
+  for (int pass = 0; pass < kNW / 16; ++pass) {
+    if ((slot >> 3) == pass) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      float* d = sA2 + ((slot * kS2 + br * kF2 + 16 * mt + g) * kF1 + 8 * nt + 2 * t);
-      *reinterpret_cast<float2*>(d) = make_float2(sacc[mt][nt][0], sacc[mt][nt][1]);
-      *reinterpret_cast<float2*>(d + 8 * kF1) = make_float2(sacc[mt][nt][2], sacc[mt][nt][3]);
+        for (int nt = 0; nt < 2; ++nt) {
+          float* d = sA2 + (((slot & 7) * kS2 + br * kF2 + 16 * mt + g) * kF1 + 8 * nt + 2 * t);
+          float2 lo = make_float2(sacc[mt][nt][0], sacc[mt][nt][1]), hi = make_float2(sacc[mt][nt][2], sacc[mt][nt][3]);
+          if (pass > 0) {
+            const float2 plo = *reinterpret_cast<const float2*>(d), phi = *reinterpret_cast<const float2*>(d + 8 * kF1);
+            lo.x += plo.x; lo.y += plo.y; hi.x += phi.x; hi.y += phi.y;
+          }
+          *reinterpret_cast<float2*>(d) = lo;
+          *reinterpret_cast<float2*>(d + 8 * kF1) = hi;
+        }
     }
+    if (pass + 1 < kNW / 16) __syncthreads();
+  }
 }
 
 // dA2_br [n x 16] = Mask_br [n x 32] V_br [32 x 16] with V[c][k] = dG[c]/n * W2[c][k]: the left operand is the 0/1 sign mask of Z2 (exact
@@ -696,7 +883,7 @@ __device__ __noinline__ void conv2_backward_input(int w2_off, int dg_off, int ma
       split_tf32(sDG[c0 + 4] * sW2[(c0 + 4) * kF1 + k], vh[ks][nt].y, vl[ks][nt].y);
     }
   const int n_tiles = (n + 15) / 16;
-  for (int tl = slot; tl < n_tiles; tl += 8) {
+  for (int tl = slot; tl < n_tiles; tl += kNW / 2) {
     const int ra = tl * 16 + g, rb = ra + 8;
     const uint32_t mwa = ra < n ? sMaskZ[ra * 2 + br] : 0u, mwb = rb < n ? sMaskZ[rb * 2 + br] : 0u;
     float acc[2][4];
@@ -723,23 +910,25 @@ __device__ __noinline__ void conv2_backward_input(int w2_off, int dg_off, int ma
 
 // dW1s[m, k] = sum_r Q[r, m] x[r, k]: lane -> (mg: 4 outputs m, kgl: 4 features k), warp -> (k block of 16, row split wn);
 // the four row-split partials go to sScr[wn][m][kp]
-__device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off, int n, int kp) {
+__device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off, int n, int kp, int fi) {
   const float* sQ = sm<float>(q_off);
-  const float* sX = sm<float>(x_off);
+  const float* sX = sm<float>(x_off);  // unpadded rows (stride fi), 4-byte aligned: features k0..k0+3 beyond fi read the next row (never stored)
   float* sScr = sm<float>(scr_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wk = warp & 3, wn = warp >> 2;
   const int mg = lane & 7, kgl = lane >> 3;
   const int k0 = wk * 16 + kgl * 4;
-  if (k0 >= kp) return;  // kp is a multiple of 4: a float4 of features is all-in or all-out
+  const bool active = k0 < kp;  // kp is a multiple of 4: a float4 of features is all-in or all-out
   float2 dw[4][2];  // [m][k pair]
 #pragma unroll
   for (int i = 0; i < 4; ++i) dw[i][0] = dw[i][1] = make_float2(0.f, 0.f);
   const float* qp = sQ + mg * 4;
   const float* xp = sX + k0;
-  for (int r = wn; r < n; r += 4) {
+  const bool in0 = k0 < fi, in1 = k0 + 1 < fi, in2 = k0 + 2 < fi, in3 = k0 + 3 < fi;
+  for (int r = wn; active && r < n; r += kNW / 4) {
     const float4 qa = *reinterpret_cast<const float4*>(qp + r * kS1);
-    const float4 xb = *reinterpret_cast<const float4*>(xp + r * kp);
+    const float* xr = xp + r * fi;
+    const float4 xb = make_float4(in0 ? xr[0] : 0.f, in1 ? xr[1] : 0.f, in2 ? xr[2] : 0.f, in3 ? xr[3] : 0.f);
     const float qv[4] = {qa.x, qa.y, qa.z, qa.w};
     const float2 x01 = make_float2(xb.x, xb.y), x23 = make_float2(xb.z, xb.w);
 #pragma unroll
@@ -749,9 +938,22 @@ __device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off
       dw[i][1] = __ffma2_rn(qq, x23, dw[i][1]);
     }
   }
+  // row splits 0..3 store their partials; with 32 warps splits 4..7 then add theirs on top (fixed order: deterministic)
+  for (int pass = 0; pass < kNW / 16; ++pass) {
+    if (active && (wn >> 2) == pass) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(sScr + (wn * kS1 + mg * 4 + i) * kp + k0) = make_float4(dw[i][0].x, dw[i][0].y, dw[i][1].x, dw[i][1].y);
+      for (int i = 0; i < 4; ++i) {
+        float4* d = reinterpret_cast<float4*>(sScr + ((wn & 3) * kS1 + mg * 4 + i) * kp + k0);
+        float4 v = make_float4(dw[i][0].x, dw[i][0].y, dw[i][1].x, dw[i][1].y);
+        if (pass > 0) {
+          const float4 p = *d;
+          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        *d = v;
+      }
+    }
+    if (pass + 1 < kNW / 16) __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -759,6 +961,7 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   unsigned char* smem = g_smem;
   __shared__ int s_meta[2][8];
+  __shared__ __align__(8) unsigned long long s_bar[2];  // mbarriers of the two bulk copies per graph: [0] x rows, [1] fc1 weight
   const Layout L = make_layout(a.fi, a.rows_cap, a.ent_cap);
   const int kp = L.kp;
   float* sT0 = reinterpret_cast<float*>(smem + L.t0);
@@ -776,7 +979,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   IndexPlan plan;
   plan.cstride = a.rows_cap;
   plan.cnt_r = L.t0;
-  plan.cnt_c = L.t0 + kNW * a.rows_cap * 2;
+  plan.cnt_c = L.t0 + kNWI * a.rows_cap * 2;
   plan.stash = a.stash_off;
   plan.ranks = a.ranks_off;
   plan.csc = a.csc_off;
@@ -787,6 +990,27 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
   plan.csr = L.idx;
   plan.scan = L.head + kHScan * 4;
 
+  // ---- the first graph's offsets, and its edge slice and node rows on their way from HBM to L2 while the weights are set up
+  if (tid == 0) {
+    const int slot = blockIdx.x;
+    const int g0 = a.order != nullptr ? __ldg(a.order + slot) : slot;
+    s_meta[0][0] = g0;
+    s_meta[0][1] = __ldg(a.graph_ptr + g0);
+    s_meta[0][2] = __ldg(a.graph_ptr + g0 + 1) - s_meta[0][1];
+    s_meta[0][3] = __ldg(a.edge_ptr + g0);
+    s_meta[0][4] = __ldg(a.edge_ptr + g0 + 1) - s_meta[0][3];
+  }
+  __syncthreads();
+  {
+    const long long nn = s_meta[0][2], nen = s_meta[0][4];
+    if (a.pairs == DRK_EDGES_LOCAL_PAIRS16) {
+      prefetch_range_l2(reinterpret_cast<const int32_t*>(a.erow) + s_meta[0][3], nen * 4);
+    } else {
+      prefetch_range_l2(a.erow + s_meta[0][3], nen * 8);
+      prefetch_range_l2(a.ecol + s_meta[0][3], nen * 8);
+    }
+    prefetch_range_l2(a.x + (long long)s_meta[0][1] * a.ldx, nn * a.ldx * 4);
+  }
   // ---- weights once per CTA.  W1s^T as pre-split TF32 B fragments: entry [(k-step * 4 + column tile) * 32 + lane] =
   // (hi.b0, hi.b1, lo.b0, lo.b1) with b0 = W1s[8 nt + g][8 ks + t], b1 = W1s[8 nt + g][8 ks + t + 4] (zero beyond F)
   {
@@ -807,21 +1031,25 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     sW2[e] = __ldg(a.w2a + e);
     sW2[kF2 * kF1 + e] = __ldg(a.w2b + e);
   }
+  // the head's small operands once per CTA: fc1 bias, fc2 bias, fc2 weight (fc1's 32 KB weight streams into tile 1 per graph)
+  float* sHW = reinterpret_cast<float*>(smem + L.hw);
+  for (int e = tid; e < kHid; e += kT) sHW[kHW1B + e] = __ldg(a.fc1_b + e);
+  if (tid < a.out_dim) sHW[kHW2B + tid] = __ldg(a.fc2_b + tid);
+  for (int e = tid; e < a.out_dim * kHid; e += kT) sHW[kHW2 + e] = __ldg(a.fc2_w + e);
+  const unsigned long long rng_step = (TRAIN && a.rng_step != nullptr) ? (unsigned long long)*a.rng_step : 0ull;  // advanced by the finalize kernel
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_init_fence();
+  }
+  uint32_t x_phase = 0, w_phase = 0;  // parity of the next completion of s_bar[0] / s_bar[1]
 
   // Static schedule: CTA b processes slots b, b + grid, ... of `order` (the host lays the graphs out longest-processing-time-first,
   // data.py:snake_order, so every CTA's total work is about equal).  The NEXT slot's offsets are fetched by one thread while the
   // current graph is processed: {graph id, node0, n, e0, ne} go through shared memory one iteration ahead.
-  if (tid == 0) {
-    const int slot = blockIdx.x;
-    const int g0 = a.order != nullptr ? __ldg(a.order + slot) : slot;
-    s_meta[0][0] = g0;
-    s_meta[0][1] = __ldg(a.graph_ptr + g0);
-    s_meta[0][2] = __ldg(a.graph_ptr + g0 + 1) - s_meta[0][1];
-    s_meta[0][3] = __ldg(a.edge_ptr + g0);
-    s_meta[0][4] = __ldg(a.edge_ptr + g0 + 1) - s_meta[0][3];
-  }
   int buf = 0;
   for (int g_slot = blockIdx.x; g_slot < a.num_graphs; g_slot += gridDim.x, buf ^= 1) {
+    fence_proxy_async();  // this thread's accesses to the x region so far come before the copy engine's writes of the next graph's rows
     __syncthreads();  // previous graph is finished with every region; weights and this graph's offsets are visible
     const int g = s_meta[buf][0], node0 = s_meta[buf][1], n = s_meta[buf][2], e0 = s_meta[buf][3];
     const int ne = a.pairs ? 2 * s_meta[buf][4] : s_meta[buf][4];  // directed edges of the graph
@@ -844,11 +1072,50 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       }
       continue;
     }
-    // ---- the graph index, then x rows (the index build uses the x region as scratch)
-    const int csc_entries = a.pairs == DRK_EDGES_LOCAL_PAIRS16 ? build_index<TRAIN, true>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs)
-                                                               : build_index<TRAIN, false>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs);
-    stage_rows(sX, a.x, a.ldx, a.fi, kp, node0, n, a.x_vec);
-    cp_async_commit();
+    DRK_MARK(0);
+    // ---- x rows: ONE bulk copy (TMA) of the graph's contiguous [n, fi] block into the x region, unpadded; it lands underneath the
+    // index build.  The copy must start and end on 16-byte boundaries: it starts up to 12 bytes early (the previous graph's last
+    // floats, `x_mis` bytes in front of row 0) and the last 0..12 bytes travel through ordinary loads.
+    const long long x_byte0 = (long long)node0 * a.fi * 4;
+    const int x_mis = a.x_bulk ? (int)(x_byte0 & 15) : 0;
+    const int x_off = L.x + x_mis;
+    auto issue_x = [&]() {
+      if (a.x_bulk) {
+        const int total = x_mis + n * a.fi * 4, bulk = total & ~15;
+        if (tid == 0) {
+          fence_proxy_async();  // the previous graph's generic reads of the x region are ordered before the copy engine's writes
+          mbar_expect_tx(&s_bar[0], (uint32_t)bulk);
+          if (bulk > 0) bulk_copy_g2s(smem + L.x, reinterpret_cast<const char*>(a.x) + x_byte0 - x_mis, (uint32_t)bulk, &s_bar[0]);
+        }
+        if (tid >= 32 && tid < 32 + ((total - bulk) >> 2)) {
+          const int w = (bulk >> 2) + (tid - 32);  // float index inside the region
+          reinterpret_cast<float*>(smem + L.x)[w] = __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.x) + x_byte0 - x_mis) + w);
+        }
+      } else {
+        stage_rows(sX, a.x, a.ldx, a.fi, a.fi, node0, n, a.x_vec);  // strided or misaligned x: per-row cp.async, same unpadded layout
+        cp_async_commit();
+      }
+    };
+    auto wait_x = [&]() {
+      if (a.x_bulk) {
+        mbar_wait(&s_bar[0], x_phase);
+        x_phase ^= 1u;
+      } else {
+        cp_async_wait<0>();
+      }
+    };
+    issue_x();
+    // ---- the graph index: bitmap builder for duplicate-free symmetric graphs (tile 1 holds the bitmap), else the general stable
+    // builder, which uses the x region as scratch (x is fetched again behind it)
+    int csc_entries = -1;
+    if (!build_index_bitmap<TRAIN>(plan, L.t1, a.rows_cap * kS1 * 4, a.erow, a.ecol, e0, s_meta[buf][4], node0, n, a.status, a.pairs, a.clk != nullptr ? a.clk + (size_t)g_slot * kClkMarks : nullptr)) {
+      wait_x();
+      __syncthreads();
+      csc_entries = a.pairs == DRK_EDGES_LOCAL_PAIRS16 ? build_index<TRAIN, true>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs)
+                                                       : build_index<TRAIN, false>(plan, a.erow, a.ecol, e0, ne, node0, n, a.status, a.pairs);
+      issue_x();
+    }
+    DRK_MARK(1);
     const bool have_csc = TRAIN && csc_entries >= 0;  // false: symmetric adjacency, the backward pass gathers through the CSR
     uint16_t* spill = TRAIN ? a.csc_spill + (size_t)blockIdx.x * a.ent_cap : nullptr;
     if (have_csc) {  // CSC -> global scratch of this CTA (16-byte chunks); it comes back into the index region for the backward pass
@@ -863,10 +1130,15 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       nx[2] = __ldg(a.edge_ptr + gn);
       nx[3] = __ldg(a.edge_ptr + gn + 1);
     }
-    cp_async_wait<0>();
+    if (tid >= 64 && tid < 64 + a.out_dim && TRAIN) {  // this graph's targets, long before the loss needs them
+      if (a.loss_kind == DRK_LOSS_MSE) sHead[kHY + tid - 64] = __ldg(a.y + (size_t)g * a.out_dim + (tid - 64));
+      else if (tid == 64) reinterpret_cast<int*>(sHead)[kHCls] = (int)max(-1ll, min((long long)__ldg(a.y_cls + g), (long long)kMaxOut));
+    }
+    wait_x();
     __syncthreads();
+    DRK_MARK(2);
 
-    project_x(L.x, L.w1, L.t0, n, a.rows_cap, kp, (a.fi + 7) / 8);
+    project_x(x_off, L.w1, L.t0, n, a.fi, (a.fi + 7) / 8);
     if (tid == 32 && have_next) {
       s_meta[buf ^ 1][0] = gn;
       s_meta[buf ^ 1][1] = nx[0];
@@ -886,11 +1158,22 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       }
       prefetch_range_l2(a.x + (long long)node0n * a.ldx, nn * a.ldx * 4);
     }
+    DRK_MARK(3);
     // ---- H1 = relu(A P) -> tile 1 ; A2 = A H1 -> tile 0
-    aggregate<0>(L.t0, L.t1, L.rinfo, L.rperm, L.idx, n);
+    aggregate<0>(L.t0, L.t1, L.rinfo, L.rperm, L.idx, L.hmask, n);
     __syncthreads();
-    aggregate<1>(L.t1, L.t0, L.rinfo, L.rperm, L.idx, n);
+    DRK_MARK(4);
+    aggregate<1>(L.t1, L.t0, L.rinfo, L.rperm, L.idx, L.hmask, n);
+    fence_proxy_async();
     __syncthreads();
+    DRK_MARK(5);
+    // H1 lives on as its sign mask: tile 1 is free until dZ1 is written.  fc1's weight [128, 64] (32 KB, contiguous) streams into it
+    // with one bulk copy and is there by the time the head needs it.
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar[1], (uint32_t)(kHid * kS2 * 4));
+      bulk_copy_g2s(smem + L.t1, a.fc1_w, (uint32_t)(kHid * kS2 * 4), &s_bar[1]);
+    }
     if (have_csc) {  // the CSR is consumed: bring the CSC back (asynchronous, needed only after the head)
       const int chunks = (csc_entries + 7) / 8;
       for (int i = tid; i < chunks; i += kT) cp_async_cg16(sIdx + i * 8, spill + i * 8);  // L2 only: this CTA wrote it moments ago
@@ -898,6 +1181,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     }
     conv2_readout<TRAIN>(L.t0, L.w2, L.maskz, L.red, n, a.rows_cap);
     __syncthreads();
+    DRK_MARK(6);
     float* hG = sHead + kHG;
     float* hDG = sHead + kHDG;
     float* hH = sHead + kHH;
@@ -909,7 +1193,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     if (tid < kS2) {
       float s = 0.f;
 #pragma unroll
-      for (int rl = 0; rl < 8; ++rl) s += sRed[rl * kS2 + tid];
+      for (int rl = 0; rl < kNW / 2; ++rl) s += sRed[rl * kS2 + tid];
       const float gm = s / cnt;
       hG[tid] = gm;
       if (a.gvec != nullptr) a.gvec[(size_t)og * kS2 + tid] = gm;
@@ -923,65 +1207,69 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       }
     }
     __syncthreads();
-    // ---- head: h = dropout(relu(fc1 G + b1)); pred = fc2 h + b2
+    DRK_MARK(13);
+    // ---- head: h = dropout(relu(fc1 G + b1)); pred = fc2 h + b2.  fc1's weight is in tile 1 by now (bulk copy issued after A2),
+    // every other operand has been in shared memory since the CTA started: no global load on this chain.
+    mbar_wait(&s_bar[1], w_phase);
+    w_phase ^= 1u;
+    const float* sFc1 = sT1;  // [128][64]
     {
-      const int j = tid >> 2, q = tid & 3;
-      const float4* wrow = reinterpret_cast<const float4*>(a.fc1_w + (size_t)j * kS2 + q * 16);
-      float s = 0.f;
+      // 16 lanes x float4 = one 256-byte weight row (conflict-free), two rows per warp instruction, kHid / (2 kNW) sweeps
+      const int half = lane >> 4, l16 = lane & 15;
+      const float4 gv = *reinterpret_cast<const float4*>(hG + l16 * 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 wv = __ldg(wrow + i);
-        const float4 gv = *reinterpret_cast<const float4*>(hG + q * 16 + i * 4);
-        s = fmaf(wv.x, gv.x, s);
-        s = fmaf(wv.y, gv.y, s);
-        s = fmaf(wv.z, gv.z, s);
-        s = fmaf(wv.w, gv.w, s);
-      }
-      s += __shfl_xor_sync(kFull, s, 1);
-      s += __shfl_xor_sync(kFull, s, 2);
-      if (q == 0) {
-        const float pre = s + __ldg(a.fc1_b + j);
-        float scale = 1.f;
-        if (TRAIN && a.drop_p > 0.f) {
-          const unsigned long long step = a.rng_step != nullptr ? (unsigned long long)*a.rng_step : 0ull;
-          const uint4 rnd = philox4x32(make_uint4((unsigned)g, (unsigned)(j >> 2), (unsigned)step, (unsigned)(step >> 32)),
-                                       make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
-          const unsigned bits = (j & 3) == 0 ? rnd.x : (j & 3) == 1 ? rnd.y : (j & 3) == 2 ? rnd.z : rnd.w;
-          const float u = (float)(bits >> 8) * (1.f / 16777216.f);  // uniform [0, 1)
-          scale = u < a.drop_p ? 0.f : 1.f / (1.f - a.drop_p);
+      for (int it = 0; it < kHid / (2 * kNW); ++it) {
+        const int j = (it * kNW + warp) * 2 + half;
+        const float4 wv = *reinterpret_cast<const float4*>(sFc1 + j * kS2 + l16 * 4);
+        float s = fmaf(wv.x, gv.x, fmaf(wv.y, gv.y, fmaf(wv.z, gv.z, wv.w * gv.w)));
+        s += __shfl_xor_sync(kFull, s, 8);
+        s += __shfl_xor_sync(kFull, s, 4);
+        s += __shfl_xor_sync(kFull, s, 2);
+        s += __shfl_xor_sync(kFull, s, 1);
+        if (l16 == 0) {
+          const float pre = s + sHW[kHW1B + j];
+          float scale = 1.f;
+          if (TRAIN && a.drop_p > 0.f) {
+            const uint4 rnd = philox4x32(make_uint4((unsigned)g, (unsigned)(j >> 2), (unsigned)rng_step, (unsigned)(rng_step >> 32)),
+                                         make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+            const unsigned bits = (j & 3) == 0 ? rnd.x : (j & 3) == 1 ? rnd.y : (j & 3) == 2 ? rnd.z : rnd.w;
+            const float u = (float)(bits >> 8) * (1.f / 16777216.f);  // uniform [0, 1)
+            scale = u < a.drop_p ? 0.f : 1.f / (1.f - a.drop_p);
+          }
+          const float hv = pre > 0.f ? pre * scale : 0.f;
+          hH[j] = hv;
+          hHM[j] = pre > 0.f ? scale : 0.f;  // d h / d pre
+          if (TRAIN) a.hvec[(size_t)og * kHid + j] = hv;
         }
-        const float hv = pre > 0.f ? pre * scale : 0.f;
-        hH[j] = hv;
-        hHM[j] = pre > 0.f ? scale : 0.f;  // d h / d pre
-        if (TRAIN) a.hvec[(size_t)og * kHid + j] = hv;
       }
     }
     __syncthreads();
     if (warp < a.out_dim) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(a.fc2_w + (size_t)warp * kHid) + lane);
+      const float4 wv = *reinterpret_cast<const float4*>(sHW + kHW2 + warp * kHid + lane * 4);
       const float4 hv = *reinterpret_cast<const float4*>(hH + lane * 4);
       float s = fmaf(wv.x, hv.x, fmaf(wv.y, hv.y, fmaf(wv.z, hv.z, wv.w * hv.w)));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
       if (lane == 0) {
-        const float pv = s + __ldg(a.fc2_b + warp);
+        const float pv = s + sHW[kHW2B + warp];
         hPred[warp] = pv;
         a.pred[(size_t)og * a.out_dim + warp] = pv;
       }
     }
     if (!TRAIN) continue;
     __syncthreads();
-    // ---- loss term and d loss / d pred (thread 0: out_dim <= 8 values)
+    DRK_MARK(14);
+    // ---- loss term and d loss / d pred (thread 0: out_dim <= 8 values; the targets were fetched at the start of the graph)
     if (tid == 0) {
       float term = 0.f;
       if (a.loss_kind == DRK_LOSS_MSE) {  // mean over all B*out elements: d/dpred = 2 (pred - y) * dloss_scale
         for (int o = 0; o < a.out_dim; ++o) {
-          const float d = hPred[o] - __ldg(a.y + (size_t)g * a.out_dim + o);
+          const float d = hPred[o] - sHead[kHY + o];
           term += d * d;
           hDPred[o] = 2.f * d * a.dloss_scale;
         }
       } else {  // cross entropy over the out_dim logits, mean over graphs
-        const int t = (int)__ldg(a.y_cls + g);
+        const int t = reinterpret_cast<const int*>(sHead)[kHCls];
         float m = hPred[0];
         for (int o = 1; o < a.out_dim; ++o) m = fmaxf(m, hPred[o]);
         float se = 0.f;
@@ -996,23 +1284,25 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int o = 0; o < a.out_dim; ++o) a.dpvec[(size_t)og * a.out_dim + o] = hDPred[o];
     }
     __syncthreads();
+    DRK_MARK(15);
     // ---- d pre-activation of fc1
     if (tid < kHid) {
       float s = 0.f;
-      for (int o = 0; o < a.out_dim; ++o) s = fmaf(hDPred[o], __ldg(a.fc2_w + (size_t)o * kHid + tid), s);
+      for (int o = 0; o < a.out_dim; ++o) s = fmaf(hDPred[o], sHW[kHW2 + o * kHid + tid], s);
       s *= hHM[tid];
       hDH[tid] = s;
       a.dhvec[(size_t)og * kHid + tid] = s;
     }
     __syncthreads();
-    // ---- dG = fc1_w^T dh: thread -> (column c, 16 rows j of fc1_w), coalesced rows
+    // ---- dG = fc1_w^T dh: thread -> (column c, 16 rows j of fc1_w); lanes read consecutive columns of one row: conflict-free
     {
+      constexpr int kRows = kHid / (kT / 64);  // rows of fc1_w per thread
       const int c = tid & 63, jg = tid >> 6;
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = jg * 16 + i;
-        s = fmaf(hDH[j], __ldg(a.fc1_w + (size_t)j * kS2 + c), s);
+      for (int i = 0; i < kRows; ++i) {
+        const int j = jg * kRows + i;
+        s = fmaf(hDH[j], sFc1[j * kS2 + c], s);
       }
       sRed[jg * kS2 + c] = s;
     }
@@ -1020,10 +1310,11 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     if (tid < kS2) {
       float s = 0.f;
 #pragma unroll
-      for (int jg = 0; jg < 8; ++jg) s += sRed[jg * kS2 + tid];
+      for (int jg = 0; jg < kT / 64; ++jg) s += sRed[jg * kS2 + tid];
       hDG[tid] = s / cnt;  // d mean / d row = dG / max(n, 1) (true division)
     }
     __syncthreads();
+    DRK_MARK(7);
     // ---- dW2 contribution of this graph and V = diag(dG/n) W2
     float* part = a.part + (size_t)og * a.part_stride;
     for (int e = tid; e < kS2 * kF1; e += kT) {
@@ -1034,19 +1325,24 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     conv2_backward_input(L.w2, L.head + kHDG * 4, L.maskz, L.t0, n);
     cp_async_wait<0>();  // the CSC is back in the index region
     __syncthreads();
+    DRK_MARK(8);
     // ---- dZ1 = (A^T dA2) * (H1 > 0) in place in tile 1 ; Q = A^T dZ1 -> tile 0
-    aggregate<2>(L.t0, L.t1, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, n);
+    aggregate<2>(L.t0, L.t1, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, L.hmask, n);
     __syncthreads();
-    aggregate<1>(L.t1, L.t0, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, n);
+    DRK_MARK(9);
+    aggregate<1>(L.t1, L.t0, have_csc ? L.cinfo : L.rinfo, have_csc ? L.cperm : L.rperm, L.idx, L.hmask, n);
     __syncthreads();
-    conv1_weight_grad(L.t0, L.x, L.t1, n, kp);
+    DRK_MARK(10);
+    conv1_weight_grad(L.t0, x_off, L.t1, n, kp, a.fi);
     __syncthreads();
+    DRK_MARK(11);
     for (int e = tid; e < kS1 * kp; e += kT) {
       float s = 0.f;
 #pragma unroll
       for (int w4 = 0; w4 < 4; ++w4) s += sT1[w4 * kS1 * kp + e];
       part[e] = s;
     }
+    DRK_MARK(12);
   }
 }
 
@@ -1116,34 +1412,34 @@ __global__ void __launch_bounds__(256) k_step_finalize(const FinalArgs a) {
     if (e < n1) {
       const int m = e / a.fi, k = e - m * a.fi;
       const float* p = a.part + m * a.kp + k;
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
       if (m < kF1) { dst = a.dw1a + e; live = 0; li = e; } else { dst = a.dw1b + (e - kF1 * a.fi); live = 1; li = e - kF1 * a.fi; }
     } else if ((e -= n1) < n2) {
       const float* p = a.part + kS1 * a.kp + e;
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc += p[(size_t)g * a.part_stride];
       if (e < kF2 * kF1) { dst = a.dw2a + e; live = 2; li = e; } else { dst = a.dw2b + (e - kF2 * kF1); live = 3; li = e - kF2 * kF1; }
     } else if ((e -= n2) < n3) {
       const int j = e / kS2, c = e - j * kS2;
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dhvec[(size_t)g * kHid + j], a.gvec[(size_t)g * kS2 + c], acc);
       dst = a.dfc1_w + e; live = 4; li = e;
     } else if ((e -= n3) < n4) {
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc += a.dhvec[(size_t)g * kHid + e];
       dst = a.dfc1_b + e; live = 5; li = e;
     } else if ((e -= n4) < n5) {
       const int o = e / kHid, j = e - o * kHid;
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc = fmaf(a.dpvec[(size_t)g * a.out_dim + o], a.hvec[(size_t)g * kHid + j], acc);
       dst = a.dfc2_w + e; live = 6; li = e;
     } else if ((e -= n5) < n6) {
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc += a.dpvec[(size_t)g * a.out_dim + e];
       dst = a.dfc2_b + e; live = 7; li = e;
     } else if ((e -= n6) == 0) {
-#pragma unroll 8
+#pragma unroll 16
       for (int g = ty; g < B; g += kFinSlices) acc += a.loss_terms[g];
       scale = a.loss_scale;
       dst = a.loss;
@@ -1237,13 +1533,13 @@ struct BlockedIndexArgs {
   int32_t rows_cap, e_cap, num_nodes; int64_t num_edges;
 };
 
-__global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs a) {
+__global__ void __launch_bounds__(kTI, 2) k_index_blocked(const BlockedIndexArgs a) {
   unsigned char* smem = g_smem;
-  // regions: stash [e_cap] u32 | cnt_r, cnt_c [kNW][rows_cap] u16 | degrees/starts [rows_cap] u32 x2 | scan
+  // regions: stash [e_cap] u32 | cnt_r, cnt_c [kNWI][rows_cap] u16 | degrees/starts [rows_cap] u32 x2 | scan
   uint32_t* stash = reinterpret_cast<uint32_t*>(smem);
   uint16_t* cnt_r = reinterpret_cast<uint16_t*>(stash + a.e_cap);
-  uint16_t* cnt_c = cnt_r + kNW * a.rows_cap;
-  uint32_t* start_r = reinterpret_cast<uint32_t*>(cnt_c + kNW * a.rows_cap);
+  uint16_t* cnt_c = cnt_r + kNWI * a.rows_cap;
+  uint32_t* start_r = reinterpret_cast<uint32_t*>(cnt_c + kNWI * a.rows_cap);
   uint32_t* start_c = start_r + a.rows_cap;
   uint32_t* scan = start_c + a.rows_cap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1261,9 +1557,9 @@ __global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs 
     }
     {
       uint32_t* z = reinterpret_cast<uint32_t*>(cnt_r);
-      for (int i = tid; i < kNW * a.rows_cap; i += kT) z[i] = 0u;  // both histograms (2 x kNW*rows_cap u16)
+      for (int i = tid; i < kNWI * a.rows_cap; i += kTI) z[i] = 0u;  // both histograms (2 x kNWI*rows_cap u16)
     }
-    const int chunk = ((ne + kNW - 1) / kNW + 31) & ~31;
+    const int chunk = ((ne + kNWI - 1) / kNWI + 31) & ~31;
     const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
     bool bad = false;
     for (int i0 = wb; i0 < we; i0 += 128) {
@@ -1302,11 +1598,11 @@ __global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs 
     }
     __syncthreads();
     uint32_t carry_r = 0, carry_c = 0;
-    for (int vb = 0; vb < n; vb += kT) {
+    for (int vb = 0; vb < n; vb += kTI) {
       const int v = vb + tid;
       uint32_t dr = 0, dc = 0;
       if (v < n) {
-        for (int w = 0; w < kNW; ++w) {
+        for (int w = 0; w < kNWI; ++w) {
           const uint32_t t = cnt_r[w * a.rows_cap + v];
           cnt_r[w * a.rows_cap + v] = (uint16_t)dr;
           dr += t;
@@ -1316,8 +1612,8 @@ __global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs 
         }
       }
       uint32_t tot_r, tot_c;
-      const uint32_t ex_r = block_excl_scan(dr, scan, tot_r) + carry_r;
-      const uint32_t ex_c = block_excl_scan(dc, scan, tot_c) + carry_c;
+      const uint32_t ex_r = block_excl_scan<kNWI>(dr, scan, tot_r) + carry_r;
+      const uint32_t ex_c = block_excl_scan<kNWI>(dc, scan, tot_c) + carry_c;
       if (v < n) {
         start_r[v] = ex_r;
         start_c[v] = ex_c;
@@ -1328,12 +1624,12 @@ __global__ void __launch_bounds__(kT, 2) k_index_blocked(const BlockedIndexArgs 
       carry_c += tot_c;
     }
     // edges dropped as malformed leave a gap at the end of the graph's slice: keep the arrays well defined
-    for (int i = (int)carry_r + tid; i < ne; i += kT) {
+    for (int i = (int)carry_r + tid; i < ne; i += kTI) {
       a.colidx[e0 + i] = node0;
       a.perm[e0 + i] = e0 + i;
     }
     if (want_csc)
-      for (int i = (int)carry_c + tid; i < ne; i += kT) {
+      for (int i = (int)carry_c + tid; i < ne; i += kTI) {
         a.rowidx[e0 + i] = node0;
         a.permT[e0 + i] = e0 + i;
       }
@@ -1402,7 +1698,7 @@ static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
   // projection -- the x region (x is loaded afterwards), tile 1, tile 0 behind the histograms -- and, if those are too small
   // (few node features), into an extra region at the end
   Layout L = make_layout(fi, p.rows_cap, p.ent_cap);
-  const int tile = p.rows_cap * kS1 * 4, cnt = 2 * kNW * p.rows_cap * 2;
+  const int tile = p.rows_cap * kS1 * 4, cnt = 2 * kNWI * p.rows_cap * 2;
   if (cnt > tile) return false;
   int base[3] = {L.x, L.t1, L.t0 + cnt};
   int left[3] = {p.rows_cap * L.kp * 4, tile, tile - cnt};
@@ -1436,7 +1732,16 @@ static bool make_plan(int fi, int max_nodes, int max_edges, PlanResult& p) {
 }  // namespace gs
 }  // namespace drk
 
+static long long* g_phase_clocks = nullptr;
+static int32_t g_phase_clock_slots = 0;
+
 extern "C" {
+
+int drk_ginet_step_set_phase_clocks(int64_t* clocks, int32_t num_slots) {
+  g_phase_clocks = reinterpret_cast<long long*>(clocks);
+  g_phase_clock_slots = clocks != nullptr ? num_slots : 0;
+  return DRK_OK;
+}
 
 int32_t drk_ginet_step_exchange_floats(int32_t fi, int32_t out_dim) {
   using namespace drk::gs;
@@ -1509,6 +1814,8 @@ int drk_ginet_step(const float* x, int64_t ldx, int32_t fi, const int64_t* edge_
   a.pred = pred; a.status = status;
   a.rows_cap = p.rows_cap; a.e_cap = p.e_cap; a.ent_cap = p.ent_cap;
   a.stash_off = p.stash_off; a.ranks_off = p.ranks_off; a.csc_off = p.csc_off;
+  a.clk = (g_phase_clocks != nullptr && num_graphs <= g_phase_clock_slots) ? g_phase_clocks : nullptr;
+  a.x_bulk = (ldx == fi && aligned16(x)) ? 1 : 0;
   a.x_vec = 1;
   if (ldx % 4 == 0 && fi % 4 == 0 && aligned16(x)) a.x_vec = 4;
   else if (ldx % 2 == 0 && fi % 2 == 0 && aligned8(x)) a.x_vec = 2;
@@ -1590,7 +1897,7 @@ int drk_edge_ptr(const int64_t* edge_index, int64_t num_edges, const int32_t* gr
 int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges) {
   if (max_graph_nodes < 0 || max_graph_edges < 0 || max_graph_nodes > 65535 || max_graph_edges > 65535) return 0;
   const size_t rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8), e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
-  const size_t smem = e_cap * 4 + 2 * drk::gs::kNW * rows_cap * 2 + 2 * rows_cap * 4 + 128;
+  const size_t smem = e_cap * 4 + 2 * drk::gs::kNWI * rows_cap * 2 + 2 * rows_cap * 4 + 128;
   return smem <= drk::gs::kSmemBudget ? 1 : 0;
 }
 
@@ -1616,12 +1923,12 @@ int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, 
   a.rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8);
   a.e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
   a.num_nodes = num_nodes; a.num_edges = num_edges;
-  const size_t smem = (size_t)a.e_cap * 4 + (size_t)2 * kNW * a.rows_cap * 2 + (size_t)2 * a.rows_cap * 4 + 128;
+  const size_t smem = (size_t)a.e_cap * 4 + (size_t)2 * kNWI * a.rows_cap * 2 + (size_t)2 * a.rows_cap * 4 + 128;
   cudaError_t e = cudaFuncSetAttribute(k_index_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "blocked index: smem opt-in: %s", cudaGetErrorString(e));
   const int ctas_per_sm = std::max<int>(1, std::min<int>(4, (int)(kSmemBudget / (smem + 1024))));
   const int grid = std::min(num_graphs, kNumSM * ctas_per_sm);
-  k_index_blocked<<<grid, kT, smem, as_stream(stream)>>>(a);
+  k_index_blocked<<<grid, kTI, smem, as_stream(stream)>>>(a);
   return finish_launch("blocked index");
 }
 

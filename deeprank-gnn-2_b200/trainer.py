@@ -434,8 +434,9 @@ class Trainer:
                 return None
             gset = ResidentGraphSet(graphs, self.device)
             cache[id(dataset)] = gset
-        loss_fn = self.lossfunction
-        in_place = not isinstance(loss_fn, type) and GINetFusedStep.supports(self.model, loss_fn)
+        loss_fn = getattr(self, "lossfunction", None)
+        model = getattr(self, "model", None)
+        in_place = model is not None and loss_fn is not None and not isinstance(loss_fn, type) and GINetFusedStep.supports(model, loss_fn)
         if in_place:
             fi, out = int(gset.batch.x.shape[1]), int(self.model.fc2.weight.shape[0])
             if gset.batch.__dict__.get("_pairs") is None and gset.batch.__dict__.get("_edge_ptr32") is None:
@@ -544,11 +545,13 @@ class Trainer:
         count = 0
         preds, ys, names = [], [], []
         t0 = time()
+        in_place_loader = isinstance(loader, ResidentBatches) and not loader.collate
         for batch, global_size in loader:
             if batch is None:
-                if train and ((isinstance(loader, ResidentBatches) and not loader.collate) or (self._fused is not None and self._fused is not False)):
+                # ragged tail: this rank has no graphs but must join the step's collectives -- on the path the other ranks take
+                if train and (in_place_loader or self._fused_step(None) is not None):
                     self._ensure_fused().empty_step()
-                elif train and self._grad_sync is not None:  # ragged tail: this rank has no graphs but must join the all-reduce
+                elif train and self._grad_sync is not None:
                     self.optimizer.zero_grad()
                     self._grad_sync(local_weight=0.0)
                     self.optimizer.step()
@@ -604,8 +607,26 @@ class Trainer:
         target_vals = []
         for y, p in zip(ys, preds):
             target_vals += y.cpu().numpy().tolist() if y is not None else [None] * p.shape[0]
-        epoch_loss = float(loss_sum.item()) / count if count > 0 else None
-        self._output_exporters.process(pass_name, epoch_number, names, outputs, target_vals, epoch_loss)
+        bad_targets = getattr(self, "_bad_targets", None)
+        self._bad_targets = None
+        if self._distributed():
+            # every rank must see the SAME epoch loss: it drives best-model selection and early stopping, and ranks that disagree
+            # would leave the epoch loop at different times (the others then hang in the gradient exchange)
+            tot = torch.stack([loss_sum, torch.tensor(float(count), dtype=torch.float64, device=self.device)])
+            dist.all_reduce(tot)
+            total_loss, total_count = (float(v) for v in tot.tolist())
+            epoch_loss = total_loss / total_count if total_count > 0 else None
+            # the exporters get the whole pass on rank 0 (every rank holds only its slices of the mini-batches)
+            gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+            dist.gather_object((names, outputs, target_vals), gathered, dst=0)
+            if gathered is not None:
+                names, outputs, target_vals = ([v for part in gathered for v in part[i]] for i in range(3))
+        else:
+            epoch_loss = float(loss_sum.item()) / count if count > 0 else None
+        if bad_targets is not None and bool(bad_targets.item()):
+            raise ValueError(f"a target value of the {pass_name} pass is not one of the dataset's classes {self.classes} (trainer.py:812 raises KeyError there)")
+        if not self._distributed() or dist.get_rank() == 0:
+            self._output_exporters.process(pass_name, epoch_number, names, outputs, target_vals, epoch_loss)
         _log.info(f"{pass_name} loss {epoch_loss} | time {time() - t0}")
         return epoch_loss
 
@@ -630,9 +651,16 @@ class Trainer:
             else:
                 world = dist.get_world_size() if self._distributed() else 1
                 self._fused = GINetFusedStep(self.model, self.optimizer, loss_fn, target_fn=lambda b: self._format_output(None, b.y)[1], world_size=world)
-        if self._fused is False or not step_supported(self.model, batch):
+        if self._fused is False:  # decided by model and loss alone: the same on every rank
             return None
-        return self._fused
+        ok = batch is None or step_supported(self.model, batch)
+        if self._distributed():
+            # the choice must be collective: the fused path's in-kernel gradient exchange and the autograd path's NCCL all-reduce are
+            # different protocols, and this rank's shard may hold a graph that does not fit the kernel's plan while the others' do not
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        return self._fused if ok else None
 
     def _epoch(self, epoch_number: int, pass_name: str):
         return self._run_pass(self.train_loader, epoch_number, pass_name, train=True)
@@ -649,7 +677,11 @@ class Trainer:
             if table is None or table.device != target.device:
                 table = torch.tensor([float(c) for c in self.classes], device=target.device)
                 self._class_table = table
-            target = (target.reshape(-1, 1).to(table.dtype) == table.reshape(1, -1)).to(torch.int64).argmax(dim=1)
+            match = target.reshape(-1, 1).to(table.dtype) == table.reshape(1, -1)
+            missing = (~match.any(dim=1)).any()  # a value outside `classes`: the reference's dict lookup raises; checked at the pass's read-back
+            prev = getattr(self, "_bad_targets", None)
+            self._bad_targets = missing if prev is None else (prev | missing)
+            target = match.to(torch.int64).argmax(dim=1)
             if isinstance(self.lossfunction, (nn.BCELoss, nn.BCEWithLogitsLoss)):
                 raise ValueError("BCELoss and BCEWithLogitsLoss are currently not supported.\n\tFor further details see: https://github.com/DeepRank/deeprank2/issues/318")
             if isinstance(self.lossfunction, losses.classification_losses) and not isinstance(self.lossfunction, losses.classification_tested):
@@ -712,8 +744,8 @@ class Trainer:
         self._select_device()
 
     def _load_pretrained_model(self) -> None:
+        self._put_model_to_device(self.dataset_test)  # the model first: the loader asks it which step kernels apply
         self.test_loader = self._loader(self.dataset_test, 1, False)
-        self._put_model_to_device(self.dataset_test)
         self.optimizer = self.optimizer(self.model.parameters(), lr=self.lr, weight_decay=self.weight_decay)
         self.optimizer.load_state_dict(self.opt_loaded_state_dict)
         self.model.load_state_dict(self.model_load_state_dict)
@@ -740,7 +772,12 @@ def _divide_dataset(dataset: GraphDataset, splitsize: float | int | None = None)
     if splitsize == 0:
         return dataset, None
     indices = np.arange(full_size)
-    np.random.default_rng().shuffle(indices)
+    seed = None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [int(np.random.SeedSequence().entropy % (2**63)) if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)  # every rank must draw the same train / validation split
+        seed = box[0]
+    np.random.default_rng(seed).shuffle(indices)
     main, split = copy.copy(dataset), copy.copy(dataset)
     main.index_entries = [dataset.index_entries[i] for i in indices[n_split:]]
     split.index_entries = [dataset.index_entries[i] for i in indices[:n_split]]

@@ -294,6 +294,11 @@ typedef struct DrkAdam {
   DrkAdamTensor dead[8];
 } DrkAdam;
 DRK_API int32_t drk_ginet_step_ctas(int32_t num_graphs);
+/* Profiling hook (process-wide, not for production): when `clocks` is non-null every later drk_ginet_step launch of at most
+ * `num_slots` graphs writes the SM clock (clock64) at its phase boundaries to clocks[slot * 16 + mark]; null switches it off.
+ * Marks: 0 graph start, 1 index built, 2 x staged, 3 projected, 4 H1, 5 A2, 6 conv2+readout, 7 head+loss, 8 dA2, 9 dZ1, 10 Q,
+ * 11 dW1 partials, 12 graph done. */
+DRK_API int drk_ginet_step_set_phase_clocks(int64_t* clocks, int32_t num_slots);
 DRK_API int32_t drk_ginet_step_exchange_floats(int32_t num_node_features, int32_t out_dim);
 DRK_API int drk_ginet_step_supported(int32_t num_node_features, int32_t out_dim, int32_t max_graph_nodes, int32_t max_graph_edges);
 DRK_API size_t drk_ginet_step_workspace_bytes(int32_t num_node_features, int32_t out_dim, int32_t num_graphs,

@@ -1,15 +1,20 @@
-"""TEST INFRASTRUCTURE ONLY (and only usable in the build container).
+"""TEST INFRASTRUCTURE ONLY.
 
-Imports the UNMODIFIED DeepRank2 model files from ``/root/reference`` so their
-own arithmetic can be executed to (a) validate ``oracle/restate.py`` and (b)
-generate the golden vectors under ``tests/golden/`` (``oracle/make_golden.py``).
+Imports the UNMODIFIED DeepRank2 model files so their own arithmetic can be executed to
+(a) validate ``oracle/restate.py``, (b) generate the golden vectors under ``tests/golden/``
+(``oracle/make_golden.py``) and (c) serve as ``bench.py``'s reference arm / ``cpu_baseline``
+(``kind: "reference"``).  The files come from ``/root/reference`` in the build container, or
+from ``oracle/_ref/`` -- the reference package installed there by ``oracle/install_reference.py``
+(``pip install --no-deps --target oracle/_ref``; git-ignored, travels to the GPU box with the
+snapshot).
 
 ``import deeprank2`` itself cannot work here (torch_geometric, torch_scatter,
 h5py, markov_clustering, community, matplotlib are not installed and there is no
 network), so the nine third-party symbols the model files import are provided
 by ``oracle/thirdparty.py`` through ``sys.modules`` and the five model files are
-then loaded by path.  ``/root/reference`` does not exist on the GPU box: nothing
-under ``tests/ -m gpu``, ``bench.py`` or ``smoke()`` may call this module.
+then loaded by path.  ``/root/reference`` does not exist on the GPU box: there only the
+``oracle/_ref`` install is available (``bench.py``'s reference legs); the ``-m gpu`` tests and
+``smoke()`` never call this module.
 """
 from __future__ import annotations
 
@@ -19,7 +24,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DRK_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """First existing of: $DRK_REFERENCE_ROOT, /root/reference (build container), oracle/_ref (installed copy)."""
+    for cand in (os.environ.get("DRK_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "deeprank2", "neuralnets", "gnn")):
+            return cand
+    return os.environ.get("DRK_REFERENCE_ROOT") or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBBED = False
 
