@@ -355,13 +355,10 @@ def measure_c4(dev, config: str, steps: int = 40):
     step(batch)
     torch.cuda.synchronize()
     launches = _lib.launch_count() - c0
+    # every network's step is free of host read-backs (the clustered ones size their pooled batch from the collate's meta): captured once
     mode = "CUDA-graph replay"
-    if getattr(net, "capturable", config == "c4-vanilla"):
-        g = GraphedTrainStep(step, batch, warmup=1)
-        run = g.replay
-    else:  # the pooled batch is sized on the host (as the reference does): not capturable
-        mode = "eager launches (host-sized pooling)"
-        run = lambda: step(batch)  # noqa: E731
+    g = GraphedTrainStep(step, batch, warmup=1)
+    run = g.replay
     for _ in range(3):
         run()
     torch.cuda.synchronize()

@@ -1,0 +1,177 @@
+// Community pooling structure on the device (reference: deeprank2/utils/community_pooling.py:165-242 and the PyG 2.4 helpers it
+// calls -- consecutive_cluster, pool_edge (relabel, remove_self_loops, coalesce), pool_batch).
+//
+// The data-dependent sizes (number of distinct clusters, number of distinct pooled edges) are properties of the GRAPHS, not of the
+// weights: the host collate knows them (or an upper bound) when it builds the batch, so every output below is allocated by the caller
+// and nothing is read back -- a whole train step of a clustered network can be captured into a CUDA graph.  Each kernel also writes
+// the count it found to a device scalar and raises DRK_STATUS_INDEX_RANGE if it exceeds the capacity it was given.
+//
+//   consecutive_cluster(c):   drk_segment_index_build(c, K)            nodes grouped by cluster id, stable  (drk_index.cu)
+//                             drk_compact_segments                     empty ids dropped: rank[id] (= torch.unique's inverse through
+//                                                                      rank[c]), compact ptr, last member of every cluster (= perm)
+//   pool_edge(c, ei, ea):     drk_pool_edge_keys                       key = dense id of the pooled pair inside its graph's C_g x C_g
+//                                                                      block (self loops -> one junk segment at the end)
+//                             drk_segment_index_build(key, KK + 1)     edges grouped by pooled pair, ascending edge id inside a pair
+//                             drk_compact_segments                     distinct pairs in (row, col) order = coalesce's order
+//                             drk_pool_edge_decode                     pooled edge_index from the dense ids
+//                             drk_spmm(SUM)                            merged edge attributes, summed in ascending edge id (drk_sparse.cu)
+#include <algorithm>
+
+#include "drk_common.cuh"
+
+namespace drk {
+namespace pool {
+
+constexpr int kCT = 1024;
+
+// One CTA walks the K segment sizes in tiles of kCT with a block scan and keeps the non-empty ones.
+__global__ void __launch_bounds__(kCT) k_compact_segments(const int32_t* __restrict__ ptr, int32_t num_segments, const int32_t* __restrict__ perm,
+                                                         int64_t* __restrict__ rank, int32_t* __restrict__ ptr_out, int32_t* __restrict__ ids_out,
+                                                         int64_t* __restrict__ last_out, int32_t cap, int32_t* __restrict__ count_out,
+                                                         int32_t* __restrict__ status) {
+  __shared__ int s_warp[kCT / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < num_segments; base += kCT) {
+    const int k = base + tid;
+    int lo = 0, hi = 0;
+    if (k < num_segments) {
+      lo = __ldg(ptr + k);
+      hi = __ldg(ptr + k + 1);
+    }
+    const int present = hi > lo ? 1 : 0;
+    int inc = present;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp[lane];
+      int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      s_warp[lane] = winc - w;
+      if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const int pos = carry + s_warp[warp] + inc - present;  // compact index of this segment if it is present
+    if (k < num_segments) {
+      if (rank != nullptr) rank[k] = present ? (int64_t)pos : (int64_t)-1;
+      if (present && pos < cap) {
+        ptr_out[pos] = lo;
+        if (ids_out != nullptr) ids_out[pos] = k;
+        if (last_out != nullptr) last_out[pos] = (int64_t)__ldg(perm + hi - 1);  // stable grouping: the last member has the largest index
+      }
+    }
+    carry += s_warp[32];
+    __syncthreads();
+  }
+  const int total = num_segments > 0 ? __ldg(ptr + num_segments) : 0;
+  for (int i = min(carry, cap) + tid; i <= cap; i += kCT) ptr_out[i] = total;  // trailing (unused) capacity = empty segments
+  if (tid == 0) {
+    if (count_out != nullptr) *count_out = carry;
+    if (carry > cap && status != nullptr) atomicOr(status, DRK_STATUS_INDEX_RANGE);
+  }
+}
+
+// key[e] = kkptr[g] + (inv[row] - cptr[g]) * C_g + (inv[col] - cptr[g]) with g the graph of the edge's row node; self loops of the
+// pooled graph and edges whose endpoints fall outside the graph's cluster range go to the junk segment `junk`.
+__global__ void __launch_bounds__(256) k_pool_edge_keys(const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int64_t num_edges,
+                                                       const int64_t* __restrict__ inv, int32_t num_nodes, const int32_t* __restrict__ batch32,
+                                                       const int64_t* __restrict__ cptr, const int64_t* __restrict__ kkptr, int32_t num_graphs,
+                                                       int64_t junk, int64_t* __restrict__ key, int32_t* __restrict__ status) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += stride) {
+    const unsigned long long r = (unsigned long long)ld_stream_i64(erow + e), c = (unsigned long long)ld_stream_i64(ecol + e);
+    int64_t k = junk;
+    if (r < (unsigned long long)num_nodes && c < (unsigned long long)num_nodes) {
+      const int g = __ldg(batch32 + r);
+      if ((unsigned)g < (unsigned)num_graphs) {
+        const int64_t c0 = __ldg(cptr + g), cg = __ldg(cptr + g + 1) - c0;
+        const int64_t pr = __ldg(inv + r) - c0, pc = __ldg(inv + c) - c0;
+        if (pr >= 0 && pr < cg && pc >= 0 && pc < cg) {
+          if (pr != pc) k = __ldg(kkptr + g) + pr * cg + pc;
+        } else {
+          bad = true;  // an edge that joins two graphs, or a cluster id outside its graph's range
+        }
+      } else {
+        bad = true;
+      }
+    } else {
+      bad = true;
+    }
+    key[e] = k;
+  }
+  if (bad && status != nullptr) atomicOr(status, DRK_STATUS_CROSS_GRAPH);
+}
+
+// pooled edge_index [2, count] from the dense pair ids (ascending = sorted by (row, col), graphs in order)
+__global__ void __launch_bounds__(256) k_pool_edge_decode(const int32_t* __restrict__ ids, int32_t cap, const int32_t* __restrict__ count,
+                                                         const int64_t* __restrict__ cptr, const int64_t* __restrict__ kkptr, int32_t num_graphs,
+                                                         int64_t* __restrict__ out_row, int64_t* __restrict__ out_col) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  if (i >= min(__ldg(count), cap)) {  // capacity beyond the pairs found (the host's bound was not tight): keep the arrays well defined
+    out_row[i] = 0;
+    out_col[i] = 0;
+    return;
+  }
+  const int64_t k = (int64_t)__ldg(ids + i);
+  int lo = 0, hi = num_graphs;  // last g with kkptr[g] <= k
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(kkptr + mid) <= k) lo = mid;
+    else hi = mid;
+  }
+  const int64_t c0 = __ldg(cptr + lo), cg = __ldg(cptr + lo + 1) - c0, local = k - __ldg(kkptr + lo);
+  out_row[i] = c0 + local / cg;
+  out_col[i] = c0 + local % cg;
+}
+
+}  // namespace pool
+}  // namespace drk
+
+extern "C" {
+
+int drk_compact_segments(const int32_t* ptr, int32_t num_segments, const int32_t* perm, int64_t* rank, int32_t* ptr_out, int32_t* ids_out,
+                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_segments >= 0 && capacity >= 0, DRK_EINVAL, "compact segments: negative size");
+  DRK_REQUIRE(ptr && ptr_out, DRK_EINVAL, "compact segments: null pointer");
+  DRK_REQUIRE(last_out == nullptr || perm != nullptr, DRK_EINVAL, "compact segments: last_out needs perm");
+  pool::k_compact_segments<<<1, pool::kCT, 0, as_stream(stream)>>>(ptr, num_segments, perm, rank, ptr_out, ids_out, last_out, capacity, count_out, status);
+  return finish_launch("compact segments");
+}
+
+int drk_pool_edge_keys(const int64_t* edge_index, int64_t num_edges, const int64_t* inv, int32_t num_nodes, const int32_t* batch32,
+                       const int64_t* cluster_ptr, const int64_t* pair_ptr, int32_t num_graphs, int64_t junk_key, int64_t* key, int32_t* status,
+                       void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_edges >= 0 && num_nodes >= 0 && num_graphs >= 0 && junk_key >= 0, DRK_EINVAL, "pool edge keys: negative size");
+  if (num_edges == 0) return DRK_OK;
+  DRK_REQUIRE(edge_index && inv && batch32 && cluster_ptr && pair_ptr && key, DRK_EINVAL, "pool edge keys: null pointer");
+  const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(num_edges, 256), (int64_t)kNumSM * 8);
+  pool::k_pool_edge_keys<<<grid, 256, 0, as_stream(stream)>>>(edge_index, edge_index + num_edges, num_edges, inv, num_nodes, batch32, cluster_ptr, pair_ptr,
+                                                             num_graphs, junk_key, key, status);
+  return finish_launch("pool edge keys");
+}
+
+int drk_pool_edge_decode(const int32_t* ids, int32_t capacity, const int32_t* count, const int64_t* cluster_ptr, const int64_t* pair_ptr, int32_t num_graphs,
+                         int64_t* edge_index_out, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(capacity >= 0 && num_graphs >= 0, DRK_EINVAL, "pool edge decode: negative size");
+  if (capacity == 0) return DRK_OK;
+  DRK_REQUIRE(ids && count && cluster_ptr && pair_ptr && edge_index_out, DRK_EINVAL, "pool edge decode: null pointer");
+  pool::k_pool_edge_decode<<<ceil_div(capacity, 256), 256, 0, as_stream(stream)>>>(ids, capacity, count, cluster_ptr, pair_ptr, num_graphs, edge_index_out,
+                                                                                 edge_index_out + capacity);
+  return finish_launch("pool edge decode");
+}
+
+}  // extern "C"

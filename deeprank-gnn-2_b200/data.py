@@ -42,6 +42,36 @@ def _is_doubled(d, ei) -> bool:
     return ok
 
 
+def pool_sizes(d) -> tuple | None:
+    """Sizes of the two community-pooling levels of ONE graph -- properties of the graph and its stored clustering, not of any
+    weight: ``(k0, c0, e1, k1, c1)`` = id bound (max + 1) and number of distinct ids of ``cluster0``, number of distinct pooled
+    edges without self loops (PyG ``pool_edge``), id bound and distinct ids of ``cluster1``.  Computed once per graph on the host
+    (the dataset hands out the same ``Data`` objects epoch after epoch) so that a collated batch knows the shapes of its pooled
+    tensors and the device never has to report them back.  None if the graph carries no (host) clustering."""
+    c0, c1, ei = d.__dict__.get("cluster0"), d.__dict__.get("cluster1"), d.__dict__.get("edge_index")
+    if not (isinstance(c0, torch.Tensor) and isinstance(c1, torch.Tensor) and isinstance(ei, torch.Tensor)) or c0.is_cuda or c1.is_cuda or ei.is_cuda:
+        return None
+    key = (c0.data_ptr(), c0._version, c1.data_ptr(), c1._version, ei.data_ptr(), ei._version, tuple(ei.shape))
+    cached = d.__dict__.get("_pool_sizes")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    import numpy as np
+
+    a0, a1, e = c0.numpy().reshape(-1), c1.numpy().reshape(-1), ei.numpy()
+    if (a0.size and a0.min() < 0) or (a1.size and a1.min() < 0):
+        return None
+    uniq0, inv0 = np.unique(a0, return_inverse=True)
+    n_c0 = int(uniq0.size)
+    e1 = 0
+    if e.size and n_c0:
+        pr, pc = inv0[e[0]].astype(np.int64), inv0[e[1]].astype(np.int64)
+        keep = pr != pc
+        e1 = int(np.unique(pr[keep] * n_c0 + pc[keep]).size)
+    out = (int(a0.max()) + 1 if a0.size else 0, n_c0, e1, int(a1.max()) + 1 if a1.size else 0, int(np.unique(a1).size))
+    d.__dict__["_pool_sizes"] = (key, out)
+    return out
+
+
 def _takes_node_offset(key: str) -> bool:
     return any(tag in key for tag in _OFFSET_KEYS)
 
@@ -277,7 +307,31 @@ class Batch(Data):
                 out.__dict__["_pairs"] = local.contiguous()
                 out.__dict__["_pair_ptr32"] = (eptr // 2).to(torch.int32)
         out.__dict__[cls._META_KEY] = {"num_graphs": len(sizes), "max_graph_nodes": max(sizes), "max_graph_edges": max(e_sizes), "num_edges_total": sum(e_sizes)}
+        out._attach_pool_sizes([pool_sizes(d) for d in data_list])
         return out
+
+    def _attach_pool_sizes(self, per_graph) -> None:
+        """Batch-level shapes of the community-pooling chain from the per-graph sizes (``pool_sizes``): totals in the meta dict
+        (``pool``: K0 C0 E1 KK K1 C1) and, as tensors that travel with the batch, the first pooled node of every graph
+        (``_pool_cptr`` int64 [B+1]) and the first dense pooled-pair id of every graph (``_pool_kkptr`` int64 [B+1], blocks of C_g^2)."""
+        import numpy as np
+
+        if not per_graph or any(p is None for p in per_graph):
+            return
+        m = np.asarray(per_graph, dtype=np.int64).reshape(len(per_graph), 5)
+        cptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
+        np.cumsum(m[:, 1], out=cptr[1:])
+        kkptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
+        np.cumsum(m[:, 1] * m[:, 1], out=kkptr[1:])
+        if kkptr[-1] + 1 >= 2**31 or m[:, 0].sum() >= 2**31:
+            return
+        eptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
+        np.cumsum(m[:, 2], out=eptr[1:])
+        self.__dict__["_pool_cptr"] = torch.from_numpy(cptr)
+        self.__dict__["_pool_kkptr"] = torch.from_numpy(kkptr)
+        self.__dict__["_pool_eptr32"] = torch.from_numpy(eptr.astype(np.int32))  # edges of the pooled graphs: contiguous slices, like _edge_ptr32
+        self.__dict__.setdefault(self._META_KEY, {})["pool"] = {"K0": int(m[:, 0].sum()), "C0": int(m[:, 1].sum()), "E1": int(m[:, 2].sum()), "KK": int(kkptr[-1]),
+                                                                 "K1": int(m[:, 3].sum()), "C1": int(m[:, 4].sum()), "max_C0": int(m[:, 1].max()), "max_E1": int(m[:, 2].max())}
 
 
 STEP_CTAS = 148  # CTAs of the per-graph kernels = SMs of a B200 (drk_ginet_step_ctas)

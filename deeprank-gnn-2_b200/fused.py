@@ -443,6 +443,9 @@ class ResidentGraphSet:
             np.cumsum(sizes, out=starts[1:])
             self._extents[k] = (dim, sizes, starts)
         self._lists = {k: v for k, v in host.__dict__.items() if not k.startswith("_") and isinstance(v, list)}
+        from .data import pool_sizes
+
+        self._pool_sizes = [pool_sizes(g) for g in graphs]  # per-graph shapes of the community-pooling chain (None: no clustering)
         self.batch = host.to(torch.device(device))
         self._info = None
 
@@ -513,6 +516,10 @@ class ResidentGraphSet:
                 out.__dict__["_edge_ptr32"] = gathers[plan_of["edge_index"]][3].to(torch.int32)
             out.__dict__[Batch._META_KEY] = {"num_graphs": b, "max_graph_nodes": int(n_plan[0].max()), "max_graph_edges": int(e_plan[0].max()),
                                              "num_edges_total": int(e_plan[2][-1])}
+        out._attach_pool_sizes([self._pool_sizes[i] for i in ids.tolist()])
+        for k in ("_pool_cptr", "_pool_kkptr", "_pool_eptr32"):
+            if k in out.__dict__:
+                out.__dict__[k] = out.__dict__[k].to(dev, non_blocking=True)
         return out
 
     def select(self, ids):

@@ -9,7 +9,7 @@ from torch.nn.functional import dropout, relu
 
 from ... import ops
 from ...graph import graph_index
-from ...utils.community_pooling import community_pooling, get_preloaded_cluster, max_pool_x
+from ...utils.community_pooling import community_pooling, get_preloaded_cluster, max_pool_x, pool_meta
 from ._common import GINetConvLayer, num_graphs_of  # noqa: F401
 
 
@@ -34,12 +34,13 @@ class GINet(nn.Module):
         ng = num_graphs_of(data)
         x = conv1(data.x, data.edge_index, data.edge_attr, graph=graph_index(data), relu=True)
         data.x = x
-        cluster = get_preloaded_cluster(data.cluster0, data.batch, ng)
+        # (the offsets are added in place: on a copy, so that a batch that is used again -- CUDA-graph replay, resident sets -- stays intact)
+        cluster = get_preloaded_cluster(data.cluster0.clone(), data.batch, ng)
         data = community_pooling(cluster, data)
 
         data.x = conv2(data.x, data.edge_index, data.edge_attr, graph=graph_index(data), relu=True)
-        cluster = get_preloaded_cluster(data.cluster1, data.batch, ng)
-        x, batch = max_pool_x(cluster, data.x, data.batch)
+        cluster = get_preloaded_cluster(data.cluster1.clone(), data.batch, ng)
+        x, batch = max_pool_x(cluster, data.x, data.batch, meta=pool_meta(data, 1))
         return ops.scatter_mean(x, batch, dim=0, dim_size=ng)
 
     def forward(self, data):

@@ -595,6 +595,14 @@ class SegmentPlan:
         self.n_src = int(index.numel())
         self.ptr, self.perm, self.status = segment_index(index, self.n_seg)
 
+    @classmethod
+    def from_parts(cls, index: torch.Tensor, ptr: torch.Tensor, perm: torch.Tensor, n_seg: int, status: torch.Tensor | None = None) -> "SegmentPlan":
+        """A plan whose grouping already exists (e.g. the compacted cluster index of ``utils.community_pooling``)."""
+        plan = cls.__new__(cls)
+        plan.index, plan.n_seg, plan.n_src = index, int(n_seg), int(index.numel())
+        plan.ptr, plan.perm, plan.status = ptr, perm, status
+        return plan
+
     def count(self) -> torch.Tensor:
         return (self.ptr[1:] - self.ptr[:-1]).to(torch.float32)
 

@@ -623,6 +623,10 @@ class Trainer:
                 names, outputs, target_vals = ([v for part in gathered for v in part[i]] for i in range(3))
         else:
             epoch_loss = float(loss_sum.item()) / count if count > 0 else None
+        if self.device.type == "cuda":
+            from .utils.community_pooling import check_status as check_pool_status
+
+            check_pool_status(self.device)  # the pooling kernels' status words, accumulated on the device during the pass
         if bad_targets is not None and bool(bad_targets.item()):
             raise ValueError(f"a target value of the {pass_name} pass is not one of the dataset's classes {self.classes} (trainer.py:812 raises KeyError there)")
         if not self._distributed() or dist.get_rank() == 0:

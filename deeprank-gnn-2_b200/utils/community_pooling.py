@@ -8,22 +8,45 @@ Integer outputs (relabelled clusters, pooled ``edge_index``, pooled ``batch``) a
 reference semantics (PyG 2.4 ``consecutive_cluster`` / ``pool_edge`` / ``pool_batch``); ``x`` is a max (exact),
 pooled ``edge_attr`` / ``pos`` are sums in ascending element order (fp32 tolerance).
 
-The number of clusters is data dependent and sizes the outputs, so each pooling step reads ONE scalar back
-to the host (``torch.unique``); the reference does ``B`` synchronisations in ``get_preloaded_cluster`` alone.
+Everything runs in our own kernels (``csrc/drk_pool.cu`` + the counting sort of ``csrc/drk_index.cu``): no ``torch.unique``, no
+sort, and NO host read-back on the step path.  The data-dependent sizes -- distinct clusters, distinct pooled edges -- are
+properties of the graphs and their stored clusterings, so the host collate computes them once per graph
+(``data.pool_sizes``) and a batch carries their totals (``Batch.meta("pool")``): outputs are allocated from those, the kernels
+write the counts they find to device scalars (checked at the end of a pass through the status word), and a train step of
+``FoutNet`` / clustered ``GINet`` / ``SGAT`` can be captured into a CUDA graph.  Tensors without that meta (hand-made
+batches) take ONE host round trip to size the outputs -- the reference does ``B`` of them in ``get_preloaded_cluster`` alone.
 """
 from __future__ import annotations
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..data import Batch, Data
-from ..graph import GraphIndex
+from ..graph import GraphIndex, stream_ptr
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
 
 
 def _node_graph_index(batch: torch.Tensor, num_graphs: int | None) -> GraphIndex:
     """graph offsets of a (pooled) batch vector, without edges."""
     empty = torch.empty((2, 0), dtype=torch.int64, device=batch.device)
     return GraphIndex.build(empty, batch.numel(), batch=batch, num_graphs=num_graphs, with_csc=False)
+
+
+def pool_meta(data, level: int):
+    """``{"K": id bound, "C": distinct clusters, ...}`` of pooling level 0 (``cluster0`` on the input batch) or 1 (``cluster1`` on the
+    pooled batch) if the batch came out of ``Batch.from_data_list`` / ``ResidentGraphSet.collate``; else None."""
+    m = data.__dict__.get(getattr(data, "_META_KEY", "_meta"), {}).get("pool") if hasattr(data, "__dict__") else None
+    if m is None:
+        return None
+    if level == 0:
+        cptr, kkptr = data.__dict__.get("_pool_cptr"), data.__dict__.get("_pool_kkptr")
+        if cptr is None or kkptr is None or not cptr.is_cuda:
+            return None
+        return {"K": m["K0"], "C": m["C0"], "E": m["E1"], "KK": m["KK"], "cptr": cptr, "kkptr": kkptr}
+    return {"K": m["K1"], "C": m["C1"]}
 
 
 def get_preloaded_cluster(cluster, batch, num_graphs: int | None = None):
@@ -37,64 +60,193 @@ def get_preloaded_cluster(cluster, batch, num_graphs: int | None = None):
     return cluster
 
 
-def consecutive_cluster(src: torch.Tensor):
-    """PyG ``consecutive_cluster``: ``(inverse, perm)`` with ``perm[c]`` = the LARGEST node index of cluster c (what
-    the reference's CPU ``scatter_`` leaves there: last writer wins)."""
-    uniq, inv = torch.unique(src, sorted=True, return_inverse=True)
-    n_clusters = int(uniq.numel())
-    plan = ops.SegmentPlan(inv, n_clusters)
-    last = plan.perm[(plan.ptr[1:] - 1).long()].to(torch.int64)
-    return inv, last, plan
+_STATUS: dict = {}
+
+
+def _note_status(status: torch.Tensor) -> None:
+    """OR a kernel's status word into the device's accumulator (no host sync); ``check_status`` reads it once per pass."""
+    acc = _STATUS.get(status.device)
+    if acc is None:
+        _STATUS[status.device] = status.clone()
+    else:
+        acc.bitwise_or_(status)
+
+
+def check_status(device=None) -> None:
+    """Host sync: raise if any pooling kernel since the last call found an id outside the sizes it was given (a clustering that does
+    not match the batch's collate meta) or an edge joining two graphs.  The Trainer calls it at the end of every pass."""
+    for dev, acc in list(_STATUS.items()):
+        want = torch.device(device) if device is not None else None
+        if want is not None and (want.type != dev.type or (want.index is not None and want.index != dev.index)):
+            continue
+        flags = int(acc.item())
+        acc.zero_()
+        if flags & _lib.STATUS_INDEX_RANGE:
+            raise IndexError("community pooling: a cluster id / pooled edge count exceeds the sizes recorded for the batch (stale `pool` meta?)")
+        if flags & _lib.STATUS_CROSS_GRAPH:
+            raise ValueError("community pooling: an edge joins two graphs of the batch, or a cluster spans two graphs")
+
+
+class _Structure:
+    """What ``consecutive_cluster`` yields on the device: ``inv`` int64 [N] (new id of every node), ``last`` int64 [C] (PyG's ``perm``:
+    the largest node index of every cluster), a segment plan (nodes grouped by new id, ascending) and the status / count words."""
+
+    __slots__ = ("inv", "last", "plan", "count", "status", "n_clusters")
+
+
+def _host_sizes(cluster: torch.Tensor) -> tuple[int, int]:
+    """(id bound, distinct ids) by ONE host round trip -- only for tensors that did not come with collate meta."""
+    if cluster.numel() == 0:
+        return 0, 0
+    bound = int(cluster.max()) + 1
+    present = torch.zeros(bound, dtype=torch.bool, device=cluster.device)
+    present[cluster] = True
+    return bound, int(present.sum())
+
+
+def consecutive_cluster(src: torch.Tensor, meta: dict | None = None):
+    """PyG ``consecutive_cluster``: ``(inverse, perm, plan)`` with ``perm[c]`` = the LARGEST node index of cluster c (what the
+    reference's CPU ``scatter_`` leaves there: last writer wins).  ``meta = {"K": id bound, "C": distinct ids}`` (from the collate)
+    avoids the host round trip."""
+    st = _consecutive(src, meta)
+    return st.inv, st.last, st.plan
+
+
+def _consecutive(src: torch.Tensor, meta: dict | None) -> _Structure:
+    lib = _lib.load()
+    if not src.is_cuda or src.dtype != torch.int64 or src.dim() != 1:
+        raise TypeError("cluster must be a 1-D int64 CUDA tensor")
+    src = src.contiguous()
+    bound, n_clusters = (int(meta["K"]), int(meta["C"])) if meta is not None else _host_sizes(src)
+    dev, n = src.device, int(src.numel())
+    ptr_k, perm, status = ops.segment_index(src, bound)  # nodes grouped by id, stable: ascending node index inside a cluster
+    rank = torch.empty(max(bound, 1), dtype=torch.int64, device=dev)
+    ptr_c = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+    last = torch.empty(n_clusters, dtype=torch.int64, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.drk_compact_segments(_p(ptr_k), bound, _p(perm), _p(rank), _p(ptr_c), None, _p(last), n_clusters, _p(count), _p(status), stream_ptr())
+    _lib.check(rc, "drk_compact_segments")
+    st = _Structure()
+    st.inv = rank[src] if n else torch.empty(0, dtype=torch.int64, device=dev)
+    st.last, st.count, st.status, st.n_clusters = last, count, status, n_clusters
+    st.plan = ops.SegmentPlan.from_parts(st.inv, ptr_c, perm, n_clusters, status)
+    _note_status(status)
+    return st
 
 
 def pool_batch(perm, batch):
     return batch[perm]
 
 
-def pool_edge(cluster, edge_index, edge_attr=None):
+def _host_pool_meta(inv: torch.Tensor, n_clusters: int, edge_index: torch.Tensor, batch: torch.Tensor | None):
+    """cptr / kkptr / pooled-edge count for tensors without collate meta: one host round trip (the tensors are read on the CPU)."""
+    import numpy as np
+
+    dev = inv.device
+    inv_h, ei_h = inv.cpu().numpy(), edge_index.cpu().numpy()
+    b_h = batch.cpu().numpy() if batch is not None else np.zeros(inv_h.size, dtype=np.int64)
+    n_graphs = int(b_h.max()) + 1 if b_h.size else 1
+    graph_of_cluster = np.zeros(n_clusters, dtype=np.int64)
+    graph_of_cluster[inv_h] = b_h
+    counts = np.bincount(graph_of_cluster, minlength=n_graphs).astype(np.int64)
+    cptr = np.zeros(n_graphs + 1, dtype=np.int64)
+    np.cumsum(counts, out=cptr[1:])
+    kkptr = np.zeros(n_graphs + 1, dtype=np.int64)
+    np.cumsum(counts * counts, out=kkptr[1:])
+    pr, pc = inv_h[ei_h[0]], inv_h[ei_h[1]]
+    keep = pr != pc
+    n_pooled = int(np.unique(pr[keep] * max(n_clusters, 1) + pc[keep]).size)
+    return {"E": n_pooled, "KK": int(kkptr[-1]), "cptr": torch.from_numpy(cptr).to(dev), "kkptr": torch.from_numpy(kkptr).to(dev)}
+
+
+def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, batch: torch.Tensor | None = None, batch32: torch.Tensor | None = None):
     """PyG ``pool_edge(reduce='sum')``: relabel by cluster, drop self loops, sort by (row, col), merge duplicates and
-    sum their attributes.  The result is row-major sorted."""
-    num_nodes = cluster.size(0)
-    ei = cluster[edge_index.view(-1)].view(2, -1)
-    keep = ei[0] != ei[1]
-    ei = ei[:, keep]
-    if edge_attr is not None:
-        edge_attr = edge_attr[keep]
-    if ei.numel() == 0:
-        return ei, edge_attr
-    key = ei[0] * num_nodes + ei[1]
-    uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
-    pooled_index = torch.stack([torch.div(uniq, num_nodes, rounding_mode="floor"), uniq % num_nodes])
+    sum their attributes.  The result is row-major sorted.  ``cluster`` is the CONSECUTIVE relabelling (``inv``); ``meta`` carries the
+    collate's sizes (``E`` pooled edges, ``KK`` dense pair ids, ``cptr`` / ``kkptr`` per-graph offsets)."""
+    lib = _lib.load()
+    dev = cluster.device
+    n, e = int(cluster.numel()), int(edge_index.shape[1])
+    if e == 0:
+        return edge_index, edge_attr
+    if meta is None or "cptr" not in meta:
+        n_clusters = int(cluster.max()) + 1 if n else 0
+        meta = _host_pool_meta(cluster, n_clusters, edge_index, batch)
+    cptr, kkptr = meta["cptr"], meta["kkptr"]
+    n_graphs = int(cptr.numel()) - 1
+    n_pairs, n_pooled = int(meta["KK"]), int(meta["E"])
+    if n_pairs + 1 >= 2**31:
+        raise NotImplementedError("pool_edge: the batch has more than 2^31 candidate pooled pairs")
+    if batch32 is None:
+        batch32 = batch.to(torch.int32) if batch is not None else torch.zeros(n, dtype=torch.int32, device=dev)
+    edge_index = edge_index.contiguous()
+    key = torch.empty(e, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.drk_pool_edge_keys(_p(edge_index), e, _p(cluster), n, _p(batch32), _p(cptr), _p(kkptr), n_graphs, n_pairs, _p(key), _p(status), stream_ptr())
+    _lib.check(rc, "drk_pool_edge_keys")
+    ptr_k, perm, st2 = ops.segment_index(key, n_pairs + 1)  # edges grouped by pooled pair (the junk segment of self loops comes last)
+    ptr_s = torch.empty(n_pooled + 1, dtype=torch.int32, device=dev)
+    ids = torch.empty(max(n_pooled, 1), dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    pooled_index = torch.empty((2, n_pooled), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.drk_compact_segments(_p(ptr_k), n_pairs, None, None, _p(ptr_s), _p(ids), None, n_pooled, _p(count), _p(status), stream_ptr())
+        _lib.check(rc, "drk_compact_segments")
+        rc = lib.drk_pool_edge_decode(_p(ids), n_pooled, _p(count), _p(cptr), _p(kkptr), n_graphs, _p(pooled_index), stream_ptr())
+        _lib.check(rc, "drk_pool_edge_decode")
+    _note_status(status)
+    _note_status(st2)
     if edge_attr is None:
         return pooled_index, None
+    if n_pooled == 0:
+        return pooled_index, edge_attr[:0]
+    if edge_attr.requires_grad:
+        raise NotImplementedError("pool_edge: gradients with respect to edge_attr are not on the DeepRank2 path")
     squeeze = edge_attr.dim() == 1
-    merged = ops.scatter_sum(edge_attr if not squeeze else edge_attr.unsqueeze(1), inv, dim=0, dim_size=int(uniq.numel()))
+    src = edge_attr.unsqueeze(1) if squeeze else edge_attr
+    merged = ops.spmm(ptr_s, perm, src, n_pooled, reduce=ops.REDUCE_SUM)  # sums in ascending edge id, as scatter_add_ over the sorted list does
     return pooled_index, merged.squeeze(1) if squeeze else merged
 
 
-def max_pool_x(cluster, x, batch):
+def max_pool_x(cluster, x, batch, meta: dict | None = None):
     """PyG ``max_pool_x(cluster, x, batch)`` -> ``(x_pooled, batch_pooled)`` (``ginet.py:103,114``, ``foutnet.py:111``)."""
-    inv, last, plan = consecutive_cluster(cluster)
-    pooled, _ = ops.scatter_max(x, inv, dim=0, plan=plan)
-    return pooled, pool_batch(last, batch)
+    st = _consecutive(cluster, meta)
+    pooled, _ = ops.scatter_max(x, st.inv, dim=0, plan=st.plan)
+    return pooled, pool_batch(st.last, batch)
 
 
-def community_pooling(cluster, data):
+def community_pooling(cluster, data, meta: dict | None = None):
     """Pool all members of a cluster into one node (``community_pooling.py:165-242``): feature-wise max of ``x``,
     pooled + coalesced edges with summed attributes, mean position, pooled batch vector; ``cluster0/1`` carried."""
-    inv, last, plan = consecutive_cluster(cluster)
+    if meta is None:
+        meta = pool_meta(data, 0)
+    st = _consecutive(cluster, meta)
+    inv, last, plan = st.inv, st.last, st.plan
     x, _ = ops.scatter_max(data.x, inv, dim=0, plan=plan)
-    edge_index, edge_attr = pool_edge(inv, data.edge_index, data.edge_attr)
+    batch = getattr(data, "batch", None)
+    gi = data.__dict__.get("_graph_index")
+    batch32 = gi.batch32 if gi is not None and gi.batch32 is not None else None
+    edge_index, edge_attr = pool_edge(inv, data.edge_index, data.edge_attr, meta=meta, batch=batch, batch32=batch32)
     pos = ops.scatter_mean(data.pos, inv, dim=0, plan=plan) if getattr(data, "pos", None) is not None else None
     c0, c1 = getattr(data, "cluster0", None), getattr(data, "cluster1", None)
-    if getattr(data, "batch", None) is not None:
-        out = Batch(batch=pool_batch(last, data.batch), x=x, edge_index=edge_index, edge_attr=edge_attr, pos=pos)
+    if batch is not None:
+        out = Batch(batch=pool_batch(last, batch), x=x, edge_index=edge_index, edge_attr=edge_attr, pos=pos)
         ng = data.__dict__.get("_num_graphs")
         if ng is None and data.__dict__.get("ptr") is not None:
             ng = int(data.ptr.numel()) - 1
         if ng is not None:
             out.__dict__["_num_graphs"] = ng
+        m = data.__dict__.get(getattr(data, "_META_KEY", "_meta"), {}).get("pool")
+        eptr = data.__dict__.get("_pool_eptr32")
+        if m is not None and meta is not None and "cptr" in meta and eptr is not None and eptr.is_cuda and m["C0"] < 2**31:
+            # the pooled batch is a collated batch again: per-graph node / edge slices for the blocked index build, and level-1 sizes
+            out.__dict__["_node_ptr32"] = meta["cptr"].to(torch.int32)
+            out.__dict__["_edge_ptr32"] = eptr
+            out.__dict__[out._META_KEY] = {"num_graphs": ng, "max_graph_nodes": m["max_C0"], "max_graph_edges": m["max_E1"], "num_edges_total": m["E1"],
+                                           "pool": m}
     else:
         out = Data(x=x, edge_index=edge_index, edge_attr=edge_attr, pos=pos)
     out.cluster0, out.cluster1 = c0, c1
+    out.__dict__["_pool_status"] = st.status
     return out

@@ -315,6 +315,30 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
                    float* dfc1_w, float* dfc1_b, float* dfc2_w, float* dfc2_b,
                    const DrkAdam* adam, const DrkPeers* peers, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ community pooling structure
+ * Replaces PyG's consecutive_cluster (torch.unique + scatter_) and pool_edge (relabel, remove_self_loops, coalesce) as called from
+ * deeprank2/utils/community_pooling.py:206-219 and torch_geometric's max_pool_x (ginet.py:103,114; foutnet.py:111).  Sizes that depend
+ * on the data (distinct clusters, distinct pooled edges) are passed in as CAPACITIES known to the host collate (exact counts or upper
+ * bounds); the counts found are written to device scalars, DRK_STATUS_INDEX_RANGE is raised when a capacity is exceeded, and nothing
+ * is read back, so the chain can be captured into a CUDA graph.
+ *
+ * drk_compact_segments: drop the empty segments of a segment index (ptr [num_segments+1], perm from drk_segment_index_build).
+ *   rank [num_segments] int64 (nullable): compact id of every non-empty segment, -1 for empty ones (consecutive_cluster's inverse map
+ *   is rank[cluster]); ptr_out [capacity+1]: compact offsets (entries beyond the count = total: empty segments); ids_out [capacity]
+ *   (nullable): original id of every kept segment; last_out [capacity] int64 (nullable, needs perm): the LAST member of every kept
+ *   segment = the largest node index of the cluster (what PyG's perm holds on CPU: last writer wins); count_out: device int32.
+ * drk_pool_edge_keys: key[e] = pair_ptr[g] + (inv[row_e] - cluster_ptr[g]) * C_g + (inv[col_e] - cluster_ptr[g]) with g =
+ *   batch32[row_e], C_g = cluster_ptr[g+1] - cluster_ptr[g]: a dense id of the pooled pair, ascending in (row, col) order; pooled
+ *   self loops get junk_key (= pair_ptr[num_graphs]).  cluster_ptr / pair_ptr: int64 [num_graphs+1], pair_ptr[g+1] - pair_ptr[g] = C_g^2.
+ * drk_pool_edge_decode: pooled edge_index [2, capacity] int64 from the dense ids kept by drk_compact_segments. */
+DRK_API int drk_compact_segments(const int32_t* ptr, int32_t num_segments, const int32_t* perm, int64_t* rank, int32_t* ptr_out, int32_t* ids_out,
+                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* stream);
+DRK_API int drk_pool_edge_keys(const int64_t* edge_index, int64_t num_edges, const int64_t* inv, int32_t num_nodes, const int32_t* batch32,
+                       const int64_t* cluster_ptr, const int64_t* pair_ptr, int32_t num_graphs, int64_t junk_key, int64_t* key, int32_t* status,
+                       void* stream);
+DRK_API int drk_pool_edge_decode(const int32_t* ids, int32_t capacity, const int32_t* count, const int64_t* cluster_ptr, const int64_t* pair_ptr,
+                         int32_t num_graphs, int64_t* edge_index_out, void* stream);
+
 /* ------------------------------------------------------------------ GINet attention with a segment softmax per destination
  * The operator the reference's GINetConvLayer sets up (ginet.py:45-52: logit = leaky_relu(fc_attention([fc(x)[row], fc(x)[col],
  * fc_edge_attr(edge_attr)]))) normalised over the edges of each destination node -- BASELINE.json north_star, SURVEY 8f rank 4.

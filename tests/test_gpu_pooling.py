@@ -110,3 +110,113 @@ def test_scatter_max_ties_pick_first():
     out, arg = ops.scatter_max(src, index, dim=0, dim_size=3)
     assert out.flatten().tolist() == [3.0, 2.0, 0.0]
     assert arg.flatten().tolist() == [1, 3, 5]
+
+
+def _clustered_batch(n_graphs=12, first=300):
+    from deeprank2_b200.synthetic import make_batch
+
+    return make_batch(n_graphs, first=first, with_clusters=True)
+
+
+def test_pooling_with_collate_sizes_has_no_readback_and_matches_the_reference_semantics():
+    """Batches made by ``Batch.from_data_list`` carry the shapes of their pooled tensors (``meta("pool")``): the chain then runs without a
+    single host synchronisation (checked with ``torch.cuda.set_sync_debug_mode("error")``) and gives, bit for bit, what PyG's
+    consecutive_cluster / pool_edge / max_pool_x give on the CPU (oracle/thirdparty.py)."""
+    from deeprank2_b200.utils import community_pooling as cp
+
+    host = _clustered_batch()
+    m = host.meta("pool")
+    assert m is not None and m["C0"] > 0 and m["E1"] > 0
+    b = host.clone().to(DEV)
+    ng = host.num_graphs
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        c0 = cp.get_preloaded_cluster(b.cluster0.clone(), b.batch, ng)
+        pooled = cp.community_pooling(c0, b)
+        c1 = cp.get_preloaded_cluster(pooled.cluster1.clone(), pooled.batch, ng)
+        x2, b2 = cp.max_pool_x(c1, pooled.x, pooled.batch, meta=cp.pool_meta(pooled, 1))
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    cp.check_status(DEV)
+    # reference semantics on the CPU
+    rc0 = host.cluster0.clone()
+    for g in range(1, ng):
+        rc0[host.batch == g] += rc0[host.batch == g - 1].max() + 1
+    inv, perm = tp.consecutive_cluster(rc0)
+    r_x, _ = tp.scatter_max(host.x, inv, dim=0)
+    r_ei, r_ea = tp.pool_edge(inv, host.edge_index, host.edge_attr)
+    assert_equal_int(pooled.edge_index, r_ei, "pooled edge_index")
+    assert pooled.edge_index.shape[1] == m["E1"] and pooled.x.shape[0] == m["C0"]
+    assert torch.equal(pooled.x.cpu(), r_x)
+    assert_close(pooled.edge_attr, r_ea, "pooled edge_attr")
+    assert_equal_int(pooled.batch, host.batch[perm], "pooled batch")
+    assert_close(pooled.pos, tp.scatter_mean(host.pos, inv, dim=0), "pooled pos")
+    rc1 = host.cluster1.clone()
+    pb = host.batch[perm]
+    for g in range(1, ng):
+        rc1[pb == g] += rc1[pb == g - 1].max() + 1
+    r_x2, r_b2 = tp.max_pool_x(rc1, r_x, pb)
+    assert torch.equal(x2.cpu(), r_x2) and x2.shape[0] == m["C1"]
+    assert_equal_int(b2, r_b2, "pool2 batch")
+    # the pooled batch is a collated batch again: its graph index comes from the per-graph (blocked) builder
+    from deeprank2_b200.graph import graph_index
+
+    gi = graph_index(pooled)
+    ref_ptr = torch.zeros(m["C0"] + 1, dtype=torch.int64)
+    ref_ptr[1:] = torch.cumsum(torch.bincount(r_ei[0], minlength=m["C0"]), 0)
+    assert_equal_int(gi.rowptr, ref_ptr, "rowptr of the pooled graph")
+    assert_equal_int(gi.colidx, r_ei[1], "pool_edge's output is already destination sorted")
+
+
+def test_pooling_flags_sizes_that_do_not_match_the_batch():
+    from deeprank2_b200.utils import community_pooling as cp
+
+    host = _clustered_batch(4)
+    b = host.clone().to(DEV)
+    b.meta("pool")["C0"] -= 3  # stale meta: fewer clusters than the data holds
+    c0 = cp.get_preloaded_cluster(b.cluster0.clone(), b.batch, host.num_graphs)
+    cp.community_pooling(c0, b)
+    with pytest.raises(IndexError):
+        cp.check_status(DEV)
+    cp.check_status(DEV)  # the accumulator was reset
+
+
+@pytest.mark.parametrize("net_name", ["foutnet", "ginet", "sgat"])
+def test_clustered_train_step_replays_from_a_cuda_graph(net_name):
+    """No host read-back anywhere in the step of a clustered network: it can be captured once and replayed; two replays on the same
+    weights are bit-identical to two eager steps."""
+    import copy
+    import importlib
+
+    from deeprank2_b200.step import GraphedTrainStep, TrainStep
+
+    cls = {"foutnet": "FoutNet", "ginet": "GINet", "sgat": "SGAT"}[net_name]
+    mod = importlib.import_module(f"deeprank2_b200.neuralnets.gnn.{net_name}")
+    batch = _clustered_batch(16).to(DEV)
+    loss_fn = torch.nn.MSELoss()
+
+    def build():
+        torch.manual_seed(3)
+        net = getattr(mod, cls)(50, 1, 1).to(DEV).eval()  # eval: no dropout stream to keep in step
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        inner = TrainStep(net, opt, loss_fn)
+
+        def step(b):
+            view = copy.copy(b)
+            view.__dict__ = dict(b.__dict__)
+            return inner(view)
+
+        return net, step
+
+    net_e, step_e = build()
+    losses_e = [float(step_e(batch)[0]) for _ in range(3)]
+    net_g, step_g = build()
+    graphed = GraphedTrainStep(step_g, batch, warmup=1)  # the warm-up step is the first of the three
+    losses_g = [losses_e[0]]
+    for _ in range(2):
+        loss, _ = graphed.replay()
+        losses_g.append(float(loss))
+    assert losses_g[1:] == losses_e[1:], (losses_g, losses_e)
+    for (k, p), q in zip(net_e.named_parameters(), net_g.parameters()):
+        assert torch.equal(p, q), k
