@@ -25,6 +25,7 @@ ACT_NONE, ACT_RELU = 0, 1
 REDUCE_SUM, REDUCE_MEAN_CLAMP, REDUCE_MEAN_NAN = 0, 1, 2
 LOSS_MSE, LOSS_CROSS_ENTROPY = 0, 1
 EDGES_DIRECTED, EDGES_UNDIRECTED_PAIRS, EDGES_LOCAL_PAIRS16 = 0, 1, 2
+POOL_JUNK_SEGMENTS = 4096
 
 _P = c_void_p
 _I32 = c_int32

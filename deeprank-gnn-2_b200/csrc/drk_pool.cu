@@ -10,7 +10,8 @@
 //                             drk_compact_segments                     empty ids dropped: rank[id] (= torch.unique's inverse through
 //                                                                      rank[c]), compact ptr, last member of every cluster (= perm)
 //   pool_edge(c, ei, ea):     drk_pool_edge_keys                       key = dense id of the pooled pair inside its graph's C_g x C_g
-//                                                                      block (self loops -> one junk segment at the end)
+//                                                                      block (self loops -> DRK_POOL_JUNK_SEGMENTS junk segments at the end,
+//                                                                      spread by edge id: the counting sort ranks inside a segment)
 //                             drk_segment_index_build(key, KK + 1)     edges grouped by pooled pair, ascending edge id inside a pair
 //                             drk_compact_segments                     distinct pairs in (row, col) order = coalesce's order
 //                             drk_pool_edge_decode                     pooled edge_index from the dense ids
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kCT) k_compact_segments(const int32_t* __restr
 }
 
 // key[e] = kkptr[g] + (inv[row] - cptr[g]) * C_g + (inv[col] - cptr[g]) with g the graph of the edge's row node; self loops of the
-// pooled graph and edges whose endpoints fall outside the graph's cluster range go to the junk segment `junk`.
+// pooled graph and edges whose endpoints fall outside the graph's cluster range go to the junk segments [junk, junk + DRK_POOL_JUNK_SEGMENTS).
 __global__ void __launch_bounds__(256) k_pool_edge_keys(const int64_t* __restrict__ erow, const int64_t* __restrict__ ecol, int64_t num_edges,
                                                        const int64_t* __restrict__ inv, int32_t num_nodes, const int32_t* __restrict__ batch32,
                                                        const int64_t* __restrict__ cptr, const int64_t* __restrict__ kkptr, int32_t num_graphs,
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) k_pool_edge_keys(const int64_t* __restric
   bool bad = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += stride) {
     const unsigned long long r = (unsigned long long)ld_stream_i64(erow + e), c = (unsigned long long)ld_stream_i64(ecol + e);
-    int64_t k = junk;
+    int64_t k = junk + (e & (DRK_POOL_JUNK_SEGMENTS - 1));
     if (r < (unsigned long long)num_nodes && c < (unsigned long long)num_nodes) {
       const int g = __ldg(batch32 + r);
       if ((unsigned)g < (unsigned)num_graphs) {

@@ -323,7 +323,7 @@ class Batch(Data):
         np.cumsum(m[:, 1], out=cptr[1:])
         kkptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
         np.cumsum(m[:, 1] * m[:, 1], out=kkptr[1:])
-        if kkptr[-1] + 1 >= 2**31 or m[:, 0].sum() >= 2**31:
+        if kkptr[-1] + 4096 >= 2**31 or m[:, 0].sum() >= 2**31:
             return
         eptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
         np.cumsum(m[:, 2], out=eptr[1:])

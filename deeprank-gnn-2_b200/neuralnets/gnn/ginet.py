@@ -30,26 +30,33 @@ class GINet(nn.Module):
         self.clustering = "mcl"
         self.dropout = 0.4
 
-    def _branch(self, data, conv1, conv2):
+    def _branch(self, data, conv1, conv2, shared):
+        """``shared``: the pooling structure of the batch (relabelled clusters, pooled edges / attributes / positions / batch vector,
+        the pooled batch's graph index) -- identical for both branches, built by the first and reused by the second."""
         ng = num_graphs_of(data)
         x = conv1(data.x, data.edge_index, data.edge_attr, graph=graph_index(data), relu=True)
         data.x = x
         # (the offsets are added in place: on a copy, so that a batch that is used again -- CUDA-graph replay, resident sets -- stays intact)
-        cluster = get_preloaded_cluster(data.cluster0.clone(), data.batch, ng)
-        data = community_pooling(cluster, data)
+        cluster = get_preloaded_cluster(data.cluster0.clone(), data.batch, ng) if "level0" not in shared else None
+        data = community_pooling(cluster, data, shared=shared)
 
         data.x = conv2(data.x, data.edge_index, data.edge_attr, graph=graph_index(data), relu=True)
-        cluster = get_preloaded_cluster(data.cluster1.clone(), data.batch, ng)
-        x, batch = max_pool_x(cluster, data.x, data.batch, meta=pool_meta(data, 1))
+        cluster = get_preloaded_cluster(data.cluster1.clone(), data.batch, ng) if "level1" not in shared else None
+        x, batch = max_pool_x(cluster, data.x, data.batch, meta=pool_meta(data, 1), shared=shared)
         return ops.scatter_mean(x, batch, dim=0, dim_size=ng)
 
     def forward(self, data):
-        # the reference clones the batch for the second branch (ginet.py:92) because get_preloaded_cluster edits
-        # cluster0/cluster1 in place; the same is done here (x / edge tensors are only read, so a shallow copy of
-        # everything but the two cluster vectors would do, but clone() keeps the semantics obvious).
-        data_ext = data.clone()
-        x = self._branch(data, self.conv1, self.conv2)
-        x_ext = self._branch(data_ext, self.conv1_ext, self.conv2_ext)
+        # The reference deep-copies the batch for the second branch (ginet.py:92) because get_preloaded_cluster edits cluster0 / cluster1
+        # in place.  Here the cluster vectors are offset on copies (see _branch), nothing else of the batch is written but `x`: a shallow view
+        # suffices, and both branches share the batch's graph index and its pooling structure.
+        import copy
+
+        graph_index(data)
+        data_ext = copy.copy(data)
+        data_ext.__dict__ = dict(data.__dict__)
+        shared: dict = {}
+        x = self._branch(data, self.conv1, self.conv2, shared)
+        x_ext = self._branch(data_ext, self.conv1_ext, self.conv2_ext, shared)
 
         x = torch.cat([x, x_ext], dim=1)
         x = relu(self.fc1(x))

@@ -175,7 +175,7 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
     cptr, kkptr = meta["cptr"], meta["kkptr"]
     n_graphs = int(cptr.numel()) - 1
     n_pairs, n_pooled = int(meta["KK"]), int(meta["E"])
-    if n_pairs + 1 >= 2**31:
+    if n_pairs + _lib.POOL_JUNK_SEGMENTS >= 2**31:
         raise NotImplementedError("pool_edge: the batch has more than 2^31 candidate pooled pairs")
     if batch32 is None:
         batch32 = batch.to(torch.int32) if batch is not None else torch.zeros(n, dtype=torch.int32, device=dev)
@@ -185,7 +185,7 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
     with torch.cuda.device(dev):
         rc = lib.drk_pool_edge_keys(_p(edge_index), e, _p(cluster), n, _p(batch32), _p(cptr), _p(kkptr), n_graphs, n_pairs, _p(key), _p(status), stream_ptr())
     _lib.check(rc, "drk_pool_edge_keys")
-    ptr_k, perm, st2 = ops.segment_index(key, n_pairs + 1)  # edges grouped by pooled pair (the junk segment of self loops comes last)
+    ptr_k, perm, st2 = ops.segment_index(key, n_pairs + _lib.POOL_JUNK_SEGMENTS)  # edges grouped by pooled pair (the junk segments of the self loops come last)
     ptr_s = torch.empty(n_pooled + 1, dtype=torch.int32, device=dev)
     ids = torch.empty(max(n_pooled, 1), dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
@@ -209,16 +209,35 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
     return pooled_index, merged.squeeze(1) if squeeze else merged
 
 
-def max_pool_x(cluster, x, batch, meta: dict | None = None):
-    """PyG ``max_pool_x(cluster, x, batch)`` -> ``(x_pooled, batch_pooled)`` (``ginet.py:103,114``, ``foutnet.py:111``)."""
-    st = _consecutive(cluster, meta)
+def max_pool_x(cluster, x, batch, meta: dict | None = None, shared: dict | None = None):
+    """PyG ``max_pool_x(cluster, x, batch)`` -> ``(x_pooled, batch_pooled)`` (``ginet.py:103,114``, ``foutnet.py:111``).
+    ``shared``: a dict in which the weight-independent part (relabelling, pooled batch vector) is kept for a second call on the same
+    clustering -- the two branches of the clustered GINet; ``cluster`` may then be None on the second call."""
+    if shared is not None and "level1" in shared:
+        st, pooled_batch = shared["level1"]
+    else:
+        st = _consecutive(cluster, meta)
+        pooled_batch = pool_batch(st.last, batch)
+        if shared is not None:
+            shared["level1"] = (st, pooled_batch)
     pooled, _ = ops.scatter_max(x, st.inv, dim=0, plan=st.plan)
-    return pooled, pool_batch(st.last, batch)
+    return pooled, pooled_batch
 
 
-def community_pooling(cluster, data, meta: dict | None = None):
+def community_pooling(cluster, data, meta: dict | None = None, shared: dict | None = None):
     """Pool all members of a cluster into one node (``community_pooling.py:165-242``): feature-wise max of ``x``,
-    pooled + coalesced edges with summed attributes, mean position, pooled batch vector; ``cluster0/1`` carried."""
+    pooled + coalesced edges with summed attributes, mean position, pooled batch vector; ``cluster0/1`` carried.
+    ``shared``: a dict in which everything that does not depend on ``data.x`` (relabelling, pooled edges and attributes, positions,
+    batch vector, and later the pooled batch's graph index) is kept for a second call on the same graph and clustering -- the two
+    branches of the clustered GINet pool the same batch twice; ``cluster`` may then be None on the second call."""
+    if shared is not None and "level0" in shared:
+        import copy
+
+        st, template = shared["level0"]
+        out = copy.copy(template)
+        out.__dict__ = dict(template.__dict__)  # the template's caches (graph index of the pooled batch) are shared, x is this call's
+        out.x, _ = ops.scatter_max(data.x, st.inv, dim=0, plan=st.plan)
+        return out
     if meta is None:
         meta = pool_meta(data, 0)
     st = _consecutive(cluster, meta)
@@ -249,4 +268,6 @@ def community_pooling(cluster, data, meta: dict | None = None):
         out = Data(x=x, edge_index=edge_index, edge_attr=edge_attr, pos=pos)
     out.cluster0, out.cluster1 = c0, c1
     out.__dict__["_pool_status"] = st.status
+    if shared is not None:
+        shared["level0"] = (st, out)
     return out
