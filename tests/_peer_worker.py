@@ -35,10 +35,29 @@ def main():
     if os.environ.get("DRK_REQUIRE_PEER") and mode != "peer":
         raise RuntimeError("the peer-memory exchange was not set up")
     ref_net, ref_opt, ref_step = build(1)
+
+    def assert_grads_match(what):
+        g, r = step.flat_grad, ref_step.flat_grad
+        bound = 1e-5 * float(r.abs().max()) + 1e-5 * r.abs()
+        worst = float(((g - r).abs() - bound).max())
+        assert worst <= 0.0, f"{what}: data-parallel gradient differs from the single-process gradient (excess {worst:.3e}, max|g| {float(r.abs().max()):.3e})"
+
+    # the exchanged gradient itself, before any optimizer arithmetic: the sum over ranks must be the single-process gradient (fp32 bar)
+    step.forward_backward(mine, global_size=per * world)
+    ref_step.forward_backward(everything)
+    torch.cuda.synchronize()
+    assert_grads_match(f"{mode} exchange")
     losses = []
-    for _ in range(3):
+    for i in range(3):
+        if mode == "nccl":
+            # torch's own Adam applies this mode's update: compare GRADIENTS from identical weights at every step instead of weights
+            # after sign-like Adam steps (a near-zero gradient component may legitimately move its weight by lr either way)
+            net.load_state_dict(ref_net.state_dict())
         loss, _ = step(mine, global_size=per * world)
         ref_loss, _ = ref_step(everything)
+        if mode == "nccl":
+            torch.cuda.synchronize()
+            assert_grads_match(f"nccl step {i}")
         total = loss.clone()
         if mode == "nccl":
             dist.all_reduce(total)  # the NCCL path leaves the rank-local share in `loss`; the peer path already holds the global value
@@ -55,16 +74,14 @@ def main():
     # 1e-7 can still move a near-zero-gradient weight by a fraction of lr: the first loss is tight, the rest within lr-sized drift.
     tight = mode == "peer"
     for i, (a, b) in enumerate(losses):
-        rtol = 1e-5 if (tight or i == 0) else 2e-4
-        assert abs(a - b) <= rtol * abs(b) + 1e-7, f"loss {a} vs single-process {b} at step {i}"
+        assert abs(a - b) <= 1e-5 * abs(b) + 1e-7, f"loss {a} vs single-process {b} at step {i}"
     flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     ref = torch.cat([p.detach().reshape(-1) for p in ref_net.parameters()])
     diff = (flat - ref).abs()
     err = float(diff.max())
     if tight:
         assert err <= 2e-6, f"weights after 4 data-parallel steps differ from the single-process run by {err:.3e}"
-    else:
-        assert err <= 8e-3 and float((diff > 5e-5).float().mean()) < 0.02, f"weights drifted: max {err:.3e}"
+    # (nccl mode: gradients were compared step by step above; the weights are only required to be identical across ranks)
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     assert all(torch.equal(gathered[0], t) for t in gathered), "ranks hold different weights"
