@@ -47,6 +47,8 @@ SIGNATURES = {
     "drk_weight_grad_workspace_bytes": (c_size_t, [_I32, _I32]),
     "drk_weight_grad": (c_int32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, c_size_t, _P]),
     "drk_spmm": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+    "drk_spmm_tiled_supported": (c_int32, [_I32, _I32]),
+    "drk_spmm_tiled": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "drk_segment_mean": (c_int32, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
     "drk_segment_mean_bwd": (c_int32, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
     "drk_ginet_fused_max_nodes": (c_int32, [_I32]),

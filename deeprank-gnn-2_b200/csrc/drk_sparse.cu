@@ -204,6 +204,160 @@ static void launch_spmm(const SpmmArgs& a, int blocks, cudaStream_t stream) {
   else k_spmm<LPR, VEC, false, false><<<blocks, kSpmmThreads, 0, stream>>>(a);
 }
 
+// ---------------------------------------------------------------- per-graph tiled variant (block-diagonal adjacency)
+// For collated batches whose graphs are too big for the whole-step kernel but whose source rows still fit one SM: atom-level graphs
+// of ~3 k nodes.  A work unit is (graph g, group of 16 columns, slice of the graph's destination rows): the CTA
+// copies the [n_g x 16] column slice of `src` into shared memory ONCE (cp.async, 64-byte rows, <= 3584 rows = 224 KB) and every
+// gathered row is then a shared-memory read instead of an L2 sector request; the destination rows of a graph are split over several
+// CTAs so that the grid covers all 148 SMs (the tile is re-read from L2 by each of them, from HBM once).  Same lane layout, visiting
+// order (CSR order, sequential fp32 accumulation) and epilogues as k_spmm: bit-identical results.  A source row outside the graph's
+// range (not a block-diagonal adjacency) is fetched from global memory instead -- correct, just not fast.
+constexpr int kTileThreads = 1024;  // one CTA per SM (the tile takes the shared memory): 32 warps to hide the latency of the index stream
+constexpr int kTileCols = 16;
+constexpr int kTileMaxRows = 3584;  // 3584 x 64 B = 224 KB
+
+struct SpmmTileArgs {
+  SpmmArgs base;
+  const int32_t* graph_ptr;
+  int32_t num_graphs, col_groups, row_splits;
+};
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(kTileThreads, 1) k_spmm_tiled(const SpmmTileArgs t) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  constexpr int LPR = 4, VEC = 4, kRowsPerWarp = 8, kWarps = kTileThreads / 32, kBatch = 8;
+  constexpr unsigned kFull = 0xffffffffu;
+  const SpmmArgs& a = t.base;
+  const int lane = lane_id(), sub = lane / LPR, sl = lane % LPR, group_base = sub * LPR, warp = threadIdx.x >> 5;
+  int unit = blockIdx.x;
+  const int split = unit % t.row_splits;
+  unit /= t.row_splits;
+  const int cg = unit % t.col_groups;
+  const int g = unit / t.col_groups;
+  const int n0 = __ldg(t.graph_ptr + g), n = __ldg(t.graph_ptr + g + 1) - n0;
+  const int c = cg * kTileCols + sl * VEC;
+  // ---- the column slice of the graph's source rows -> shared memory (row r at byte 64 r), by the copy engine (cp.async.bulk): one
+  // request when the slice is contiguous in global memory (width 16, dense rows), else one 64-byte request per row, issued by all the
+  // threads of the CTA in parallel.  (Thread-issued cp.async moves only ~10 B/clk/SM here: 20 k cycles for a 3 k-row tile.)
+  __shared__ __align__(8) unsigned long long tile_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&tile_bar, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  {
+    const char* src_cg = reinterpret_cast<const char*>(a.src + cg * kTileCols);
+    const uint64_t ld_bytes = (uint64_t)a.ld_src * 4u;
+    if (threadIdx.x == 0) mbar_expect_tx(&tile_bar, (uint32_t)n * 64u);
+    __syncthreads();  // the expectation is registered before any copy can complete
+    if (ld_bytes == 64) {
+      if (threadIdx.x == 0 && n > 0) bulk_copy_g2s(tile_smem, src_cg + (uint64_t)(uint32_t)n0 * 64u, (uint32_t)n * 64u, &tile_bar);
+    } else {
+      for (int r = threadIdx.x; r < n; r += kTileThreads) bulk_copy_g2s(tile_smem + (size_t)r * 64, src_cg + (uint64_t)(uint32_t)(n0 + r) * ld_bytes, 64u, &tile_bar);
+    }
+  }
+  const int per = (((n + t.row_splits - 1) / t.row_splits) + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
+  const int row0 = n0 + split * per, row_end = min(row0 + per, n0 + n);
+  const char* src_c = reinterpret_cast<const char*>(a.src + c);
+  const uint32_t ld_src_bytes = a.ld_src * 4u;
+  bool tile_ready = false;
+  for (int rw = row0 + warp * kRowsPerWarp; rw < row_end; rw += kWarps * kRowsPerWarp) {
+    const int r = rw + sub;
+    const bool row_ok = r < row_end;
+    int beg = 0, len = 0;
+    if (row_ok) {
+      beg = __ldg(a.ptr + r);
+      len = __ldg(a.ptr + r + 1) - beg;
+    }
+    int max_len = len;
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) max_len = max(max_len, __shfl_xor_sync(kFull, max_len, o));
+    float acc[VEC] = {0.f, 0.f, 0.f, 0.f};
+    // 8 edges per trip: every lane of the row's group fetches two index words, the group shares them by shuffle
+    int next_idx[2];
+    float next_w[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = q * LPR + sl;
+      next_idx[q] = -1;
+      next_w[q] = 0.f;
+      if (e < len) {
+        next_idx[q] = ld_stream_i32(a.idx + beg + e);
+        if (HAS_W) next_w[q] = ld_stream_f32(a.w + beg + e);
+      }
+    }
+    if (!tile_ready) {  // the first rows' offsets and indices are on their way while the tile lands
+      mbar_wait(&tile_bar, 0);
+      tile_ready = true;
+    }
+    for (int off = 0; off < max_len; off += kBatch) {
+      int my_idx[2];
+      float my_w[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        my_idx[q] = next_idx[q];
+        my_w[q] = next_w[q];
+        const int e = off + kBatch + q * LPR + sl;
+        next_idx[q] = -1;
+        if (e < len) {
+          next_idx[q] = ld_stream_i32(a.idx + beg + e);
+          if (HAS_W) next_w[q] = ld_stream_f32(a.w + beg + e);
+        }
+      }
+      float4 v[kBatch];
+      int srow[kBatch];
+      float tw[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        srow[u] = __shfl_sync(kFull, my_idx[u / LPR], group_base + (u % LPR));
+        if (HAS_W) tw[u] = __shfl_sync(kFull, my_w[u / LPR], group_base + (u % LPR));
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (srow[u] >= 0) {
+          const unsigned local = (unsigned)(srow[u] - n0);
+          if (local < (unsigned)n) v[u] = *reinterpret_cast<const float4*>(tile_smem + (size_t)local * 64 + sl * 16);
+          else v[u] = ld_gather_f4(reinterpret_cast<const float*>(src_c + (uint64_t)(uint32_t)srow[u] * ld_src_bytes));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (srow[u] >= 0) {  // strictly sequential accumulation in CSR order
+          if (HAS_W) {
+            acc[0] = fmaf(tw[u], v[u].x, acc[0]); acc[1] = fmaf(tw[u], v[u].y, acc[1]); acc[2] = fmaf(tw[u], v[u].z, acc[2]); acc[3] = fmaf(tw[u], v[u].w, acc[3]);
+          } else {
+            acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w;
+          }
+        }
+      }
+    }
+    if (!row_ok) continue;
+    if (a.reduce != DRK_REDUCE_SUM) {
+      const float deg = (float)len;
+      const float den = a.reduce == DRK_REDUCE_MEAN_CLAMP ? fmaxf(deg, 1.f) : deg;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = acc[k] / den;
+    }
+    if (a.addend != nullptr) {
+      Vec<VEC> ad;
+      ad.load(a.addend + (size_t)r * a.ld_addend + c);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] += ad.v[k];
+    }
+    if (a.act == DRK_ACT_RELU) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = relu_keep_nan(acc[k]);
+    }
+    if (a.mask != nullptr) {
+      Vec<VEC> m;
+      m.load(a.mask + (size_t)r * a.ld_mask + c);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = relu_grad_mask(acc[k], m.v[k]);
+    }
+    *reinterpret_cast<float4*>(a.out + (size_t)r * a.ld_out + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 // ---------------------------------------------------------------- per-graph mean (one CTA per graph)
 constexpr int kMeanThreads = 256;
 
@@ -325,6 +479,43 @@ int drk_spmm(const int32_t* ptr, const int32_t* idx, const float* w, const float
   else DRK_SPMM_CASE(4, 1); else DRK_SPMM_CASE(8, 1); else DRK_SPMM_CASE(16, 1); else DRK_SPMM_CASE(32, 1);
 #undef DRK_SPMM_CASE
   return finish_launch("spmm");
+}
+
+int drk_spmm_tiled_supported(int32_t max_graph_nodes, int32_t width) {
+  return (max_graph_nodes >= 0 && max_graph_nodes <= drk::kTileMaxRows && width > 0 && width % drk::kTileCols == 0) ? 1 : 0;
+}
+
+int drk_spmm_tiled(const int32_t* ptr, const int32_t* idx, const float* w, const float* src, int64_t ld_src, const float* addend, int64_t ld_addend,
+                   const float* mask, int64_t ld_mask, float* out, int64_t ld_out, const int32_t* graph_ptr, int32_t num_graphs,
+                   int32_t max_graph_nodes, int32_t width, int32_t reduce, int32_t act, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_graphs >= 0 && width >= 0 && max_graph_nodes >= 0, DRK_EINVAL, "spmm tiled: negative size");
+  if (num_graphs == 0 || width == 0) return DRK_OK;
+  DRK_REQUIRE(drk_spmm_tiled_supported(max_graph_nodes, width), DRK_EUNSUPPORTED, "spmm tiled: graphs of %d nodes / width %d do not fit (<= %d rows, width %% %d == 0)",
+              max_graph_nodes, width, kTileMaxRows, kTileCols);
+  DRK_REQUIRE(ptr && idx && src && out && graph_ptr, DRK_EINVAL, "spmm tiled: null pointer");
+  DRK_REQUIRE(reduce >= DRK_REDUCE_SUM && reduce <= DRK_REDUCE_MEAN_NAN, DRK_EINVAL, "spmm tiled: unknown reduce %d", reduce);
+  DRK_REQUIRE(act == DRK_ACT_NONE || act == DRK_ACT_RELU, DRK_EINVAL, "spmm tiled: unknown activation %d", act);
+  DRK_REQUIRE(ld_src >= 0 && ld_src < (int64_t)1 << 30 && ld_out >= 0 && ld_out < (int64_t)1 << 30 && ld_addend < (int64_t)1 << 30 && ld_mask < (int64_t)1 << 30,
+              DRK_EUNSUPPORTED, "spmm tiled: leading dimension out of range");
+  DRK_REQUIRE(aligned16(src) && aligned16(out) && ld_src % 4 == 0 && ld_out % 4 == 0 && (!addend || (aligned16(addend) && ld_addend % 4 == 0)) &&
+                  (!mask || (aligned16(mask) && ld_mask % 4 == 0)),
+              DRK_EUNSUPPORTED, "spmm tiled: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
+  SpmmTileArgs t{};
+  t.base = SpmmArgs{ptr, idx, w, src, addend, mask, out, (uint32_t)ld_src, (uint32_t)ld_addend, (uint32_t)ld_mask, (uint32_t)ld_out, 0, width, reduce, act, 0};
+  t.graph_ptr = graph_ptr;
+  t.num_graphs = num_graphs;
+  t.col_groups = width / kTileCols;
+  // destination rows of a graph over enough CTAs for ~2 waves of the 148 SMs (one CTA per SM: the tile takes the whole shared memory)
+  const int units = num_graphs * t.col_groups;
+  t.row_splits = std::max(1, std::min(8, ceil_div(2 * kNumSM, units)));
+  const size_t smem = (size_t)std::max(max_graph_nodes, 1) * 64;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaFuncSetAttribute(w ? k_spmm_tiled<true> : k_spmm_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "spmm tiled: smem opt-in: %s", cudaGetErrorString(e));
+  if (w) k_spmm_tiled<true><<<units * t.row_splits, kTileThreads, smem, st>>>(t);
+  else k_spmm_tiled<false><<<units * t.row_splits, kTileThreads, smem, st>>>(t);
+  return finish_launch("spmm tiled");
 }
 
 int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int32_t width, float* out,

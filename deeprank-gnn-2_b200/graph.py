@@ -46,7 +46,7 @@ class GraphIndex:
     __slots__ = (
         "num_nodes", "num_edges", "num_graphs", "device",
         "rowptr", "colidx", "perm", "colptr", "rowidx", "permT",
-        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree", "_slot_map", "_attr_csr",
+        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree", "_slot_map", "_attr_csr", "max_graph_nodes",
     )
 
     def __init__(self):
@@ -196,6 +196,7 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
         blocks = (node_ptr, edge_ptr, meta["max_graph_nodes"], meta["max_graph_edges"])
     gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc, blocks=blocks)
     gi._key = key
+    gi.max_graph_nodes = meta.get("max_graph_nodes")  # known on the host for collated batches: lets the aggregation pick the tiled kernel
     data.__dict__["_graph_index"] = gi
     return gi
 

@@ -78,8 +78,24 @@ def weight_grad(dy, x, want_bias=False, dw=None, dbias=None, accumulate=False):
     return (dw, dbias) if want_bias else dw
 
 
-def spmm(ptr, idx, src, n_out, w=None, addend=None, mask=None, reduce=REDUCE_SUM, act=ACT_NONE, out=None):
-    """``out[i] = epi(reduce_{s in [ptr[i], ptr[i+1])} w[s] * src[idx[s]])`` -- gather + segmented reduce."""
+# drk_spmm_tiled is OPT-IN (DRK_SPMM_TILED=1): on B200 it measured slower than the L2-gather kernel on the C3 adjacency (59 vs 43 us at
+# width 16, 107 vs 62 us at width 32, profiles/spmm_probe.py) -- one 1024-thread CTA per SM cannot hide the index stream's latency the way
+# 32-64 resident warps of the generic kernel do, and L2 already delivers 5.7 TB/s of gathered rows.  Kept because it is bit-identical
+# and the right shape once the index stream is staged too.
+SPMM_TILED = bool(__import__("os").environ.get("DRK_SPMM_TILED"))
+SPMM_TILE_MIN_NODES = int(__import__("os").environ.get("DRK_SPMM_TILE_MIN_NODES", "1024"))
+
+
+def _tileable(t) -> bool:
+    return t is None or (t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0)
+
+
+def spmm(ptr, idx, src, n_out, w=None, addend=None, mask=None, reduce=REDUCE_SUM, act=ACT_NONE, out=None, graph=None):
+    """``out[i] = epi(reduce_{s in [ptr[i], ptr[i+1])} w[s] * src[idx[s]])`` -- gather + segmented reduce.
+
+    ``graph`` (the :class:`GraphIndex` ``ptr`` / ``idx`` belong to) + ``DRK_SPMM_TILED=1``: for collated batches of LARGE graphs (atom
+    level, >= 1024 nodes, <= 3584) the block-diagonal kernel ``drk_spmm_tiled`` stages every graph's source rows in shared memory
+    instead of gathering through L2; same result bit for bit (opt-in: not faster yet, see above)."""
     lib = _lib.load()
     src = _f32_cuda(src, "src")
     width = src.shape[1]
@@ -89,6 +105,15 @@ def spmm(ptr, idx, src, n_out, w=None, addend=None, mask=None, reduce=REDUCE_SUM
         addend = _f32_cuda(addend, "addend")
     if mask is not None:
         mask = _f32_cuda(mask, "mask")
+    big = getattr(graph, "max_graph_nodes", None) if graph is not None else None
+    if (SPMM_TILED and big is not None and big >= SPMM_TILE_MIN_NODES and idx is not None and graph.graph_ptr is not None and n_out == graph.num_nodes == src.shape[0]
+            and lib.drk_spmm_tiled_supported(int(big), width) and all(_tileable(t) for t in (src, out, addend, mask))):
+        with torch.cuda.device(src.device):
+            rc = lib.drk_spmm_tiled(_p(ptr), _p(idx), _p(w), _p(src), _ld(src), _p(addend), _ld(addend) if addend is not None else 0,
+                                    _p(mask), _ld(mask) if mask is not None else 0, _p(out), _ld(out), _p(graph.graph_ptr), graph.num_graphs, int(big),
+                                    width, reduce, act, stream_ptr())
+        _lib.check(rc, "drk_spmm_tiled")
+        return out
     with torch.cuda.device(src.device):
         rc = lib.drk_spmm(_p(ptr), _p(idx), _p(w), _p(src), _ld(src), _p(addend), _ld(addend) if addend is not None else 0,
                           _p(mask), _ld(mask) if mask is not None else 0, _p(out), _ld(out), n_out, width, reduce, act, stream_ptr())
@@ -170,10 +195,10 @@ class GINetConvFunction(torch.autograd.Function):
         n = x.shape[0]
         if project_first:
             p = node_linear(x, weight, True, bias)
-            z = spmm(graph.rowptr, graph.colidx, p, n, act=act)
+            z = spmm(graph.rowptr, graph.colidx, p, n, act=act, graph=graph)
             saved = x
         else:
-            a = spmm(graph.rowptr, graph.colidx, x, n)
+            a = spmm(graph.rowptr, graph.colidx, x, n, graph=graph)
             z = node_linear(a, weight, True, None, act=act)
             saved = a
         ctx.graph = graph
@@ -197,7 +222,7 @@ class GINetConvFunction(torch.autograd.Function):
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = dw = db = None
         if ctx.project_first:
-            dp = spmm(g.colptr, g.rowidx, dz, n)  # A^T dz
+            dp = spmm(g.colptr, g.rowidx, dz, n, graph=g)  # A^T dz
             if need_w or ctx.has_bias:
                 if ctx.has_bias:
                     dw, db = weight_grad(dp, saved, want_bias=True)
@@ -210,7 +235,7 @@ class GINetConvFunction(torch.autograd.Function):
                 dw = weight_grad(dz, saved)
             if need_x:
                 da = node_linear(dz, weight, False)
-                dx = spmm(g.colptr, g.rowidx, da, n)
+                dx = spmm(g.colptr, g.rowidx, da, n, graph=g)
         dead = [torch.zeros_like(t) if (t is not None and ctx.needs_input_grad[3 + i]) else None for i, t in enumerate(ctx.dead)]
         return dx, dw, db, dead[0], dead[1], None, None
 
@@ -365,8 +390,8 @@ class GINetStackFunction(torch.autograd.Function):
         f2 = w2.shape[0]          # 32
         w1s = torch.cat([w1, w1e], dim=0)
         p = node_linear(x, w1s, True)
-        h1 = spmm(graph.rowptr, graph.colidx, p, n, act=ACT_RELU)
-        a2 = spmm(graph.rowptr, graph.colidx, h1, n)
+        h1 = spmm(graph.rowptr, graph.colidx, p, n, act=ACT_RELU, graph=graph)
+        a2 = spmm(graph.rowptr, graph.colidx, h1, n, graph=graph)
         h2 = torch.empty((n, 2 * f2), dtype=torch.float32, device=x.device)
         node_linear(a2[:, :f1], w2, True, act=ACT_RELU, out=h2[:, :f2])
         node_linear(a2[:, f1:], w2e, True, act=ACT_RELU, out=h2[:, f2:])
@@ -389,8 +414,8 @@ class GINetStackFunction(torch.autograd.Function):
         da2 = torch.empty_like(a2)
         node_linear(dz2[:, :f2], w2, False, out=da2[:, :f1])
         node_linear(dz2[:, f2:], w2e, False, out=da2[:, f1:])
-        dz1 = spmm(g.colptr, g.rowidx, da2, n, mask=h1)
-        q = spmm(g.colptr, g.rowidx, dz1, n)
+        dz1 = spmm(g.colptr, g.rowidx, da2, n, mask=h1, graph=g)
+        q = spmm(g.colptr, g.rowidx, dz1, n, graph=g)
         dw1s = weight_grad(q, x)
         dx = node_linear(q, w1s, False) if ctx.needs_input_grad[0] else None
         dead = tuple(torch.zeros_like(t) if ctx.needs_input_grad[6 + i] else None for i, t in enumerate(ctx.dead))
@@ -549,7 +574,7 @@ class FoutConvFunction(torch.autograd.Function):
         wcat = torch.cat([wc, wn], dim=1)                                    # [Fi, 2Fo]
         bias2 = torch.cat([bias, torch.zeros_like(bias)]) if bias is not None else None
         ab = node_linear(x, wcat, False, bias2)                              # alpha + b | beta
-        out = spmm(graph.rowptr, graph.colidx, ab[:, fo:], n, addend=ab[:, :fo], reduce=REDUCE_MEAN_NAN, act=ACT_RELU if relu else ACT_NONE)
+        out = spmm(graph.rowptr, graph.colidx, ab[:, fo:], n, addend=ab[:, :fo], reduce=REDUCE_MEAN_NAN, act=ACT_RELU if relu else ACT_NONE, graph=graph)
         ctx.graph, ctx.relu, ctx.fo, ctx.has_bias = graph, relu, fo, bias is not None
         ctx.save_for_backward(x, wcat, out if relu else None)
         return out
@@ -566,7 +591,7 @@ class FoutConvFunction(torch.autograd.Function):
         dab[:, :fo].copy_(dout)
         # d beta[j] = sum_{e: col_e = j} dout[row_e] / deg(row_e): scale rows once, then A^T through the CSC half
         scaled = dout / g.degree().unsqueeze(1)
-        spmm(g.colptr, g.rowidx, scaled, n, out=dab[:, fo:])
+        spmm(g.colptr, g.rowidx, scaled, n, out=dab[:, fo:], graph=g)
         dwcat = weight_grad(x, dab)                                          # x^T dab = [Fi, 2Fo]
         db2 = dout.sum(0) if ctx.has_bias else None
         dx = node_linear(dab, wcat, True) if ctx.needs_input_grad[0] else None

@@ -143,6 +143,13 @@ DRK_API int drk_spmm(const int32_t* ptr, const int32_t* idx, const float* w,
 
 /* Per-graph mean readout  g[b,:] = sum_{i in graph b} x[i,:] / max(n_b, 1)   (one CTA per graph)
  * scatter_mean(data.x, data.batch, dim=0): ginet_nocluster.py:103-104, ginet.py:117-118, vanilla_gnn.py:62, foutnet.py:114. */
+/* The same operation for a BLOCK-DIAGONAL adjacency (a collated batch: rows [graph_ptr[g], graph_ptr[g+1]) gather from the same range)
+ * whose graphs have up to 3584 nodes: every 16-column slice of a graph's source rows is staged in shared memory once and gathered from
+ * there (atom-level graphs).  idx is required; width % 16 == 0; operands 16-byte aligned.  Bit-identical to drk_spmm. */
+DRK_API int drk_spmm_tiled_supported(int32_t max_graph_nodes, int32_t width);
+DRK_API int drk_spmm_tiled(const int32_t* ptr, const int32_t* idx, const float* w, const float* src, int64_t ld_src, const float* addend, int64_t ld_addend,
+                   const float* mask, int64_t ld_mask, float* out, int64_t ld_out, const int32_t* graph_ptr, int32_t num_graphs,
+                   int32_t max_graph_nodes, int32_t width, int32_t reduce, int32_t act, void* stream);
 DRK_API int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int32_t width,
                      float* out, int64_t ld_out, void* stream);
 /* its backward: dx[i,:] = dg[batch[i],:] / max(n_b,1), optionally * (mask[i,:] > 0) (the ReLU that fed the readout). */

@@ -302,3 +302,36 @@ def test_cpu_tensors_are_rejected():
     ops = _ops()
     with pytest.raises(RuntimeError):
         ops.node_linear(torch.zeros(2, 2), torch.zeros(2, 2))
+
+
+@pytest.mark.parametrize("width", [16, 32, 64])
+def test_spmm_tiled_is_bitwise_the_generic_kernel(width, monkeypatch):
+    """drk_spmm_tiled (block-diagonal batches of large graphs: the graph's source rows staged in shared memory) against drk_spmm on an
+    atom-level batch: every reduce mode / epilogue / weight combination, forward (CSR) and transposed (CSC) -- bit for bit."""
+    from deeprank2_b200 import _lib, ops
+    from deeprank2_b200.graph import graph_index
+    from deeprank2_b200.synthetic import ATOM, make_batch
+
+    monkeypatch.setattr(ops, "SPMM_TILED", True)  # opt-in kernel (DRK_SPMM_TILED=1)
+    host = make_batch(3, first=70, n_node_features=4, n_edge_features=1, level=dict(ATOM, n_lo=1100, n_hi=1500))
+    b = host.clone().to(DEV)
+    gi = graph_index(b)
+    assert gi.max_graph_nodes is not None and gi.max_graph_nodes >= 1024
+    assert _lib.load().drk_spmm_tiled_supported(gi.max_graph_nodes, width)
+    n, e = b.num_nodes, b.num_edges
+    gen = torch.Generator().manual_seed(width)
+    src = torch.randn(n, 2 * width, generator=gen).to(DEV)[:, width:]  # a column-sliced view: leading dimension != width
+    addend = torch.randn(n, width, generator=gen).to(DEV)
+    mask = torch.randn(n, width, generator=gen).to(DEV)
+    w = torch.rand(e, generator=gen).to(DEV)
+    for ptr, idx in ((gi.rowptr, gi.colidx), (gi.colptr, gi.rowidx)):
+        for kw in (dict(), dict(act=ops.ACT_RELU), dict(reduce=ops.REDUCE_MEAN_NAN, addend=addend, act=ops.ACT_RELU), dict(reduce=ops.REDUCE_MEAN_CLAMP, w=w),
+                   dict(mask=mask)):
+            tiled = ops.spmm(ptr, idx, src, n, graph=gi, **kw)
+            plain = ops.spmm(ptr, idx, src, n, **kw)
+            assert torch.equal(tiled.isnan(), plain.isnan())
+            assert torch.equal(torch.nan_to_num(tiled), torch.nan_to_num(plain)), (width, sorted(kw))
+    # and it is the tiled kernel that ran: its launches are counted under their own name
+    before = _lib.launch_count()
+    ops.spmm(gi.rowptr, gi.colidx, src, n, graph=gi)
+    assert _lib.launch_count() == before + 1

@@ -189,3 +189,57 @@ def test_resident_and_streamed_training_agree(monkeypatch):
         assert isinstance(trainer.train_loader, ResidentBatches if resident else BatchLoader)
         results.append(torch.cat([p.detach().reshape(-1) for p in trainer.model.parameters()]).cpu())
     assert float((results[0] - results[1]).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("net_name", ["ginet_nocluster", "vanilla"])
+def test_pretrained_model_reloads_on_cuda_and_tests(net_name, tmp_path, monkeypatch):
+    """Train on the GPU, save, build a second Trainer from the checkpoint with ``cuda=True`` and run ``test()``: the loader of the
+    pretrained path must not ask the (not yet built) model which step kernels apply, and the reloaded weights must reproduce the
+    first Trainer's test predictions."""
+    import numpy as np
+
+    seeded = np.random.Generator(np.random.PCG64(11))
+    monkeypatch.setattr(np.random, "default_rng", lambda *a, **k: seeded)
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.neuralnets.gnn import ginet_nocluster, vanilla_gnn
+    from deeprank2_b200.trainer import Trainer
+
+    net = {"ginet_nocluster": ginet_nocluster.GINet, "vanilla": vanilla_gnn.VanillaNetwork}[net_name]
+    graphs = _graphs(20)
+    train = InMemoryGraphDataset(graphs[:14])
+    test = InMemoryGraphDataset(graphs[14:], train_source=train)
+    sink = _Collect()
+    torch.manual_seed(0)
+    trainer = Trainer(net, train, dataset_test=test, cuda=True, output_exporters=[sink])
+    path = str(tmp_path / "model.pth.tar")
+    trainer.train(nepoch=2, batch_size=7, validate=False, filename=path)
+    trainer.test(batch_size=3)
+    first = [c for c in sink.calls if c[0] == "testing"][-1]
+
+    sink2 = _Collect()
+    again = Trainer(net, dataset_test=InMemoryGraphDataset(graphs[14:], train_source=train), pretrained_model=path, cuda=True, output_exporters=[sink2])
+    assert next(again.model.parameters()).is_cuda
+    again.test(batch_size=3)
+    second = [c for c in sink2.calls if c[0] == "testing"][-1]
+    assert first[2] == second[2]
+    assert_close(torch.tensor(second[3]), torch.tensor(first[3]), "predictions of the reloaded model")
+    for (k, p), q in zip(trainer.model.state_dict().items(), again.model.state_dict().values()):
+        assert torch.equal(p, q), k
+
+
+def test_classification_target_outside_the_classes_is_reported():
+    """The reference looks every target up in ``classes_to_index`` and raises for an unknown label (trainer.py:812); here the check
+    rides on the pass's single read-back."""
+    from deeprank2_b200.dataset import InMemoryGraphDataset
+    from deeprank2_b200.domain import targetstorage as targets
+    from deeprank2_b200.neuralnets.gnn import ginet_nocluster
+    from deeprank2_b200.trainer import Trainer
+
+    graphs = _graphs(8)
+    for i, g in enumerate(graphs):
+        g.y = torch.tensor([float(i % 2)])
+    graphs[5].y = torch.tensor([7.0])  # not a class
+    ds = InMemoryGraphDataset(graphs, task=targets.CLASSIF, classes=[0, 1])
+    trainer = Trainer(ginet_nocluster.GINet, ds, cuda=True, output_exporters=[_Collect()])
+    with pytest.raises(ValueError, match="not one of the dataset's classes"):
+        trainer.train(nepoch=1, batch_size=4, validate=False, filename=None)
