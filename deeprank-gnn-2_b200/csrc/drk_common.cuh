@@ -134,11 +134,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
 // TF32 product (2^-11) would not be.
 // Fragment layout (PTX ISA, g = lane >> 2, t = lane & 3):  A 16x8 row-major: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
 // B 8x8: b0 (k = t, n = g) b1 (k = t+4, n = g);  C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
+// fp32 -> tf32 (10-bit mantissa), round to nearest with ties away from zero: exactly what `cvt.rna.tf32.f32` computes for finite values,
+// done with one integer add and one mask.  The conversion instruction runs on the XU pipe (16 lanes/clk/SM); the 3xTF32 split needs
+// two conversions per operand element and was what bounded every tensor-core phase of the step kernel (ncu: math-pipe throttle on the
+// cvt lines; ~7 k of the 12 k cycles of the dW1 phase), while IADD / LOP3 issue at the full rate.
+__device__ __forceinline__ uint32_t to_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(v);
   lo = to_tf32(v - __uint_as_float(hi));

@@ -74,13 +74,13 @@ __host__ __device__ inline Layout make_layout(int fi, int rows_cap, int ent_cap,
   L.hmask = o; o += align16(rows_cap * 4);  // sign of H1, one 32-bit word per row (what the backward pass needs of H1)
   L.maskz = o; o += align16(rows_cap * 8);
   L.red = o; o += (kNW / 2) * kS2 * 4;
-  L.head = o; o += 848 * 4;
+  L.head = o; o += (848 + kHid) * 4;
   L.extra = o; o += align16(extra_bytes);  // index-build scratch that found no idle region
   L.total = o;
   return L;
 }
 // head scratch (floats): G[64] dG[64] H[128] HM[128] DH[128] pred[8] dpred[8] scan[40] degree bins / cursors [256] y[8] class[1]
-constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528, kHY = 824, kHCls = 832;  // scan 40 + 256 words; y[8]; class index
+constexpr int kHG = 0, kHDG = 64, kHH = 128, kHHM = 256, kHDH = 384, kHPred = 512, kHDPred = 520, kHScan = 528, kHY = 824, kHCls = 832, kHDrop = 848;  // scan 40 + 256 words; y[8]; class index; dropout scale [128]
 
 struct StepArgs {
   const float* x; int64_t ldx; int32_t fi;
@@ -688,23 +688,25 @@ __device__ __noinline__ void aggregate(int src_off, int dst_off, int info_off, i
 // (Reading the A fragments straight from global/L2 so that the x tile could stream in under the forward pass was measured
 // 3 us per step SLOWER than staging x first: 28 dependent-latency loads per lane with 16 warps per SM are not hidden.)
 // sW holds the B fragments of W1s^T pre-split once per CTA: [k-step][column tile][lane] x (hi.b0, hi.b1, lo.b0, lo.b1).
-__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int fi, int ksteps) {
-  const float* sX = sm<float>(x_off);
-  const uint4* sW = sm<uint4>(w1_off);
-  float* sP = sm<float>(p_off);
+// A work unit is (16-row tile, pair of 8-column tiles): twice as many units as row tiles, so 19 row tiles spread over 16 warps in
+// 2.4 half-size rounds instead of 2 full ones.  The three MMAs of a compensated product are issued column tile by column tile
+// (lo*hi for both, hi*lo for both, hi*hi for both): dependent MMAs are never back to back.
+template <int KSTEPS>
+__device__ __forceinline__ void project_x_impl(const float* sX, const uint4* sW, float* sP, int n, int fi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int n_tiles = (n + 15) / 16;
-  for (int tl = warp; tl < n_tiles; tl += kNW) {
-    const int r0 = tl * 16;
+  const int n_units = 2 * ((n + 15) / 16);
+  for (int u = warp; u < n_units; u += kNW) {
+    const int r0 = (u >> 1) * 16, nt0 = (u & 1) * 2;
     const float* xa = sX + min(r0 + g, n - 1) * fi + t;      // rows beyond n: results are not stored
     const float* xb = sX + min(r0 + g + 8, n - 1) * fi + t;
-    float acc[4][4];
+    float acc[2][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-    for (int ks = 0; ks < ksteps; ++ks) {
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
       const int k0 = ks * 8;
       const bool in1 = k0 + t < fi, in2 = k0 + t + 4 < fi;  // the last k-step reaches past the (unpadded) row: those operands are zero
       uint32_t ahi[4], alo[4];
@@ -712,17 +714,35 @@ __device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, 
       split_tf32(in1 ? xb[k0] : 0.f, ahi[1], alo[1]);
       split_tf32(in2 ? xa[k0 + 4] : 0.f, ahi[2], alo[2]);
       split_tf32(in2 ? xb[k0 + 4] : 0.f, ahi[3], alo[3]);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const uint4 w = sW[(ks * 4 + nt) * 32 + lane];
-        mma_3xtf32(acc[nt], ahi, alo, make_uint2(w.x, w.y), make_uint2(w.z, w.w));
-      }
+      const uint4 w0 = sW[(ks * 4 + nt0) * 32 + lane], w1 = sW[(ks * 4 + nt0 + 1) * 32 + lane];
+      mma_tf32(acc[0], alo, w0.x, w0.y);
+      mma_tf32(acc[1], alo, w1.x, w1.y);
+      mma_tf32(acc[0], ahi, w0.z, w0.w);
+      mma_tf32(acc[1], ahi, w1.z, w1.w);
+      mma_tf32(acc[0], ahi, w0.x, w0.y);
+      mma_tf32(acc[1], ahi, w1.x, w1.y);
     }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      if (r0 + g < n) *reinterpret_cast<float2*>(sP + (r0 + g) * kS1 + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
-      if (r0 + g + 8 < n) *reinterpret_cast<float2*>(sP + (r0 + g + 8) * kS1 + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    for (int j = 0; j < 2; ++j) {
+      if (r0 + g < n) *reinterpret_cast<float2*>(sP + (r0 + g) * kS1 + (nt0 + j) * 8 + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+      if (r0 + g + 8 < n) *reinterpret_cast<float2*>(sP + (r0 + g + 8) * kS1 + (nt0 + j) * 8 + 2 * t) = make_float2(acc[j][2], acc[j][3]);
     }
+  }
+}
+
+__device__ __noinline__ void project_x(int x_off, int w1_off, int p_off, int n, int fi, int ksteps) {
+  const float* sX = sm<float>(x_off);
+  const uint4* sW = sm<uint4>(w1_off);
+  float* sP = sm<float>(p_off);
+  switch (ksteps) {  // the k loop fully unrolled (F <= 64): loads and splits of the next k-step are scheduled under this one's MMAs
+    case 1: project_x_impl<1>(sX, sW, sP, n, fi); break;
+    case 2: project_x_impl<2>(sX, sW, sP, n, fi); break;
+    case 3: project_x_impl<3>(sX, sW, sP, n, fi); break;
+    case 4: project_x_impl<4>(sX, sW, sP, n, fi); break;
+    case 5: project_x_impl<5>(sX, sW, sP, n, fi); break;
+    case 6: project_x_impl<6>(sX, sW, sP, n, fi); break;
+    case 7: project_x_impl<7>(sX, sW, sP, n, fi); break;
+    default: project_x_impl<8>(sX, sW, sP, n, fi); break;
   }
 }
 
@@ -908,48 +928,72 @@ __device__ __noinline__ void conv2_backward_input(int w2_off, int dg_off, int ma
   }
 }
 
-// dW1s[m, k] = sum_r Q[r, m] x[r, k]: lane -> (mg: 4 outputs m, kgl: 4 features k), warp -> (k block of 16, row split wn);
-// the four row-split partials go to sScr[wn][m][kp]
+// dW1s[m, k] = sum_r Q[r, m] x[r, k] on the tensor cores (3xTF32, fp32 accumulate): an [32 x n] x [n x F] product with the rows as the
+// contraction.  Warp -> (16 outputs m: mt, half of the feature tiles: ng, row split rs); A = Q^T fragments (a0 = Q[r0+t][m0+g], ...: four
+// rows of the tile share a bank, a 4-way conflict on ~5 k wavefronts per graph -- irrelevant next to the 7 k of the SIMT version), B = x
+// fragments from the unpadded rows (stride fi).  Rows >= n and features >= fi enter as exact zeros.  The row-split partials go to
+// sScr[rs & 3][m][kp] (32 warps: splits 4..7 are added on top in a second pass) and are summed by the caller.
 __device__ __noinline__ void conv1_weight_grad(int q_off, int x_off, int scr_off, int n, int kp, int fi) {
   const float* sQ = sm<float>(q_off);
-  const float* sX = sm<float>(x_off);  // unpadded rows (stride fi), 4-byte aligned: features k0..k0+3 beyond fi read the next row (never stored)
+  const float* sX = sm<float>(x_off);
   float* sScr = sm<float>(scr_off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wk = warp & 3, wn = warp >> 2;
-  const int mg = lane & 7, kgl = lane >> 3;
-  const int k0 = wk * 16 + kgl * 4;
-  const bool active = k0 < kp;  // kp is a multiple of 4: a float4 of features is all-in or all-out
-  float2 dw[4][2];  // [m][k pair]
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = warp & 1, ng = (warp >> 1) & 1, rs = warp >> 2;
+  constexpr int kSplits = kNW / 4;
+  const int n_tiles = (fi + 7) / 8;
+  const int nt0 = ng * 4, nt_cnt = max(0, min(4, n_tiles - nt0));
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dw[i][0] = dw[i][1] = make_float2(0.f, 0.f);
-  const float* qp = sQ + mg * 4;
-  const float* xp = sX + k0;
-  const bool in0 = k0 < fi, in1 = k0 + 1 < fi, in2 = k0 + 2 < fi, in3 = k0 + 3 < fi;
-  for (int r = wn; active && r < n; r += kNW / 4) {
-    const float4 qa = *reinterpret_cast<const float4*>(qp + r * kS1);
-    const float* xr = xp + r * fi;
-    const float4 xb = make_float4(in0 ? xr[0] : 0.f, in1 ? xr[1] : 0.f, in2 ? xr[2] : 0.f, in3 ? xr[3] : 0.f);
-    const float qv[4] = {qa.x, qa.y, qa.z, qa.w};
-    const float2 x01 = make_float2(xb.x, xb.y), x23 = make_float2(xb.z, xb.w);
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 qq = make_float2(qv[i], qv[i]);
-      dw[i][0] = __ffma2_rn(qq, x01, dw[i][0]);
-      dw[i][1] = __ffma2_rn(qq, x23, dw[i][1]);
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  const float* qa = sQ + mt * 16 + g;
+  const int n_ks = (n + 7) / 8;
+  for (int ks = rs; ks < n_ks; ks += kSplits) {
+    const int r0 = ks * 8 + t, r1 = r0 + 4;
+    const bool v0 = r0 < n, v1 = r1 < n;
+    uint32_t ahi[4], alo[4];
+    split_tf32(v0 ? qa[r0 * kS1] : 0.f, ahi[0], alo[0]);
+    split_tf32(v0 ? qa[r0 * kS1 + 8] : 0.f, ahi[1], alo[1]);
+    split_tf32(v1 ? qa[r1 * kS1] : 0.f, ahi[2], alo[2]);
+    split_tf32(v1 ? qa[r1 * kS1 + 8] : 0.f, ahi[3], alo[3]);
+    uint2 bh[4], bl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = (nt0 + j) * 8 + g;
+      const bool kin = j < nt_cnt && k < fi;
+      split_tf32((v0 && kin) ? sX[r0 * fi + k] : 0.f, bh[j].x, bl[j].x);
+      split_tf32((v1 && kin) ? sX[r1 * fi + k] : 0.f, bh[j].y, bl[j].y);
     }
+    // the three MMAs of a compensated product, feature tile by feature tile: dependent MMAs are never back to back
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nt_cnt) mma_tf32(acc[j], alo, bh[j].x, bh[j].y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nt_cnt) mma_tf32(acc[j], ahi, bl[j].x, bl[j].y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nt_cnt) mma_tf32(acc[j], ahi, bh[j].x, bh[j].y);
   }
   // row splits 0..3 store their partials; with 32 warps splits 4..7 then add theirs on top (fixed order: deterministic)
   for (int pass = 0; pass < kNW / 16; ++pass) {
-    if (active && (wn >> 2) == pass) {
+    if ((rs >> 2) == pass) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4* d = reinterpret_cast<float4*>(sScr + ((wn & 3) * kS1 + mg * 4 + i) * kp + k0);
-        float4 v = make_float4(dw[i][0].x, dw[i][0].y, dw[i][1].x, dw[i][1].y);
-        if (pass > 0) {
-          const float4 p = *d;
-          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      for (int j = 0; j < 4; ++j) {
+        const int k = (nt0 + j) * 8 + 2 * t;
+        if (j < nt_cnt && k < kp) {  // kp is even: the pair (k, k+1) is all-in or all-out; columns fi..kp-1 hold exact zeros
+          float2* d0 = reinterpret_cast<float2*>(sScr + ((rs & 3) * kS1 + mt * 16 + g) * kp + k);
+          float2* d1 = reinterpret_cast<float2*>(sScr + ((rs & 3) * kS1 + mt * 16 + g + 8) * kp + k);
+          float2 lo = make_float2(acc[j][0], acc[j][1]), hi = make_float2(acc[j][2], acc[j][3]);
+          if (pass > 0) {
+            const float2 plo = *d0, phi = *d1;
+            lo.x += plo.x; lo.y += plo.y; hi.x += phi.x; hi.y += phi.y;
+          }
+          *d0 = lo;
+          *d1 = hi;
         }
-        *d = v;
       }
     }
     if (pass + 1 < kNW / 16) __syncthreads();
@@ -1130,6 +1174,18 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       nx[2] = __ldg(a.edge_ptr + gn);
       nx[3] = __ldg(a.edge_ptr + gn + 1);
     }
+    if (TRAIN && a.drop_p > 0.f && tid >= kT - 32) {
+      // the graph's dropout scales (Philox4x32-10, four units per call), by the last warp while the others already wait for x: its
+      // late start into the projection is covered by the warps that take a second row tile there
+      const int q = tid - (kT - 32);
+      const uint4 rnd = philox4x32(make_uint4((unsigned)g, (unsigned)q, (unsigned)rng_step, (unsigned)(rng_step >> 32)), make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+      const unsigned bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float u = (float)(bits[i] >> 8) * (1.f / 16777216.f);  // uniform [0, 1)
+        sHead[kHDrop + 4 * q + i] = u < a.drop_p ? 0.f : 1.f / (1.f - a.drop_p);
+      }
+    }
     if (tid >= 64 && tid < 64 + a.out_dim && TRAIN) {  // this graph's targets, long before the loss needs them
       if (a.loss_kind == DRK_LOSS_MSE) sHead[kHY + tid - 64] = __ldg(a.y + (size_t)g * a.out_dim + (tid - 64));
       else if (tid == 64) reinterpret_cast<int*>(sHead)[kHCls] = (int)max(-1ll, min((long long)__ldg(a.y_cls + g), (long long)kMaxOut));
@@ -1139,6 +1195,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     DRK_MARK(2);
 
     project_x(x_off, L.w1, L.t0, n, a.fi, (a.fi + 7) / 8);
+    DRK_MARK(13);
     if (tid == 32 && have_next) {
       s_meta[buf ^ 1][0] = gn;
       s_meta[buf ^ 1][1] = nx[0];
@@ -1147,6 +1204,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       s_meta[buf ^ 1][4] = nx[3] - nx[2];
     }
     __syncthreads();
+    DRK_MARK(14);
     if (have_next) {  // warm L2 with the next graph's edge slice and node rows while this one is being processed
       const int node0n = s_meta[buf ^ 1][1], e0n = s_meta[buf ^ 1][3];
       const long long nn = s_meta[buf ^ 1][2], nen = s_meta[buf ^ 1][4];
@@ -1207,7 +1265,6 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       }
     }
     __syncthreads();
-    DRK_MARK(13);
     // ---- head: h = dropout(relu(fc1 G + b1)); pred = fc2 h + b2.  fc1's weight is in tile 1 by now (bulk copy issued after A2),
     // every other operand has been in shared memory since the CTA started: no global load on this chain.
     mbar_wait(&s_bar[1], w_phase);
@@ -1228,14 +1285,7 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
         s += __shfl_xor_sync(kFull, s, 1);
         if (l16 == 0) {
           const float pre = s + sHW[kHW1B + j];
-          float scale = 1.f;
-          if (TRAIN && a.drop_p > 0.f) {
-            const uint4 rnd = philox4x32(make_uint4((unsigned)g, (unsigned)(j >> 2), (unsigned)rng_step, (unsigned)(rng_step >> 32)),
-                                         make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
-            const unsigned bits = (j & 3) == 0 ? rnd.x : (j & 3) == 1 ? rnd.y : (j & 3) == 2 ? rnd.z : rnd.w;
-            const float u = (float)(bits >> 8) * (1.f / 16777216.f);  // uniform [0, 1)
-            scale = u < a.drop_p ? 0.f : 1.f / (1.f - a.drop_p);
-          }
+          const float scale = (TRAIN && a.drop_p > 0.f) ? sHead[kHDrop + j] : 1.f;
           const float hv = pre > 0.f ? pre * scale : 0.f;
           hH[j] = hv;
           hHM[j] = pre > 0.f ? scale : 0.f;  // d h / d pre
@@ -1258,7 +1308,6 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
     }
     if (!TRAIN) continue;
     __syncthreads();
-    DRK_MARK(14);
     // ---- loss term and d loss / d pred (thread 0: out_dim <= 8 values; the targets were fetched at the start of the graph)
     if (tid == 0) {
       float term = 0.f;
@@ -1284,7 +1333,6 @@ __global__ void __launch_bounds__(kT, 1) k_ginet_step(const StepArgs a) {
       for (int o = 0; o < a.out_dim; ++o) a.dpvec[(size_t)og * a.out_dim + o] = hDPred[o];
     }
     __syncthreads();
-    DRK_MARK(15);
     // ---- d pre-activation of fc1
     if (tid < kHid) {
       float s = 0.f;
