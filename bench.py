@@ -823,13 +823,18 @@ def _finish(distributed):
     os._exit(0)
 
 
-def _ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_ginet_step launch on the C2 batch, from the committed ncu capture
-    (profiles/step_traffic.json; the input is deterministic, so the figure is a property of the build, not of the run)."""
+def _ncu_capture():
+    """Counters of one k_ginet_step launch on the C2 batch from the committed ncu capture (profiles/step_traffic.json; the input is
+    deterministic, so they are properties of the build, not of the run): dram__bytes_read.sum + dram__bytes_write.sum and
+    l1tex__data_pipe_lsu_wavefronts_mem_shared.sum."""
     path = os.path.join(ROOT, "profiles", "step_traffic.json")
     if not os.path.exists(path):
-        return None
-    return json.load(open(path)).get("dram_bytes_per_launch")
+        return {}
+    return json.load(open(path))
+
+
+def _ncu_traffic():
+    return _ncu_capture().get("dram_bytes_per_launch")
 
 
 def _peak():
@@ -866,8 +871,25 @@ def step_roofline(args, dev, dev_batches, model, loss_fn):
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     achieved = total_bytes / (ms * 1e-3) / 1e9
+    # second roofline: what actually bounds the fused kernel.  Everything between the two inputs and the per-graph results lives in
+    # shared memory, so the floor is the shared-memory pipe: one 128-byte wavefront per clock per SM.
+    smem = None
+    wavefronts = _ncu_capture().get("smem_wavefronts_per_launch")
+    if wavefronts:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            sm_mhz = pynvml.nvmlDeviceGetMaxClockInfo(pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0), pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            sm_mhz = 1965
+        floor_us = wavefronts / (148 * sm_mhz)  # wavefronts / (SMs x clocks per microsecond)
+        smem = {"wavefronts_per_launch": wavefronts, "peak_wavefronts_per_us": 148 * sm_mhz, "floor_us": floor_us, "frac": floor_us / (1e3 * ms / reps),
+                "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of profiles/r02_step_v13_raw.txt; peak = 148 SMs x 1 wavefront per clock at the max SM clock"}
     return {
         "bound": "hbm",
+        "limited_by": "shared-memory bandwidth and issue latency, not HBM: the fused kernel moves 0.08x the algorithmic bytes through DRAM (see `traffic`); `smem` is the roofline of the pipe that does bound it",
+        "smem": smem,
         "kernel": "drk_ginet_step (k_ginet_step<train> + k_step_finalize): index build + forward + loss + backward of one 256-graph batch, L2 flushed before every launch",
         "achieved": achieved,
         "peak": peak,
