@@ -50,6 +50,7 @@ SIGNATURES = {
     "drk_spmm_tiled_supported": (c_int32, [_I32, _I32]),
     "drk_spmm_tiled": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "drk_segment_mean": (c_int32, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
+    "drk_segment_mean_rows": (c_int32, [_P, _I64, _P, _I32, _I64, _I32, _P, _I64, _P]),
     "drk_segment_mean_bwd": (c_int32, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
     "drk_ginet_fused_max_nodes": (c_int32, [_I32]),
     "drk_ginet_fused_fwd": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),

@@ -56,26 +56,57 @@ struct LinearArgs {
   int32_t a2_vec;
 };
 
-// ---------------------------------------------------------------- tensor-core variant for wide outputs (M > 32)
+// ---------------------------------------------------------------- tensor-core variant (row-contiguous operands)
 // Same contract as k_node_linear, products on mma.sync m16n8k8 TF32 with error compensation (3xTF32, drk_common.cuh: fp32-level
-// accuracy, profiles/tf32_emulation.py).  OPT-IN (DRK_LINEAR_TC=1), see the dispatcher.  A CTA owns a 64-column slab of the output: the weights of that slab are split into
-// hi/lo B fragments ONCE per CTA (shared memory, [k-step][column tile][lane]), then the CTA walks 64-row tiles of A (4 warps x 16
-// rows): rows staged in shared memory with a stride = 4 (mod 8) floats (conflict-free fragment loads), 8 accumulator tiles per
-// warp.  The SIMT kernel spends 2.5 instructions per FFMA on these shapes (~10 % of the fp32 peak); here the inner loop is
-// 3 MMAs per 1024 products.
+// accuracy, profiles/tf32_emulation.py).  A CTA owns a 64-column slab of the output: the weights of that slab are split into hi/lo
+// B fragments ONCE per CTA (shared memory, [k-step][column tile][lane]); the CTA then walks 64-row tiles of A (4 warps x 16 rows).
+// The rows of A must be contiguous in global memory (lda == k): a 64-row tile is then ONE bulk copy (cp.async.bulk, the copy engine)
+// into a double-buffered stage, so the next tile streams in while this one is multiplied -- thread-issued cp.async was measured at
+// ~10 B/clk/SM on B200, the bulk copy at ~50.  The tile is used in place (row stride k floats, no padding).
 constexpr int kTcThreads = 128;
 constexpr int kTcRows = 64;
 constexpr int kTcCols = 64;
 
 __global__ void __launch_bounds__(kTcThreads) k_node_linear_tc(const LinearArgs p, int num_tiles) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
+  __shared__ __align__(8) unsigned long long tc_bar[2];
   const int ks1 = (p.k + 7) / 8, ks2 = (p.k2 + 7) / 8, ks = ks1 + ks2;
-  const int kpad = (ks1 > ks2 ? ks1 : ks2) * 8 + 4;
-  uint4* sW = reinterpret_cast<uint4*>(tc_smem);            // [ks][8][32]: (hi.b0, hi.b1, lo.b0, lo.b1)
-  float* sA = reinterpret_cast<float*>(sW + ks * 8 * 32);   // [kTcRows][kpad]
+  const int a1_floats = kTcRows * p.k, a2_floats = kTcRows * p.k2;
+  const int stage_floats = (a1_floats + a2_floats + 3) & ~3;
+  uint4* sW = reinterpret_cast<uint4*>(tc_smem);                 // [ks][8][32]: (hi.b0, hi.b1, lo.b0, lo.b1)
+  float* sStage = reinterpret_cast<float*>(sW + ks * 8 * 32);    // 2 x [A tile | A2 tile], 4 spare floats behind the last one
   const int lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * kTcCols;
   const int nt_count = min(8, (p.m - m0 + 7) / 8);
+  if (threadIdx.x == 0) {
+    mbar_init(&tc_bar[0], 1);
+    mbar_init(&tc_bar[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  // one thread hands a tile's rows to the copy engine; the last 0..12 bytes of a ragged last tile travel through ordinary loads
+  auto issue = [&](int tile, int stage) {
+    const int64_t row0 = (int64_t)tile * kTcRows;
+    const int rows = (int)min((int64_t)kTcRows, p.n - row0);
+    float* dst = sStage + stage * stage_floats;
+    const uint32_t bytes1 = (uint32_t)rows * p.k * 4u, bytes2 = (uint32_t)rows * p.k2 * 4u;
+    const uint32_t bulk1 = bytes1 & ~15u, bulk2 = bytes2 & ~15u;
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&tc_bar[stage], bulk1 + bulk2);
+      if (bulk1) bulk_copy_g2s(dst, p.a + row0 * p.k, bulk1, &tc_bar[stage]);
+      if (bulk2) bulk_copy_g2s(dst + a1_floats, p.a2 + row0 * p.k2, bulk2, &tc_bar[stage]);
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + (int)((bytes1 - bulk1) >> 2)) {
+      const int w = (int)(bulk1 >> 2) + (threadIdx.x - 32);
+      dst[w] = __ldg(p.a + row0 * p.k + w);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + (int)((bytes2 - bulk2) >> 2)) {
+      const int w = (int)(bulk2 >> 2) + (threadIdx.x - 64);
+      dst[a1_floats + w] = __ldg(p.a2 + row0 * p.k2 + w);
+    }
+  };
+  if ((int)blockIdx.x < num_tiles) issue(blockIdx.x, 0);
   // B fragments: b0 = W[m0 + 8 nt + g][8 s + t], b1 = W[m0 + 8 nt + g][8 s + t + 4]  (W = op(B) as [M, K]; zero beyond M / K)
   for (int e = threadIdx.x; e < ks * 8 * 32; e += kTcThreads) {
     const int ln = e & 31, nt = (e >> 5) & 7, step = e >> 8;
@@ -95,41 +126,46 @@ __global__ void __launch_bounds__(kTcThreads) k_node_linear_tc(const LinearArgs 
     split_tf32(w1, q.y, q.w);
     sW[e] = q;
   }
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  __syncthreads();
+  uint32_t phase[2] = {0u, 0u};
+  int stage = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, stage ^= 1) {
     const int64_t row0 = (int64_t)tile * kTcRows;
+    if (tile + (int)gridDim.x < num_tiles) issue(tile + gridDim.x, stage ^ 1);  // that stage was released by the barrier ending the previous trip
+    mbar_wait(&tc_bar[stage], phase[stage]);
+    phase[stage] ^= 1u;
+    __syncthreads();  // the ragged-tail floats written by ordinary stores are visible too
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     for (int op = 0; op < (p.k2 > 0 ? 2 : 1); ++op) {
-      const float* __restrict__ pa = op ? p.a2 : p.a;
-      const int64_t lda = op ? p.lda2 : p.lda;
       const int ktot = op ? p.k2 : p.k;
       const int steps = op ? ks2 : ks1, step0 = op ? ks1 : 0;
-      __syncthreads();  // the previous tile / operand is done with sA (first trip: the B fragments are complete)
-      for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
-        const int64_t gr = row0 + r;
-        const float* src = pa + (gr < p.n ? gr : 0) * lda;
-        for (int kk = lane; kk < steps * 8; kk += 32) sA[r * kpad + kk] = (gr < p.n && kk < ktot) ? __ldg(src + kk) : 0.f;
-      }
-      __syncthreads();
-      const float* xa = sA + (warp * 16 + g) * kpad + t;
-      const float* xb = xa + 8 * kpad;
+      const float* xa = sStage + stage * stage_floats + (op ? a1_floats : 0) + (warp * 16 + g) * ktot + t;
+      const float* xb = xa + 8 * ktot;
       for (int s = 0; s < steps; ++s) {
+        const bool in1 = s * 8 + t < ktot, in2 = s * 8 + t + 4 < ktot;  // the last k-step reaches past the (unpadded) row: those operands are zero
         uint32_t ahi[4], alo[4];
-        split_tf32(xa[s * 8], ahi[0], alo[0]);
-        split_tf32(xb[s * 8], ahi[1], alo[1]);
-        split_tf32(xa[s * 8 + 4], ahi[2], alo[2]);
-        split_tf32(xb[s * 8 + 4], ahi[3], alo[3]);
+        split_tf32(in1 ? xa[s * 8] : 0.f, ahi[0], alo[0]);
+        split_tf32(in1 ? xb[s * 8] : 0.f, ahi[1], alo[1]);
+        split_tf32(in2 ? xa[s * 8 + 4] : 0.f, ahi[2], alo[2]);
+        split_tf32(in2 ? xb[s * 8 + 4] : 0.f, ahi[3], alo[3]);
         const uint4* wrow = sW + (size_t)(step0 + s) * 8 * 32 + lane;
+        uint4 w[8];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          if (nt < nt_count) {  // warp-uniform
-            const uint4 w = wrow[nt * 32];
-            mma_3xtf32(acc[nt], ahi, alo, make_uint2(w.x, w.y), make_uint2(w.z, w.w));
-          }
-        }
+        for (int nt = 0; nt < 8; ++nt) w[nt] = nt < nt_count ? wrow[nt * 32] : make_uint4(0u, 0u, 0u, 0u);
+        // the three MMAs of a compensated product column tile by column tile: dependent MMAs are never back to back
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          if (nt < nt_count) mma_tf32(acc[nt], alo, w[nt].x, w[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          if (nt < nt_count) mma_tf32(acc[nt], ahi, w[nt].z, w[nt].w);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          if (nt < nt_count) mma_tf32(acc[nt], ahi, w[nt].x, w[nt].y);
       }
     }
     // epilogue: bias, activation, relu-mask, store.  c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
@@ -141,17 +177,30 @@ __global__ void __launch_bounds__(kTcThreads) k_node_linear_tc(const LinearArgs 
       for (int h = 0; h < 2; ++h) {
         const int64_t gr = row0 + warp * 16 + g + 8 * h;
         if (gr >= p.n) continue;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (col + j >= p.m) continue;
-          float v = acc[nt][2 * h + j];
-          if (p.bias != nullptr) v += __ldg(p.bias + col + j);
-          if (p.act == DRK_ACT_RELU) v = v < 0.f ? 0.f : v;
-          if (p.mask != nullptr) v = p.mask[gr * p.ld_mask + col + j] <= 0.f ? 0.f : v;
-          p.c[gr * p.ldc + col + j] = v;
+        float v0 = acc[nt][2 * h], v1 = acc[nt][2 * h + 1];
+        if (p.bias != nullptr) {
+          if (col < p.m) v0 += __ldg(p.bias + col);
+          if (col + 1 < p.m) v1 += __ldg(p.bias + col + 1);
+        }
+        if (p.act == DRK_ACT_RELU) {
+          v0 = v0 < 0.f ? 0.f : v0;
+          v1 = v1 < 0.f ? 0.f : v1;
+        }
+        if (p.mask != nullptr) {
+          if (col < p.m) v0 = p.mask[gr * p.ld_mask + col] <= 0.f ? 0.f : v0;
+          if (col + 1 < p.m) v1 = p.mask[gr * p.ld_mask + col + 1] <= 0.f ? 0.f : v1;
+        }
+        float* dst = p.c + gr * p.ldc + col;
+        if (col + 1 < p.m && (p.ldc & 1) == 0 && p.c_vec >= 2) {
+          *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+        } else {
+          if (col < p.m) dst[0] = v0;
+          if (col + 1 < p.m) dst[1] = v1;
         }
       }
     }
+    fence_proxy_async();
+    __syncthreads();  // every warp is done with this stage: the next trip may hand it to the copy engine
   }
 }
 
@@ -536,20 +585,21 @@ int drk_node_linear2(const float* a, int64_t lda, const float* b, int64_t ldb, i
     kernel<<<grid, kLinThreads, smem, st>>>(p);
     return DRK_OK;
   };
-  // Opt-in (DRK_LINEAR_TC=1): wide outputs of large row counts on the tensor cores (3xTF32).  Parity-green
-  // (tests/test_gpu_kernels.py), but this single-buffered version is 7 % SLOWER than the SIMT kernel on the VanillaNetwork step
-  // (1.48 vs 1.38 ms): the A tiles need cp.async double buffering before it can become the default.
+  // Row-contiguous operands of large row counts: tensor cores (3xTF32) fed by bulk copies, see k_node_linear_tc.  DRK_LINEAR_TC=0
+  // forces the SIMT kernel (also used for column-sliced views, whose rows are not contiguous).
   const char* tc_env = std::getenv("DRK_LINEAR_TC");
-  const bool tc_on = tc_env != nullptr && tc_env[0] == '1';
-  if (tc_on && m > 32 && n >= 2048 && k <= 128 && k2 <= 128) {
+  const bool tc_off = tc_env != nullptr && tc_env[0] == '0';
+  const bool contiguous = lda == k && aligned16(a) && (k2 == 0 || (lda2 == k2 && aligned16(a2)));
+  if (!tc_off && contiguous && m >= 8 && n >= 2048 && k <= 128 && k2 <= 128 && (int64_t)n * std::max(k, k2) < ((int64_t)1 << 31)) {
     const int ks = (k + 7) / 8 + (k2 + 7) / 8;
-    const int kpad = std::max((k + 7) / 8, (k2 + 7) / 8) * 8 + 4;
-    const size_t smem = (size_t)ks * 8 * 32 * sizeof(uint4) + (size_t)kTcRows * kpad * sizeof(float);
+    const size_t stage = (size_t)((kTcRows * k + kTcRows * k2 + 3) & ~3) * sizeof(float);
+    const size_t smem = (size_t)ks * 8 * 32 * sizeof(uint4) + 2 * stage + 16;
     cudaError_t e = cudaFuncSetAttribute(k_node_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "node linear: smem opt-in: %s", cudaGetErrorString(e));
     const int num_tiles = (int)ceil_div<int64_t>(n, kTcRows);
-    const int per_sm = std::max(1, std::min(3, (int)((220 * 1024) / (smem + 1024))));
+    const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
     dim3 grid((unsigned)std::min(num_tiles, kNumSM * per_sm), (unsigned)ceil_div(m, kTcCols));
+    if (ldc % 2 == 0 && aligned8(c)) p.c_vec = std::max(p.c_vec, 2);
     k_node_linear_tc<<<grid, kTcThreads, smem, st>>>(p, num_tiles);
     return finish_launch("node linear (tensor cores)");
   }

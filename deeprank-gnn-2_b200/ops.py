@@ -126,8 +126,9 @@ def segment_mean(x, graph_ptr, num_graphs):
     x = _f32_cuda(x, "x")
     out = torch.empty((num_graphs, x.shape[1]), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        rc = lib.drk_segment_mean(_p(x), _ld(x), _p(graph_ptr), num_graphs, x.shape[1], _p(out), _ld(out), stream_ptr())
-    _lib.check(rc, "drk_segment_mean")
+        # the row count (known on the host) lets the library give big graphs a cluster of CTAs each
+        rc = lib.drk_segment_mean_rows(_p(x), _ld(x), _p(graph_ptr), num_graphs, int(x.shape[0]), x.shape[1], _p(out), _ld(out), stream_ptr())
+    _lib.check(rc, "drk_segment_mean_rows")
     return out
 
 

@@ -152,6 +152,10 @@ DRK_API int drk_spmm_tiled(const int32_t* ptr, const int32_t* idx, const float* 
                    int32_t max_graph_nodes, int32_t width, int32_t reduce, int32_t act, void* stream);
 DRK_API int drk_segment_mean(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int32_t width,
                      float* out, int64_t ld_out, void* stream);
+/* The same with the total number of rows (graph_ptr[num_graphs], known to the caller on the host) as a hint: graphs of >= 512 rows on
+ * average are summed by a thread-block cluster of 2 / 4 / 8 CTAs each (partial sums meet through distributed shared memory, rank order). */
+DRK_API int drk_segment_mean_rows(const float* x, int64_t ldx, const int32_t* graph_ptr, int32_t num_graphs, int64_t num_rows_hint, int32_t width,
+                          float* out, int64_t ld_out, void* stream);
 /* its backward: dx[i,:] = dg[batch[i],:] / max(n_b,1), optionally * (mask[i,:] > 0) (the ReLU that fed the readout). */
 DRK_API int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* graph_ptr, const int32_t* batch32,
                          const float* mask, int64_t ld_mask, int32_t num_nodes, int32_t width,
