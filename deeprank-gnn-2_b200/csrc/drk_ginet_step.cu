@@ -1715,6 +1715,135 @@ __global__ void __launch_bounds__(kTI, 2) k_index_blocked(const BlockedIndexArgs
   }
 }
 
+// The same index for graphs whose edge slice does not fit shared memory (atom-level graphs: ~3 k nodes, ~60 k directed edges): no
+// stash of the edges -- both sweeps read them from global memory (the second one out of L2) -- and one key at a time (destination for
+// the CSR, then source for the CSC) through the SAME per-warp histograms.  A graph is shared by `splits` CTAs: each owns a contiguous
+// range of key values (nodes), streams ALL the graph's edges but ranks only those whose key falls in its range; the number of valid
+// edges with a smaller key (counted on the fly) is the range's first output position.  Same stable placement (chunk offset + MATCH
+// rank): bit-identical to the global counting sort, which took 158 us on the C3 batch for ~25 k cycles of MATCH work per graph.
+__global__ void __launch_bounds__(kTI, 1) k_index_blocked_large(const BlockedIndexArgs a, int splits, int range_cap) {
+  unsigned char* smem = g_smem;
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(smem);                         // [kNWI][range_cap]
+  uint32_t* start = reinterpret_cast<uint32_t*>(cnt + kNWI * range_cap);     // [range_cap]
+  uint32_t* scan = start + range_cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = lanemask_lt();
+  const int n_keys = a.colptr != nullptr ? 2 : 1;
+  for (int unit = blockIdx.x; unit < a.num_graphs * splits; unit += gridDim.x) {
+    const int g = unit / splits, h = unit - g * splits;
+    const int node0 = __ldg(a.graph_ptr + g);
+    const int n = __ldg(a.graph_ptr + g + 1) - node0;
+    const int e0 = __ldg(a.edge_ptr + g);
+    const int ne = __ldg(a.edge_ptr + g + 1) - e0;
+    const int chunk = ((ne + kNWI - 1) / kNWI + 31) & ~31;
+    if (n > a.rows_cap || n < 0 || ne < 0 || chunk > 65535) {  // (a warp chunk's counters are 16 bit)
+      if (tid == 0) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+      continue;
+    }
+    const int per = ((n + splits - 1) / splits + 7) & ~7;
+    const int lo = min(n, h * per), hi = min(n, lo + per);  // this CTA's key range [lo, hi); per <= range_cap
+    const bool last = h == splits - 1;
+    const int wb = min(ne, warp * chunk), we = min(ne, wb + chunk);
+    for (int key = 0; key < n_keys; ++key) {
+      const int64_t* kptr = key == 0 ? a.erow : a.ecol;  // the key this round groups by
+      const int64_t* optr = key == 0 ? a.ecol : a.erow;  // the other endpoint, stored as the index entry
+      int32_t* out_ptr = key == 0 ? a.rowptr : a.colptr;
+      int32_t* out_idx = key == 0 ? a.colidx : a.rowidx;
+      int32_t* out_perm = key == 0 ? a.perm : a.permT;
+      __syncthreads();
+      {
+        uint32_t* z = reinterpret_cast<uint32_t*>(cnt);
+        for (int i = tid; i < kNWI * range_cap / 2; i += kTI) z[i] = 0u;
+      }
+      __syncthreads();
+      uint16_t* mine = cnt + warp * range_cap;
+      bool bad = false;
+      uint32_t below = 0;  // valid edges of this thread whose key lies below the range
+      // sweep 1: per-warp-chunk histograms of the key (edges with an endpoint outside the graph are dropped from both orders)
+      for (int i0 = wb; i0 < we; i0 += 256) {
+        long long kk[8], oo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          kk[u] = i < we ? ld_stream_i64(kptr + e0 + i) : 0;
+          oo[u] = i < we ? ld_stream_i64(optr + e0 + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i0 + u * 32 >= we) break;  // warp-uniform
+          const unsigned long long k = (unsigned long long)(kk[u] - node0), o = (unsigned long long)(oo[u] - node0);
+          const bool ok = i < we && k < (unsigned long long)n && o < (unsigned long long)n;
+          bad |= i < we && !ok;
+          below += (ok && (int)k < lo) ? 1u : 0u;
+          const bool in = ok && (int)k >= lo && (int)k < hi;
+          const unsigned m = __match_any_sync(kFull, in ? (unsigned)k : 0x10000u + lane);
+          if (in && (m & lt) == 0u) mine[k - lo] = (uint16_t)(mine[k - lo] + __popc(m));
+          __syncwarp();
+        }
+      }
+      if (bad && key == 0 && h == 0) atomicOr(a.status, DRK_STATUS_CROSS_GRAPH);
+      __syncthreads();
+      uint32_t carry;
+      block_excl_scan<kNWI>(below, scan, carry);  // carry = valid edges with a key below this range = the range's first position
+      for (int vb = lo; vb < hi; vb += kTI) {
+        const int v = vb + tid;
+        uint32_t d = 0;
+        if (v < hi) {
+          for (int w = 0; w < kNWI; ++w) {
+            const uint32_t t = cnt[w * range_cap + (v - lo)];
+            cnt[w * range_cap + (v - lo)] = (uint16_t)d;
+            d += t;
+          }
+        }
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan<kNWI>(d, scan, tot) + carry;
+        if (v < hi) {
+          start[v - lo] = ex;
+          out_ptr[node0 + v] = e0 + (int)ex;
+        }
+        carry += tot;
+      }
+      if (last) {
+        for (int i = (int)carry + tid; i < ne; i += kTI) {  // dropped edges leave a gap at the end of the slice: keep the arrays well defined
+          out_idx[e0 + i] = node0;
+          out_perm[e0 + i] = e0 + i;
+        }
+        if (g == a.num_graphs - 1 && tid == 0) out_ptr[a.num_nodes] = (int)a.num_edges;
+      }
+      __syncthreads();
+      // sweep 2: placement = segment start + offset of the warp chunk + rank inside the chunk
+      for (int i0 = wb; i0 < we; i0 += 256) {
+        long long kk[8], oo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          kk[u] = i < we ? ld_stream_i64(kptr + e0 + i) : 0;
+          oo[u] = i < we ? ld_stream_i64(optr + e0 + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i0 + u * 32 >= we) break;  // warp-uniform
+          const unsigned long long k = (unsigned long long)(kk[u] - node0), o = (unsigned long long)(oo[u] - node0);
+          const bool in = i < we && k < (unsigned long long)n && o < (unsigned long long)n && (int)k >= lo && (int)k < hi;
+          const unsigned m = __match_any_sync(kFull, in ? (unsigned)k : 0x10000u + lane);
+          int base = 0;
+          if (in) {
+            base = mine[k - lo];
+            const int pos = e0 + (int)start[k - lo] + base + __popc(m & lt);
+            out_idx[pos] = node0 + (int)o;
+            out_perm[pos] = e0 + i;
+          }
+          __syncwarp();
+          if (in && (m & lt) == 0u) mine[k - lo] = (uint16_t)(base + __popc(m));
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
+
 // edge_ptr[g] = first edge whose destination is >= graph_ptr[g] (binary search; valid when the edges of a collated batch are
 // grouped by graph, which the per-graph kernels verify edge by edge)
 __global__ void k_edge_ptr(const int64_t* __restrict__ erow, int64_t num_edges, const int32_t* __restrict__ graph_ptr, int num_graphs,
@@ -1945,11 +2074,20 @@ int drk_edge_ptr(const int64_t* edge_index, int64_t num_edges, const int32_t* gr
   return finish_launch("edge ptr");
 }
 
-int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges) {
-  if (max_graph_nodes < 0 || max_graph_edges < 0 || max_graph_nodes > 65535 || max_graph_edges > 65535) return 0;
+static size_t blocked_small_smem(int32_t max_graph_nodes, int32_t max_graph_edges) {
   const size_t rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8), e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
-  const size_t smem = e_cap * 4 + 2 * drk::gs::kNWI * rows_cap * 2 + 2 * rows_cap * 4 + 128;
-  return smem <= drk::gs::kSmemBudget ? 1 : 0;
+  return e_cap * 4 + 2 * drk::gs::kNWI * rows_cap * 2 + 2 * rows_cap * 4 + 128;
+}
+static size_t blocked_large_smem(int32_t max_graph_nodes) {
+  const size_t rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8);
+  return drk::gs::kNWI * rows_cap * 2 + rows_cap * 4 + 512;
+}
+
+int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges) {
+  if (max_graph_nodes < 0 || max_graph_edges < 0 || max_graph_nodes > 65535) return 0;
+  if (max_graph_edges <= 65535 && blocked_small_smem(max_graph_nodes, max_graph_edges) <= drk::gs::kSmemBudget) return 1;
+  // large graphs: no edge stash, one key at a time (k_index_blocked_large); a warp chunk (edges / 16) must fit a 16-bit counter
+  return (blocked_large_smem(max_graph_nodes) <= drk::gs::kSmemBudget && max_graph_edges / drk::gs::kNWI + 32 <= 65535) ? 1 : 0;
 }
 
 int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes, const int32_t* graph_ptr, const int32_t* edge_ptr,
@@ -1974,6 +2112,20 @@ int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, 
   a.rows_cap = std::max(32, (max_graph_nodes + 7) / 8 * 8);
   a.e_cap = std::max(32, (max_graph_edges + 31) / 32 * 32);
   a.num_nodes = num_nodes; a.num_edges = num_edges;
+  if (!(max_graph_edges <= 65535 && blocked_small_smem(max_graph_nodes, max_graph_edges) <= kSmemBudget)) {
+    // every graph over `splits` CTAs (key ranges): ~2 CTAs per SM's worth of units
+    // One CTA per graph.  (Key-range splitting over several CTAs is implemented -- `splits` -- but every CTA still has to MATCH all the
+    // edges: measured 0.58 vs 0.31 ms for the C3 inference pass.  What bounds the kernel is the scattered 4-byte stores of the placement
+    // sweep, ~1 sector per clock per SM: 119 us for 64 graphs of 60 k edges.)
+    const int splits = 1;
+    const int range_cap = (ceil_div(a.rows_cap, splits) + 7) / 8 * 8;
+    const size_t smem_large = (size_t)kNWI * range_cap * 2 + (size_t)range_cap * 4 + 512;
+    cudaError_t el = cudaFuncSetAttribute(k_index_blocked_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_large);
+    DRK_REQUIRE(el == cudaSuccess, DRK_ECUDA, "blocked index: smem opt-in: %s", cudaGetErrorString(el));
+    const int per_sm = std::max<int>(1, std::min<int>(2, (int)(kSmemBudget / (smem_large + 1024))));
+    k_index_blocked_large<<<std::min(num_graphs * splits, kNumSM * per_sm), kTI, smem_large, as_stream(stream)>>>(a, splits, range_cap);
+    return finish_launch("blocked index (large graphs)");
+  }
   const size_t smem = (size_t)a.e_cap * 4 + (size_t)2 * kNWI * a.rows_cap * 2 + (size_t)2 * a.rows_cap * 4 + 128;
   cudaError_t e = cudaFuncSetAttribute(k_index_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "blocked index: smem opt-in: %s", cudaGetErrorString(e));

@@ -92,6 +92,33 @@ def test_blocked_index_full_c2_batch_matches_global_build():
     assert_equal_int(info.node_ptr, ref.graph_ptr, "node offsets")
 
 
+@pytest.mark.parametrize("with_csc", [False, True])
+def test_blocked_index_of_atom_level_graphs_matches_global_build(with_csc):
+    """Graphs of ~3 k nodes / ~60 k directed edges: the edge slice does not fit shared memory, so the per-graph builder streams the
+    edges twice and handles one key at a time (k_index_blocked_large) -- bit for bit the global counting sort, with a malformed edge
+    dropped from both orders and flagged."""
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.graph import GraphIndex, graph_index
+    from deeprank2_b200.synthetic import ATOM, make_batch
+
+    host = make_batch(5, first=90, n_node_features=4, n_edge_features=1, level=ATOM)
+    assert host.meta("max_graph_edges") > 65535 // 2 and _lib.load().drk_graph_index_blocked_supported(host.meta("max_graph_nodes"), host.meta("max_graph_edges"))
+    batch = host.clone().to(DEV)
+    before = _lib.launch_count()
+    gi = graph_index(batch, with_csc=with_csc)  # collated batch: the blocked builder
+    assert _lib.launch_count() - before <= 2, "one per-graph kernel (+ batch offsets), not the five-kernel global sort"
+    assert int(gi.status.item()) == 0
+    ref = GraphIndex.build(batch.edge_index, batch.num_nodes, batch=batch.batch, num_graphs=5, with_csc=with_csc)
+    keys = ("rowptr", "colidx", "perm") + (("colptr", "rowidx", "permT") if with_csc else ())
+    for k in keys:
+        assert_equal_int(getattr(gi, k), getattr(ref, k), f"blocked (large) vs global {k}")
+    # an edge that leaves its graph is dropped and flagged
+    bad = host.clone().to(DEV)
+    bad.edge_index[1, 7] = bad.num_nodes - 1
+    gi_bad = graph_index(bad, with_csc=with_csc)
+    assert int(gi_bad.status.item()) & _lib.STATUS_CROSS_GRAPH
+
+
 def test_blocked_index_edge_cases():
     """isolated nodes, duplicate edges, self loops, a single-node graph, a graph without edges, non-symmetric edges, and
     32 copies of the same edge in one warp batch (ranks inside a match group)."""
