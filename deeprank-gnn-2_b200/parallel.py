@@ -1,11 +1,13 @@
-"""Data parallelism over graph mini-batches: one process per GPU, NCCL gradient all-reduce.
+"""Data parallelism over graph mini-batches, one process per GPU: the NCCL gradient all-reduce of the AUTOGRAD path (every network
+but the benchmark model, and the fallback of the fused step).  The benchmark model's step does not come through here: its gradient
+exchange is fused into the finalize kernel over NVLink peer memory (``fused.GINetFusedStep._peer_exchange``, ``k_step_finalize``).
 
 The reference's only multi-GPU mechanism is ``nn.DataParallel`` (``deeprank2/trainer.py:387-389``), a
 single-process replicate/scatter/gather that cannot split a PyG ``Batch``.  Graphs are independent (a
 batch is a block-diagonal union), so the path shards by graph: every rank builds its own batches and
 graph index, weights are replicated, and the only exchange is ONE all-reduce of the flat fp32
 gradient (11 273 parameters = 45 KB for GINet at F_in = 50) per step over NVLink/NVSwitch.  The
-message is latency bound, so everything is packed into a single NCCL call.
+message is latency bound, so on this path everything is packed into a single NCCL call.
 """
 from __future__ import annotations
 

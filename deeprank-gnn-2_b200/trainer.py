@@ -10,8 +10,11 @@ of ``_save_model`` (``:926-956``) and the exporter hook.  What changes is how a 
   pass (the reference synchronises three times per step, ``trainer.py:694-703``); the exporters receive exactly the
   same lists;
 * evaluation runs under ``torch.no_grad()`` (the reference builds and drops autograd graphs in ``_eval``);
-* under ``torchrun`` (``torch.distributed`` initialised) every rank trains on its shard of each mini-batch and the
-  gradients are averaged with one NCCL all-reduce per step -- this replaces ``nn.DataParallel`` (``:387-389``).
+* under ``torchrun`` (``torch.distributed`` initialised) every rank trains on its shard of each mini-batch; for the benchmark
+  model the gradient exchange happens inside the step's finalize kernel over NVLink peer memory (``fused.GINetFusedStep``), every
+  other network sums its gradients with one NCCL all-reduce per step (``parallel.GradAllReduce``) -- this replaces
+  ``nn.DataParallel`` (``:387-389``).  The epoch loss, the train / validation split and the per-batch choice between the two paths
+  are made identical on all ranks; the exporters receive the whole pass on rank 0.
 """
 from __future__ import annotations
 
