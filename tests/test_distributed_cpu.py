@@ -88,3 +88,78 @@ def test_shard_indices_cover_everything_once():
             assert seen == list(range(n))
             sizes = [len(shard_indices(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _TinyNet(nn.Module):
+    """A CPU network with the constructor the Trainer calls (`Net(input_shape, output_shape, input_shape_edge)`)."""
+
+    def __init__(self, input_shape, output_shape, input_shape_edge):  # noqa: ARG002
+        super().__init__()
+        self.a = nn.Linear(input_shape, 8)
+        self.b = nn.Linear(8, output_shape)
+
+    def forward(self, batch):
+        nb = int(batch.ptr.numel()) - 1
+        pooled = torch.zeros(nb, batch.x.shape[1]).index_add_(0, batch.batch, batch.x) / torch.bincount(batch.batch, minlength=nb).unsqueeze(1)
+        return self.b(torch.relu(self.a(pooled)))
+
+
+class _Sink:
+    def __init__(self):
+        self.calls = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return None
+
+    def process(self, pass_name, epoch, names, outputs, targets_, loss):
+        self.calls.append((pass_name, epoch, list(names), loss))
+
+    def is_compatible_with(self, *a):
+        return True
+
+
+def _trainer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deeprank2_b200.dataset import InMemoryGraphDataset
+        from deeprank2_b200.trainer import Trainer
+
+        torch.manual_seed(7 + rank)  # ranks start from different RNG states: the split and the weights must still agree
+        ds = InMemoryGraphDataset(_graphs(15))
+        sink = _Sink()
+        trainer = Trainer(_TinyNet, ds, val_size=4, cuda=False, output_exporters=[sink])
+        trainer.train(nepoch=3, batch_size=4, validate=True, filename=None, num_workers=0)
+        torch.save({
+            "val_entries": [str(e) for e in trainer.dataset_val.index_entries],
+            "train_entries": [str(e) for e in trainer.dataset_train.index_entries],
+            "weights": [p.detach().clone() for p in trainer.model.parameters()],
+            "saved_epoch": trainer.epoch_saved_model,
+            "calls": sink.calls,
+        }, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_ranks_stay_consistent(tmp_path):
+    """Two ranks (gloo): the train / validation split is the same on both, the epoch losses that drive best-model selection are the
+    GLOBAL ones (identical on both ranks), the weights end bit-identical, and only rank 0 feeds the exporters -- with every graph of
+    the pass, not just its own slices."""
+    mp.spawn(_trainer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(str(tmp_path / "rank0.pt"), weights_only=False)
+    r1 = torch.load(str(tmp_path / "rank1.pt"), weights_only=False)
+    assert r0["val_entries"] == r1["val_entries"] and r0["train_entries"] == r1["train_entries"]
+    assert len(r0["val_entries"]) == 4 and len(r0["train_entries"]) == 11
+    assert r0["saved_epoch"] == r1["saved_epoch"]
+    for a, b in zip(r0["weights"], r1["weights"]):
+        assert torch.equal(a, b)
+    assert r1["calls"] == [], "only rank 0 exports"
+    by_pass = {}
+    for pass_name, epoch, names, loss in r0["calls"]:
+        by_pass.setdefault(pass_name, []).append((epoch, names, loss))
+    assert all(len(names) == 11 for _, names, _ in by_pass["training"]), "the whole pass reaches rank 0's exporter"
+    assert all(len(names) == 4 for _, names, _ in by_pass["validation"])
+    assert all(loss is not None and loss == loss for _, _, loss in by_pass["training"])
