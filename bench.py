@@ -540,8 +540,10 @@ def run_ours(args):
     _lib.load()
 
     # ---- data: every rank owns its own graphs (weak scaling), generated on the host, resident in HBM
+    # the tensors the step reads are page-locked as ONE slab per batch (Data.pin_memory): a step's input travels in a single copy
+    pin_only = GINetFusedStep.FIELDS if args.path == "fused" else None
     host_batches = [
-        make_batch(GRAPHS_PER_BATCH, first=(rank * args.batches + b) * GRAPHS_PER_BATCH, n_node_features=F_NODE, n_edge_features=F_EDGE).pin_memory()
+        make_batch(GRAPHS_PER_BATCH, first=(rank * args.batches + b) * GRAPHS_PER_BATCH, n_node_features=F_NODE, n_edge_features=F_EDGE).pin_memory(only=pin_only)
         for b in range(args.batches)
     ]
     dev_batches = [hb.clone().to(dev) for hb in host_batches]
@@ -779,7 +781,7 @@ def run_ours(args):
             "edges_per_s": float(et.item()) / (ms * 1e-3),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps, "passes": e2e_passes,
-                    "mode": "median of three timed passes; eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as one packed word of graph-local ids, 4 bytes -- the kernel rebuilds the reference's doubled int64 edge list --, targets, offsets) -> device on a copy stream two batches ahead; loss.item() every step"},
+                    "mode": "median of three timed passes; eager launches; pinned host batch (the tensors the step reads: x fp32, every contact once as one packed word of graph-local ids, 4 bytes -- the kernel rebuilds the reference's doubled int64 edge list --, targets, offsets; packed in one pinned slab = one copy per step) -> device on a copy stream two batches ahead; loss.item() every step"},
             "e2e_resident": e2e_resident,
             "e2e_trainer": e2e_trainer,
             "gpu_launches": int(launches_per_step * args.steps),

@@ -152,11 +152,12 @@ class Data:
     # host-side facts about the batch that survive clone()/to(): {"num_graphs", "max_graph_nodes"}
     _META_KEY = "_meta"
     _DEVICE_CACHES = ("_graph_index", "_block_info")
+    _HOST_CACHES = ("_slab",)  # the pinned slab of pin_memory(): meaningless for copies whose tensors are no longer its views
 
     def clone(self):
         new = type(self).__new__(type(self))
         for k, v in self.__dict__.items():
-            if k in self._DEVICE_CACHES:
+            if k in self._DEVICE_CACHES or k in self._HOST_CACHES:
                 continue
             if k == "_pending":
                 new.__dict__[k] = (v[0], dict(v[1]))
@@ -172,7 +173,10 @@ class Data:
         stale = self.__dict__.pop("_pending", None)
         pending = dict(stale[1]) if stale is not None else {}
         lazy = only is not None and dev.type == "cuda"
+        moved = self._slab_to(dev, non_blocking, only)
         for k, v in list(self.__dict__.items()):
+            if k in moved or k in self._HOST_CACHES:
+                continue
             if isinstance(v, torch.Tensor):
                 if lazy and k not in only and not v.is_cuda:
                     pending[k] = self.__dict__.pop(k)
@@ -204,11 +208,45 @@ class Data:
         return self.to("cpu")
 
     def pin_memory(self, only=None):
-        """Page-lock the host tensors (all of them, or the names in ``only``: the ones an input pipeline copies ahead)."""
-        for k, v in list(self.__dict__.items()):
-            if isinstance(v, torch.Tensor) and not v.is_cuda and (only is None or k in only):
-                self.__dict__[k] = v.pin_memory()
+        """Page-lock the host tensors (all of them, or the names in ``only``: the ones an input pipeline copies ahead).
+
+        The selected tensors are packed into ONE pinned slab (256-byte aligned slices) and become views of it: ``to(device)`` then moves
+        them with a single copy instead of one DMA per tensor -- a C2 step reads seven tensors, five of them ~1 KB, and every extra
+        ``cudaMemcpyAsync`` costs microseconds of a ~0.4 ms step that runs at the PCIe rate."""
+        picked = [(k, v) for k, v in self.__dict__.items() if isinstance(v, torch.Tensor) and not v.is_cuda and (only is None or k in only)]
+        if not picked:
+            return self
+        layout, total = [], 0
+        for k, v in picked:
+            nbytes = v.numel() * v.element_size()
+            layout.append((k, total, nbytes, v.dtype, tuple(v.shape)))
+            total += (nbytes + 255) // 256 * 256
+        slab = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        for (k, off, nbytes, dtype, shape), (_, v) in zip(layout, picked):
+            view = slab[off : off + nbytes].view(dtype).view(shape)
+            view.copy_(v)
+            self.__dict__[k] = view
+        self.__dict__["_slab"] = (slab, layout)
         return self
+
+    def _slab_to(self, dev, non_blocking: bool, wanted) -> set:
+        """Move the pinned slab with one copy and re-create the views on the device; returns the names it covered."""
+        packed = self.__dict__.get("_slab")
+        if packed is None or dev.type != "cuda":
+            return set()
+        slab, layout = packed
+        names = [k for k, off, nbytes, dtype, shape in layout]
+        if any(wanted is not None and k not in wanted for k in names):
+            return set()  # the slab holds tensors that are to stay on the host: fall back to per-tensor copies
+        for k, off, nbytes, dtype, shape in layout:  # still the views made by pin_memory?
+            v = self.__dict__.get(k)
+            if not isinstance(v, torch.Tensor) or v.is_cuda or v.data_ptr() != slab.data_ptr() + off or v.dtype != dtype or tuple(v.shape) != shape:
+                return set()
+        dslab = slab.to(dev, non_blocking=non_blocking)
+        for k, off, nbytes, dtype, shape in layout:
+            self.__dict__[k] = dslab[off : off + nbytes].view(dtype).view(shape)
+        self.__dict__.pop("_slab", None)
+        return set(names)
 
 
 class Batch(Data):

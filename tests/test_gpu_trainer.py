@@ -243,3 +243,26 @@ def test_classification_target_outside_the_classes_is_reported():
     trainer = Trainer(ginet_nocluster.GINet, ds, cuda=True, output_exporters=[_Collect()])
     with pytest.raises(ValueError, match="not one of the dataset's classes"):
         trainer.train(nepoch=1, batch_size=4, validate=False, filename=None)
+
+
+def test_pinned_slab_travels_in_one_copy_and_matches_per_tensor_copies():
+    """`Batch.pin_memory(only=...)` packs the tensors a step reads into one page-locked slab; `to(device, only=...)` moves the slab with a
+    single copy and re-creates the views.  Same tensors, bit for bit, as the per-tensor route; the host batch stays usable."""
+    from deeprank2_b200.data import Batch
+    from deeprank2_b200.fused import GINetFusedStep
+    from deeprank2_b200.pipeline import shallow_host_view
+
+    plain = Batch.from_data_list(_graphs(9))
+    packed = plain.clone().pin_memory(only=GINetFusedStep.FIELDS)
+    slab, layout = packed.__dict__["_slab"]
+    assert slab.is_pinned() and {k for k, *_ in layout} == {k for k in GINetFusedStep.FIELDS if isinstance(plain.__dict__.get(k), torch.Tensor)}
+    for _ in range(2):  # the host batch can be sent again and again
+        dev = shallow_host_view(packed).to("cuda", non_blocking=True, only=GINetFusedStep.FIELDS)
+        torch.cuda.synchronize()
+        for k in GINetFusedStep.FIELDS:
+            v = plain.__dict__.get(k)
+            if isinstance(v, torch.Tensor):
+                got = dev.__dict__[k]
+                assert got.is_cuda and got.dtype == v.dtype and tuple(got.shape) == tuple(v.shape) and torch.equal(got.cpu(), v), k
+        assert torch.equal(dev.edge_attr.cpu(), plain.edge_attr), "tensors outside the slab still travel on first access"
+    assert "_slab" in packed.__dict__ and not packed.x.is_cuda
