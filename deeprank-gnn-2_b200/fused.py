@@ -95,14 +95,30 @@ def block_info(data) -> BlockInfo:
         info.order = None
         sizes = torch.stack([(info.node_ptr[1:] - info.node_ptr[:-1]).max(), (info.edge_ptr[1:] - info.edge_ptr[:-1]).max()]) if info.num_graphs else torch.zeros(2)
         info.max_nodes, info.max_edges = (int(v) for v in sizes.tolist())  # one host sync, remembered on the batch
-    info.status = torch.zeros(1, dtype=torch.int32, device=dev)
+    info.status = _status_word(dev)
     d["_block_info"] = (key, info)
     return info
+
+
+_STATUS_WORDS: dict = {}
+
+
+def _status_word(dev) -> torch.Tensor:
+    """ONE status word per device, shared by every batch descriptor (the kernels OR their data-dependent faults into it): a fresh
+    batch costs no fill launch; ``check_status`` reads it and clears it."""
+    dev = torch.device(dev)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    word = _STATUS_WORDS.get(key)
+    if word is None:
+        word = _STATUS_WORDS[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return word
 
 
 def check_status(info: BlockInfo) -> None:
     """Host sync: raise if a per-graph kernel flagged the batch (call off the hot path, e.g. at the end of a pass)."""
     flags = int(info.status.item())
+    if flags:
+        info.status.zero_()  # the word is shared by all batches of the device: report once
     if flags & _lib.STATUS_CROSS_GRAPH:
         raise ValueError("edge_index is not grouped by graph (an edge joins two graphs of the batch): not a collated batch")
     if flags & _lib.STATUS_INDEX_RANGE:

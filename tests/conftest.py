@@ -108,3 +108,23 @@ def assert_adam_close(actual: torch.Tensor, expected: torch.Tensor, what: str = 
         slack = torch.full_like(err, 0.05 * ADAM_LR)
     bad = err > (slack + RTOL * expected.abs() + 1e-9)
     assert not bool(bad.any()), f"{what}: {int(bad.sum())}/{err.numel()} weights outside the propagated gradient tolerance; max|d|={float(err.max()):.3e}"
+
+
+@pytest.fixture(autouse=True)
+def _fresh_status_words():
+    """The per-device status word of the per-graph kernels is shared by all batches (fused._status_word): a test that provokes a flag
+    and reads the word directly must not leak it into the next test."""
+    yield
+    try:
+        import sys
+
+        fused = sys.modules.get("deeprank2_b200.fused")
+        if fused is not None:
+            for word in fused._STATUS_WORDS.values():
+                word.zero_()
+        cp = sys.modules.get("deeprank2_b200.utils.community_pooling")
+        if cp is not None:
+            for word in cp._STATUS.values():
+                word.zero_()
+    except Exception:  # noqa: BLE001 - never let the cleanup fail a test
+        pass
