@@ -645,7 +645,11 @@ struct EdgeMsgArgs {
   int32_t n, fe, rows_per_block;
 };
 
-// 8 lanes per destination row (4 columns each), 4 rows per warp -- same walk as k_spmm<8,4>.
+// 8 lanes per destination row (4 columns each), 4 rows per warp -- same walk as k_spmm<8,4>.  FE = number of edge features as a
+// compile-time constant (1..8; 0 = none): the kernel is INSTRUCTION bound (ncu: 60 M warp instructions for 1.57 M edges with the
+// generic 8-feature loops, 124 registers -> 2 CTAs per SM), so the per-edge feature loops and the weight registers must not exist
+// for features the model does not have.
+template <int FE>
 __global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = lane_id();
@@ -655,11 +659,12 @@ __global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
   const int row0 = blockIdx.x * a.rows_per_block;
   const int row_end = min(row0 + a.rows_per_block, a.n);
   const int c = sl * 4;
-  float cw[4][kMaxEdgeFeat];  // this lane's 4 rows of C
+  constexpr int kF = FE > 0 ? FE : 1;
+  float cw[4][kF];  // this lane's 4 rows of C
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int k = 0; k < kMaxEdgeFeat; ++k) cw[q][k] = k < a.fe ? __ldg(a.cmat + (size_t)(c + q) * a.ldc + k) : 0.f;
+    for (int k = 0; k < kF; ++k) cw[q][k] = k < FE ? __ldg(a.cmat + (size_t)(c + q) * a.ldc + k) : 0.f;
 
   for (int rw = row0 + warp * 4; rw < row_end; rw += 32) {
     const int r = rw + sub;
@@ -680,15 +685,14 @@ __global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
       // lane sl of the group fetches source, edge id and attributes of the chunk's sl-th edge: 8 edges in flight per group, the
       // dependent loads (edge id -> attributes) happen once per chunk instead of once per edge
       int my_src = -1, my_eid = 0;
-      float my_attr[kMaxEdgeFeat];
+      float my_attr[kF];
 #pragma unroll
-      for (int k = 0; k < kMaxEdgeFeat; ++k) my_attr[k] = 0.f;
+      for (int k = 0; k < kF; ++k) my_attr[k] = 0.f;
       if (off + sl < len) {
         my_src = ld_stream_i32(a.idx + beg + off + sl);
-        my_eid = ld_stream_i32(a.perm + beg + off + sl);
+        my_eid = a.perm != nullptr ? ld_stream_i32(a.perm + beg + off + sl) : beg + off + sl;  // perm == NULL: attributes and masks live in slot order
 #pragma unroll
-        for (int k = 0; k < kMaxEdgeFeat; ++k)
-          if (k < a.fe) my_attr[k] = __ldg(a.attr + (size_t)my_eid * a.ld_attr + k);
+        for (int k = 0; k < FE; ++k) my_attr[k] = __ldg(a.attr + (size_t)my_eid * a.ld_attr + k);
       }
       float4 vv[8];
 #pragma unroll
@@ -705,12 +709,10 @@ __global__ void __launch_bounds__(256) k_edge_msg_fwd(const EdgeMsgArgs a) {
         const float4 v = vv[j];
         float m[4] = {u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w};
 #pragma unroll
-        for (int k = 0; k < kMaxEdgeFeat; ++k) {
-          if (k < a.fe) {  // warp-uniform
-            const float av = __shfl_sync(kFull, my_attr[k], group_base + j);
+        for (int k = 0; k < FE; ++k) {
+          const float av = __shfl_sync(kFull, my_attr[k], group_base + j);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) m[q] = fmaf(cw[q][k], av, m[q]);
-          }
+          for (int q = 0; q < 4; ++q) m[q] = fmaf(cw[q][k], av, m[q]);
         }
         unsigned bits = 0;
 #pragma unroll
@@ -807,6 +809,7 @@ struct EdgeMsgBwdCArgs {
 };
 
 constexpr int kBwdCWarps = 32;  // 1024 threads: the kernel is a chain of dependent global loads per row, it needs warps, not registers
+template <int FE>
 __global__ void __launch_bounds__(kBwdCWarps * 32) k_edge_msg_bwd_c(const EdgeMsgBwdCArgs a) {
   // One warp per destination row, lane = channel c for the accumulation.  The row's edges are fetched LANE-PARALLEL (edge id, ReLU mask
   // word and attributes of up to 32 edges in flight at once: three dependent global loads per 32 edges instead of per edge) and then
@@ -814,43 +817,41 @@ __global__ void __launch_bounds__(kBwdCWarps * 32) k_edge_msg_bwd_c(const EdgeMs
   __shared__ float red[kBwdCWarps][kMsg][kMaxEdgeFeat];
   const int c = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float acc[kMaxEdgeFeat];
+  float acc[FE];
 #pragma unroll
-  for (int k = 0; k < kMaxEdgeFeat; ++k) acc[k] = 0.f;
+  for (int k = 0; k < FE; ++k) acc[k] = 0.f;
   const int rows_per_block = (a.n + gridDim.x - 1) / gridDim.x;
   const int row0 = blockIdx.x * rows_per_block;
   const int row_end = min(row0 + rows_per_block, a.n);
   for (int r = row0 + warp; r < row_end; r += kBwdCWarps) {
     const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
     const float g = __ldg(a.ds + (size_t)r * a.ld_ds + c);
-    float t[kMaxEdgeFeat];
+    float t[FE];
 #pragma unroll
-    for (int k = 0; k < kMaxEdgeFeat; ++k) t[k] = 0.f;
+    for (int k = 0; k < FE; ++k) t[k] = 0.f;
     for (int s0 = beg; s0 < end; s0 += 32) {
       const int s = s0 + c;
       const bool valid = s < end;
-      const int eid = valid ? __ldg(a.perm + s) : 0;
+      const int eid = valid ? (a.perm != nullptr ? __ldg(a.perm + s) : s) : 0;
       const uint32_t m = valid ? __ldg(a.mask + eid) : 0u;
-      float av[kMaxEdgeFeat];
+      float av[FE];
 #pragma unroll
-      for (int k = 0; k < kMaxEdgeFeat; ++k) av[k] = (valid && k < a.fe) ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
+      for (int k = 0; k < FE; ++k) av[k] = valid ? __ldg(a.attr + (size_t)eid * a.ld_attr + k) : 0.f;
       const int cnt = min(32, end - s0);
       for (int j = 0; j < cnt; ++j) {
         const bool on = (__shfl_sync(0xffffffffu, m, j) >> c) & 1u;
 #pragma unroll
-        for (int k = 0; k < kMaxEdgeFeat; ++k) {
-          if (k < a.fe) {
-            const float v = __shfl_sync(0xffffffffu, av[k], j);
-            t[k] += on ? v : 0.f;
-          }
+        for (int k = 0; k < FE; ++k) {
+          const float v = __shfl_sync(0xffffffffu, av[k], j);
+          t[k] += on ? v : 0.f;
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxEdgeFeat; ++k) acc[k] = fmaf(g, t[k], acc[k]);
+    for (int k = 0; k < FE; ++k) acc[k] = fmaf(g, t[k], acc[k]);
   }
 #pragma unroll
-  for (int k = 0; k < kMaxEdgeFeat; ++k) red[warp][c][k] = acc[k];
+  for (int k = 0; k < kMaxEdgeFeat; ++k) red[warp][c][k] = k < FE ? acc[k < FE ? k : 0] : 0.f;
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
@@ -893,7 +894,19 @@ int drk_edge_msg_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t
               "edge msg: U|V and S must be 16-byte aligned with leading dimensions divisible by 4");
   EdgeMsgArgs a{rowptr, colidx, perm, uv, edge_attr, cmat, s, cnt, mask, (uint32_t)ld_uv, (uint32_t)ld_attr, (uint32_t)ld_c, (uint32_t)ld_s,
                 num_nodes, num_edge_features, rows_per_block_for(num_nodes, 32)};
-  k_edge_msg_fwd<<<ceil_div(num_nodes, a.rows_per_block), 256, 0, as_stream(stream)>>>(a);
+  const int blocks = ceil_div(num_nodes, a.rows_per_block);
+  cudaStream_t st = as_stream(stream);
+  switch (num_edge_features) {
+    case 0: k_edge_msg_fwd<0><<<blocks, 256, 0, st>>>(a); break;
+    case 1: k_edge_msg_fwd<1><<<blocks, 256, 0, st>>>(a); break;
+    case 2: k_edge_msg_fwd<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: k_edge_msg_fwd<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: k_edge_msg_fwd<4><<<blocks, 256, 0, st>>>(a); break;
+    case 5: k_edge_msg_fwd<5><<<blocks, 256, 0, st>>>(a); break;
+    case 6: k_edge_msg_fwd<6><<<blocks, 256, 0, st>>>(a); break;
+    case 7: k_edge_msg_fwd<7><<<blocks, 256, 0, st>>>(a); break;
+    default: k_edge_msg_fwd<8><<<blocks, 256, 0, st>>>(a); break;
+  }
   return finish_launch("edge msg fwd");
 }
 
@@ -917,11 +930,21 @@ int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const float* 
   using namespace drk;
   DRK_REQUIRE(num_nodes >= 0 && num_edge_features >= 0 && num_edge_features <= kMaxEdgeFeat, DRK_EINVAL, "edge msg bwd c: bad size");
   if (num_edge_features == 0) return DRK_OK;
-  DRK_REQUIRE(rowptr && perm && ds && mask && edge_attr && dc, DRK_EINVAL, "edge msg bwd c: null pointer");
+  DRK_REQUIRE(rowptr && ds && mask && edge_attr && dc, DRK_EINVAL, "edge msg bwd c: null pointer");
   DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_edge_msg_bwd_c_workspace_bytes(), DRK_EWORKSPACE, "edge msg bwd c: workspace too small");
   const int blocks = kNumSM * 2;
   EdgeMsgBwdCArgs a{rowptr, perm, ds, mask, edge_attr, static_cast<float*>(workspace), (uint32_t)ld_ds, (uint32_t)ld_attr, num_nodes, num_edge_features};
-  k_edge_msg_bwd_c<<<blocks, kBwdCWarps * 32, 0, as_stream(stream)>>>(a);
+  cudaStream_t st = as_stream(stream);
+  switch (num_edge_features) {
+    case 1: k_edge_msg_bwd_c<1><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 2: k_edge_msg_bwd_c<2><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 3: k_edge_msg_bwd_c<3><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 4: k_edge_msg_bwd_c<4><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 5: k_edge_msg_bwd_c<5><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 6: k_edge_msg_bwd_c<6><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    case 7: k_edge_msg_bwd_c<7><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+    default: k_edge_msg_bwd_c<8><<<blocks, kBwdCWarps * 32, 0, st>>>(a); break;
+  }
   k_edge_msg_bwd_c_reduce<<<1, 32 * kMaxEdgeFeat, 0, as_stream(stream)>>>(static_cast<float*>(workspace), blocks, num_edge_features, dc, ld_dc);
   return finish_launch("edge msg bwd c", 2);
 }

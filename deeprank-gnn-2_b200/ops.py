@@ -455,18 +455,20 @@ MESSAGE_SIZE = 32  # vanilla_gnn.py:20
 
 
 def edge_msg_fwd(graph: GraphIndex, uv, edge_attr, cmat):
-    """S[i] = sum_e relu(U[i] + V[col_e] + C attr_e); returns (S [N,32], cnt [N,32], mask uint32 [E])."""
+    """S[i] = sum_e relu(U[i] + V[col_e] + C attr_e); returns (S [N,32], cnt [N,32], mask uint32 [E] in CSR-SLOT order).
+    The edge attributes are read in slot order too (``graph.attr_in_slot_order``: one gather per batch, shared by both layers and
+    their backward passes), so the kernel streams them instead of chasing ``perm -> attr`` per edge."""
     lib = _lib.load()
     uv = _f32_cuda(uv, "uv")
     n = uv.shape[0]
     fe = 0 if edge_attr is None else edge_attr.shape[1]
     if fe:
-        edge_attr = _f32_cuda(edge_attr, "edge_attr")
+        edge_attr = graph.attr_in_slot_order(_f32_cuda(edge_attr, "edge_attr"))
     s = torch.empty((n, MESSAGE_SIZE), dtype=torch.float32, device=uv.device)
     cnt = torch.empty_like(s)
     mask = torch.empty(max(graph.num_edges, 1), dtype=torch.int32, device=uv.device)
     with torch.cuda.device(uv.device):
-        rc = lib.drk_edge_msg_fwd(_p(graph.rowptr), _p(graph.colidx), _p(graph.perm), _p(uv), _ld(uv), _p(edge_attr) if fe else None,
+        rc = lib.drk_edge_msg_fwd(_p(graph.rowptr), _p(graph.colidx), None, _p(uv), _ld(uv), _p(edge_attr) if fe else None,
                                   _ld(edge_attr) if fe else 0, fe, _p(cmat) if fe else None, int(cmat.stride(0)) if fe else 0, _p(s), _ld(s),
                                   _p(cnt), _p(mask), n, stream_ptr())
     _lib.check(rc, "drk_edge_msg_fwd")
@@ -477,7 +479,8 @@ def edge_msg_bwd_src(graph: GraphIndex, ds, mask, out):
     lib = _lib.load()
     ds = _f32_cuda(ds, "ds")
     with torch.cuda.device(ds.device):
-        rc = lib.drk_edge_msg_bwd_src(_p(graph.colptr), _p(graph.rowidx), _p(graph.permT), _p(ds), _ld(ds), _p(mask), _p(out), _ld(out),
+        # masks are kept per CSR slot: the source-side walk reaches them through the CSC-slot -> CSR-slot map
+        rc = lib.drk_edge_msg_bwd_src(_p(graph.colptr), _p(graph.rowidx), _p(graph.slot_map()), _p(ds), _ld(ds), _p(mask), _p(out), _ld(out),
                                       ds.shape[0], stream_ptr())
     _lib.check(rc, "drk_edge_msg_bwd_src")
     return out
@@ -486,10 +489,10 @@ def edge_msg_bwd_src(graph: GraphIndex, ds, mask, out):
 def edge_msg_bwd_c(graph: GraphIndex, ds, mask, edge_attr, out):
     lib = _lib.load()
     ds = _f32_cuda(ds, "ds")
-    edge_attr = _f32_cuda(edge_attr, "edge_attr")
+    edge_attr = graph.attr_in_slot_order(_f32_cuda(edge_attr, "edge_attr"))
     with torch.cuda.device(ds.device):
         ws = workspace(lib.drk_edge_msg_bwd_c_workspace_bytes(), ds.device)
-        rc = lib.drk_edge_msg_bwd_c(_p(graph.rowptr), _p(graph.perm), _p(ds), _ld(ds), _p(mask), _p(edge_attr), _ld(edge_attr),
+        rc = lib.drk_edge_msg_bwd_c(_p(graph.rowptr), None, _p(ds), _ld(ds), _p(mask), _p(edge_attr), _ld(edge_attr),
                                     edge_attr.shape[1], _p(out), int(out.stride(0)), ds.shape[0], _p(ws), ws.numel(), stream_ptr())
     _lib.check(rc, "drk_edge_msg_bwd_c")
     return out

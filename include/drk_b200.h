@@ -167,6 +167,8 @@ DRK_API int drk_segment_mean_bwd(const float* dg, int64_t ld_dg, const int32_t* 
  *   m_e = relu(U[row_e] + V[col_e] + C attr_e),  S[i] = sum_{e in row i} m_e            (message size fixed at 32)
  *   uv [N,64] = U | V;  edge_attr [E,Fe] in ORIGINAL edge order (Fe <= 8);  cmat [32, ld_c]
  *   outputs: s [N,32];  cnt [N,32] = active edges per (node, channel) (dU = dS * cnt);  mask uint32 [E] per edge id.
+ *   perm == NULL: edge_attr and mask are indexed by CSR SLOT instead of by original edge id (attributes permuted once per batch, masks
+ *   written and read as streams; drk_edge_msg_bwd_src then takes the CSC-slot -> CSR-slot map of drk_attn_slot_map as its `permT`).
  * backward:  drk_edge_msg_bwd_src  dV[j] = sum_{e: col_e = j} dS[row_e] * mask_e   (over the CSC half)
  *            drk_edge_msg_bwd_c    dC[c,k] = sum_e dS[row_e,c] mask_e[c] attr[e,k]  (two-stage fixed-order reduction) */
 DRK_API int drk_edge_msg_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* perm,
