@@ -107,24 +107,39 @@ __global__ void __launch_bounds__(kTcThreads) k_node_linear_tc(const LinearArgs 
     }
   };
   if ((int)blockIdx.x < num_tiles) issue(blockIdx.x, 0);
-  // B fragments: b0 = W[m0 + 8 nt + g][8 s + t], b1 = W[m0 + 8 nt + g][8 s + t + 4]  (W = op(B) as [M, K]; zero beyond M / K)
-  for (int e = threadIdx.x; e < ks * 8 * 32; e += kTcThreads) {
-    const int ln = e & 31, nt = (e >> 5) & 7, step = e >> 8;
-    const bool second = step >= ks1;
-    const int kk = (second ? step - ks1 : step) * 8 + (ln & 3);
-    const int ktot = second ? p.k2 : p.k;
-    const float* __restrict__ pb = second ? p.b2 : p.b;
-    const int64_t ldb = second ? p.ldb2 : p.ldb;
-    const int gm = m0 + nt * 8 + (ln >> 2);
-    float w0 = 0.f, w1 = 0.f;
-    if (gm < p.m) {
-      if (kk < ktot) w0 = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk) : __ldg(pb + (int64_t)kk * ldb + gm);
-      if (kk + 4 < ktot) w1 = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk + 4) : __ldg(pb + (int64_t)(kk + 4) * ldb + gm);
+  // B fragments: b0 = W[m0 + 8 nt + g][8 s + t], b1 = W[m0 + 8 nt + g][8 s + t + 4]  (W = op(B) as [M, K]; zero beyond M / K).
+  // All of a thread's weight loads are issued before the first split (4 entries = 8 loads in flight per trip): the build used to be a
+  // chain of ~14 dependent L2 round trips per CTA, as long as the two row tiles a CTA multiplies afterwards.
+  for (int e0 = threadIdx.x; e0 < ks * 8 * 32; e0 += 4 * kTcThreads) {
+    float w0[4], w1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kTcThreads;
+      w0[u] = w1[u] = 0.f;
+      if (e < ks * 8 * 32) {
+        const int ln = e & 31, nt = (e >> 5) & 7, step = e >> 8;
+        const bool second = step >= ks1;
+        const int kk = (second ? step - ks1 : step) * 8 + (ln & 3);
+        const int ktot = second ? p.k2 : p.k;
+        const float* __restrict__ pb = second ? p.b2 : p.b;
+        const int64_t ldb = second ? p.ldb2 : p.ldb;
+        const int gm = m0 + nt * 8 + (ln >> 2);
+        if (gm < p.m) {
+          if (kk < ktot) w0[u] = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk) : __ldg(pb + (int64_t)kk * ldb + gm);
+          if (kk + 4 < ktot) w1[u] = p.trans_b ? __ldg(pb + (int64_t)gm * ldb + kk + 4) : __ldg(pb + (int64_t)(kk + 4) * ldb + gm);
+        }
+      }
     }
-    uint4 q;
-    split_tf32(w0, q.x, q.z);
-    split_tf32(w1, q.y, q.w);
-    sW[e] = q;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kTcThreads;
+      if (e < ks * 8 * 32) {
+        uint4 q;
+        split_tf32(w0[u], q.x, q.z);
+        split_tf32(w1[u], q.y, q.w);
+        sW[e] = q;
+      }
+    }
   }
   __syncthreads();
   uint32_t phase[2] = {0u, 0u};
