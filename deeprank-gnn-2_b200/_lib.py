@@ -36,6 +36,7 @@ SIGNATURES = {
     "drk_abi_version": (c_int32, []),
     "drk_last_error": (c_char_p, []),
     "drk_launch_count": (c_int64, []),
+    "drk_runtime_init": (c_int32, []),
     "drk_graph_index_workspace_bytes": (c_size_t, [_I64, _I32]),
     "drk_graph_index_build": (c_int32, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "drk_segment_index_workspace_bytes": (c_size_t, [_I64, _I32]),
@@ -147,6 +148,14 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.drk_abi_version() != ABI_VERSION:
         raise ImportError(f"libdrk_b200.so has ABI {lib.drk_abi_version()}, this package expects {ABI_VERSION}: rebuild it")
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.init()
+            lib.drk_runtime_init()
+    except ImportError:  # a host without torch binds the C ABI directly
+        pass
     _lib = lib
     return lib
 

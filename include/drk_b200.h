@@ -64,6 +64,9 @@ DRK_API int drk_abi_version(void);
 DRK_API const char* drk_last_error(void);
 /* number of kernels this library has launched from the calling process (all threads); bench.py's gpu_launches */
 DRK_API int64_t drk_launch_count(void);
+/* clears (and returns) a non-sticky CUDA error another user of the runtime left pending in this process, so that it is not
+ * reported against this library's first launch; the host layer calls it once after loading the library on a CUDA box */
+DRK_API int drk_runtime_init(void);
 
 /* ------------------------------------------------------------------ graph index
  * Replaces what the reference leaves implicit in `row, col = edge_index` + torch_scatter's
