@@ -81,6 +81,11 @@ SIGNATURES = {
     "drk_edge_msg_bwd_src": (c_int32, [_P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _P]),
     "drk_edge_msg_bwd_c_workspace_bytes": (c_size_t, []),
     "drk_edge_msg_bwd_c": (c_int32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _P, _I64, _I32, _P, c_size_t, _P]),
+    "drk_vanilla_layer_supported": (c_int32, [_I32, _I32, _I32]),
+    "drk_vanilla_layer_fwd": (c_int32, [_P, _I32, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "drk_vanilla_layer_bwd_workspace_bytes": (c_size_t, [_I32, _I32]),
+    "drk_vanilla_layer_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _I64, _P, _P, _I64, _P,
+                                        _P, _I64, _P, _P, _P, c_size_t, _P]),
     "drk_attn_supported": (c_int32, [_I32, _I32]),
     "drk_attn_fwd": (c_int32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _P, ctypes.c_float, _P, _I64, _P, _P, _I32, _I32, _I32, _P]),
     "drk_attn_bwd_dst": (c_int32, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, ctypes.c_float, _P, _P, _I64, _I32, _I32, _I32, _P]),

@@ -46,7 +46,7 @@ class GraphIndex:
     __slots__ = (
         "num_nodes", "num_edges", "num_graphs", "device",
         "rowptr", "colidx", "perm", "colptr", "rowidx", "permT",
-        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree", "_slot_map", "_attr_csr", "max_graph_nodes",
+        "graph_ptr", "batch32", "status", "_storage", "_key", "_degree", "_slot_map", "_attr_csr", "max_graph_nodes", "order",
     )
 
     def __init__(self):
@@ -197,6 +197,10 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
     gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc, blocks=blocks)
     gi._key = key
     gi.max_graph_nodes = meta.get("max_graph_nodes")  # known on the host for collated batches: lets the aggregation pick the tiled kernel
+    # issue order of the per-graph kernels (largest graphs first, data.py:snake_order); only meaningful for the batch it was made for
+    order = getattr(data, "_order32", None)
+    if order is not None and order.is_cuda and order.device == ei.device and gi.num_graphs and int(order.numel()) == gi.num_graphs:
+        gi.order = order
     data.__dict__["_graph_index"] = gi
     return gi
 

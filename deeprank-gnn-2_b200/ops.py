@@ -6,6 +6,8 @@ tensors (``_f32_cuda`` raises).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -498,6 +500,70 @@ def edge_msg_bwd_c(graph: GraphIndex, ds, mask, edge_attr, out):
     return out
 
 
+# ------------------------------------------------------------------------------ per-graph fused Vanilla layer (drk_vanilla.cu)
+VANILLA_FUSED = os.environ.get("DRK_VANILLA_FUSED", "1") != "0"
+
+
+def _vanilla_fused_ok(x, we, wn, graph: GraphIndex, f: int, fe: int) -> bool:
+    """One CTA per graph needs the graphs' node ranges (collated batches) and every graph to fit one SM's shared memory."""
+    if not VANILLA_FUSED or graph.graph_ptr is None or not graph.max_graph_nodes or graph.colptr is None or graph.num_graphs < 1:
+        return False
+    if not (x.is_cuda and x.dtype == torch.float32 and we.dtype == torch.float32 and wn.dtype == torch.float32):
+        return False
+    return bool(_lib.load().drk_vanilla_layer_supported(f, fe, int(graph.max_graph_nodes)))
+
+
+def _rows16(t: torch.Tensor) -> torch.Tensor:
+    """Row-contiguous and 16-byte aligned (what the bulk copies of the per-graph kernels need)."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def vanilla_layer_fwd(x, edge_attr, we, be, wn, bn, graph: GraphIndex):
+    """``VanillaConvolutionalLayer.forward`` in one launch; returns (out, S, cnt, tf, mask) -- see include/drk_b200.h."""
+    lib = _lib.load()
+    x = _rows16(x)
+    n, f = x.shape
+    fe = 0 if edge_attr is None else edge_attr.shape[1]
+    attr = graph.attr_in_slot_order(_f32_cuda(edge_attr, "edge_attr")).contiguous() if fe else None
+    we = we if we.stride(1) == 1 else we.contiguous()
+    wn = wn if wn.stride(1) == 1 else wn.contiguous()
+    dev = x.device
+    out = torch.empty((n, f), dtype=torch.float32, device=dev)
+    s = torch.empty((n, MESSAGE_SIZE), dtype=torch.float32, device=dev)
+    cnt = torch.empty_like(s)
+    tf = torch.empty((n, fe, MESSAGE_SIZE), dtype=torch.float32, device=dev) if fe else None
+    mask = torch.empty(max(graph.num_edges, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.drk_vanilla_layer_fwd(_p(x), f, _p(graph.rowptr), _p(graph.colidx), _p(attr), fe, _p(graph.graph_ptr), _p(graph.order), graph.num_graphs,
+                                       int(graph.max_graph_nodes), _p(we), int(we.stride(0)), _p(be), _p(wn), int(wn.stride(0)), _p(bn), _p(out), _p(s),
+                                       _p(cnt), _p(tf), _p(mask), _p(graph.status), stream_ptr())
+    _lib.check(rc, "drk_vanilla_layer_fwd")
+    return out, s, cnt, tf, mask
+
+
+def vanilla_layer_bwd(x, s, out, dout, cnt, tf, mask, we, wn, graph: GraphIndex, has_be: bool, has_bn: bool, need_dx: bool):
+    lib = _lib.load()
+    x, dout = _rows16(x), _rows16(dout)
+    n, f = x.shape
+    fe = we.shape[1] - 2 * f
+    dev = x.device
+    we = we if we.stride(1) == 1 else we.contiguous()
+    wn = wn if wn.stride(1) == 1 else wn.contiguous()
+    dx = torch.empty_like(x) if need_dx else None
+    dwe, dwn = torch.empty(we.shape, dtype=torch.float32, device=dev), torch.empty(wn.shape, dtype=torch.float32, device=dev)
+    dbe = torch.empty(MESSAGE_SIZE, dtype=torch.float32, device=dev) if has_be else None
+    dbn = torch.empty(f, dtype=torch.float32, device=dev) if has_bn else None
+    with torch.cuda.device(dev):
+        ws = workspace(lib.drk_vanilla_layer_bwd_workspace_bytes(f, graph.num_graphs), dev)
+        rc = lib.drk_vanilla_layer_bwd(_p(x), _p(s), _p(out), _p(dout), _p(cnt), _p(tf), f, fe, _p(mask), _p(graph.colptr), _p(graph.rowidx),
+                                       _p(graph.slot_map()), _p(graph.graph_ptr), _p(graph.order), graph.num_graphs, int(graph.max_graph_nodes),
+                                       _p(we), int(we.stride(0)), _p(wn), int(wn.stride(0)), _p(dx), _p(dwe), int(dwe.stride(0)), _p(dbe),
+                                       _p(dwn), int(dwn.stride(0)), _p(dbn), _p(graph.status), _p(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "drk_vanilla_layer_bwd")
+    return dx, dwe, dbe, dwn, dbn
+
+
 class VanillaConvFunction(torch.autograd.Function):
     """``VanillaConvolutionalLayer.forward`` (reference ``vanilla_gnn.py:26-38``) as one autograd node.
 
@@ -516,15 +582,20 @@ class VanillaConvFunction(torch.autograd.Function):
             raise ValueError(f"edge MLP weight has shape {tuple(we.shape)}, expected [32, 2*{f}+Fe]")
         if fe > 0 and (edge_attr is None or edge_attr.dim() != 2 or edge_attr.shape[1] != fe):
             raise ValueError(f"edge_attr must be [E, {fe}] (2-D, like the reference requires), got {None if edge_attr is None else tuple(edge_attr.shape)}")
+        ctx.graph = graph
+        ctx.f, ctx.fe = f, fe
+        ctx.has_be, ctx.has_bn = be is not None, bn is not None
+        ctx.fused = _vanilla_fused_ok(x, we, wn, graph, f, fe)
+        if ctx.fused:
+            out, s, cnt, tf, mask = vanilla_layer_fwd(x, edge_attr if fe else None, we, be, wn, bn, graph)
+            ctx.save_for_backward(x, None, we, wn, tf, s, cnt, mask, out)
+            return out
         wab = torch.cat([we[:, :f], we[:, f : 2 * f]], dim=0)                       # [64, F]
         bias64 = torch.cat([be, torch.zeros_like(be)]) if be is not None else None  # b belongs to U only
         uv = node_linear(x, wab, True, bias64)                                        # [N, 64] = U | V
         cmat = we[:, 2 * f :]                                                         # [32, Fe] view, row stride 2F+Fe
         s, cnt, mask = edge_msg_fwd(graph, uv, edge_attr if fe else None, cmat)
         out = node_linear2(x, wn[:, :f], s, wn[:, f:], True, bn, act=ACT_RELU)        # relu(cat[x, s] Wn^T + bn)
-        ctx.graph = graph
-        ctx.f, ctx.fe = f, fe
-        ctx.has_be, ctx.has_bn = be is not None, bn is not None
         ctx.save_for_backward(x, edge_attr if fe else None, we, wn, wab, s, cnt, mask, out)
         return out
 
@@ -534,6 +605,9 @@ class VanillaConvFunction(torch.autograd.Function):
         g = ctx.graph
         f, fe = ctx.f, ctx.fe
         n = x.shape[0]
+        if ctx.fused:  # the fifth saved tensor is tf (sum of active edge attributes), not the stacked weight
+            dx, dwe, dbe, dwn, dbn = vanilla_layer_bwd(x, s, out, dout, cnt, wab, mask, we, wn, g, ctx.has_be, ctx.has_bn, ctx.needs_input_grad[0])
+            return dx, None, dwe, dbe, dwn, dbn, None
         dz = torch.ops.aten.threshold_backward(dout.contiguous(), out, 0.0)          # ReLU of the node MLP
         # node MLP: dWn = dZ^T [x | s], dbn = sum dZ, dS = dZ Wn[:, F:]
         dwn = torch.empty_like(wn)

@@ -186,6 +186,31 @@ DRK_API int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const
                        const float* edge_attr, int64_t ld_attr, int32_t num_edge_features, float* dc, int64_t ld_dc,
                        int32_t num_nodes, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ VanillaConvolutionalLayer, one kernel per direction
+ * Replaces the whole forward / backward of vanilla_gnn.py:26-38 (cat[x_i, x_j, e] -> _edge_mlp -> ReLU -> scatter_sum -> cat[x, S] ->
+ * _node_mlp -> ReLU) for a collated batch whose graphs each fit one SM's shared memory: one CTA per graph, V rows and dS rows stay in
+ * shared memory, the projections run on the tensor cores with error-compensated TF32 (fp32-level accuracy).  Same tensors as the
+ * batch-level route drk_node_linear -> drk_edge_msg_fwd -> drk_node_linear (and interchangeable with it):
+ *   x, out [N,F] row-contiguous (F <= 64); s, cnt [N,32]; tf [N,Fe,32] = sum of the ACTIVE edges' attributes per (node, feature, channel)
+ *   (dC = sum_i dS[i] * tf[i]); mask uint32 [E] per CSR slot; attr_slots [E,Fe] = edge_attr[perm]; we [32, 2F+Fe], wn [F, F+32] (nn.Linear
+ *   weights, row strides ld_*); graph_ptr int32 [G+1] node offsets of the graphs; order int32 [G] = slot -> graph issue order or NULL.
+ *   x, s, dout must be 16-byte aligned.  cnt / tf may be NULL in the forward call (inference).
+ * Edges that leave their graph raise DRK_STATUS_CROSS_GRAPH, graphs of more than max_graph_nodes nodes DRK_STATUS_INDEX_RANGE.
+ * drk_vanilla_layer_supported == 0 -> DRK_EUNSUPPORTED: use the batch-level kernels.
+ * backward: dx may be NULL (input without gradient); dbe / dbn may be NULL; gradients are summed per CTA and then in CTA order
+ * (deterministic, no atomics); workspace = drk_vanilla_layer_bwd_workspace_bytes. */
+DRK_API int drk_vanilla_layer_supported(int32_t num_features, int32_t num_edge_features, int32_t max_graph_nodes);
+DRK_API int drk_vanilla_layer_fwd(const float* x, int32_t num_features, const int32_t* rowptr, const int32_t* colidx, const float* attr_slots,
+                          int32_t num_edge_features, const int32_t* graph_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes,
+                          const float* we, int64_t ld_we, const float* be, const float* wn, int64_t ld_wn, const float* bn, float* out, float* s,
+                          float* cnt, float* tf, uint32_t* mask, int32_t* status, void* stream);
+DRK_API size_t drk_vanilla_layer_bwd_workspace_bytes(int32_t num_features, int32_t num_graphs);
+DRK_API int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, const float* dout, const float* cnt, const float* tf,
+                          int32_t num_features, int32_t num_edge_features, const uint32_t* mask, const int32_t* colptr, const int32_t* rowidx,
+                          const int32_t* slot_map, const int32_t* graph_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes,
+                          const float* we, int64_t ld_we, const float* wn, int64_t ld_wn, float* dx, float* dwe, int64_t ld_dwe, float* dbe,
+                          float* dwn, int64_t ld_dwn, float* dbn, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ community pooling
  * drk_segment_max: torch_scatter.scatter_max(x, cluster, dim=0) (community_pooling.py:209) and PyG max_pool_x
  *   (ginet.py:103): out[c,:] = max over the segment, arg = element id of the FIRST maximum, empty segment -> (0, n_src).
