@@ -340,7 +340,7 @@ def measure_c4(dev, config: str, steps: int = 40):
     batch = host.clone().to(dev)
     torch.manual_seed(0)
     net = cls(F_NODE, 1, F_EDGE).to(dev).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=True)  # what Trainer configures on a GPU (trainer.py: fused Adam)
     inner = TrainStep(net, opt, torch.nn.MSELoss())
 
     def step(b):
@@ -446,7 +446,7 @@ def e2e_generic(dev, config: str, steps: int):
     else:
         cls = {"c4-vanilla": vanilla_gnn.VanillaNetwork, "c4-fout": foutnet.FoutNet, "c4-ginet": ginet.GINet}[config]
         net = cls(F_NODE, 1, F_EDGE).to(dev).train()
-        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=True)
         inner = TrainStep(net, opt, torch.nn.MSELoss())
 
         def run(b):

@@ -636,17 +636,21 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
       // the first 32 incoming-edge records of this warp's 4 source nodes, and the per-node counts
       int c_len[4], c_beg[4], c_row[4];
       uint32_t c_msk[4];
-      float c_cnt[4];
+      float c_cnt[4], c_tf[4][kF];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int li = tile * kRows + warp + kNW * k;
         c_beg[k] = 0;
         c_len[k] = 0;
         c_cnt[k] = 0.f;
+#pragma unroll
+        for (int q = 0; q < kF; ++q) c_tf[k][q] = 0.f;
         if (li < n) {
           c_beg[k] = sCp[li];
           c_len[k] = sCp[li + 1] - c_beg[k];
           c_cnt[k] = ld_stream_f32(a.cnt + (int64_t)(n0 + li) * kMsg + lane);
+#pragma unroll
+          for (int q = 0; q < FE; ++q) c_tf[k][q] = ld_stream_f32(a.tf + ((int64_t)(n0 + li) * FE + q) * kMsg + lane);  // consumed after the wait below
         }
         c_row[k] = 0;
         c_msk[k] = 0u;
@@ -686,7 +690,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
           du = ds * c_cnt[k];
           if (FE > 0) {
 #pragma unroll
-            for (int q = 0; q < FE; ++q) accC[q] = fmaf(ds, ld_stream_f32(a.tf + ((int64_t)(n0 + li) * FE + q) * kMsg + lane), accC[q]);
+            for (int q = 0; q < FE; ++q) accC[q] = fmaf(ds, c_tf[k][q], accC[q]);
           }
           for (int off = 0; off < c_len[k]; off += 32) {
             int rr = c_row[k];

@@ -58,6 +58,7 @@ for r in sorted(rows, key=lambda r: -r[4])[:top]:
 if ranges:
     print()
     for lo, hi, label in ranges:
-        sel = [r for r in rows if r[0].startswith("drk_ginet_step") and lo <= r[1] <= hi]
+        main = max({r[0] for r in rows if r[0].startswith("drk_")}, key=lambda fn: sum(r[3] for r in rows if r[0] == fn))  # the kernel's own file
+        sel = [r for r in rows if r[0] == main and lo <= r[1] <= hi]
         print(f"{label:28s} lines {lo}-{hi}: inst {100 * sum(r[3] for r in sel) / max(tot_inst, 1):5.1f}%  samples {100 * sum(r[4] for r in sel) / max(tot_samp, 1):5.1f}%  "
               f"wavefronts {100 * sum(r[5] for r in sel) / max(tot_wf, 1):5.1f}% (excess {sum(r[6] for r in sel):.0f})")
