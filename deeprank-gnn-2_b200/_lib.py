@@ -74,7 +74,8 @@ SIGNATURES = {
     "drk_segment_max_bwd": (c_int32, [_P, _I64, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "drk_cluster_offsets_workspace_bytes": (c_size_t, [_I32]),
     "drk_cluster_offsets": (c_int32, [_P, _P, _P, _I32, _I32, _P, _P, c_size_t, _P]),
-    "drk_compact_segments": (c_int32, [_P, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "drk_compact_segments_workspace_bytes": (c_size_t, [_I32]),
+    "drk_compact_segments": (c_int32, [_P, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, c_size_t, _P]),
     "drk_pool_edge_keys": (c_int32, [_P, _I64, _P, _I32, _P, _P, _P, _I32, _I64, _P, _P, _P]),
     "drk_pool_edge_decode": (c_int32, [_P, _I32, _P, _P, _P, _I32, _P, _P]),
     "drk_edge_msg_fwd": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _I32, _P, _I64, _P, _I64, _P, _P, _I32, _P]),

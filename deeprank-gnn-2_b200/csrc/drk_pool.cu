@@ -25,15 +25,66 @@ namespace pool {
 
 constexpr int kCT = 1024;
 
-// One CTA walks the K segment sizes in tiles of kCT with a block scan and keeps the non-empty ones.
+// Two launches over chunks of kCT * kCI segment sizes: (1) every CTA counts the non-empty segments of its chunk; (2) every CTA adds up the
+// counts of the chunks before its own (a few hundred integers), then scans its chunk tile by tile and writes the kept segments.  The first
+// version walked all K segments with ONE CTA: 141 us for the ~370 k dense pair ids of a pooled C2 batch, 0.42 of the 1.0 ms train step of the
+// clustered networks (profiles/r02_launches_c4-ginet_v2).
+constexpr int kCI = 4;  // tiles per chunk
+
+__global__ void __launch_bounds__(kCT) k_compact_count(const int32_t* __restrict__ ptr, int32_t num_segments, int32_t* __restrict__ chunk_count) {
+  const int base = blockIdx.x * kCT * kCI;
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < kCI; ++i) {
+    const int k = base + i * kCT + threadIdx.x;
+    if (k < num_segments) mine += __ldg(ptr + k + 1) > __ldg(ptr + k) ? 1 : 0;
+  }
+  const int total = __reduce_add_sync(0xffffffffu, mine);
+  __shared__ int s_warp[kCT / 32];
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int v = __reduce_add_sync(0xffffffffu, s_warp[threadIdx.x]);
+    if (threadIdx.x == 0) chunk_count[blockIdx.x] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kCT) k_compact_segments(const int32_t* __restrict__ ptr, int32_t num_segments, const int32_t* __restrict__ perm,
                                                          int64_t* __restrict__ rank, int32_t* __restrict__ ptr_out, int32_t* __restrict__ ids_out,
                                                          int64_t* __restrict__ last_out, int32_t cap, int32_t* __restrict__ count_out,
-                                                         int32_t* __restrict__ status) {
+                                                         int32_t* __restrict__ status, const int32_t* __restrict__ chunk_count) {
   __shared__ int s_warp[kCT / 32 + 1];
+  __shared__ int s_base[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int carry = 0;
-  for (int base = 0; base < num_segments; base += kCT) {
+  // kept segments before this chunk, and in total: fixed-order integer sums
+  {
+    int before = 0, all = 0;
+    for (int b = tid; b < (int)gridDim.x; b += kCT) {
+      const int c = __ldg(chunk_count + b);
+      all += c;
+      if (b < (int)blockIdx.x) before += c;
+    }
+    before = __reduce_add_sync(0xffffffffu, before);
+    all = __reduce_add_sync(0xffffffffu, all);
+    __shared__ int s_b[kCT / 32], s_a[kCT / 32];
+    if (lane == 0) {
+      s_b[warp] = before;
+      s_a[warp] = all;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int vb = __reduce_add_sync(0xffffffffu, s_b[lane]), va = __reduce_add_sync(0xffffffffu, s_a[lane]);
+      if (lane == 0) {
+        s_base[0] = vb;
+        s_base[1] = va;
+      }
+    }
+    __syncthreads();
+  }
+  int carry = s_base[0];
+  const int kept = s_base[1];
+  const int chunk0 = blockIdx.x * kCT * kCI;
+  for (int base = chunk0; base < min(chunk0 + kCT * kCI, num_segments); base += kCT) {
     const int k = base + tid;
     int lo = 0, hi = 0;
     if (k < num_segments) {
@@ -74,10 +125,10 @@ __global__ void __launch_bounds__(kCT) k_compact_segments(const int32_t* __restr
     __syncthreads();
   }
   const int total = num_segments > 0 ? __ldg(ptr + num_segments) : 0;
-  for (int i = min(carry, cap) + tid; i <= cap; i += kCT) ptr_out[i] = total;  // trailing (unused) capacity = empty segments
-  if (tid == 0) {
-    if (count_out != nullptr) *count_out = carry;
-    if (carry > cap && status != nullptr) atomicOr(status, DRK_STATUS_INDEX_RANGE);
+  for (int i = min(kept, cap) + (int)blockIdx.x * kCT + tid; i <= cap; i += (int)gridDim.x * kCT) ptr_out[i] = total;  // trailing (unused) capacity = empty segments
+  if (blockIdx.x == 0 && tid == 0) {
+    if (count_out != nullptr) *count_out = kept;
+    if (kept > cap && status != nullptr) atomicOr(status, DRK_STATUS_INDEX_RANGE);
   }
 }
 
@@ -141,14 +192,25 @@ __global__ void __launch_bounds__(256) k_pool_edge_decode(const int32_t* __restr
 
 extern "C" {
 
+size_t drk_compact_segments_workspace_bytes(int32_t num_segments) {
+  using namespace drk;
+  const int chunks = std::max(1, ceil_div(std::max(num_segments, 0), pool::kCT * pool::kCI));
+  return (size_t)chunks * sizeof(int32_t);
+}
+
 int drk_compact_segments(const int32_t* ptr, int32_t num_segments, const int32_t* perm, int64_t* rank, int32_t* ptr_out, int32_t* ids_out,
-                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* stream) {
+                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace drk;
   DRK_REQUIRE(num_segments >= 0 && capacity >= 0, DRK_EINVAL, "compact segments: negative size");
   DRK_REQUIRE(ptr && ptr_out, DRK_EINVAL, "compact segments: null pointer");
   DRK_REQUIRE(last_out == nullptr || perm != nullptr, DRK_EINVAL, "compact segments: last_out needs perm");
-  pool::k_compact_segments<<<1, pool::kCT, 0, as_stream(stream)>>>(ptr, num_segments, perm, rank, ptr_out, ids_out, last_out, capacity, count_out, status);
-  return finish_launch("compact segments");
+  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= drk_compact_segments_workspace_bytes(num_segments), DRK_EWORKSPACE, "compact segments: workspace too small");
+  const int chunks = std::max(1, ceil_div(num_segments, pool::kCT * pool::kCI));
+  int32_t* chunk_count = static_cast<int32_t*>(workspace);
+  pool::k_compact_count<<<chunks, pool::kCT, 0, as_stream(stream)>>>(ptr, num_segments, chunk_count);
+  pool::k_compact_segments<<<chunks, pool::kCT, 0, as_stream(stream)>>>(ptr, num_segments, perm, rank, ptr_out, ids_out, last_out, capacity, count_out, status,
+                                                                     chunk_count);
+  return finish_launch("compact segments", 2);
 }
 
 int drk_pool_edge_keys(const int64_t* edge_index, int64_t num_edges, const int64_t* inv, int32_t num_nodes, const int32_t* batch32,

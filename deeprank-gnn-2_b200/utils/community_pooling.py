@@ -22,7 +22,7 @@ import torch
 
 from .. import _lib, ops
 from ..data import Batch, Data
-from ..graph import GraphIndex, stream_ptr
+from ..graph import GraphIndex, stream_ptr, workspace
 
 
 def _p(t):
@@ -125,7 +125,9 @@ def _consecutive(src: torch.Tensor, meta: dict | None) -> _Structure:
     last = torch.empty(n_clusters, dtype=torch.int64, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.drk_compact_segments(_p(ptr_k), bound, _p(perm), _p(rank), _p(ptr_c), None, _p(last), n_clusters, _p(count), _p(status), stream_ptr())
+        ws = workspace(lib.drk_compact_segments_workspace_bytes(bound), dev)
+        rc = lib.drk_compact_segments(_p(ptr_k), bound, _p(perm), _p(rank), _p(ptr_c), None, _p(last), n_clusters, _p(count), _p(status), _p(ws), ws.numel(),
+                                      stream_ptr())
     _lib.check(rc, "drk_compact_segments")
     st = _Structure()
     st.inv = rank[src] if n else torch.empty(0, dtype=torch.int64, device=dev)
@@ -191,7 +193,8 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
     count = torch.empty(1, dtype=torch.int32, device=dev)
     pooled_index = torch.empty((2, n_pooled), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.drk_compact_segments(_p(ptr_k), n_pairs, None, None, _p(ptr_s), _p(ids), None, n_pooled, _p(count), _p(status), stream_ptr())
+        ws = workspace(lib.drk_compact_segments_workspace_bytes(n_pairs), dev)
+        rc = lib.drk_compact_segments(_p(ptr_k), n_pairs, None, None, _p(ptr_s), _p(ids), None, n_pooled, _p(count), _p(status), _p(ws), ws.numel(), stream_ptr())
         _lib.check(rc, "drk_compact_segments")
         rc = lib.drk_pool_edge_decode(_p(ids), n_pooled, _p(count), _p(cptr), _p(kkptr), n_graphs, _p(pooled_index), stream_ptr())
         _lib.check(rc, "drk_pool_edge_decode")

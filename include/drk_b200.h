@@ -367,15 +367,18 @@ DRK_API int drk_ginet_step(const float* x, int64_t ldx, int32_t num_node_feature
  *   rank [num_segments] int64 (nullable): compact id of every non-empty segment, -1 for empty ones (consecutive_cluster's inverse map
  *   is rank[cluster]); ptr_out [capacity+1]: compact offsets (entries beyond the count = total: empty segments); ids_out [capacity]
  *   (nullable): original id of every kept segment; last_out [capacity] int64 (nullable, needs perm): the LAST member of every kept
- *   segment = the largest node index of the cluster (what PyG's perm holds on CPU: last writer wins); count_out: device int32.
+ *   segment = the largest node index of the cluster (what PyG's perm holds on CPU: last writer wins); count_out: device int32;
+ *   workspace: drk_compact_segments_workspace_bytes (per-chunk counts of the two-launch scan).
  * drk_pool_edge_keys: key[e] = pair_ptr[g] + (inv[row_e] - cluster_ptr[g]) * C_g + (inv[col_e] - cluster_ptr[g]) with g =
  *   batch32[row_e], C_g = cluster_ptr[g+1] - cluster_ptr[g]: a dense id of the pooled pair, ascending in (row, col) order; pooled
  *   self loops get junk_key + (e mod DRK_POOL_JUNK_SEGMENTS) with junk_key = pair_ptr[num_graphs]: group the keys with
  *   drk_segment_index_build(key, E, junk_key + DRK_POOL_JUNK_SEGMENTS) and compact the first junk_key segments.  cluster_ptr / pair_ptr: int64 [num_graphs+1], pair_ptr[g+1] - pair_ptr[g] = C_g^2.
  * drk_pool_edge_decode: pooled edge_index [2, capacity] int64 from the dense ids kept by drk_compact_segments. */
 #define DRK_POOL_JUNK_SEGMENTS 4096
+DRK_API size_t drk_compact_segments_workspace_bytes(int32_t num_segments);
 DRK_API int drk_compact_segments(const int32_t* ptr, int32_t num_segments, const int32_t* perm, int64_t* rank, int32_t* ptr_out, int32_t* ids_out,
-                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* stream);
+                         int64_t* last_out, int32_t capacity, int32_t* count_out, int32_t* status, void* workspace, size_t workspace_bytes,
+                         void* stream);
 DRK_API int drk_pool_edge_keys(const int64_t* edge_index, int64_t num_edges, const int64_t* inv, int32_t num_nodes, const int32_t* batch32,
                        const int64_t* cluster_ptr, const int64_t* pair_ptr, int32_t num_graphs, int64_t junk_key, int64_t* key, int32_t* status,
                        void* stream);
