@@ -127,12 +127,13 @@ struct TileCursor {
 
 // node range of the graph in `slot`: n < 0 past the last slot; a graph that does not fit (or a bad id in `order`) has no tiles and is reported
 __device__ __forceinline__ bool load_slot(const int32_t* __restrict__ graph_ptr, const int32_t* __restrict__ order, int num_graphs, int rows_cap, int slot, int& n0,
-                                          int& n) {
+                                          int& n, int* graph = nullptr) {
   n0 = 0;
   n = -1;
   bool invalid = false;
   if (slot < num_graphs) {
     const int g = order != nullptr ? __ldg(order + slot) : slot;
+    if (graph != nullptr) *graph = g;
     n = 0;
     if ((unsigned)g < (unsigned)num_graphs) {
       n0 = __ldg(graph_ptr + g);
@@ -411,8 +412,8 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
 //                            dU[i] = dS[i] * cnt[i],  dV[j] = sum_{e: col_e = j} mask_e * dS[row_e]   (CSC walk, dS rows from shared memory)
 //                            dx    = [dZ | dU | dV] [Wn[:, :F] ; Wa ; Wb]
 //                            dWn|dbn += dZ^T [x | S | 1],   dWa;dWb|dbe += [dU | dV]^T [x | 1],   dC += dS * tf
-// The weight gradients accumulate in registers (MMA accumulators) over ALL the graphs of a CTA and are written once, as one partial per
-// CTA; k_vanilla_reduce adds the partials in CTA order -- no floating-point atomics, the result depends only on the static schedule.
+// The weight gradients accumulate in registers (MMA accumulators) over the tiles of a graph and are written as one partial per graph;
+// k_vanilla_reduce adds the partials in graph order -- no floating-point atomics, the result does not depend on the CTA schedule.
 struct BwdArgs {
   const float* x;
   const float* s;
@@ -429,7 +430,7 @@ struct BwdArgs {
   const float* we;
   const float* wn;
   float* dx;       // [N, F] or NULL
-  float* partial;  // [gridDim.x][partial_stride]
+  float* partial;  // [num_graphs][partial_stride]
   int32_t* status;
   int64_t ld_we, ld_wn;
   int32_t num_graphs, f, fe, rows_cap, partial_stride;
@@ -568,12 +569,17 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
 
   bool bad = false, too_big = false;
   uint32_t it = 0;
-  int nx_n0, nx_n;
-  too_big |= load_slot(a.graph_ptr, a.order, a.num_graphs, a.rows_cap, blockIdx.x, nx_n0, nx_n);
+  const int ldn = f + kMsg + 1, ldab = f + 1;
+  int nx_n0, nx_n, nx_g = -1;
+  too_big |= load_slot(a.graph_ptr, a.order, a.num_graphs, a.rows_cap, blockIdx.x, nx_n0, nx_n, &nx_g);
   for (int slot = blockIdx.x; slot < a.num_graphs; slot += gridDim.x) {
-    const int n0 = nx_n0, n = nx_n;
-    too_big |= load_slot(a.graph_ptr, a.order, a.num_graphs, a.rows_cap, slot + gridDim.x, nx_n0, nx_n);
-    if (n <= 0) continue;
+    const int n0 = nx_n0, n = nx_n, gr = nx_g;
+    too_big |= load_slot(a.graph_ptr, a.order, a.num_graphs, a.rows_cap, slot + gridDim.x, nx_n0, nx_n, &nx_g);
+    if (n <= 0) {  // an empty (or rejected) graph contributes a zero partial
+      if ((unsigned)gr < (unsigned)a.num_graphs)
+        for (int i = tid; i < a.partial_stride; i += kT) a.partial[(size_t)gr * a.partial_stride + i] = 0.f;
+      continue;
+    }
     for (int j = tid; j <= n; j += kT) sCp[j] = __ldg(a.colptr + n0 + j);
     // ---- pass 0: dS for every node
     const int tiles_a = (n + kRowsA - 1) / kRowsA;
@@ -794,48 +800,58 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
       __syncthreads();
       if (warp == 0) produce(stage);
     }
-  }
-  // ---- this CTA's partial: [F][F + 33] (dWn | dbn), [64][F + 1] (dWa ; dWb | dbe), [32][8] (dC)
-  float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
-  const int ldn = f + kMsg + 1, ldab = f + 1;
+    // ---- this graph's partial: [F][F + 33] (dWn | dbn), [64][F + 1] (dWa ; dWb | dbe), [32][8] (dC).  One partial per GRAPH, added up in
+    // graph order by k_vanilla_reduce: the gradients do not depend on which CTA ran which graph (the issue order is a scheduling hint)
+    {
+      float* part = a.partial + (size_t)gr * a.partial_stride;
 #pragma unroll
-  for (int j = 0; j < kNtN; ++j) {
-    if (j >= cntN) continue;
-    const int c = (cg + 4 * j) * 8 + 2 * t;
+      for (int j = 0; j < kNtN; ++j) {
+        if (j >= cntN) continue;
+        const int c = (cg + 4 * j) * 8 + 2 * t;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = mt * 16 + g + 8 * h;
-      if (m >= f) continue;
-      if (c < ldn) part[m * ldn + c] = accN[j][2 * h];
-      if (c + 1 < ldn) part[m * ldn + c + 1] = accN[j][2 * h + 1];
-    }
-  }
-  float* part_ab = part + f * ldn;
-#pragma unroll
-  for (int j = 0; j < kNtAB; ++j) {
-    if (j >= cntAB) continue;
-    const int c = (cg + 4 * j) * 8 + 2 * t;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = mt * 16 + g + 8 * h;
-      if (c < ldab) part_ab[m * ldab + c] = accAB[j][2 * h];
-      if (c + 1 < ldab) part_ab[m * ldab + c + 1] = accAB[j][2 * h + 1];
-    }
-  }
-  // dC: the warps' channel sums, folded in warp order
-  float* red = sDuv;  // [warps][32][kF]
-#pragma unroll
-  for (int q = 0; q < kF; ++q) red[(warp * kMsg + lane) * kF + q] = accC[q];
-  __syncthreads();
-  if (warp == 0) {
-    float* part_c = part_ab + 2 * kMsg * ldab;
-#pragma unroll
-    for (int q = 0; q < kMaxFe; ++q) {
-      float sum = 0.f;
-      if (q < FE) {
-        for (int w = 0; w < kNW; ++w) sum += red[(w * kMsg + lane) * kF + q];
+        for (int h = 0; h < 2; ++h) {
+          const int m = mt * 16 + g + 8 * h;
+          if (m < f) {
+            if (c < ldn) part[m * ldn + c] = accN[j][2 * h];
+            if (c + 1 < ldn) part[m * ldn + c + 1] = accN[j][2 * h + 1];
+          }
+          accN[j][2 * h] = 0.f;
+          accN[j][2 * h + 1] = 0.f;
+        }
       }
-      part_c[lane * kMaxFe + q] = sum;
+      float* part_ab = part + f * ldn;
+#pragma unroll
+      for (int j = 0; j < kNtAB; ++j) {
+        if (j >= cntAB) continue;
+        const int c = (cg + 4 * j) * 8 + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = mt * 16 + g + 8 * h;
+          if (c < ldab) part_ab[m * ldab + c] = accAB[j][2 * h];
+          if (c + 1 < ldab) part_ab[m * ldab + c + 1] = accAB[j][2 * h + 1];
+          accAB[j][2 * h] = 0.f;
+          accAB[j][2 * h + 1] = 0.f;
+        }
+      }
+      // dC: the warps' channel sums, folded in warp order (sDuv is free: the last tile ended with a barrier)
+      float* red = sDuv;  // [warps][32][kF]
+#pragma unroll
+      for (int q = 0; q < kF; ++q) {
+        red[(warp * kMsg + lane) * kF + q] = accC[q];
+        accC[q] = 0.f;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        float* part_c = part_ab + 2 * kMsg * ldab;
+#pragma unroll
+        for (int q = 0; q < kMaxFe; ++q) {
+          float sum = 0.f;
+          if (q < FE) {
+            for (int w = 0; w < kNW; ++w) sum += red[(w * kMsg + lane) * kF + q];
+          }
+          part_c[lane * kMaxFe + q] = sum;
+        }
+      }
     }
   }
   if (a.status != nullptr) {
@@ -844,15 +860,17 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
   }
 }
 
-// dwe [32, 2F + fe] | dbe [32] | dwn [F, F + 32] | dbn [F] = sum of the CTAs' partials, in CTA order
+// dwe [32, 2F + fe] | dbe [32] | dwn [F, F + 32] | dbn [F] = sum of the graphs' partials.  Block = 32 outputs x 8 contiguous ranges of graphs;
+// a range is summed in graph order (4 interleaved running sums), the 8 range sums in range order: a fixed association.
 __global__ void __launch_bounds__(256) k_vanilla_reduce(const float* __restrict__ partial, int parts, int stride, int f, int fe, float* __restrict__ dwe,
                                                        int64_t ld_dwe, float* __restrict__ dbe, float* __restrict__ dwn, int64_t ld_dwn, float* __restrict__ dbn) {
+  __shared__ float s_sum[8][32];
   const int ldn = f + kMsg + 1, ldab = f + 1;
   const int n_we = kMsg * (2 * f + fe), n_be = kMsg, n_wn = f * (f + kMsg), n_bn = f;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_we + n_be + n_wn + n_bn) return;
-  int src;
-  float* dst;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
+  int src = 0;
+  float* dst = nullptr;
   if (i < n_we) {
     const int c = i / (2 * f + fe), k = i % (2 * f + fe);
     src = k < f ? f * ldn + c * ldab + k : (k < 2 * f ? f * ldn + (kMsg + c) * ldab + (k - f) : f * ldn + 2 * kMsg * ldab + c * kMaxFe + (k - 2 * f));
@@ -865,15 +883,29 @@ __global__ void __launch_bounds__(256) k_vanilla_reduce(const float* __restrict_
     const int j = i - n_we - n_be, m = j / (f + kMsg), k = j % (f + kMsg);
     src = m * ldn + k;
     dst = dwn + (int64_t)m * ld_dwn + k;
-  } else {
+  } else if (i < n_we + n_be + n_wn + n_bn) {
     const int m = i - n_we - n_be - n_wn;
     src = m * ldn + f + kMsg;
     dst = dbn != nullptr ? dbn + m : nullptr;
   }
-  if (dst == nullptr) return;
-  float sum = 0.f;
-  for (int p = 0; p < parts; ++p) sum += partial[(size_t)p * stride + src];
-  *dst = sum;
+  const int chunk = (parts + 7) / 8, p0 = ty * chunk, p1 = min(parts, p0 + chunk);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dst != nullptr) {
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += partial[(size_t)(p + u) * stride + src];
+    }
+    for (int u = 0; p < p1; ++p, ++u) acc[u] += partial[(size_t)p * stride + src];
+  }
+  s_sum[ty][tx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (ty == 0 && dst != nullptr) {
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sum += s_sum[r][tx];
+    *dst = sum;
+  }
 }
 
 static int partial_stride_for(int f) { return (f * (f + kMsg + 1) + 2 * kMsg * (f + 1) + kMsg * kMaxFe + 3) & ~3; }
@@ -956,7 +988,7 @@ int drk_vanilla_layer_fwd(const float* x, int32_t f, const int32_t* rowptr, cons
 size_t drk_vanilla_layer_bwd_workspace_bytes(int32_t f, int32_t num_graphs) {
   using namespace drk;
   if (f < 1 || num_graphs < 1) return 16;
-  return (size_t)std::min(num_graphs, kNumSM) * (size_t)vanilla::partial_stride_for(f) * sizeof(float);
+  return (size_t)num_graphs * (size_t)vanilla::partial_stride_for(f) * sizeof(float);
 }
 
 int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, const float* dout, const float* cnt, const float* tf, int32_t f, int32_t fe,
@@ -973,7 +1005,8 @@ int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, cons
   cudaStream_t st = as_stream(stream);
   const int grid = std::max(1, std::min(num_graphs, kNumSM));
   const int stride = partial_stride_for(f);
-  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)grid * stride * sizeof(float), DRK_EWORKSPACE, "vanilla layer backward: workspace too small");
+  DRK_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)std::max(num_graphs, 1) * stride * sizeof(float), DRK_EWORKSPACE,
+              "vanilla layer backward: workspace too small");
   const int n_out = kMsg * (2 * f + fe) + kMsg + f * (f + kMsg) + f;
   int launches = 1;
   if (num_graphs > 0) {
@@ -1004,7 +1037,7 @@ int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, cons
 #undef DRK_VANILLA_BWD
     launches = 2;
   }
-  k_vanilla_reduce<<<ceil_div(n_out, 256), 256, 0, st>>>(static_cast<const float*>(workspace), num_graphs > 0 ? grid : 0, stride, f, fe, dwe, ld_dwe, dbe, dwn,
+  k_vanilla_reduce<<<ceil_div(n_out, 32), 256, 0, st>>>(static_cast<const float*>(workspace), num_graphs, stride, f, fe, dwe, ld_dwe, dbe, dwn,
                                                          ld_dwn, dbn);
   return finish_launch("vanilla layer backward", launches);
 }

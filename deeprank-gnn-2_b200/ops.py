@@ -159,8 +159,9 @@ def gather_rows(src, perm):
     return out
 
 
-def segment_index(index: torch.Tensor, num_segments: int):
-    """Stable counting sort of an int64 key vector -> (ptr int32 [S+1], perm int32 [n], status int32 [1])."""
+def segment_index(index: torch.Tensor, num_segments: int, status: torch.Tensor | None = None):
+    """Stable counting sort of an int64 key vector -> (ptr int32 [S+1], perm int32 [n], status int32 [1]).  ``status``: an existing
+    status word to OR the faults into (saves the fill launch of a fresh one)."""
     lib = _lib.load()
     if not index.is_cuda or index.dtype != torch.int64:
         raise TypeError("segment_index: expected an int64 CUDA tensor")
@@ -169,7 +170,8 @@ def segment_index(index: torch.Tensor, num_segments: int):
     dev = index.device
     ptr = torch.empty(num_segments + 1, dtype=torch.int32, device=dev)
     perm = torch.empty(n, dtype=torch.int32, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         ws = workspace(lib.drk_segment_index_workspace_bytes(n, num_segments), dev)
         rc = lib.drk_segment_index_build(_p(index), n, num_segments, _p(ptr), _p(perm), _p(status), _p(ws), ws.numel(), stream_ptr())
@@ -510,7 +512,10 @@ def _vanilla_fused_ok(x, we, wn, graph: GraphIndex, f: int, fe: int) -> bool:
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and we.dtype == torch.float32 and wn.dtype == torch.float32):
         return False
-    return bool(_lib.load().drk_vanilla_layer_supported(f, fe, int(graph.max_graph_nodes)))
+    lib = _lib.load()
+    if lib.drk_vanilla_layer_bwd_workspace_bytes(f, graph.num_graphs) > (1 << 28):  # one gradient partial per graph: batches of many thousand tiny graphs
+        return False
+    return bool(lib.drk_vanilla_layer_supported(f, fe, int(graph.max_graph_nodes)))
 
 
 def _rows16(t: torch.Tensor) -> torch.Tensor:

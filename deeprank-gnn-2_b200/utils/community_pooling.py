@@ -63,13 +63,16 @@ def get_preloaded_cluster(cluster, batch, num_graphs: int | None = None):
 _STATUS: dict = {}
 
 
-def _note_status(status: torch.Tensor) -> None:
-    """OR a kernel's status word into the device's accumulator (no host sync); ``check_status`` reads it once per pass."""
-    acc = _STATUS.get(status.device)
+def _status_word(dev) -> torch.Tensor:
+    """ONE status word per device: every pooling kernel ORs its data-dependent faults into it (no fill launch per call, no host sync);
+    ``check_status`` reads and clears it once per pass."""
+    dev = torch.device(dev)
+    if dev.index is None:
+        dev = torch.device(dev.type, torch.cuda.current_device())
+    acc = _STATUS.get(dev)
     if acc is None:
-        _STATUS[status.device] = status.clone()
-    else:
-        acc.bitwise_or_(status)
+        acc = _STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return acc
 
 
 def check_status(device=None) -> None:
@@ -119,7 +122,7 @@ def _consecutive(src: torch.Tensor, meta: dict | None) -> _Structure:
     src = src.contiguous()
     bound, n_clusters = (int(meta["K"]), int(meta["C"])) if meta is not None else _host_sizes(src)
     dev, n = src.device, int(src.numel())
-    ptr_k, perm, status = ops.segment_index(src, bound)  # nodes grouped by id, stable: ascending node index inside a cluster
+    ptr_k, perm, status = ops.segment_index(src, bound, _status_word(src.device))  # nodes grouped by id, stable: ascending node index inside a cluster
     rank = torch.empty(max(bound, 1), dtype=torch.int64, device=dev)
     ptr_c = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
     last = torch.empty(n_clusters, dtype=torch.int64, device=dev)
@@ -133,7 +136,6 @@ def _consecutive(src: torch.Tensor, meta: dict | None) -> _Structure:
     st.inv = rank[src] if n else torch.empty(0, dtype=torch.int64, device=dev)
     st.last, st.count, st.status, st.n_clusters = last, count, status, n_clusters
     st.plan = ops.SegmentPlan.from_parts(st.inv, ptr_c, perm, n_clusters, status)
-    _note_status(status)
     return st
 
 
@@ -183,11 +185,11 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
         batch32 = batch.to(torch.int32) if batch is not None else torch.zeros(n, dtype=torch.int32, device=dev)
     edge_index = edge_index.contiguous()
     key = torch.empty(e, dtype=torch.int64, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    status = _status_word(dev)
     with torch.cuda.device(dev):
         rc = lib.drk_pool_edge_keys(_p(edge_index), e, _p(cluster), n, _p(batch32), _p(cptr), _p(kkptr), n_graphs, n_pairs, _p(key), _p(status), stream_ptr())
     _lib.check(rc, "drk_pool_edge_keys")
-    ptr_k, perm, st2 = ops.segment_index(key, n_pairs + _lib.POOL_JUNK_SEGMENTS)  # edges grouped by pooled pair (the junk segments of the self loops come last)
+    ptr_k, perm, _ = ops.segment_index(key, n_pairs + _lib.POOL_JUNK_SEGMENTS, status)  # edges grouped by pooled pair (the junk segments of the self loops come last)
     ptr_s = torch.empty(n_pooled + 1, dtype=torch.int32, device=dev)
     ids = torch.empty(max(n_pooled, 1), dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
@@ -198,8 +200,6 @@ def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, bat
         _lib.check(rc, "drk_compact_segments")
         rc = lib.drk_pool_edge_decode(_p(ids), n_pooled, _p(count), _p(cptr), _p(kkptr), n_graphs, _p(pooled_index), stream_ptr())
         _lib.check(rc, "drk_pool_edge_decode")
-    _note_status(status)
-    _note_status(st2)
     if edge_attr is None:
         return pooled_index, None
     if n_pooled == 0:

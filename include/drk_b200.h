@@ -197,8 +197,8 @@ DRK_API int drk_edge_msg_bwd_c(const int32_t* rowptr, const int32_t* perm, const
  *   x, s, dout must be 16-byte aligned.  cnt / tf may be NULL in the forward call (inference).
  * Edges that leave their graph raise DRK_STATUS_CROSS_GRAPH, graphs of more than max_graph_nodes nodes DRK_STATUS_INDEX_RANGE.
  * drk_vanilla_layer_supported == 0 -> DRK_EUNSUPPORTED: use the batch-level kernels.
- * backward: dx may be NULL (input without gradient); dbe / dbn may be NULL; gradients are summed per CTA and then in CTA order
- * (deterministic, no atomics); workspace = drk_vanilla_layer_bwd_workspace_bytes. */
+ * backward: dx may be NULL (input without gradient); dbe / dbn may be NULL; the weight gradients are summed per graph and then in graph
+ * order (no atomics: bit-reproducible and independent of `order`); workspace = drk_vanilla_layer_bwd_workspace_bytes (one partial per graph). */
 DRK_API int drk_vanilla_layer_supported(int32_t num_features, int32_t num_edge_features, int32_t max_graph_nodes);
 DRK_API int drk_vanilla_layer_fwd(const float* x, int32_t num_features, const int32_t* rowptr, const int32_t* colidx, const float* attr_slots,
                           int32_t num_edge_features, const int32_t* graph_ptr, const int32_t* order, int32_t num_graphs, int32_t max_graph_nodes,
