@@ -18,6 +18,8 @@ batches) take ONE host round trip to size the outputs -- the reference does ``B`
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib, ops
@@ -61,6 +63,21 @@ def get_preloaded_cluster(cluster, batch, num_graphs: int | None = None):
 
 
 _STATUS: dict = {}
+POOL_BLOCKED = os.environ.get("DRK_POOL_BLOCKED", "1") != "0"  # per-graph pool_edge kernel for collated batches
+
+
+def _pool_blocks(data):
+    """(edge_ptr, pooled_edge_ptr, max clusters, max edges per graph) if ``data`` is a collated batch that still has its own edge list."""
+    d = data.__dict__
+    m = d.get(getattr(data, "_META_KEY", "_meta"), {})
+    pool = m.get("pool")
+    ei = d.get("edge_index")
+    if pool is None or ei is None or m.get("num_edges_total") != int(ei.shape[1]) or m.get("max_graph_edges") is None or not pool.get("max_C0"):
+        return None
+    edge_ptr, pooled_ptr = getattr(data, "_edge_ptr32", None), getattr(data, "_pool_eptr32", None)
+    if edge_ptr is None or pooled_ptr is None or not edge_ptr.is_cuda or not pooled_ptr.is_cuda:
+        return None
+    return edge_ptr, pooled_ptr, int(pool["max_C0"]), int(m["max_graph_edges"])
 
 
 def _status_word(dev) -> torch.Tensor:
@@ -164,15 +181,48 @@ def _host_pool_meta(inv: torch.Tensor, n_clusters: int, edge_index: torch.Tensor
     return {"E": n_pooled, "KK": int(kkptr[-1]), "cptr": torch.from_numpy(cptr).to(dev), "kkptr": torch.from_numpy(kkptr).to(dev)}
 
 
-def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, batch: torch.Tensor | None = None, batch32: torch.Tensor | None = None):
+def _pool_edge_blocked(cluster, edge_index, edge_attr, meta: dict, blocks: tuple):
+    """``pool_edge`` of a collated batch in ONE launch (``drk_pool_edge_blocked``: one CTA per graph, in shared memory)."""
+    lib = _lib.load()
+    dev = cluster.device
+    edge_ptr32, pooled_eptr32, max_clusters, max_edges = blocks
+    n, e, n_pooled = int(cluster.numel()), int(edge_index.shape[1]), int(meta["E"])
+    cptr = meta["cptr"]
+    n_graphs = int(cptr.numel()) - 1
+    edge_index = edge_index.contiguous()
+    pooled_index = torch.empty((2, n_pooled), dtype=torch.int64, device=dev)
+    src = merged = None
+    if edge_attr is not None:
+        if edge_attr.requires_grad:
+            raise NotImplementedError("pool_edge: gradients with respect to edge_attr are not on the DeepRank2 path")
+        src = (edge_attr.unsqueeze(1) if edge_attr.dim() == 1 else edge_attr).contiguous().to(torch.float32)
+        merged = torch.empty((n_pooled, src.shape[1]), dtype=torch.float32, device=dev)
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        rc = lib.drk_pool_edge_blocked(_p(edge_index), e, _p(edge_ptr32), _p(cluster), n, _p(cptr), _p(pooled_eptr32), n_graphs, int(max_clusters), int(max_edges),
+                                       _p(src), int(src.shape[1]) if src is not None else 0, int(src.shape[1]) if src is not None else 0, _p(pooled_index),
+                                       n_pooled, _p(merged), _p(status), stream_ptr())
+    _lib.check(rc, "drk_pool_edge_blocked")
+    if merged is not None and edge_attr.dim() == 1:
+        merged = merged.squeeze(1)
+    return pooled_index, merged
+
+
+def pool_edge(cluster, edge_index, edge_attr=None, meta: dict | None = None, batch: torch.Tensor | None = None, batch32: torch.Tensor | None = None,
+              blocks: tuple | None = None):
     """PyG ``pool_edge(reduce='sum')``: relabel by cluster, drop self loops, sort by (row, col), merge duplicates and
     sum their attributes.  The result is row-major sorted.  ``cluster`` is the CONSECUTIVE relabelling (``inv``); ``meta`` carries the
-    collate's sizes (``E`` pooled edges, ``KK`` dense pair ids, ``cptr`` / ``kkptr`` per-graph offsets)."""
+    collate's sizes (``E`` pooled edges, ``KK`` dense pair ids, ``cptr`` / ``kkptr`` per-graph offsets); ``blocks`` =
+    (edge_ptr int32 [G+1], pooled_edge_ptr int32 [G+1], max clusters per graph, max edges per graph) of a collated batch selects the
+    per-graph kernel."""
     lib = _lib.load()
     dev = cluster.device
     n, e = int(cluster.numel()), int(edge_index.shape[1])
     if e == 0:
         return edge_index, edge_attr
+    if (POOL_BLOCKED and blocks is not None and meta is not None and "cptr" in meta and int(meta["E"]) > 0
+            and lib.drk_pool_edge_blocked_supported(int(blocks[2]), int(blocks[3]))):
+        return _pool_edge_blocked(cluster, edge_index, edge_attr, meta, blocks)
     if meta is None or "cptr" not in meta:
         n_clusters = int(cluster.max()) + 1 if n else 0
         meta = _host_pool_meta(cluster, n_clusters, edge_index, batch)
@@ -249,7 +299,7 @@ def community_pooling(cluster, data, meta: dict | None = None, shared: dict | No
     batch = getattr(data, "batch", None)
     gi = data.__dict__.get("_graph_index")
     batch32 = gi.batch32 if gi is not None and gi.batch32 is not None else None
-    edge_index, edge_attr = pool_edge(inv, data.edge_index, data.edge_attr, meta=meta, batch=batch, batch32=batch32)
+    edge_index, edge_attr = pool_edge(inv, data.edge_index, data.edge_attr, meta=meta, batch=batch, batch32=batch32, blocks=_pool_blocks(data))
     pos = ops.scatter_mean(data.pos, inv, dim=0, plan=plan) if getattr(data, "pos", None) is not None else None
     c0, c1 = getattr(data, "cluster0", None), getattr(data, "cluster1", None)
     if batch is not None:

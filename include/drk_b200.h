@@ -384,6 +384,17 @@ DRK_API int drk_pool_edge_keys(const int64_t* edge_index, int64_t num_edges, con
                        void* stream);
 DRK_API int drk_pool_edge_decode(const int32_t* ids, int32_t capacity, const int32_t* count, const int64_t* cluster_ptr, const int64_t* pair_ptr,
                          int32_t num_graphs, int64_t* edge_index_out, void* stream);
+/* drk_pool_edge_blocked: the whole pool_edge of a COLLATED batch in one launch, one CTA per graph in shared memory (edge_ptr int32 [G+1]:
+ *   the edges of a graph are one slice of edge_index; pooled_edge_ptr int32 [G+1]: where each graph's pooled edges go -- the collate
+ *   counts them per graph).  Same outputs as the chain above: pooled_index int64 [2, num_pooled] sorted by (row, col), pooled_attr
+ *   [num_pooled, Fe] = attributes of merged edges added in ascending edge id (NULL: no attributes).  A graph whose clustering yields
+ *   another number of pooled edges than pooled_edge_ptr says raises DRK_STATUS_INDEX_RANGE, an edge between graphs DRK_STATUS_CROSS_GRAPH.
+ *   drk_pool_edge_blocked_supported == 0 (more than 255 clusters per graph, or lists that do not fit a CTA) -> use the chain above. */
+DRK_API int drk_pool_edge_blocked_supported(int32_t max_graph_clusters, int32_t max_graph_edges);
+DRK_API int drk_pool_edge_blocked(const int64_t* edge_index, int64_t num_edges, const int32_t* edge_ptr, const int64_t* inv, int32_t num_nodes,
+                          const int64_t* cluster_ptr, const int32_t* pooled_edge_ptr, int32_t num_graphs, int32_t max_graph_clusters,
+                          int32_t max_graph_edges, const float* edge_attr, int64_t ld_attr, int32_t num_edge_features, int64_t* pooled_index,
+                          int64_t num_pooled, float* pooled_attr, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------ GINet attention with a segment softmax per destination
  * The operator the reference's GINetConvLayer sets up (ginet.py:45-52: logit = leaky_relu(fc_attention([fc(x)[row], fc(x)[col],

@@ -220,3 +220,77 @@ def test_clustered_train_step_replays_from_a_cuda_graph(net_name):
     assert losses_g[1:] == losses_e[1:], (losses_g, losses_e)
     for (k, p), q in zip(net_e.named_parameters(), net_g.parameters()):
         assert torch.equal(p, q), k
+
+
+@pytest.mark.parametrize("num_segments,density,slack", [(0, 0.5, 3), (1, 1.0, 0), (4096, 0.3, 0), (4097, 0.9, 5), (50_000, 0.05, 0), (370_001, 0.25, 17), (20_000, 0.6, -40)])
+def test_compact_segments_multi_chunk_scan_vs_numpy(num_segments, density, slack):
+    """``drk_compact_segments`` (two launches over chunks of 4096 segment sizes) against numpy: rank, compact offsets, kept ids, last member,
+    count, trailing capacity filled with the total, and the status flag when the capacity is too small (slack < 0)."""
+    import numpy as np
+
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.graph import stream_ptr, workspace
+
+    lib = _lib.load()
+    rng = np.random.default_rng(num_segments + 1)
+    sizes = (rng.random(num_segments) < density) * rng.integers(1, 4, size=num_segments)
+    ptr = np.zeros(num_segments + 1, dtype=np.int32)
+    np.cumsum(sizes, out=ptr[1:])
+    total = int(ptr[-1])
+    perm = rng.permutation(max(total, 1)).astype(np.int32)
+    kept = np.flatnonzero(sizes > 0)
+    cap = max(len(kept) + slack, 0)
+    dev = torch.device("cuda")
+    t_ptr, t_perm = torch.from_numpy(ptr).to(dev), torch.from_numpy(perm).to(dev)
+    rank = torch.full((max(num_segments, 1),), -7, dtype=torch.int64, device=dev)
+    ptr_out = torch.full((cap + 1,), -7, dtype=torch.int32, device=dev)
+    ids = torch.full((max(cap, 1),), -7, dtype=torch.int32, device=dev)
+    last = torch.full((max(cap, 1),), -7, dtype=torch.int64, device=dev)
+    count = torch.full((1,), -7, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace(lib.drk_compact_segments_workspace_bytes(num_segments), dev)
+    rc = lib.drk_compact_segments(t_ptr.data_ptr(), num_segments, t_perm.data_ptr(), rank.data_ptr(), ptr_out.data_ptr(), ids.data_ptr(), last.data_ptr(), cap,
+                                  count.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr())
+    _lib.check(rc, "drk_compact_segments")
+    assert int(count.item()) == len(kept)
+    assert bool(int(status.item()) & _lib.STATUS_INDEX_RANGE) == (len(kept) > cap)
+    want_rank = np.full(num_segments, -1, dtype=np.int64)
+    want_rank[kept] = np.arange(len(kept))
+    assert np.array_equal(rank.cpu().numpy()[:num_segments], want_rank)
+    m = min(len(kept), cap)
+    assert np.array_equal(ptr_out.cpu().numpy()[:m], ptr[kept[:m]])
+    assert np.all(ptr_out.cpu().numpy()[m:] == total)
+    assert np.array_equal(ids.cpu().numpy()[:m], kept[:m].astype(np.int32))
+    assert np.array_equal(last.cpu().numpy()[:m], perm[ptr[kept[:m] + 1] - 1].astype(np.int64))
+
+
+@pytest.mark.parametrize("n_graphs,fe", [(5, 1), (12, 3)])
+def test_per_graph_pool_edge_equals_the_global_route(n_graphs, fe, monkeypatch):
+    """``drk_pool_edge_blocked`` (one CTA per graph, shared memory) against the global chain (dense pair ids -> counting sort ->
+    compaction -> decode -> segmented sum): same pooled edge_index bit for bit, same merged attributes (both add in ascending edge
+    id; the global route's segmented sum splits long lists over lanes, hence a tolerance), and against PyG's pool_edge on the CPU."""
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.synthetic import make_batch
+    from deeprank2_b200.utils import community_pooling as cp
+
+    host = make_batch(n_graphs, first=40, n_edge_features=fe, with_clusters=True)
+    outs = []
+    for blocked in (True, False):
+        monkeypatch.setattr(cp, "POOL_BLOCKED", blocked)
+        b = host.clone().to(DEV)
+        assert (cp._pool_blocks(b) is not None)
+        c0 = cp.get_preloaded_cluster(b.cluster0.clone(), b.batch, host.num_graphs)
+        before = _lib.launch_count()
+        pooled = cp.community_pooling(c0, b)
+        outs.append((pooled.edge_index.clone(), pooled.edge_attr.clone(), pooled.x.clone(), _lib.launch_count() - before))
+        cp.check_status(DEV)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
+    assert_close(outs[0][1], outs[1][1], "merged attributes, per-graph kernel vs global route")
+    assert outs[0][3] < outs[1][3] - 8, "the per-graph kernel replaces the ten launches of the global chain"
+    rc0 = host.cluster0.clone()
+    for g in range(1, host.num_graphs):
+        rc0[host.batch == g] += rc0[host.batch == g - 1].max() + 1
+    inv, _ = tp.consecutive_cluster(rc0)
+    r_ei, r_ea = tp.pool_edge(inv, host.edge_index, host.edge_attr)
+    assert_equal_int(outs[0][0], r_ei, "pooled edge_index")
+    assert_close(outs[0][1], r_ea, "pooled edge_attr")
