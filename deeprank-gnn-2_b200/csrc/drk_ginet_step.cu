@@ -1675,7 +1675,7 @@ __global__ void __launch_bounds__(kTI, 2) k_index_blocked(const BlockedIndexArgs
     // edges dropped as malformed leave a gap at the end of the graph's slice: keep the arrays well defined
     for (int i = (int)carry_r + tid; i < ne; i += kTI) {
       a.colidx[e0 + i] = node0;
-      a.perm[e0 + i] = e0 + i;
+      if (a.perm != nullptr) a.perm[e0 + i] = e0 + i;
     }
     if (want_csc)
       for (int i = (int)carry_c + tid; i < ne; i += kTI) {
@@ -1699,7 +1699,7 @@ __global__ void __launch_bounds__(kTI, 2) k_index_blocked(const BlockedIndexArgs
         base_r = my_r[r];
         const int pos = e0 + (int)start_r[r] + base_r + __popc(mr & lt);
         a.colidx[pos] = node0 + (int)c;
-        a.perm[pos] = e0 + i;
+        if (a.perm != nullptr) a.perm[pos] = e0 + i;  // NULL: the caller only aggregates (inference without edge attributes)
         base_c = my_c[c];
         if (want_csc) {
           const int posc = e0 + (int)start_c[c] + base_c + __popc(mc & lt);
@@ -1807,7 +1807,7 @@ __global__ void __launch_bounds__(kTI, 1) k_index_blocked_large(const BlockedInd
       if (last) {
         for (int i = (int)carry + tid; i < ne; i += kTI) {  // dropped edges leave a gap at the end of the slice: keep the arrays well defined
           out_idx[e0 + i] = node0;
-          out_perm[e0 + i] = e0 + i;
+          if (out_perm != nullptr) out_perm[e0 + i] = e0 + i;
         }
         if (g == a.num_graphs - 1 && tid == 0) out_ptr[a.num_nodes] = (int)a.num_edges;
       }
@@ -1833,7 +1833,7 @@ __global__ void __launch_bounds__(kTI, 1) k_index_blocked_large(const BlockedInd
             base = mine[k - lo];
             const int pos = e0 + (int)start[k - lo] + base + __popc(m & lt);
             out_idx[pos] = node0 + (int)o;
-            out_perm[pos] = e0 + i;
+            if (out_perm != nullptr) out_perm[pos] = e0 + i;  // half of the sweep's scattered stores
           }
           __syncwarp();
           if (in && (m & lt) == 0u) mine[k - lo] = (uint16_t)(base + __popc(m));
@@ -2098,8 +2098,9 @@ int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, 
   DRK_REQUIRE(num_graphs >= 0 && num_edges >= 0 && num_nodes >= 0, DRK_EINVAL, "blocked index: negative size");
   DRK_REQUIRE(drk_graph_index_blocked_supported(max_graph_nodes, max_graph_edges), DRK_EUNSUPPORTED,
               "blocked index: graphs of %d nodes / %d edges do not fit shared memory", max_graph_nodes, max_graph_edges);
-  DRK_REQUIRE(graph_ptr && edge_ptr && rowptr && colidx && perm && status && (edge_index || num_edges == 0), DRK_EINVAL, "blocked index: null pointer");
+  DRK_REQUIRE(graph_ptr && edge_ptr && rowptr && colidx && status && (edge_index || num_edges == 0), DRK_EINVAL, "blocked index: null pointer");
   DRK_REQUIRE((colptr == nullptr) == (rowidx == nullptr) && (colptr == nullptr) == (permT == nullptr), DRK_EINVAL, "blocked index: CSC outputs come together");
+  DRK_REQUIRE(perm != nullptr || colptr == nullptr, DRK_EINVAL, "blocked index: perm may only be omitted together with the CSC half");
   DRK_REQUIRE(num_graphs > 0 || num_nodes == 0, DRK_EINVAL, "blocked index: nodes without graphs");
   if (num_graphs == 0) {
     cudaMemsetAsync(rowptr, 0, sizeof(int32_t), as_stream(stream));

@@ -56,10 +56,12 @@ class GraphIndex:
     # ------------------------------------------------------------------ construction
     @classmethod
     def build(cls, edge_index: torch.Tensor, num_nodes: int, batch: torch.Tensor | None = None, num_graphs: int | None = None, with_csc: bool = True,
-              blocks: tuple | None = None) -> "GraphIndex":
+              blocks: tuple | None = None, with_perm: bool = True) -> "GraphIndex":
         """``blocks`` = (node_ptr int32 [B+1], edge_ptr int32 [B+1], max_graph_nodes, max_graph_edges) of a collated batch (the edges
         of a graph are one contiguous slice of ``edge_index``): the index is then built per graph in shared memory
-        (``drk_graph_index_build_blocked``, ~10x faster than the global sort, bit-identical result)."""
+        (``drk_graph_index_build_blocked``, ~10x faster than the global sort, bit-identical result).  ``with_perm=False`` (only
+        honoured by the per-graph builder, and only without the CSC half): ``perm`` -- the original edge id of every CSR slot -- is not
+        written and ``gi.perm`` is None; for callers that only aggregate node rows (inference without edge attributes)."""
         lib = _lib.load()
         _require_cuda(edge_index, "edge_index")
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -107,10 +109,12 @@ class GraphIndex:
             and bool(lib.drk_graph_index_blocked_supported(int(blocks[2]), int(blocks[3])))
         )
         if use_blocks:
+            if not with_perm and not with_csc:
+                gi.perm = None
             with torch.cuda.device(dev):
                 rc = lib.drk_graph_index_build_blocked(
                     edge_index.data_ptr(), e, n, blocks[0].data_ptr(), blocks[1].data_ptr(), b, int(blocks[2]), int(blocks[3]),
-                    gi.rowptr.data_ptr(), gi.colidx.data_ptr(), gi.perm.data_ptr(),
+                    gi.rowptr.data_ptr(), gi.colidx.data_ptr(), gi.perm.data_ptr() if gi.perm is not None else None,
                     gi.colptr.data_ptr() if with_csc else None, gi.rowidx.data_ptr() if with_csc else None, gi.permT.data_ptr() if with_csc else None,
                     gi.status.data_ptr(), stream_ptr(),
                 )
@@ -175,12 +179,12 @@ class GraphIndex:
             raise ValueError("batch vector is not sorted: graphs of a Batch must occupy consecutive node ranges")
 
 
-def graph_index(data, with_csc: bool = True) -> GraphIndex:
+def graph_index(data, with_csc: bool = True, with_perm: bool = True) -> GraphIndex:
     """The (cached) :class:`GraphIndex` of a ``Batch``/``Data`` living on the GPU."""
     ei = data.edge_index
     key = (ei.data_ptr(), ei._version, tuple(ei.shape), str(ei.device), bool(with_csc))
     cached = data.__dict__.get("_graph_index")
-    if cached is not None and cached._key[:4] == key[:4] and (cached.colptr is not None or not with_csc):
+    if cached is not None and cached._key[:4] == key[:4] and (cached.colptr is not None or not with_csc) and (cached.perm is not None or not with_perm):
         return cached
     batch = getattr(data, "batch", None)
     ptr = data.__dict__.get("ptr")
@@ -194,7 +198,7 @@ def graph_index(data, with_csc: bool = True) -> GraphIndex:
     if (node_ptr is not None and edge_ptr is not None and batch is not None and meta.get("num_edges_total") == int(ei.shape[1])
             and meta.get("max_graph_nodes") is not None and meta.get("max_graph_edges") is not None):
         blocks = (node_ptr, edge_ptr, meta["max_graph_nodes"], meta["max_graph_edges"])
-    gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc, blocks=blocks)
+    gi = GraphIndex.build(ei, data.num_nodes, batch=batch, num_graphs=num_graphs, with_csc=with_csc, blocks=blocks, with_perm=with_perm or with_csc)
     gi._key = key
     gi.max_graph_nodes = meta.get("max_graph_nodes")  # known on the host for collated batches: lets the aggregation pick the tiled kernel
     # issue order of the per-graph kernels (largest graphs first, data.py:snake_order); only meaningful for the batch it was made for

@@ -55,7 +55,8 @@ class GINet(nn.Module):
             if data.x.is_cuda and _fused.step_supported(self, data):
                 return _fused.ginet_infer(self, data)  # inference: the whole forward pass as one per-graph kernel
         # CSR/CSC + graph offsets, built once on the device and shared by all layers; the CSC half only serves the backward pass
-        g = graph_index(data, with_csc=torch.is_grad_enabled())
+        # (and `perm`, the edge id of every CSR slot, only a pass that reads edge attributes: the reference-mode convolutions do not)
+        g = graph_index(data, with_csc=torch.is_grad_enabled(), with_perm=torch.is_grad_enabled() or not self._stackable())
         # the reference deep-copies the batch (data.clone(), :86) and overwrites data.x in place (:90,:93);
         # neither has a numerical effect, so no copy is made here.
         if self._stackable():

@@ -255,7 +255,8 @@ DRK_API int drk_ginet_fused_bwd(const float* x, int64_t ldx, int32_t num_node_fe
  * same bit-exact, stable CSR / CSC as drk_graph_index_build inside shared memory (per-warp histograms, ordered placement;
  * no atomics, no global sort).  drk_edge_ptr derives edge_ptr from edge_index + graph_ptr when collate did not keep it.
  * An edge whose endpoints leave its graph sets DRK_STATUS_CROSS_GRAPH (the caller falls back to drk_graph_index_build).
- * colptr/rowidx/permT may be NULL together (no CSC). */
+ * colptr/rowidx/permT may be NULL together (no CSC); without them perm may be NULL too (a caller that only aggregates -- inference
+ * without edge attributes -- skips half of the placement sweep's scattered stores). */
 DRK_API int drk_edge_ptr(const int64_t* edge_index, int64_t num_edges, const int32_t* graph_ptr, int32_t num_graphs,
                  int32_t* edge_ptr, void* stream);
 DRK_API int drk_graph_index_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_edges);

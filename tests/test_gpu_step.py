@@ -525,3 +525,18 @@ def test_captured_selection_step_equals_eager_selection_steps():
         outs.append((losses, torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()))
     assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6)
     assert float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-7
+
+
+def test_blocked_index_without_perm_gives_the_same_csr():
+    """Inference without edge attributes skips `perm` (the edge id of every CSR slot): rowptr / colidx must not change, for the
+    residue-level kernel and for the atom-level one (no edge stash)."""
+    from deeprank2_b200.graph import graph_index
+    from deeprank2_b200.synthetic import ATOM, make_batch
+
+    for kwargs in (dict(n_graphs=6), dict(n_graphs=2, first=50, n_node_features=38, n_edge_features=1, level=ATOM)):
+        host = make_batch(**kwargs)
+        full = graph_index(host.clone().to(DEV), with_csc=False)
+        lean = graph_index(host.clone().to(DEV), with_csc=False, with_perm=False)
+        assert full.perm is not None and lean.perm is None
+        assert torch.equal(full.rowptr, lean.rowptr) and torch.equal(full.colidx, lean.colidx)
+        assert int(lean.status.item()) == 0
