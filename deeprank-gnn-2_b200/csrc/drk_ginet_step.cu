@@ -19,6 +19,8 @@
 //
 // Graphs that do not fit (nodes, edges or features beyond the shared-memory plan) make the wrapper return
 // DRK_EUNSUPPORTED; the host then runs the layer kernels (same results, more launches).
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -1844,6 +1846,141 @@ __global__ void __launch_bounds__(kTI, 1) k_index_blocked_large(const BlockedInd
   }
 }
 
+// The large-graph index with a graph shared by a CLUSTER of two CTAs, each taking one half of the graph's EDGES (not of its keys: every
+// CTA matches only its own edges).  A batch of atom-level graphs has fewer graphs than the GPU has SMs (C3: 64 graphs, 148 SMs), so the
+// one-CTA-per-graph kernel leaves more than half of the SMs idle.  Both CTAs histogram their warp chunks in their own shared memory,
+// publish their per-key totals, read the partner's totals through distributed shared memory, and place their edges at
+// segment start (+ the first half's total for the second CTA) + offset of the warp chunk + MATCH rank: the same stable order.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTI, 1) k_index_blocked_pair(const BlockedIndexArgs a, int range_cap) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  unsigned char* smem = g_smem;
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(smem);                       // [kNWI][range_cap]
+  uint32_t* start = reinterpret_cast<uint32_t*>(cnt + kNWI * range_cap);   // [range_cap]
+  uint32_t* tot = start + range_cap;                                       // [range_cap] this CTA's edges per key (read by the partner)
+  uint32_t* scan = tot + range_cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = lanemask_lt();
+  const int rank = (int)cluster.block_rank();
+  const uint32_t* tot_other = cluster.map_shared_rank(tot, rank ^ 1);
+  const int n_keys = a.colptr != nullptr ? 2 : 1;
+  const int n_clusters = gridDim.x >> 1;
+  for (int g = blockIdx.x >> 1; g < a.num_graphs; g += n_clusters) {
+    const int node0 = __ldg(a.graph_ptr + g);
+    const int n = __ldg(a.graph_ptr + g + 1) - node0;
+    const int e0 = __ldg(a.edge_ptr + g);
+    const int ne = __ldg(a.edge_ptr + g + 1) - e0;
+    const int half = ((ne + 1) / 2 + 31) & ~31;
+    const int hb = min(ne, rank * half), he = min(ne, hb + half);  // this CTA's edges
+    const int chunk = ((he - hb + kNWI - 1) / kNWI + 31) & ~31;
+    if (n > range_cap || n < 0 || ne < 0 || ((half + kNWI - 1) / kNWI + 32) > 65535) {  // (a warp chunk's counters are 16 bit); uniform over the cluster
+      if (tid == 0 && rank == 0) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+      continue;
+    }
+    const int wb = min(he, hb + warp * chunk), we = min(he, wb + chunk);
+    for (int key = 0; key < n_keys; ++key) {
+      const int64_t* kptr = key == 0 ? a.erow : a.ecol;
+      const int64_t* optr = key == 0 ? a.ecol : a.erow;
+      int32_t* out_ptr = key == 0 ? a.rowptr : a.colptr;
+      int32_t* out_idx = key == 0 ? a.colidx : a.rowidx;
+      int32_t* out_perm = key == 0 ? a.perm : a.permT;
+      cluster.sync();  // the partner has read this CTA's totals of the previous round
+      {
+        uint32_t* z = reinterpret_cast<uint32_t*>(cnt);
+        for (int i = tid; i < kNWI * range_cap / 2; i += kTI) z[i] = 0u;
+      }
+      __syncthreads();
+      uint16_t* mine = cnt + warp * range_cap;
+      bool bad = false;
+      for (int i0 = wb; i0 < we; i0 += 256) {
+        long long kk[8], oo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          kk[u] = i < we ? ld_stream_i64(kptr + e0 + i) : 0;
+          oo[u] = i < we ? ld_stream_i64(optr + e0 + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i0 + u * 32 >= we) break;  // warp-uniform
+          const unsigned long long k = (unsigned long long)(kk[u] - node0), o = (unsigned long long)(oo[u] - node0);
+          const bool ok = i < we && k < (unsigned long long)n && o < (unsigned long long)n;
+          bad |= i < we && !ok;
+          const unsigned m = __match_any_sync(kFull, ok ? (unsigned)k : 0x10000u + lane);
+          if (ok && (m & lt) == 0u) mine[k] = (uint16_t)(mine[k] + __popc(m));
+          __syncwarp();
+        }
+      }
+      if (bad && key == 0) atomicOr(a.status, DRK_STATUS_CROSS_GRAPH);
+      __syncthreads();
+      // this CTA's edges per key; the chunk counters become offsets inside the CTA's share of the segment
+      for (int v = tid; v < n; v += kTI) {
+        uint32_t d = 0;
+        for (int w = 0; w < kNWI; ++w) {
+          const uint32_t t = cnt[w * range_cap + v];
+          cnt[w * range_cap + v] = (uint16_t)d;
+          d += t;
+        }
+        tot[v] = d;
+      }
+      cluster.sync();  // both CTAs' totals are published
+      uint32_t carry = 0;
+      for (int vb = 0; vb < n; vb += kTI) {
+        const int v = vb + tid;
+        uint32_t own = 0, other = 0;
+        if (v < n) {
+          own = tot[v];
+          other = tot_other[v];
+        }
+        uint32_t total;
+        const uint32_t ex = block_excl_scan<kNWI>(own + other, scan, total) + carry;
+        if (v < n) {
+          start[v] = ex + (rank == 1 ? other : 0u);  // the first half's edges of a key come first
+          if (rank == 0) out_ptr[node0 + v] = e0 + (int)ex;
+        }
+        carry += total;
+      }
+      if (rank == 0) {
+        for (int i = (int)carry + tid; i < ne; i += kTI) {  // dropped edges leave a gap at the end of the slice: keep the arrays well defined
+          out_idx[e0 + i] = node0;
+          if (out_perm != nullptr) out_perm[e0 + i] = e0 + i;
+        }
+        if (g == a.num_graphs - 1 && tid == 0) out_ptr[a.num_nodes] = (int)a.num_edges;
+      }
+      __syncthreads();
+      for (int i0 = wb; i0 < we; i0 += 256) {
+        long long kk[8], oo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          kk[u] = i < we ? ld_stream_i64(kptr + e0 + i) : 0;
+          oo[u] = i < we ? ld_stream_i64(optr + e0 + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i0 + u * 32 >= we) break;  // warp-uniform
+          const unsigned long long k = (unsigned long long)(kk[u] - node0), o = (unsigned long long)(oo[u] - node0);
+          const bool in = i < we && k < (unsigned long long)n && o < (unsigned long long)n;
+          const unsigned m = __match_any_sync(kFull, in ? (unsigned)k : 0x10000u + lane);
+          int base = 0;
+          if (in) {
+            base = mine[k];
+            const int pos = e0 + (int)start[k] + base + __popc(m & lt);
+            out_idx[pos] = node0 + (int)o;
+            if (out_perm != nullptr) out_perm[pos] = e0 + i;
+          }
+          __syncwarp();
+          if (in && (m & lt) == 0u) mine[k] = (uint16_t)(base + __popc(m));
+          __syncwarp();
+        }
+      }
+    }
+  }
+  cluster.sync();  // a CTA's shared memory stays alive until its partner has read the last totals
+}
+
 // edge_ptr[g] = first edge whose destination is >= graph_ptr[g] (binary search; valid when the edges of a collated batch are
 // grouped by graph, which the per-graph kernels verify edge by edge)
 __global__ void k_edge_ptr(const int64_t* __restrict__ erow, int64_t num_edges, const int32_t* __restrict__ graph_ptr, int num_graphs,
@@ -2118,6 +2255,18 @@ int drk_graph_index_build_blocked(const int64_t* edge_index, int64_t num_edges, 
     // One CTA per graph.  (Key-range splitting over several CTAs is implemented -- `splits` -- but every CTA still has to MATCH all the
     // edges: measured 0.58 vs 0.31 ms for the C3 inference pass.  What bounds the kernel is the scattered 4-byte stores of the placement
     // sweep, ~1 sector per clock per SM: 119 us for 64 graphs of 60 k edges.)
+    const char* pair_env = std::getenv("DRK_INDEX_PAIR");  // "0": one CTA per graph even for few graphs (tests exercise both kernels)
+    if (num_graphs * 2 <= kNumSM + 20 && !(pair_env != nullptr && pair_env[0] == '0')) {  // few large graphs: a cluster of two CTAs per graph, half of the edges each
+      const int cap = (a.rows_cap + 7) / 8 * 8;
+      const size_t smem_pair = (size_t)kNWI * cap * 2 + (size_t)2 * cap * 4 + 512;
+      if (smem_pair <= kSmemBudget) {
+        cudaError_t ep = cudaFuncSetAttribute(k_index_blocked_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair);
+        DRK_REQUIRE(ep == cudaSuccess, DRK_ECUDA, "blocked index: smem opt-in: %s", cudaGetErrorString(ep));
+        const int clusters = std::min(num_graphs, kNumSM / 2);
+        k_index_blocked_pair<<<2 * clusters, kTI, smem_pair, as_stream(stream)>>>(a, cap);
+        return finish_launch("blocked index (large graphs, CTA pairs)");
+      }
+    }
     const int splits = 1;
     const int range_cap = (ceil_div(a.rows_cap, splits) + 7) / 8 * 8;
     const size_t smem_large = (size_t)kNWI * range_cap * 2 + (size_t)range_cap * 4 + 512;

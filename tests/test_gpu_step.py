@@ -92,12 +92,16 @@ def test_blocked_index_full_c2_batch_matches_global_build():
     assert_equal_int(info.node_ptr, ref.graph_ptr, "node offsets")
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
 @pytest.mark.parametrize("with_csc", [False, True])
-def test_blocked_index_of_atom_level_graphs_matches_global_build(with_csc):
+def test_blocked_index_of_atom_level_graphs_matches_global_build(with_csc, pair, monkeypatch):
     """Graphs of ~3 k nodes / ~60 k directed edges: the edge slice does not fit shared memory, so the per-graph builder streams the
-    edges twice and handles one key at a time (k_index_blocked_large) -- bit for bit the global counting sort, with a malformed edge
-    dropped from both orders and flagged."""
+    edges twice and handles one key at a time -- one CTA per graph (k_index_blocked_large, DRK_INDEX_PAIR=0 or many graphs) or a
+    cluster of two CTAs per graph, half of the edges each (k_index_blocked_pair, batches of few graphs) -- bit for bit the global
+    counting sort, with a malformed edge dropped from both orders and flagged."""
     from deeprank2_b200 import _lib
+
+    monkeypatch.setenv("DRK_INDEX_PAIR", pair)
     from deeprank2_b200.graph import GraphIndex, graph_index
     from deeprank2_b200.synthetic import ATOM, make_batch
 
