@@ -78,6 +78,8 @@ SIGNATURES = {
     "drk_compact_segments": (c_int32, [_P, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, c_size_t, _P]),
     "drk_pool_edge_keys": (c_int32, [_P, _I64, _P, _I32, _P, _P, _P, _I32, _I64, _P, _P, _P]),
     "drk_pool_edge_decode": (c_int32, [_P, _I32, _P, _P, _P, _I32, _P, _P]),
+    "drk_consecutive_blocked_supported": (c_int32, [_I32, _I32]),
+    "drk_consecutive_blocked": (c_int32, [_P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "drk_pool_edge_blocked_supported": (c_int32, [_I32, _I32]),
     "drk_pool_edge_blocked": (c_int32, [_P, _I64, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P, _I64, _I32, _P, _I64, _P, _P, _P]),
     "drk_edge_msg_fwd": (c_int32, [_P, _P, _P, _P, _I64, _P, _I64, _I32, _P, _I64, _P, _I64, _P, _P, _I32, _P]),

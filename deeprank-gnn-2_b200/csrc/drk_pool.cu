@@ -209,7 +209,7 @@ struct PoolBlockedArgs {
   int64_t* out_col;                // [E1]
   float* out_attr;                 // [E1, fe] or NULL
   int32_t* status;
-  int64_t ld_attr;
+  int64_t ld_attr, num_pooled;  // num_pooled = rows the caller allocated
   int32_t num_nodes, fe, cap_clusters, cap_edges;
 };
 
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kPT) k_pool_edge_blocked(const PoolBlockedArgs
     carry_p += tot_p;
   }
   if (tid == 0) s_start[kk] = carry_e;
-  const bool miscount = carry_p != want;  // the collate's count of distinct pooled edges does not hold for this clustering
+  const bool miscount = carry_p != want || (int64_t)o0 + want > a.num_pooled;  // the collate's count of distinct pooled edges does not hold
   __syncthreads();
   for (int e = tid; e < ne; e += kPT) {
     const unsigned short key = s_key[e];
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kPT) k_pool_edge_blocked(const PoolBlockedArgs
   __syncthreads();
   for (int k = tid; k < kk; k += kPT) {
     const int pid = s_pid[k];
-    if (pid < 0 || pid >= want) continue;
+    if (pid < 0 || pid >= want || (int64_t)o0 + pid >= a.num_pooled) continue;
     const int lo = s_start[k], hi = s_start[k + 1];
     for (int i = lo + 1; i < hi; ++i) {  // the atomics dropped the members in arbitrary order: ascending edge id (short lists)
       const int v = s_mem[i];
@@ -335,6 +335,133 @@ __global__ void __launch_bounds__(kPT) k_pool_edge_blocked(const PoolBlockedArgs
   if (a.status != nullptr) {
     if (bad) atomicOr(a.status, DRK_STATUS_CROSS_GRAPH);
     if (miscount && tid == 0) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// consecutive_cluster for collated batches, one CTA per graph: the ids of a graph's nodes (globally unique after get_preloaded_cluster,
+// i.e. a contiguous range per graph) are relabelled 0..C_g-1 in ascending id order and offset by the graph's first new id, which the
+// collate knows (cluster_ptr).  One launch instead of the eight of drk_segment_index_build + drk_compact_segments + the rank gather:
+//   inv [N]        new id of every node                      (PyG: the `inverse` of torch.unique)
+//   last [C]       largest node index of every cluster       (PyG's `perm` on CPU: last writer wins)
+//   ptr_c [C + 1], perm [N]   nodes grouped by new id, ascending node index inside a cluster (the segment plan of scatter_max / _mean)
+constexpr int kCBT = 256;
+
+struct ConsecutiveArgs {
+  const int64_t* cluster;   // [N]
+  const int32_t* node_ptr;  // [G + 1]
+  const int64_t* cptr;      // [G + 1] first new id of every graph
+  int64_t* inv;
+  int64_t* last;
+  int32_t* ptr_c;
+  int32_t* perm;
+  int32_t* status;
+  int32_t num_graphs, num_nodes, cap_nodes, cap_ids, capacity;  // capacity = clusters the caller allocated
+};
+
+__global__ void __launch_bounds__(kCBT) k_consecutive_blocked(const ConsecutiveArgs a) {
+  extern __shared__ __align__(16) unsigned char pool_smem[];
+  __shared__ long long s_min[kCBT / 32];
+  __shared__ int s_scan[kCBT / 32 + 1];
+  int* s_cnt = reinterpret_cast<int*>(pool_smem);  // [cap_ids] nodes per old id, then the first perm slot of the id
+  int* s_rank = s_cnt + a.cap_ids;                 // [cap_ids] new (graph-local) id, -1 for absent ids
+  int* s_key = s_rank + a.cap_ids;                 // [cap_nodes] old id - smallest id of the graph
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int node0 = __ldg(a.node_ptr + g), n = __ldg(a.node_ptr + g + 1) - node0;
+  const int64_t c0 = __ldg(a.cptr + g);
+  const int want = (int)(__ldg(a.cptr + g + 1) - c0);
+  if (g == a.num_graphs - 1 && tid == 0) {
+    const int64_t total = __ldg(a.cptr + a.num_graphs);
+    a.ptr_c[min(total, (int64_t)a.capacity)] = a.num_nodes;
+    if (total != a.capacity && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);  // stale sizes
+  }
+  if (n < 0 || n > a.cap_nodes) {
+    if (tid == 0 && a.status != nullptr) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+    return;
+  }
+  if (n == 0) return;
+  long long lo = 0x7fffffffffffffffll;
+  for (int i = tid; i < n; i += kCBT) lo = min(lo, (long long)ld_stream_i64(a.cluster + node0 + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+  if (lane == 0) s_min[warp] = lo;
+  for (int k = tid; k < a.cap_ids; k += kCBT) s_cnt[k] = 0;
+  __syncthreads();
+  lo = s_min[0];
+#pragma unroll
+  for (int w = 1; w < kCBT / 32; ++w) lo = min(lo, s_min[w]);
+  bool bad = false;
+  for (int i = tid; i < n; i += kCBT) {
+    const long long k = (long long)ld_stream_i64(a.cluster + node0 + i) - lo;
+    int key = -1;
+    if (k < a.cap_ids) {
+      key = (int)k;
+      atomicAdd(&s_cnt[key], 1);
+    } else {
+      bad = true;  // the ids of this graph span more than the id bound recorded for the batch
+    }
+    s_key[i] = key;
+    a.perm[node0 + i] = node0 + i;  // a well-defined entry even for nodes a flagged batch leaves without a slot
+  }
+  __syncthreads();
+  // new ids = number of present ids below; perm slots = number of nodes with a smaller id
+  int carry_n = 0, carry_c = 0;
+  for (int base = 0; base < a.cap_ids; base += kCBT) {
+    const int k = base + tid;
+    const int c = k < a.cap_ids ? s_cnt[k] : 0;
+    int incn = c, incc = c > 0 ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tn = __shfl_up_sync(0xffffffffu, incn, o), tc = __shfl_up_sync(0xffffffffu, incc, o);
+      if (lane >= o) {
+        incn += tn;
+        incc += tc;
+      }
+    }
+    if (lane == 31) s_scan[warp] = (incn << 12) | incc;  // n <= cap_nodes < 2^19, ids per tile <= 256
+    __syncthreads();
+    int wn = 0, wc = 0, tn_all = 0, tc_all = 0;
+    for (int w = 0; w < kCBT / 32; ++w) {
+      const int v = s_scan[w];
+      if (w < warp) {
+        wn += v >> 12;
+        wc += v & 0xfff;
+      }
+      tn_all += v >> 12;
+      tc_all += v & 0xfff;
+    }
+    __syncthreads();
+    if (k < a.cap_ids) {
+      s_cnt[k] = carry_n + wn + incn - c;
+      s_rank[k] = c > 0 ? carry_c + wc + incc - 1 : -1;
+    }
+    carry_n += tn_all;
+    carry_c += tc_all;
+  }
+  const bool miscount = carry_c != want;
+  __syncthreads();
+  for (int i = tid; i < n; i += kCBT) {
+    const int key = s_key[i];
+    const int r = key >= 0 ? s_rank[key] : -1;
+    a.inv[node0 + i] = (r >= 0 && r < want && c0 + r < a.capacity) ? c0 + r : min(c0, (int64_t)max(a.capacity - 1, 0));  // (a flagged batch still gets in-range ids)
+  }
+  for (int k = tid; k < a.cap_ids; k += kCBT) {
+    const int r = s_rank[k];
+    if (r < 0) continue;
+    const bool keep = r < want && c0 + r < a.capacity;
+    int pos = node0 + s_cnt[k], last = node0;
+    if (keep) a.ptr_c[c0 + r] = pos;
+    for (int i = 0; i < n; ++i) {  // members in ascending node index (n is a few hundred, the ids a few dozen)
+      if (s_key[i] == k) {
+        a.perm[pos++] = node0 + i;
+        last = node0 + i;
+      }
+    }
+    if (keep) a.last[c0 + r] = last;
+  }
+  if (a.status != nullptr) {
+    if (bad) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);
+    if (miscount && tid == 0) atomicOr(a.status, DRK_STATUS_INDEX_RANGE);  // the collate's count of distinct ids does not hold for this graph
   }
 }
 
@@ -412,12 +539,34 @@ int drk_pool_edge_blocked(const int64_t* edge_index, int64_t num_edges, const in
               "pool edge blocked: null pointer");
   DRK_REQUIRE(pooled_attr == nullptr || edge_attr != nullptr, DRK_EINVAL, "pool edge blocked: pooled_attr needs edge_attr");
   pool::PoolBlockedArgs a{edge_index, edge_index + num_edges, edge_ptr, inv, cluster_ptr, pooled_edge_ptr, edge_attr, pooled_index, pooled_index + num_pooled,
-                          pooled_attr, status, ld_attr, num_nodes, num_edge_features, max_graph_clusters, max_graph_edges};
+                          pooled_attr, status, ld_attr, num_pooled, num_nodes, num_edge_features, max_graph_clusters, max_graph_edges};
   const size_t smem = pool::pool_blocked_smem(max_graph_clusters, max_graph_edges);
   cudaError_t e = cudaFuncSetAttribute(pool::k_pool_edge_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "pool edge blocked: smem opt-in: %s", cudaGetErrorString(e));
   pool::k_pool_edge_blocked<<<num_graphs, pool::kPT, smem, as_stream(stream)>>>(a);
   return finish_launch("pool edge blocked");
+}
+
+int drk_consecutive_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_ids) {
+  if (max_graph_nodes < 1 || max_graph_ids < 1 || max_graph_nodes >= (1 << 19)) return 0;
+  return ((size_t)2 * max_graph_ids + (size_t)max_graph_nodes) * sizeof(int) + 16 <= (size_t)200 * 1024 ? 1 : 0;
+}
+
+int drk_consecutive_blocked(const int64_t* cluster, int32_t num_nodes, const int32_t* node_ptr, const int64_t* cluster_ptr, int32_t num_graphs,
+                            int32_t max_graph_nodes, int32_t max_graph_ids, int32_t capacity, int64_t* inv, int64_t* last, int32_t* ptr_c, int32_t* perm,
+                            int32_t* status, void* stream) {
+  using namespace drk;
+  DRK_REQUIRE(num_nodes >= 0 && num_graphs >= 0 && capacity >= 0, DRK_EINVAL, "consecutive blocked: negative size");
+  if (num_graphs == 0) return DRK_OK;
+  DRK_REQUIRE(drk_consecutive_blocked_supported(max_graph_nodes, max_graph_ids), DRK_EUNSUPPORTED,
+              "consecutive blocked: %d nodes / %d ids per graph do not fit one CTA (use the global route)", max_graph_nodes, max_graph_ids);
+  DRK_REQUIRE(node_ptr && cluster_ptr && inv && last && ptr_c && perm && (cluster || num_nodes == 0), DRK_EINVAL, "consecutive blocked: null pointer");
+  pool::ConsecutiveArgs a{cluster, node_ptr, cluster_ptr, inv, last, ptr_c, perm, status, num_graphs, num_nodes, max_graph_nodes, max_graph_ids, capacity};
+  const size_t smem = ((size_t)2 * max_graph_ids + (size_t)max_graph_nodes) * sizeof(int) + 16;
+  cudaError_t e = cudaFuncSetAttribute(pool::k_consecutive_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "consecutive blocked: smem opt-in: %s", cudaGetErrorString(e));
+  pool::k_consecutive_blocked<<<num_graphs, pool::kCBT, smem, as_stream(stream)>>>(a);
+  return finish_launch("consecutive blocked");
 }
 
 }  // extern "C"

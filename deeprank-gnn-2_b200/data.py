@@ -368,8 +368,12 @@ class Batch(Data):
         self.__dict__["_pool_cptr"] = torch.from_numpy(cptr)
         self.__dict__["_pool_kkptr"] = torch.from_numpy(kkptr)
         self.__dict__["_pool_eptr32"] = torch.from_numpy(eptr.astype(np.int32))  # edges of the pooled graphs: contiguous slices, like _edge_ptr32
+        c1ptr = np.zeros(len(per_graph) + 1, dtype=np.int64)
+        np.cumsum(m[:, 4], out=c1ptr[1:])
+        self.__dict__["_pool_c1ptr"] = torch.from_numpy(c1ptr)  # first level-1 cluster of every graph
         self.__dict__.setdefault(self._META_KEY, {})["pool"] = {"K0": int(m[:, 0].sum()), "C0": int(m[:, 1].sum()), "E1": int(m[:, 2].sum()), "KK": int(kkptr[-1]),
-                                                                 "K1": int(m[:, 3].sum()), "C1": int(m[:, 4].sum()), "max_C0": int(m[:, 1].max()), "max_E1": int(m[:, 2].max())}
+                                                                 "K1": int(m[:, 3].sum()), "C1": int(m[:, 4].sum()), "max_C0": int(m[:, 1].max()), "max_E1": int(m[:, 2].max()),
+                                                                 "max_K0": int(m[:, 0].max()), "max_K1": int(m[:, 3].max())}
 
 
 STEP_CTAS = 148  # CTAs of the per-graph kernels = SMs of a B200 (drk_ginet_step_ctas)

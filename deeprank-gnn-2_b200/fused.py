@@ -533,7 +533,7 @@ class ResidentGraphSet:
             out.__dict__[Batch._META_KEY] = {"num_graphs": b, "max_graph_nodes": int(n_plan[0].max()), "max_graph_edges": int(e_plan[0].max()),
                                              "num_edges_total": int(e_plan[2][-1])}
         out._attach_pool_sizes([self._pool_sizes[i] for i in ids.tolist()])
-        for k in ("_pool_cptr", "_pool_kkptr", "_pool_eptr32"):
+        for k in ("_pool_cptr", "_pool_kkptr", "_pool_eptr32", "_pool_c1ptr"):
             if k in out.__dict__:
                 out.__dict__[k] = out.__dict__[k].to(dev, non_blocking=True)
         return out

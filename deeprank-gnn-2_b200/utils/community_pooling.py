@@ -43,12 +43,21 @@ def pool_meta(data, level: int):
     m = data.__dict__.get(getattr(data, "_META_KEY", "_meta"), {}).get("pool") if hasattr(data, "__dict__") else None
     if m is None:
         return None
+    node_ptr = getattr(data, "_node_ptr32", None)
+    whole = data.__dict__.get(getattr(data, "_META_KEY", "_meta"), {})
     if level == 0:
-        cptr, kkptr = data.__dict__.get("_pool_cptr"), data.__dict__.get("_pool_kkptr")
+        cptr, kkptr = getattr(data, "_pool_cptr", None), getattr(data, "_pool_kkptr", None)
         if cptr is None or kkptr is None or not cptr.is_cuda:
             return None
-        return {"K": m["K0"], "C": m["C0"], "E": m["E1"], "KK": m["KK"], "cptr": cptr, "kkptr": kkptr}
-    return {"K": m["K1"], "C": m["C1"]}
+        out = {"K": m["K0"], "C": m["C0"], "E": m["E1"], "KK": m["KK"], "cptr": cptr, "kkptr": kkptr}
+        if node_ptr is not None and node_ptr.is_cuda and whole.get("max_graph_nodes") and m.get("max_K0"):
+            out["blocks"] = (node_ptr, cptr, int(whole["max_graph_nodes"]), int(m["max_K0"]))  # per-graph consecutive_cluster
+        return out
+    out = {"K": m["K1"], "C": m["C1"]}
+    c1ptr = getattr(data, "_pool_c1ptr", None)
+    if node_ptr is not None and node_ptr.is_cuda and c1ptr is not None and c1ptr.is_cuda and whole.get("max_graph_nodes") and m.get("max_K1"):
+        out["blocks"] = (node_ptr, c1ptr, int(whole["max_graph_nodes"]), int(m["max_K1"]))
+    return out
 
 
 def get_preloaded_cluster(cluster, batch, num_graphs: int | None = None):
@@ -139,6 +148,24 @@ def _consecutive(src: torch.Tensor, meta: dict | None) -> _Structure:
     src = src.contiguous()
     bound, n_clusters = (int(meta["K"]), int(meta["C"])) if meta is not None else _host_sizes(src)
     dev, n = src.device, int(src.numel())
+    blocks = meta.get("blocks") if meta is not None else None
+    if (POOL_BLOCKED and blocks is not None and n > 0 and int(blocks[0].numel()) >= 2 and int(blocks[0].numel()) == int(blocks[1].numel())
+            and lib.drk_consecutive_blocked_supported(int(blocks[2]), int(blocks[3]))):
+        # collated batch: one CTA per graph relabels the graph's ids in shared memory (one launch instead of eight)
+        node_ptr, cptr, max_nodes, max_ids = blocks
+        status = _status_word(dev)
+        inv = torch.empty(n, dtype=torch.int64, device=dev)
+        last = torch.empty(n_clusters, dtype=torch.int64, device=dev)
+        ptr_c = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.drk_consecutive_blocked(_p(src), n, _p(node_ptr), _p(cptr), int(node_ptr.numel()) - 1, max_nodes, max_ids, n_clusters, _p(inv), _p(last),
+                                             _p(ptr_c), _p(perm), _p(status), stream_ptr())
+        _lib.check(rc, "drk_consecutive_blocked")
+        st = _Structure()
+        st.inv, st.last, st.count, st.status, st.n_clusters = inv, last, None, status, n_clusters
+        st.plan = ops.SegmentPlan.from_parts(inv, ptr_c, perm, n_clusters, status)
+        return st
     ptr_k, perm, status = ops.segment_index(src, bound, _status_word(src.device))  # nodes grouped by id, stable: ascending node index inside a cluster
     rank = torch.empty(max(bound, 1), dtype=torch.int64, device=dev)
     ptr_c = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
@@ -315,6 +342,8 @@ def community_pooling(cluster, data, meta: dict | None = None, shared: dict | No
             # the pooled batch is a collated batch again: per-graph node / edge slices for the blocked index build, and level-1 sizes
             out.__dict__["_node_ptr32"] = meta["cptr"].to(torch.int32)
             out.__dict__["_edge_ptr32"] = eptr
+            if getattr(data, "_pool_c1ptr", None) is not None:
+                out.__dict__["_pool_c1ptr"] = data._pool_c1ptr
             out.__dict__[out._META_KEY] = {"num_graphs": ng, "max_graph_nodes": m["max_C0"], "max_graph_edges": m["max_E1"], "num_edges_total": m["E1"],
                                            "pool": m}
     else:

@@ -391,6 +391,17 @@ DRK_API int drk_pool_edge_decode(const int32_t* ids, int32_t capacity, const int
  *   [num_pooled, Fe] = attributes of merged edges added in ascending edge id (NULL: no attributes).  A graph whose clustering yields
  *   another number of pooled edges than pooled_edge_ptr says raises DRK_STATUS_INDEX_RANGE, an edge between graphs DRK_STATUS_CROSS_GRAPH.
  *   drk_pool_edge_blocked_supported == 0 (more than 255 clusters per graph, or lists that do not fit a CTA) -> use the chain above. */
+/* drk_consecutive_blocked: consecutive_cluster of a COLLATED batch in one launch, one CTA per graph (node_ptr int32 [G+1]: the nodes of a
+ *   graph are contiguous; cluster ids globally unique after drk_cluster_offsets, so a graph's ids form a range of at most max_graph_ids
+ *   values; cluster_ptr int64 [G+1]: first NEW id of every graph, counted by the collate).  Outputs as drk_segment_index_build +
+ *   drk_compact_segments give them: inv [N] (new id of every node), last [C] (largest node index of every cluster), ptr_c [C+1] / perm
+ *   [N] (nodes grouped by new id, ascending).  A graph with another number of distinct ids than cluster_ptr says, or ids spanning more
+ *   than max_graph_ids, raises DRK_STATUS_INDEX_RANGE; capacity = the number of clusters last / ptr_c were allocated for (nothing is
+ *   written beyond it). */
+DRK_API int drk_consecutive_blocked_supported(int32_t max_graph_nodes, int32_t max_graph_ids);
+DRK_API int drk_consecutive_blocked(const int64_t* cluster, int32_t num_nodes, const int32_t* node_ptr, const int64_t* cluster_ptr, int32_t num_graphs,
+                            int32_t max_graph_nodes, int32_t max_graph_ids, int32_t capacity, int64_t* inv, int64_t* last, int32_t* ptr_c,
+                            int32_t* perm, int32_t* status, void* stream);
 DRK_API int drk_pool_edge_blocked_supported(int32_t max_graph_clusters, int32_t max_graph_edges);
 DRK_API int drk_pool_edge_blocked(const int64_t* edge_index, int64_t num_edges, const int32_t* edge_ptr, const int64_t* inv, int32_t num_nodes,
                           const int64_t* cluster_ptr, const int32_t* pooled_edge_ptr, int32_t num_graphs, int32_t max_graph_clusters,

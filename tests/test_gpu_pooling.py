@@ -294,3 +294,35 @@ def test_per_graph_pool_edge_equals_the_global_route(n_graphs, fe, monkeypatch):
     r_ei, r_ea = tp.pool_edge(inv, host.edge_index, host.edge_attr)
     assert_equal_int(outs[0][0], r_ei, "pooled edge_index")
     assert_close(outs[0][1], r_ea, "pooled edge_attr")
+
+
+def test_per_graph_consecutive_cluster_equals_the_global_route(monkeypatch):
+    """``drk_consecutive_blocked`` (one CTA per graph) against the global chain (counting sort + compaction + rank gather) on both pooling
+    levels of a collated batch: relabelling, PyG's ``perm`` (last member), the segment plan -- bit for bit -- and fewer launches."""
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.synthetic import make_batch
+    from deeprank2_b200.utils import community_pooling as cp
+
+    host = make_batch(9, first=70, with_clusters=True)
+    outs = []
+    for blocked in (True, False):
+        monkeypatch.setattr(cp, "POOL_BLOCKED", blocked)
+        b = host.clone().to(DEV)
+        m0 = cp.pool_meta(b, 0)
+        assert "blocks" in m0
+        c0 = cp.get_preloaded_cluster(b.cluster0.clone(), b.batch, host.num_graphs)
+        before = _lib.launch_count()
+        st0 = cp._consecutive(c0, m0)
+        n0 = _lib.launch_count() - before
+        pooled = cp.community_pooling(c0, b)
+        m1 = cp.pool_meta(pooled, 1)
+        assert "blocks" in m1
+        c1 = cp.get_preloaded_cluster(pooled.cluster1.clone(), pooled.batch, host.num_graphs)
+        st1 = cp._consecutive(c1, m1)
+        x2, b2 = cp.max_pool_x(c1, pooled.x, pooled.batch, meta=m1)
+        cp.check_status(DEV)
+        outs.append((n0, [t.clone() for st in (st0, st1) for t in (st.inv, st.last, st.plan.ptr, st.plan.perm)], x2.clone(), b2.clone()))
+    assert outs[0][0] == 1 and outs[1][0] >= 7
+    for a, b_ in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b_)
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
