@@ -266,23 +266,36 @@ __global__ void __launch_bounds__(kPT) k_pool_edge_blocked(const PoolBlockedArgs
   }
   __syncthreads();
   bool bad = false;
-  for (int e = tid; e < ne; e += kPT) {
-    const unsigned long long r = (unsigned long long)ld_stream_i64(a.erow + e0 + e), c = (unsigned long long)ld_stream_i64(a.ecol + e0 + e);
-    unsigned short key = 0xffffu;
-    if (r < (unsigned long long)a.num_nodes && c < (unsigned long long)a.num_nodes) {
-      const int64_t pr = __ldg(a.inv + r) - c0, pc = __ldg(a.inv + c) - c0;
-      if (pr >= 0 && pr < C && pc >= 0 && pc < C) {
-        if (pr != pc) {
-          key = (unsigned short)(pr * C + pc);
+  for (int eb = tid; eb < ne; eb += 4 * kPT) {  // 4 edges per thread and trip: the endpoint -> cluster lookups are two dependent L2 round trips
+    unsigned long long r[4], c[4];
+    int64_t pr[4], pc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = eb + u * kPT;
+      r[u] = e < ne ? (unsigned long long)ld_stream_i64(a.erow + e0 + e) : 0ull;
+      c[u] = e < ne ? (unsigned long long)ld_stream_i64(a.ecol + e0 + e) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool in = r[u] < (unsigned long long)a.num_nodes && c[u] < (unsigned long long)a.num_nodes;
+      pr[u] = in ? __ldg(a.inv + r[u]) - c0 : -1;
+      pc[u] = in ? __ldg(a.inv + c[u]) - c0 : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = eb + u * kPT;
+      if (e >= ne) continue;
+      unsigned short key = 0xffffu;
+      if (pr[u] >= 0 && pr[u] < C && pc[u] >= 0 && pc[u] < C) {
+        if (pr[u] != pc[u]) {
+          key = (unsigned short)(pr[u] * C + pc[u]);
           atomicAdd(&s_start[key], 1);
         }
       } else {
-        bad = true;  // an edge that joins two graphs, or a cluster id outside its graph's range
+        bad = true;  // an endpoint outside the batch, an edge that joins two graphs, or a cluster id outside its graph's range
       }
-    } else {
-      bad = true;
+      s_key[e] = key;
     }
-    s_key[e] = key;
   }
   __syncthreads();
   // offsets of the member lists and compact index of the non-empty pairs: one scan over the C x C block, kPT pairs at a time
@@ -327,7 +340,14 @@ __global__ void __launch_bounds__(kPT) k_pool_edge_blocked(const PoolBlockedArgs
     if (a.out_attr != nullptr) {
       for (int f = 0; f < a.fe; ++f) {
         float sum = 0.f;
-        for (int i = lo; i < hi; ++i) sum += __ldg(a.attr + (int64_t)(e0 + s_mem[i]) * a.ld_attr + f);
+        for (int i0 = lo; i0 < hi; i0 += 8) {  // 8 gathers in flight, added in ascending edge id
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = i0 + u < hi ? __ldg(a.attr + (int64_t)(e0 + s_mem[i0 + u]) * a.ld_attr + f) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i0 + u < hi) sum += v[u];
+        }
         a.out_attr[o * a.fe + f] = sum;
       }
     }
