@@ -131,3 +131,57 @@ def test_fused_network_train_step_is_capturable_and_few_launches(monkeypatch):
     torch.cuda.synchronize()
     # backward of two fused layers = 2 x (layer kernel + reduction) + the readout's backward + the slot map of the graph index
     assert _lib.launch_count() - before <= 8
+
+
+def test_fused_kernels_stay_inside_their_output_buffers():
+    """Every output of the two kernels is a window of a larger sentinel-filled buffer: the guard bands on both sides must survive
+    (compute-sanitizer is not available on the GPU pool, so the C ABI is called directly with guarded windows)."""
+    from deeprank2_b200 import _lib
+    from deeprank2_b200.graph import graph_index, stream_ptr, workspace
+
+    lib = _lib.load()
+    f, fe, guard = 50, 1, 1024
+    batch = _batch(5, [70, 1, 200, 33, 129, 64], f, fe, 0.08).to(DEV)
+    g = graph_index(batch)
+    n, e, ngraphs = batch.x.shape[0], batch.edge_index.shape[1], g.num_graphs
+    torch.manual_seed(0)
+    we = (torch.randn(32, 2 * f + fe, device=DEV) * 0.2).contiguous()
+    wn = (torch.randn(f, f + 32, device=DEV) * 0.2).contiguous()
+    be, bn = torch.randn(32, device=DEV), torch.randn(f, device=DEV)
+    attr = g.attr_in_slot_order(batch.edge_attr).contiguous()
+
+    def window(numel, dtype, fill):
+        buf = torch.full((numel + 2 * guard,), fill, dtype=dtype, device=DEV)
+        return buf, buf[guard : guard + numel]
+
+    def intact(buf, numel, fill):
+        lo, hi = buf[:guard], buf[guard + numel :]
+        return bool(((lo == fill) | (lo != lo)).all()) and bool(((hi == fill) | (hi != hi)).all()) if buf.dtype.is_floating_point else bool((lo == fill).all() and (hi == fill).all())
+
+    nan = float("nan")
+    bufs = {}
+    for name, numel, dtype, fill in (("out", n * f, torch.float32, nan), ("s", n * 32, torch.float32, nan), ("cnt", n * 32, torch.float32, nan),
+                                     ("tf", n * fe * 32, torch.float32, nan), ("mask", e, torch.int32, -7), ("dx", n * f, torch.float32, nan),
+                                     ("dwe", we.numel(), torch.float32, nan), ("dbe", 32, torch.float32, nan), ("dwn", wn.numel(), torch.float32, nan),
+                                     ("dbn", f, torch.float32, nan)):
+        bufs[name] = window(numel, dtype, fill) + (numel, fill)
+    x = batch.x.contiguous()
+    p = lambda k: bufs[k][1].data_ptr()  # noqa: E731
+    rc = lib.drk_vanilla_layer_fwd(x.data_ptr(), f, g.rowptr.data_ptr(), g.colidx.data_ptr(), attr.data_ptr(), fe, g.graph_ptr.data_ptr(), None, ngraphs,
+                                   int(g.max_graph_nodes), we.data_ptr(), we.stride(0), be.data_ptr(), wn.data_ptr(), wn.stride(0), bn.data_ptr(), p("out"), p("s"),
+                                   p("cnt"), p("tf"), p("mask"), g.status.data_ptr(), stream_ptr())
+    _lib.check(rc, "drk_vanilla_layer_fwd")
+    dout = torch.randn(n, f, device=DEV)
+    ws = workspace(lib.drk_vanilla_layer_bwd_workspace_bytes(f, ngraphs), torch.device(DEV))
+    rc = lib.drk_vanilla_layer_bwd(x.data_ptr(), p("s"), p("out"), dout.data_ptr(), p("cnt"), p("tf"), f, fe, p("mask"), g.colptr.data_ptr(), g.rowidx.data_ptr(),
+                                   g.slot_map().data_ptr(), g.graph_ptr.data_ptr(), None, ngraphs, int(g.max_graph_nodes), we.data_ptr(), we.stride(0),
+                                   wn.data_ptr(), wn.stride(0), p("dx"), p("dwe"), we.stride(0), p("dbe"), p("dwn"), wn.stride(0), p("dbn"),
+                                   g.status.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr())
+    _lib.check(rc, "drk_vanilla_layer_bwd")
+    torch.cuda.synchronize()
+    assert int(g.status.item()) == 0
+    for name, (buf, view, numel, fill) in bufs.items():
+        assert intact(buf, numel, fill), f"{name}: a guard band was overwritten"
+        if view.dtype.is_floating_point:
+            assert bool(torch.isfinite(view).all()), f"{name}: not every element was written"
+    assert bool((bufs["mask"][1][: g.num_edges] != -7).any())
