@@ -23,7 +23,14 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"{name} must live on a CUDA device: deeprank2_b200 has no CPU path (got {t.device})")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of the current stream of the current device (the raw getter costs ~0.3 us against ~15 us for building a
+    ``torch.cuda.Stream`` object; an eager train step of the layer kernels asks ~30 times)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -32,7 +39,8 @@ _workspaces: dict = {}
 
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     """Scratch buffer re-used by every call on (device, current stream); stream order makes that safe."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, _raw_stream(index) if _raw_stream is not None else torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
