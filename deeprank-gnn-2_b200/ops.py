@@ -524,8 +524,9 @@ def _rows16(t: torch.Tensor) -> torch.Tensor:
     return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
-def vanilla_layer_fwd(x, edge_attr, we, be, wn, bn, graph: GraphIndex):
-    """``VanillaConvolutionalLayer.forward`` in one launch; returns (out, S, cnt, tf, mask) -- see include/drk_b200.h."""
+def vanilla_layer_fwd(x, edge_attr, we, be, wn, bn, graph: GraphIndex, for_backward: bool = True):
+    """``VanillaConvolutionalLayer.forward`` in one launch; returns (out, S, cnt, tf, mask) -- see include/drk_b200.h.
+    ``for_backward=False`` (inference): the per-node counts of active edges / attribute sums are not produced."""
     lib = _lib.load()
     x = _rows16(x)
     n, f = x.shape
@@ -536,8 +537,8 @@ def vanilla_layer_fwd(x, edge_attr, we, be, wn, bn, graph: GraphIndex):
     dev = x.device
     out = torch.empty((n, f), dtype=torch.float32, device=dev)
     s = torch.empty((n, MESSAGE_SIZE), dtype=torch.float32, device=dev)
-    cnt = torch.empty_like(s)
-    tf = torch.empty((n, fe, MESSAGE_SIZE), dtype=torch.float32, device=dev) if fe else None
+    cnt = torch.empty_like(s) if for_backward else None
+    tf = torch.empty((n, fe, MESSAGE_SIZE), dtype=torch.float32, device=dev) if fe and for_backward else None
     mask = torch.empty(max(graph.num_edges, 1), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.drk_vanilla_layer_fwd(_p(x), f, _p(graph.rowptr), _p(graph.colidx), _p(attr), fe, _p(graph.graph_ptr), _p(graph.order), graph.num_graphs,
@@ -592,7 +593,7 @@ class VanillaConvFunction(torch.autograd.Function):
         ctx.has_be, ctx.has_bn = be is not None, bn is not None
         ctx.fused = _vanilla_fused_ok(x, we, wn, graph, f, fe)
         if ctx.fused:
-            out, s, cnt, tf, mask = vanilla_layer_fwd(x, edge_attr if fe else None, we, be, wn, bn, graph)
+            out, s, cnt, tf, mask = vanilla_layer_fwd(x, edge_attr if fe else None, we, be, wn, bn, graph, for_backward=any(ctx.needs_input_grad))
             ctx.save_for_backward(x, None, we, wn, tf, s, cnt, mask, out)
             return out
         wab = torch.cat([we[:, :f], we[:, f : 2 * f]], dim=0)                       # [64, F]

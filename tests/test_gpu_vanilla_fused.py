@@ -185,3 +185,17 @@ def test_fused_kernels_stay_inside_their_output_buffers():
         if view.dtype.is_floating_point:
             assert bool(torch.isfinite(view).all()), f"{name}: not every element was written"
     assert bool((bufs["mask"][1][: g.num_edges] != -7).any())
+
+
+def test_fused_network_inference_equals_training_forward():
+    """Under ``no_grad`` the layer kernel skips the backward pass's side outputs (cnt, tf): same predictions, bit for bit."""
+    from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
+    from deeprank2_b200.synthetic import make_batch
+
+    gb = make_batch(5, first=11).to(DEV)
+    torch.manual_seed(2)
+    net = VanillaNetwork(50, 1, 1).to(DEV).eval()
+    pred_train = net(gb.clone())
+    with torch.no_grad():
+        pred_eval = net(gb.clone())
+    assert torch.equal(pred_train.detach(), pred_eval)
