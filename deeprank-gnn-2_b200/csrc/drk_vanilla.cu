@@ -183,6 +183,23 @@ __device__ __forceinline__ void copy_rows(float* dst, const float* src, int floa
   }
 }
 
+// -DDRK_VANILLA_PROBE: thread 0 of every CTA adds up the SM clocks it spends per phase (profiles/vanilla_phase_probe.py reads them)
+#ifdef DRK_VANILLA_PROBE
+__device__ long long g_vprobe[148][8];
+#define VPROBE(i)                                   \
+  do {                                              \
+    if (threadIdx.x == 0) {                         \
+      const long long now_ = clock64();             \
+      g_vprobe[blockIdx.x][i] += now_ - vprobe_t;   \
+      vprobe_t = now_;                              \
+    }                                               \
+  } while (0)
+#else
+#define VPROBE(i) \
+  do {            \
+  } while (0)
+#endif
+
 template <int FE>
 __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -200,8 +217,8 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
   float* sS = sU + kRows * kMsg;                     // [64][36]
   uint32_t* sMw = reinterpret_cast<uint32_t*>(sS + kRows * kSStride);  // [warps][32] ReLU masks of the chunk in flight
   float* sStage = reinterpret_cast<float*>(sMw + kNW * 32);
-  float* sV = sStage + kStages * stage_floats;       // [rows_cap][32]
-  int* sRp = reinterpret_cast<int*>(sV + (size_t)a.rows_cap * kMsg);   // [rows_cap + 1] CSR offsets of the graph's rows
+  float* sV = sStage + kStages * stage_floats;       // [rows_cap + 1][32], channel-paired; the last row is -inf
+  int* sRp = reinterpret_cast<int*>(sV + (size_t)(a.rows_cap + 1) * kMsg);   // [rows_cap + 1] CSR offsets of the graph's rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   if (tid == 0) {
@@ -240,11 +257,18 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
   build_frags(sWN + ks * nto * 32, a.wn, a.ld_wn, 0, f, kMsg, f, 4, nto, false);
   if (tid < kMsg) sBe[tid] = a.be != nullptr ? __ldg(a.be + tid) : 0.f;
   if (tid >= 64 && tid < 64 + kMaxF) sBn[tid - 64] = (a.bn != nullptr && tid - 64 < f) ? __ldg(a.bn + tid - 64) : 0.f;
-  float cw[kF];  // this lane's row of C (lane = message channel)
+  float2 cw2[kF];  // C rows of this lane's two message channels (lane mod 16, and + 16)
 #pragma unroll
-  for (int k = 0; k < kF; ++k) cw[k] = k < FE ? __ldg(a.we + (int64_t)lane * a.ld_we + 2 * f + k) : 0.f;
+  for (int k = 0; k < kF; ++k)
+    cw2[k] = k < FE ? make_float2(__ldg(a.we + (int64_t)(lane & 15) * a.ld_we + 2 * f + k), __ldg(a.we + (int64_t)((lane & 15) + 16) * a.ld_we + 2 * f + k))
+                    : make_float2(0.f, 0.f);
+  const int dead = a.rows_cap;  // row of -inf behind the graph's V rows: the source of padding edges
+  if (tid < kMsg) sV[(size_t)a.rows_cap * kMsg + tid] = -INFINITY;
   __syncthreads();
 
+#ifdef DRK_VANILLA_PROBE
+  long long vprobe_t = clock64();
+#endif
   bool bad = false, too_big = false;
   uint32_t it = 0;  // tiles consumed so far: stage it % kStages, barrier parity (it / kStages) & 1
   const int mt = warp & 3, ng = warp >> 2;
@@ -256,6 +280,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
     if (n <= 0) continue;
     for (int j = tid; j <= n; j += kT) sRp[j] = __ldg(a.rowptr + n0 + j);
     const int tiles = (n + kRows - 1) / kRows;
+    VPROBE(0);  // graph setup (offsets, rowptr)
     // ---- pass 0: V for every node of the graph
     for (int tile = 0; tile < tiles; ++tile, ++it) {
       const int stage = it & (kStages - 1);
@@ -263,107 +288,161 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
       mbar_wait(&s_bar[stage], (it / kStages) & 1u);
       float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
       warp_gemm<1>(acc, xt + (mt * 16 + g) * f + t, f, f, ks, sWV + ng * 32 + lane, 4, 1);
-      const int r = tile * kRows + mt * 16 + g, c = ng * 8 + 2 * t;
-      if (r < n) *reinterpret_cast<float2*>(sV + r * kMsg + c) = make_float2(acc[0][0], acc[0][1]);
-      if (r + 8 < n) *reinterpret_cast<float2*>(sV + (r + 8) * kMsg + c) = make_float2(acc[0][2], acc[0][3]);
+      // V and U are kept with channels c and c + 16 next to each other (position 2 (c mod 16) + c / 16): a lane of the edge pass owns such a pair
+      const int r = tile * kRows + mt * 16 + g, c = ng * 8 + 2 * t, pc = 2 * (c & 15) + (c >> 4);
+      if (r < n) {
+        sV[r * kMsg + pc] = acc[0][0];
+        sV[r * kMsg + pc + 2] = acc[0][1];
+      }
+      if (r + 8 < n) {
+        sV[(r + 8) * kMsg + pc] = acc[0][2];
+        sV[(r + 8) * kMsg + pc + 2] = acc[0][3];
+      }
       __syncthreads();
       if (warp == 0) produce(stage);
     }
     // ---- pass 1: per tile U -> edge messages -> node MLP
+    VPROBE(1);  // pass 0
     for (int tile = 0; tile < tiles; ++tile, ++it) {
       const int stage = it & (kStages - 1);
       const float* xt = sStage + stage * stage_floats + tile_misalign(a.x + (int64_t)(n0 + tile * kRows) * f);
-      // the first 32 edges of this warp's 4 destination rows: in flight while U is multiplied
-      int e_beg[4], e_len[4], e_src[4];
-      float e_att[4][kF];
+      // Edge pass layout: a warp sums TWO destination rows at a time -- lanes 0-15 the first, lanes 16-31 the second, lane l the channels
+      // l and l + 16 as one packed pair (FADD2 / FFMA2) -- so a warp instruction advances two edges.  Rows r = warp + 16 k, k = 0..3:
+      // pairs (k = 0, 1) and (k = 2, 3).  The first 16 edges of every row are fetched while U is multiplied.
+      const int hl = lane & 15, half = lane >> 4;
+      int e_beg[2], e_len[2], e_src[2][2];  // [pair][chunk of 16 edges]: 32 edges per row are in flight before they are needed
+      float e_att[2][2][kF];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int li = tile * kRows + warp + kNW * k;
-        e_beg[k] = 0;
-        e_len[k] = 0;
+      for (int p = 0; p < 2; ++p) {
+        const int li = tile * kRows + warp + kNW * (2 * p + half);
+        e_beg[p] = 0;
+        e_len[p] = 0;
         if (li < n) {
-          e_beg[k] = sRp[li];
-          e_len[k] = sRp[li + 1] - e_beg[k];
+          e_beg[p] = sRp[li];
+          e_len[p] = sRp[li + 1] - e_beg[p];
         }
-        e_src[k] = 0;
 #pragma unroll
-        for (int q = 0; q < kF; ++q) e_att[k][q] = 0.f;
-        if (lane < e_len[k]) {
-          e_src[k] = ld_stream_i32(a.colidx + e_beg[k] + lane) - n0;
+        for (int c = 0; c < 2; ++c) {
+          e_src[p][c] = dead;
 #pragma unroll
-          for (int q = 0; q < FE; ++q) e_att[k][q] = ld_stream_f32(a.attr + (int64_t)(e_beg[k] + lane) * FE + q);
+          for (int q = 0; q < kF; ++q) e_att[p][c][q] = 0.f;
+          if (16 * c + hl < e_len[p]) {
+            e_src[p][c] = ld_stream_i32(a.colidx + e_beg[p] + 16 * c + hl) - n0;
+#pragma unroll
+            for (int q = 0; q < FE; ++q) e_att[p][c][q] = ld_stream_f32(a.attr + (int64_t)(e_beg[p] + 16 * c + hl) * FE + q);
+          }
         }
       }
       mbar_wait(&s_bar[stage], (it / kStages) & 1u);
+      VPROBE(2);  // stage wait
       {
         float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
         warp_gemm<1>(acc, xt + (mt * 16 + g) * f + t, f, f, ks, sWU + ng * 32 + lane, 4, 1);
-        const int r = mt * 16 + g, c = ng * 8 + 2 * t;
+        const int r = mt * 16 + g, c = ng * 8 + 2 * t, pc = 2 * (c & 15) + (c >> 4);
         const float b0 = sBe[c], b1 = sBe[c + 1];
-        *reinterpret_cast<float2*>(sU + r * kMsg + c) = make_float2(acc[0][0] + b0, acc[0][1] + b1);
-        *reinterpret_cast<float2*>(sU + (r + 8) * kMsg + c) = make_float2(acc[0][2] + b0, acc[0][3] + b1);
+        sU[r * kMsg + pc] = acc[0][0] + b0;
+        sU[r * kMsg + pc + 2] = acc[0][1] + b1;
+        sU[(r + 8) * kMsg + pc] = acc[0][2] + b0;
+        sU[(r + 8) * kMsg + pc + 2] = acc[0][3] + b1;
       }
       __syncthreads();
-      uint32_t* mw = sMw + warp * 32;
+      VPROBE(3);  // U GEMM + barrier
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = warp + kNW * k, li = tile * kRows + r;
-        const float u = sU[r * kMsg + lane];
-        float sum = 0.f, active = 0.f;
-        float tf[kF];
+      for (int p = 0; p < 2; ++p) {
+        const int r = warp + kNW * (2 * p + half), li = tile * kRows + r;
+        const float2 u = *reinterpret_cast<const float2*>(sU + r * kMsg + 2 * hl);
+        const int beg = e_beg[p], len = e_len[p];
+        const int len_max = max(len, __shfl_xor_sync(kFull, len, 16));  // the two rows of the pair advance together
+        float2 sum = make_float2(0.f, 0.f), active = make_float2(0.f, 0.f);
+        float2 tf[kF];
 #pragma unroll
-        for (int q = 0; q < kF; ++q) tf[q] = 0.f;
-        for (int off = 0; off < e_len[k]; off += 32) {
-          int src = e_src[k];
+        for (int q = 0; q < kF; ++q) tf[q] = make_float2(0.f, 0.f);
+        for (int off = 0; off < len_max; off += 16) {
+          int src = off == 0 ? e_src[p][0] : e_src[p][1];
           float att[kF];
 #pragma unroll
-          for (int q = 0; q < kF; ++q) att[q] = e_att[k][q];
-          if (off > 0) {  // rows with more than 32 edges: further chunks are fetched in place
-            src = 0;
-            if (off + lane < e_len[k]) {
-              src = ld_stream_i32(a.colidx + e_beg[k] + off + lane) - n0;
+          for (int q = 0; q < kF; ++q) att[q] = off == 0 ? e_att[p][0][q] : e_att[p][1][q];
+          if (off >= 32) {  // rows with more than 32 edges: further chunks are fetched in place
+            src = dead;
 #pragma unroll
-              for (int q = 0; q < FE; ++q) att[q] = ld_stream_f32(a.attr + (int64_t)(e_beg[k] + off + lane) * FE + q);
+            for (int q = 0; q < kF; ++q) att[q] = 0.f;
+            if (off + hl < len) {
+              src = ld_stream_i32(a.colidx + beg + off + hl) - n0;
+#pragma unroll
+              for (int q = 0; q < FE; ++q) att[q] = ld_stream_f32(a.attr + (int64_t)(beg + off + hl) * FE + q);
             }
           }
-          if ((unsigned)src >= (unsigned)n) {  // an edge that leaves the graph: reported, the message reads row 0
+          if ((unsigned)src >= (unsigned)n && src != dead) {  // an edge that leaves the graph: reported, the message is dropped
             bad = true;
-            src = 0;
+            src = dead;
           }
-          const int cnt = min(32, e_len[k] - off);
+          const int cnt = min(16, len_max - off), mine = len - off;  // `mine` of the chunk's edges belong to this half's row
+          // No ballot inside the loop: a vote is a convergent operation the compiler may not move, and with one per edge the chain
+          // shuffle -> LDS -> add -> fma -> compare -> vote of edge j had to retire before edge j + 1 could start (230 cycles per trip,
+          // profiles/vanilla_phase_probe.py).  Every lane collects its own two channels' bits over the chunk (bit j = edge j); one
+          // 16 x 16 bit transpose per chunk (4 shuffle stages) then turns them into one mask word per edge.
+          // The loop body is written for the two math pipes (each takes one warp instruction every other cycle per scheduler): packed
+          // adds / fmas on the FMA pipe, the 0/1 indicator as a float (FSET) so that the running sums need no select, the mask bits
+          // shifted in with an integer multiply-add (bit order reversed, undone once per chunk).
+          unsigned bits_lo = 0u, bits_hi = 0u;
 #pragma unroll 4
           for (int j = 0; j < cnt; ++j) {
-            const int sj = __shfl_sync(kFull, src, j);
-            float m = u + sV[sj * kMsg + lane];
+            const int sj = __shfl_sync(kFull, src, j, 16);  // padding edges (the shorter row of the pair) read the -inf row: inactive
+            const float2 v = *reinterpret_cast<const float2*>(sV + sj * kMsg + 2 * hl);
+            float2 m = __fadd2_rn(u, v);
             float aj[kF];
 #pragma unroll
             for (int q = 0; q < FE; ++q) {
-              aj[q] = __shfl_sync(kFull, att[q], j);
-              m = fmaf(cw[q], aj[q], m);
+              aj[q] = __shfl_sync(kFull, att[q], j, 16);
+              m = __ffma2_rn(cw2[q], make_float2(aj[q], aj[q]), m);
             }
-            const bool on = m > 0.f;
-            sum += on ? m : 0.f;
-            active += on ? 1.f : 0.f;
+            const float2 on = make_float2(m.x > 0.f ? 1.f : 0.f, m.y > 0.f ? 1.f : 0.f);
+            sum = __fadd2_rn(sum, make_float2(fmaxf(m.x, 0.f), fmaxf(m.y, 0.f)));
+            active = __fadd2_rn(active, on);
 #pragma unroll
-            for (int q = 0; q < FE; ++q) tf[q] += on ? aj[q] : 0.f;
-            const unsigned word = __ballot_sync(kFull, on);
-            if (lane == 0) mw[j] = word;
+            for (int q = 0; q < FE; ++q) tf[q] = __ffma2_rn(on, make_float2(aj[q], aj[q]), tf[q]);
+            bits_lo = bits_lo * 2u + (__float_as_uint(on.x) >> 29 & 1u);  // 1.0f = 0x3f800000
+            bits_hi = bits_hi * 2u + (__float_as_uint(on.y) >> 29 & 1u);
           }
-          __syncwarp();
-          if (lane < cnt) a.mask[e_beg[k] + off + lane] = mw[lane];
-          __syncwarp();
+          // edge j sits at bit cnt - 1 - j: reverse
+          unsigned bits = (__brev(bits_lo) >> (32 - cnt)) | ((__brev(bits_hi) >> (32 - cnt)) << 16);  // bit j: channel hl of edge j; bit 16 + j: channel 16 + hl
+          // transpose inside each half warp: lane l ends up with bit l' of its word = bit l of lane l' -> the mask word of edge l
+          // (channels 0-15 in the low half, 16-31 in the high half: bit c = channel c)
+#pragma unroll
+          for (int st = 1; st < 16; st <<= 1) {
+            const unsigned keep = st == 1 ? 0x55555555u : st == 2 ? 0x33333333u : st == 4 ? 0x0f0f0f0fu : 0x00ff00ffu;
+            const unsigned other = __shfl_xor_sync(kFull, bits, st, 16);
+            bits = (hl & st) ? (((other >> st) & keep) | (bits & ~keep)) : ((bits & keep) | ((other & keep) << st));
+          }
+          if (hl < mine) a.mask[beg + off + hl] = bits;
         }
-        sS[r * kSStride + lane] = li < n ? sum : 0.f;
         if (li < n) {
-          a.s[(int64_t)(n0 + li) * kMsg + lane] = sum;
-          if (a.cnt != nullptr) a.cnt[(int64_t)(n0 + li) * kMsg + lane] = active;
+          sS[r * kSStride + hl] = sum.x;
+          sS[r * kSStride + 16 + hl] = sum.y;
+          float* srow = a.s + (int64_t)(n0 + li) * kMsg;
+          srow[hl] = sum.x;
+          srow[16 + hl] = sum.y;
+          if (a.cnt != nullptr) {
+            float* crow = a.cnt + (int64_t)(n0 + li) * kMsg;
+            crow[hl] = active.x;
+            crow[16 + hl] = active.y;
+          }
           if (a.tf != nullptr) {
 #pragma unroll
-            for (int q = 0; q < FE; ++q) a.tf[((int64_t)(n0 + li) * FE + q) * kMsg + lane] = tf[q];
+            for (int q = 0; q < FE; ++q) {
+              float* trow = a.tf + ((int64_t)(n0 + li) * FE + q) * kMsg;
+              trow[hl] = tf[q].x;
+              trow[16 + hl] = tf[q].y;
+            }
           }
+        } else {
+          sS[r * kSStride + hl] = 0.f;
+          sS[r * kSStride + 16 + hl] = 0.f;
         }
       }
+      VPROBE(4);  // this warp's edge pass
       __syncthreads();
+      VPROBE(5);  // barrier after the edge pass (waiting for the slowest warp)
       {
         const int per = (nto + 3) >> 2, nt0 = ng * per, cnt = min(per, nto - nt0);  // column tiles of this warp (<= 2 for F <= 64)
         if (cnt > 0) {
@@ -398,6 +477,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
       }
       __syncthreads();
       if (warp == 0) produce(stage);
+      VPROBE(6);  // out GEMM + closing barrier
     }
   }
   if (a.status != nullptr) {
@@ -928,7 +1008,7 @@ static size_t fwd_smem_bytes(int f, int rows_cap) {
   size_t b = (size_t)(ks * 4 * 32 * 2 + (ks + 4) * nto * 32) * sizeof(uint4);
   b += (size_t)(kMsg + kMaxF + kRows * kMsg + kRows * kSStride + kNW * 32) * 4;
   b += kStages * stage_floats * 4;
-  b += (size_t)rows_cap * kMsg * 4;
+  b += (size_t)(rows_cap + 1) * kMsg * 4;
   b += (size_t)(rows_cap + 4) * 4;
   return b;
 }
@@ -1041,5 +1121,16 @@ int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, cons
                                                          ld_dwn, dbn);
   return finish_launch("vanilla layer backward", launches);
 }
+
+#ifdef DRK_VANILLA_PROBE
+// probe builds only (not part of the ABI): copy the per-CTA phase clocks of the forward kernel to the host and clear them
+__attribute__((visibility("default"))) int drk_vanilla_probe_read(long long* host_out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_out, drk::vanilla::g_vprobe, sizeof(long long) * 148 * 8);
+  static long long zeros[148 * 8];
+  cudaMemcpyToSymbol(drk::vanilla::g_vprobe, zeros, sizeof(zeros));
+  return 0;
+}
+#endif
 
 }  // extern "C"
