@@ -185,7 +185,7 @@ __device__ __forceinline__ void copy_rows(float* dst, const float* src, int floa
 
 // -DDRK_VANILLA_PROBE: thread 0 of every CTA adds up the SM clocks it spends per phase (profiles/vanilla_phase_probe.py reads them)
 #ifdef DRK_VANILLA_PROBE
-__device__ long long g_vprobe[148][8];
+__device__ long long g_vprobe[148][16];  // 0-7 forward, 8-15 backward
 #define VPROBE(i)                                   \
   do {                                              \
     if (threadIdx.x == 0) {                         \
@@ -647,6 +647,9 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
   for (int q = 0; q < kF; ++q) accC[q] = 0.f;
   const int cntN = cg < ntn ? min(kNtN, (ntn - cg + 3) >> 2) : 0, cntAB = cg < ntab ? min(kNtAB, (ntab - cg + 3) >> 2) : 0;
 
+#ifdef DRK_VANILLA_PROBE
+  long long vprobe_t = clock64();
+#endif
   bool bad = false, too_big = false;
   uint32_t it = 0;
   const int ldn = f + kMsg + 1, ldab = f + 1;
@@ -661,6 +664,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
       continue;
     }
     for (int j = tid; j <= n; j += kT) sCp[j] = __ldg(a.colptr + n0 + j);
+    VPROBE(9);  // graph setup
     // ---- pass 0: dS for every node
     const int tiles_a = (n + kRowsA - 1) / kRowsA;
     for (int tile = 0; tile < tiles_a; ++tile, ++it) {
@@ -702,6 +706,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
       __syncthreads();
       if (warp == 0) produce(stage);
     }
+    VPROBE(10);  // pass 0: dS product + barriers
     // ---- pass 1
     const int tiles = (n + kRows - 1) / kRows;
     for (int tile = 0; tile < tiles; ++tile, ++it) {
@@ -766,6 +771,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
         }
         for (int idx = rows * kMsg + tid; idx < kRows * kMsg; idx += kT) st[idx] = 0.f;
       }
+      VPROBE(11);  // pass 1: prefetch, stage wait, dZ in place
       // walks: rows warp, warp + 16, ... of the tile; lane = message channel
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -807,7 +813,9 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
         sDuv[r * kDuvStride + lane] = du;
         sDuv[r * kDuvStride + kMsg + lane] = dv;
       }
+      VPROBE(12);  // this warp's walks (dU, dV)
       __syncthreads();
+      VPROBE(13);  // barrier after the walks
       // dx tile
       if (a.dx != nullptr) {
         const int per = (nto + 3) >> 2, nt0 = cg * per, cnt = min(per, nto - nt0);
@@ -838,6 +846,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
           }
         }
       }
+      VPROBE(14);  // dx product
       // weight gradients: dWn | dbn += dZ^T [x | S | 1]
       {
         const float* bp[kNtN];
@@ -879,6 +888,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
       }
       __syncthreads();
       if (warp == 0) produce(stage);
+      VPROBE(15);  // dWn / dWab products + closing barrier
     }
     // ---- this graph's partial: [F][F + 33] (dWn | dbn), [64][F + 1] (dWa ; dWb | dbe), [32][8] (dC).  One partial per GRAPH, added up in
     // graph order by k_vanilla_reduce: the gradients do not depend on which CTA ran which graph (the issue order is a scheduling hint)
@@ -933,6 +943,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_bwd(const BwdArgs a) {
         }
       }
     }
+    VPROBE(8);  // this graph's gradient partial
   }
   if (a.status != nullptr) {
     if (bad) atomicOr(a.status, DRK_STATUS_CROSS_GRAPH);
@@ -1126,8 +1137,8 @@ int drk_vanilla_layer_bwd(const float* x, const float* s, const float* out, cons
 // probe builds only (not part of the ABI): copy the per-CTA phase clocks of the forward kernel to the host and clear them
 __attribute__((visibility("default"))) int drk_vanilla_probe_read(long long* host_out) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(host_out, drk::vanilla::g_vprobe, sizeof(long long) * 148 * 8);
-  static long long zeros[148 * 8];
+  cudaMemcpyFromSymbol(host_out, drk::vanilla::g_vprobe, sizeof(long long) * 148 * 16);
+  static long long zeros[148 * 16];
   cudaMemcpyToSymbol(drk::vanilla::g_vprobe, zeros, sizeof(zeros));
   return 0;
 }
