@@ -522,6 +522,165 @@ __global__ void __launch_bounds__(256) k_weight_grad_reduce(const float* __restr
   if (lane == 0) *dst = accumulate ? *dst + s : s;
 }
 
+// ---------------------------------------------------------------- tensor-core variant (row-contiguous operands, M <= 64, K <= 64)
+// dW = dY^T X as transposed 3xTF32 products over 64-row tiles that arrive by bulk copy (double-buffered).  The 8 rows of a k-step are
+// one warp's: warp = (k-step s = warp & 7, column half h = warp >> 3) multiplies rows 8 s .. 8 s + 7 of every tile by ALL row tiles of
+// dW and its half of the column tiles, so every operand element is split by one warp (dY) or two (X) -- the SIMT kernel above runs at
+// 36 us for [77 k, 64]^T [77 k, 50], this one is bound by the 35 MB it reads.  The warps' accumulators are folded in k-step order once,
+// at the end, and every CTA writes one partial in the layout k_weight_grad_reduce expects.
+constexpr int kWtThreads = 512;
+constexpr int kWtRows = 64;
+
+struct WgradTcArgs {
+  const float* dy;
+  const float* x;
+  int64_t n;
+  int32_t k, m;
+  float* partial;
+  float* partial_bias;  // may be NULL
+  int32_t m_pad, k_pad, num_tiles;
+};
+
+__global__ void __launch_bounds__(kWtThreads, 1) k_weight_grad_tc(const WgradTcArgs p) {
+  extern __shared__ __align__(16) unsigned char wt_smem[];
+  __shared__ __align__(8) unsigned long long wt_bar[2];
+  const int m = p.m, k = p.k;
+  const int dy_floats = kWtRows * m, x_floats = kWtRows * k;
+  const int stage_floats = (dy_floats + x_floats + 7) & ~3;
+  float* sStage = reinterpret_cast<float*>(wt_smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int s = warp & 7, h = warp >> 3;
+  const int mt_count = (m + 15) >> 4, nt_total = (k + 7) >> 3, nth = (nt_total + 1) >> 1;
+  const int nt0 = h * nth, nt_count = max(0, min(nth, nt_total - nt0));
+  if (tid == 0) {
+    mbar_init(&wt_bar[0], 1);
+    mbar_init(&wt_bar[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int stage) {
+    const int64_t row0 = (int64_t)tile * kWtRows;
+    const int rows = (int)min((int64_t)kWtRows, p.n - row0);
+    float* dst = sStage + stage * stage_floats;
+    const uint32_t b1 = (uint32_t)rows * m * 4u, b2 = (uint32_t)rows * k * 4u, bulk1 = b1 & ~15u, bulk2 = b2 & ~15u;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&wt_bar[stage], bulk1 + bulk2);
+      if (bulk1) bulk_copy_g2s(dst, p.dy + row0 * m, bulk1, &wt_bar[stage]);
+      if (bulk2) bulk_copy_g2s(dst + ((dy_floats + 3) & ~3), p.x + row0 * k, bulk2, &wt_bar[stage]);
+    }
+    if (tid >= 32 && tid < 32 + (int)((b1 - bulk1) >> 2)) {
+      const int w = (int)(bulk1 >> 2) + (tid - 32);
+      dst[w] = __ldg(p.dy + row0 * m + w);
+    }
+    if (tid >= 64 && tid < 64 + (int)((b2 - bulk2) >> 2)) {
+      const int w = (int)(bulk2 >> 2) + (tid - 64);
+      dst[((dy_floats + 3) & ~3) + w] = __ldg(p.x + row0 * k + w);
+    }
+  };
+  if ((int)blockIdx.x < p.num_tiles) issue(blockIdx.x, 0);
+  float acc[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  float bias_acc = 0.f;
+  uint32_t phase[2] = {0u, 0u};
+  int stage = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, stage ^= 1) {
+    const int rows = (int)min((int64_t)kWtRows, p.n - (int64_t)tile * kWtRows);
+    if (tile + (int)gridDim.x < p.num_tiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&wt_bar[stage], phase[stage]);
+    phase[stage] ^= 1u;
+    __syncthreads();  // the ragged-tail floats written by ordinary stores are visible too
+    const float* sdy = sStage + stage * stage_floats;
+    const float* sx = sdy + ((dy_floats + 3) & ~3);
+    const int r0 = 8 * s + t, r1 = r0 + 4;
+    const bool v0 = r0 < rows, v1 = r1 < rows;  // rows of a ragged last tile beyond the matrix hold stale data
+    if (8 * s < rows) {
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = (nt0 + j) * 8 + g;
+        const bool in = j < nt_count && col < k;
+        split_tf32((in && v0) ? sx[r0 * k + col] : 0.f, bh[j][0], bl[j][0]);
+        split_tf32((in && v1) ? sx[r1 * k + col] : 0.f, bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a >= mt_count) break;
+        const int c0 = a * 16 + g, c1 = c0 + 8;
+        uint32_t ahi[4], alo[4];
+        split_tf32((v0 && c0 < m) ? sdy[r0 * m + c0] : 0.f, ahi[0], alo[0]);
+        split_tf32((v0 && c1 < m) ? sdy[r0 * m + c1] : 0.f, ahi[1], alo[1]);
+        split_tf32((v1 && c0 < m) ? sdy[r1 * m + c0] : 0.f, ahi[2], alo[2]);
+        split_tf32((v1 && c1 < m) ? sdy[r1 * m + c1] : 0.f, ahi[3], alo[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nt_count) mma_tf32(acc[a][j], alo, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nt_count) mma_tf32(acc[a][j], ahi, bl[j][0], bl[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nt_count) mma_tf32(acc[a][j], ahi, bh[j][0], bh[j][1]);
+      }
+    }
+    if (p.partial_bias != nullptr && tid < m) {  // column sums of dY in row order
+      for (int r = 0; r < rows; ++r) bias_acc += sdy[r * m + tid];
+    }
+    fence_proxy_async();
+    __syncthreads();  // every warp is done with this stage: the next trip may hand it to the copy engine
+  }
+  // fold the k-step warps' accumulators in k-step order (s = 1..7 into s = 0), then one partial per CTA
+  float* scratch = sStage;  // [2 halves][16 units][32 lanes][4]
+  for (int r = 1; r < 8; ++r) {
+    if (s == r) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(scratch + (((h * 16 + a * 4 + j) * 32 + lane) << 2)) = make_float4(acc[a][j][0], acc[a][j][1], acc[a][j][2], acc[a][j][3]);
+    }
+    __syncthreads();
+    if (s == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(scratch + (((h * 16 + a * 4 + j) * 32 + lane) << 2));
+          acc[a][j][0] += v.x;
+          acc[a][j][1] += v.y;
+          acc[a][j][2] += v.z;
+          acc[a][j][3] += v.w;
+        }
+    }
+    __syncthreads();
+  }
+  if (s == 0) {
+    float* part = p.partial + (size_t)blockIdx.x * p.m_pad * p.k_pad;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a >= mt_count) break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= nt_count) continue;
+        const int col = (nt0 + j) * 8 + 2 * t;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = a * 16 + g + 8 * hh;
+          if (row < p.m_pad) {
+            if (col < p.k_pad) part[row * p.k_pad + col] = acc[a][j][2 * hh];
+            if (col + 1 < p.k_pad) part[row * p.k_pad + col + 1] = acc[a][j][2 * hh + 1];
+          }
+        }
+      }
+    }
+  }
+  if (p.partial_bias != nullptr && tid < p.m_pad) p.partial_bias[(size_t)blockIdx.x * p.m_pad + tid] = tid < m ? bias_acc : 0.f;
+}
+
 struct WgradPlan {
   int wm, wk;
   int grid_x, grid_y, grid_z;
@@ -631,9 +790,14 @@ int drk_node_linear(const float* a, int64_t lda, const float* b, int64_t ldb, in
   return drk_node_linear2(a, lda, b, ldb, k, nullptr, 0, nullptr, 0, 0, trans_b, bias, mask, ld_mask, c, ldc, n, m, act, stream);
 }
 
+static size_t wgrad_tc_bytes(int32_t k, int32_t m) {
+  const size_t m_pad = (size_t)(m + 15) / 16 * 16, k_pad = (size_t)(k + 7) / 8 * 8;
+  return (size_t)drk::kNumSM * (m_pad * k_pad + m_pad) * sizeof(float);
+}
+
 size_t drk_weight_grad_workspace_bytes(int32_t k, int32_t m) {
   if (k <= 0 || m <= 0) return 0;
-  return drk::plan_wgrad(k, m).bytes;
+  return std::max(drk::plan_wgrad(k, m).bytes, wgrad_tc_bytes(k, m));
 }
 
 int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t n, int32_t k, int32_t m, float* dw,
@@ -644,6 +808,29 @@ int drk_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ldx,
   const WgradPlan pl = plan_wgrad(k, m);
   DRK_REQUIRE(workspace != nullptr && workspace_bytes >= pl.bytes, DRK_EWORKSPACE, "weight grad: workspace %zu < %zu bytes",
               workspace_bytes, pl.bytes);
+  // Row-contiguous operands of many rows: tensor cores (3xTF32) fed by bulk copies, see k_weight_grad_tc.  DRK_WGRAD_TC=0 disables.
+  static const bool wt_off = [] {
+    const char* e = std::getenv("DRK_WGRAD_TC");
+    return e != nullptr && e[0] == '0';
+  }();
+  if (!wt_off && ld_dy == m && ldx == k && aligned16(dy) && aligned16(x) && m <= 64 && k <= 64 && n >= 4096 && workspace_bytes >= wgrad_tc_bytes(k, m) &&
+      n * std::max(k, m) < ((int64_t)1 << 31)) {
+    const int m_pad = (m + 15) / 16 * 16, k_pad = (k + 7) / 8 * 8;
+    const int num_tiles = (int)ceil_div<int64_t>(n, kWtRows);
+    const int grid = std::min(num_tiles, kNumSM);
+    float* part = static_cast<float*>(workspace);
+    float* part_bias = part + (size_t)grid * m_pad * k_pad;
+    WgradTcArgs t{dy, x, n, k, m, part, dbias != nullptr ? part_bias : nullptr, m_pad, k_pad, num_tiles};
+    const size_t stage = (size_t)((kWtRows * m + 3) / 4 * 4 + kWtRows * k + 8) * sizeof(float);
+    const size_t smem = std::max<size_t>(2 * stage, (size_t)2 * 16 * 32 * 4 * sizeof(float)) + 64;
+    cudaError_t e = cudaFuncSetAttribute(k_weight_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DRK_REQUIRE(e == cudaSuccess, DRK_ECUDA, "weight grad: smem opt-in: %s", cudaGetErrorString(e));
+    cudaStream_t st_tc = as_stream(stream);
+    k_weight_grad_tc<<<grid, kWtThreads, smem, st_tc>>>(t);
+    const int total_tc = m * k + (dbias != nullptr ? m : 0);
+    k_weight_grad_reduce<<<ceil_div(total_tc * 32, 256), 256, 0, st_tc>>>(part, part_bias, grid, m, k, m_pad, k_pad, dw, ld_dw, dbias, accumulate);
+    return finish_launch("weight grad (tensor cores)", 2);
+  }
   float* partial = static_cast<float*>(workspace);
   float* partial_bias = partial + (size_t)pl.grid_x * pl.m_pad * pl.k_pad;
   WgradArgs a{dy, ld_dy, x, ldx, n, k, m, partial, dbias != nullptr ? partial_bias : nullptr, pl.m_pad, pl.k_pad, 1, 1};

@@ -179,7 +179,9 @@ def test_node_linear_strided_views():
     assert float(out[:, :32].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (300, 50, 16), (5000, 50, 32), (777, 16, 32), (1000, 16, 64), (640, 101, 32), (333, 82, 50), (100, 130, 70)])
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (300, 50, 16), (5000, 50, 32), (777, 16, 32), (1000, 16, 64), (640, 101, 32), (333, 82, 50), (100, 130, 70),
+                                   # row-contiguous, n >= 4096, M, K <= 64: the tensor-core kernel (ragged last tile, odd widths, one-column operands)
+                                   (4096, 16, 16), (77469, 50, 64), (9999, 50, 50), (5003, 7, 33), (4100, 64, 1), (12345, 1, 64), (8191, 32, 32)])
 def test_weight_grad(n, k, m):
     ops = _ops()
     gen = torch.Generator().manual_seed(n + k + m)
