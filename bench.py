@@ -452,12 +452,19 @@ def e2e_generic(dev, config: str, steps: int):
         def run(b):
             return inner(b)[0]
 
+    def fresh():
+        # a shallow view of the pinned host batch: `to` replaces the VIEW's tensors by device copies (one DMA out of the pinned slab) and
+        # leaves the host batch as it is.  (`host.clone()` here used to deep-copy 64 MB into pageable memory every step: 63 ms per step.)
+        view = copy.copy(host)
+        view.__dict__ = dict(host.__dict__)
+        return view.to(dev, non_blocking=True)
+
     for _ in range(3):
-        float(run(host.clone().to(dev, non_blocking=True)))
+        float(run(fresh()))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        float(run(host.clone().to(dev, non_blocking=True)))
+        float(run(fresh()))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return {"value": host.num_graphs * steps / dt, "unit": "graphs/s", "h2d_bytes_per_step": batch_nbytes(host), "d2h_bytes_per_step": 4, "steps": steps,
