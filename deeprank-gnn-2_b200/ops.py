@@ -504,11 +504,15 @@ def edge_msg_bwd_c(graph: GraphIndex, ds, mask, edge_attr, out):
 
 # ------------------------------------------------------------------------------ per-graph fused Vanilla layer (drk_vanilla.cu)
 VANILLA_FUSED = os.environ.get("DRK_VANILLA_FUSED", "1") != "0"
+# One CTA per graph: a batch of few graphs leaves most of the 148 SMs idle and the batch-level kernels win.  Measured on the C2 graphs
+# (profiles/vanilla_crossover_probe.py, train step in ms, fused / batch-level): 16 graphs 0.42 / 0.30, 64: 0.45 / 0.42, 96: 0.46 / 0.51,
+# 128: 0.48 / 0.59, 256: 0.78 / 0.89.
+VANILLA_FUSED_MIN_GRAPHS = int(os.environ.get("DRK_VANILLA_FUSED_MIN_GRAPHS", "80"))
 
 
 def _vanilla_fused_ok(x, we, wn, graph: GraphIndex, f: int, fe: int) -> bool:
     """One CTA per graph needs the graphs' node ranges (collated batches) and every graph to fit one SM's shared memory."""
-    if not VANILLA_FUSED or graph.graph_ptr is None or not graph.max_graph_nodes or graph.colptr is None or graph.num_graphs < 1:
+    if not VANILLA_FUSED or graph.graph_ptr is None or not graph.max_graph_nodes or graph.colptr is None or graph.num_graphs < max(1, VANILLA_FUSED_MIN_GRAPHS):
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and we.dtype == torch.float32 and wn.dtype == torch.float32):
         return False

@@ -227,10 +227,15 @@ def test_sgat_train_step_vs_reference(case):
     _train_step_vs_golden(g, "sgat", net)
 
 
-def test_vanilla_c2_batch_vs_oracle():
-    """Config C4: VanillaNetwork on C2-style batches (16 graphs), CUDA vs CPU oracle incl. all gradients."""
+@pytest.mark.parametrize("route", ["per-graph kernels", "batch-level kernels"])
+def test_vanilla_c2_batch_vs_oracle(route, monkeypatch):
+    """Config C4: VanillaNetwork on C2-style batches (16 graphs), CUDA vs CPU oracle incl. all gradients, through the per-graph layer
+    kernels (the default only for batches of >= 80 graphs) and through the batch-level kernels."""
+    from deeprank2_b200 import ops
     from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
     from deeprank2_b200.synthetic import make_batch
+
+    monkeypatch.setattr(ops, "VANILLA_FUSED_MIN_GRAPHS", 1 if route == "per-graph kernels" else 10**9)
 
     batch = make_batch(16)
     torch.manual_seed(1)

@@ -40,6 +40,7 @@ def _layer_run(layer, batch, gout, fused: bool, monkeypatch):
     from deeprank2_b200.graph import graph_index
 
     monkeypatch.setattr(ops, "VANILLA_FUSED", fused)
+    monkeypatch.setattr(ops, "VANILLA_FUSED_MIN_GRAPHS", 1)  # (the default sends batches of fewer than 80 graphs to the batch-level kernels)
     gb = batch.clone().to(DEV)
     g = graph_index(gb)
     assert ops._vanilla_fused_ok(gb.x, layer._edge_mlp[0].weight, layer._node_mlp[0].weight, g, gb.x.shape[1], gb.edge_attr.shape[1]) == fused
@@ -104,6 +105,7 @@ def test_fused_layer_without_input_gradient_and_without_bias(monkeypatch):
     wn = (torch.randn(20, 52) * 0.2).to(DEV).requires_grad_(True)
     gout = torch.randn(gb.x.shape[0], 20, device=DEV)
     outs = []
+    monkeypatch.setattr(ops, "VANILLA_FUSED_MIN_GRAPHS", 1)
     for fused in (True, False):
         monkeypatch.setattr(ops, "VANILLA_FUSED", fused)
         we.grad = wn.grad = None
@@ -116,10 +118,11 @@ def test_fused_layer_without_input_gradient_and_without_bias(monkeypatch):
 
 def test_fused_network_train_step_is_capturable_and_few_launches(monkeypatch):
     """VanillaNetwork train step on a collated batch: every conv layer is one launch per direction (+ one fixed-order reduction)."""
-    from deeprank2_b200 import _lib
+    from deeprank2_b200 import _lib, ops
     from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
     from deeprank2_b200.synthetic import make_batch
 
+    monkeypatch.setattr(ops, "VANILLA_FUSED_MIN_GRAPHS", 1)
     batch = make_batch(6)
     torch.manual_seed(1)
     net = VanillaNetwork(50, 1, 1).to(DEV)
@@ -187,10 +190,13 @@ def test_fused_kernels_stay_inside_their_output_buffers():
     assert bool((bufs["mask"][1][: g.num_edges] != -7).any())
 
 
-def test_fused_network_inference_equals_training_forward():
+def test_fused_network_inference_equals_training_forward(monkeypatch):
     """Under ``no_grad`` the layer kernel skips the backward pass's side outputs (cnt, tf): same predictions, bit for bit."""
+    from deeprank2_b200 import ops
     from deeprank2_b200.neuralnets.gnn.vanilla_gnn import VanillaNetwork
     from deeprank2_b200.synthetic import make_batch
+
+    monkeypatch.setattr(ops, "VANILLA_FUSED_MIN_GRAPHS", 1)
 
     gb = make_batch(5, first=11).to(DEV)
     torch.manual_seed(2)
