@@ -11,7 +11,9 @@
 // to HBM and gather V rows through L2; here V stays in shared memory for the whole graph, U and S only ever exist as 64-row tiles, and
 // the three projections run on the tensor cores (mma.sync m16n8k8 TF32 with error compensation, fp32-level accuracy: drk_common.cuh)
 // from weight fragments that a persistent CTA splits once.  Rows of x stream through a 4-deep ring of 64-row tiles filled by the copy
-// engine (cp.async.bulk), prefetched across passes and across graphs.
+// engine (cp.async.bulk), prefetched across passes and across graphs.  In the forward edge pass a warp sums two destination rows at a
+// time (half a warp each, a lane owns the channel pair (l, l + 16) as one packed fp32x2 operand) and builds the per-edge ReLU mask
+// words without a vote in the loop (one 16 x 16 bit transpose per chunk): DESIGN.md 4.5 has the phase clocks that led there.
 //
 // Data layout: x / out [N, F] row-contiguous, S [N, 32], ReLU masks one 32-bit word per edge in CSR-SLOT order (bit c = channel c),
 // edge attributes [E, Fe] in slot order (GraphIndex.attr_in_slot_order) -- all interchangeable with the batch-level kernels, which stay
@@ -215,8 +217,7 @@ __global__ void __launch_bounds__(kT, 1) k_vanilla_fwd(const FwdArgs a) {
   float* sBn = sBe + kMsg;
   float* sU = sBn + kMaxF;                           // [64][32]
   float* sS = sU + kRows * kMsg;                     // [64][36]
-  uint32_t* sMw = reinterpret_cast<uint32_t*>(sS + kRows * kSStride);  // [warps][32] ReLU masks of the chunk in flight
-  float* sStage = reinterpret_cast<float*>(sMw + kNW * 32);
+  float* sStage = sS + kRows * kSStride;
   float* sV = sStage + kStages * stage_floats;       // [rows_cap + 1][32], channel-paired; the last row is -inf
   int* sRp = reinterpret_cast<int*>(sV + (size_t)(a.rows_cap + 1) * kMsg);   // [rows_cap + 1] CSR offsets of the graph's rows
 
@@ -1017,7 +1018,7 @@ static size_t fwd_smem_bytes(int f, int rows_cap) {
   const int ks = (f + 7) / 8, nto = ks;
   const size_t stage_floats = (size_t)((kRows * f + 4 + 3) & ~3);
   size_t b = (size_t)(ks * 4 * 32 * 2 + (ks + 4) * nto * 32) * sizeof(uint4);
-  b += (size_t)(kMsg + kMaxF + kRows * kMsg + kRows * kSStride + kNW * 32) * 4;
+  b += (size_t)(kMsg + kMaxF + kRows * kMsg + kRows * kSStride) * 4;
   b += kStages * stage_floats * 4;
   b += (size_t)(rows_cap + 1) * kMsg * 4;
   b += (size_t)(rows_cap + 4) * 4;
